@@ -1,0 +1,230 @@
+"""ORACLE (test infrastructure only): torch-CPU functional restatement of the reference path.
+
+Every function issues the same ATen calls, in the same order and on the same shapes, as the
+reference method it cites, so on a given host it is bit-identical to the reference.  ``conf`` is
+a dict with the reference's ``backbone_conf`` keys (base_exp.py:40-92).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------------------------
+# T1-T3: lattice buffers
+# --------------------------------------------------------------------------------------------
+def frustum_buffer(conf):
+    """BV2:253-271 ``create_frustum`` -> (D, fH, fW, 4) = [u, v, d, 1]."""
+    H, W = conf["final_dim"]
+    fH, fW = H // conf["downsample_factor"], W // conf["downsample_factor"]
+    d = torch.arange(*conf["d_bound"], dtype=torch.float).view(-1, 1, 1).expand(-1, fH, fW)
+    D = d.shape[0]
+    u = torch.linspace(0, W - 1, fW, dtype=torch.float).view(1, 1, fW).expand(D, fH, fW)
+    v = torch.linspace(0, H - 1, fH, dtype=torch.float).view(1, fH, 1).expand(D, fH, fW)
+    return torch.stack((u, v, d, torch.ones_like(d)), -1)
+
+
+def voxel_buffer(xb, yb, zb):
+    """BV2:273-293 ``create_voxel_coords`` (norm=False) -> (Z, Y, X, 4) = [x, y, z, 1]."""
+    def axis(b):
+        return torch.linspace(b[0] + b[2] / 2., b[1] - b[2] / 2., int((b[1] - b[0]) / b[2]), dtype=torch.float)
+    zs, ys, xs = torch.meshgrid(axis(zb), axis(yb), axis(xb), indexing="ij")
+    return torch.stack([xs, ys, zs, torch.ones_like(xs)], dim=-1)
+
+
+def camera_mids(conf):
+    """BV2:243-246."""
+    t = torch.arange(*conf["d_bound"], dtype=torch.float)
+    return 0.5 * (t[..., :-1] + t[..., 1:])
+
+
+def bev_mids(conf):
+    """BV2:248-251 (flipped: top level first)."""
+    zb = conf["z_bound_det"]
+    t = torch.linspace(zb[0] + zb[2] / 2., zb[1] - zb[2] / 2., int((zb[1] - zb[0]) / zb[2]), dtype=torch.float)
+    return torch.flip(t, dims=[0])
+
+
+def build_buffers(conf):
+    return {
+        "frustum": frustum_buffer(conf),
+        "voxel_coords": voxel_buffer(conf["x_bound_seg"], conf["y_bound_seg"], conf["z_bound_seg"]),
+        "output_coords": voxel_buffer(conf["x_bound_det"], conf["y_bound_det"], conf["z_bound_det"]),
+        "camera_mids": camera_mids(conf),
+        "bev_mids": bev_mids(conf),
+    }
+
+
+# --------------------------------------------------------------------------------------------
+# G1 / G2: projective geometry
+# --------------------------------------------------------------------------------------------
+def get_geometry(buf, sensor2ego, intrin, ida, bda):
+    """BV2:314-349: frustum lattice -> ego xyz, (B, N, D, fH, fW, 3)."""
+    B, N = sensor2ego.shape[:2]
+    pts = buf["frustum"]
+    pts = ida.view(B, N, 1, 1, 1, 4, 4).inverse().matmul(pts.unsqueeze(-1))
+    pts = torch.cat((pts[:, :, :, :, :, :2] * pts[:, :, :, :, :, 2:3], pts[:, :, :, :, :, 2:]), 5)
+    comb = sensor2ego.matmul(torch.inverse(intrin))
+    pts = comb.view(B, N, 1, 1, 1, 4, 4).matmul(pts)
+    if bda is not None:
+        bda = bda.unsqueeze(1).repeat(1, N, 1, 1).view(B, N, 1, 1, 1, 4, 4)
+        pts = (bda @ pts).squeeze(-1)
+    else:
+        pts = pts.squeeze(-1)
+    return pts[..., :3]
+
+
+def get_pixel(buf, sensor2ego, intrin, ida, bda):
+    """BV2:351-388: voxel centres -> augmented-image pixel + camera depth, (B, N, Z, Y, X, 3)."""
+    B, N = sensor2ego.shape[:2]
+    pts = buf["voxel_coords"]
+    if bda is not None:
+        bda = bda.unsqueeze(1).repeat(1, N, 1, 1).view(B, N, 1, 1, 1, 4, 4)
+        pts = bda.inverse().matmul(pts.unsqueeze(-1))
+    else:
+        pts = pts.unsqueeze(-1)
+    comb = intrin.matmul(torch.inverse(sensor2ego))
+    pts = comb.view(B, N, 1, 1, 1, 4, 4).matmul(pts)
+    zc = pts[:, :, :, :, :, 2:3]
+    pts = torch.cat((pts[..., :2, :] / torch.clamp(zc, min=1e-6), pts[..., 2:, :]), dim=5)
+    pts = ida.view(B, N, 1, 1, 1, 4, 4).matmul(pts).squeeze(-1)
+    return pts[..., :3]
+
+
+# --------------------------------------------------------------------------------------------
+# L1-L4: lift + pool
+# --------------------------------------------------------------------------------------------
+def lift_outer(depth, ctx):
+    """BV2:553: (B,N,D,h,w) x (B,N,C,h,w) -> (B,N,C,D,h,w)."""
+    return depth.unsqueeze(2) * ctx.unsqueeze(3)
+
+
+def lift_norm_coords(conf, pix):
+    """BV2:493-506: validity mask and normalised (clamped) sampling coordinates."""
+    H, W = conf["final_dim"]
+    db = conf["d_bound"]
+    x, y, z = pix[..., 0], pix[..., 1], pix[..., 2]
+    xv = (x > -0.5).bool() & (x < float(W - 0.5)).bool()
+    yv = (y > -0.5).bool() & (y < float(H - 0.5)).bool()
+    zv = (z > db[0]).bool() & (z < db[1]).bool()
+    valid = (xv & yv & zv).float()
+    nx = 2.0 * (x / float(W - 1)) - 1.0
+    ny = 2.0 * (y / float(H - 1)) - 1.0
+    nz = 2.0 * ((z - db[0]) / (db[1] - db[0])) - 1.0
+    nx = torch.clamp(nx, min=-2.0, max=2.0)
+    ny = torch.clamp(ny, min=-2.0, max=2.0)
+    nz = torch.clamp(nz, min=-2.0, max=2.0)
+    return valid, torch.stack([nx, ny, nz], dim=-1)
+
+
+def get_voxel_feats(conf, buf, frustum_feats, mats):
+    """BV2:483-516: gather the frustum volume at every voxel centre, mean over seeing cameras."""
+    B, N, C, d, h, w = frustum_feats.shape
+    pix = get_pixel(buf, mats["sensor2ego_mats"][:, 0], mats["intrin_mats"][:, 0],
+                    mats["ida_mats"][:, 0], mats.get("bda_mat", None))
+    Z, Y, X = buf["voxel_coords"].shape[:3]
+    valid, nxyz = lift_norm_coords(conf, pix)
+    nxyz = nxyz.reshape(-1, Z, Y, X, 3)
+    vf = F.grid_sample(frustum_feats.reshape(-1, C, d, h, w), nxyz, align_corners=False)
+    vf = vf.reshape(B, N, C, Z, Y, X) * valid.unsqueeze(2)
+    mask = (torch.abs(vf) > 0).float()
+    numer = torch.sum(vf, dim=1)
+    denom = torch.sum(mask, dim=1) + 1e-6
+    return numer / denom
+
+
+def lift_pool(conf, buf, depth, ctx, mats):
+    """BV2:553 + 563: the fused operation the product implements."""
+    return get_voxel_feats(conf, buf, lift_outer(depth, ctx), mats)
+
+
+# --------------------------------------------------------------------------------------------
+# T4: density
+# --------------------------------------------------------------------------------------------
+def laplace_density(s, beta_param, bias, beta_min=1e-4):
+    """render_utils.py:30-46 ``ModifyLaplaceDensity``."""
+    beta = beta_param.abs() + beta_min
+    alpha = 1 / beta
+    return alpha * (0.5 + 0.5 * (s - bias).sign() * torch.expm1(-(s - bias).abs() / beta))
+
+
+# --------------------------------------------------------------------------------------------
+# R1-R6: volume rendering
+# --------------------------------------------------------------------------------------------
+def _seg_lo_ext(conf):
+    xb, yb, zb = conf["x_bound_seg"], conf["y_bound_seg"], conf["z_bound_seg"]
+    lo = torch.as_tensor([xb[0], yb[0], zb[0]])
+    ext = torch.as_tensor([xb[1] - xb[0], yb[1] - yb[0], zb[1] - zb[0]])
+    return lo, ext
+
+
+def render_norm_geom(conf, geom):
+    """BV2:397-407: normalised sample coordinates of planes 0..D-2 and the inclusive mask."""
+    lo, ext = _seg_lo_ext(conf)
+    g = (geom[:, :, :-1, :, :] - lo) / ext
+    g = g * 2. - 1.
+    m = (g[..., 0] >= -1.) & (g[..., 0] <= 1.) & (g[..., 1] >= -1.) & (g[..., 1] <= 1.) & \
+        (g[..., 2] >= -1.) & (g[..., 2] <= 1.)
+    return g, m
+
+
+def render_norm_output(conf, buf):
+    """BV2:408-417."""
+    lo, ext = _seg_lo_ext(conf)
+    g = (buf["output_coords"][..., :3] - lo) / ext
+    return g * 2. - 1.
+
+
+def volume_rendering(conf, buf, geom, density_feature, semantic_logits, voxel_features, rgb, beta_param):
+    """BV2:391-467 ``volume_rendering_from_multiple_views`` (density_mode='sdf', cat_seg=False)."""
+    B, N, d, h, w, _ = geom.shape
+    K = conf["num_classes"]
+    bias = conf["sdf_bias"]
+    vol = torch.cat([density_feature, semantic_logits, rgb, voxel_features], dim=1)
+    g, m = render_norm_geom(conf, geom)
+    go = render_norm_output(conf, buf)
+    go = go[None, ...].expand(B, *go.shape)
+    ff = F.grid_sample(vol, g.reshape(B, -1, h, w, 3), align_corners=True)
+    ff = ff.reshape(B, -1, N, d - 1, h, w).permute(0, 2, 1, 3, 4, 5) * m.unsqueeze(2)
+    ff = torch.nan_to_num(ff)
+    f_den = laplace_density(ff[:, :, :1, ...], beta_param, bias)
+    f_seg = ff[:, :, 1:K + 1, ...]
+    f_rgb = ff[:, :, K + 1:K + 4, ...]
+    f_delta = torch.norm(geom[:, :, 1:, :, :, :] - geom[:, :, :-1, :, :, :], dim=-1)
+    sd = f_den * f_delta.unsqueeze(2)
+    alpha = 1 - torch.exp(-sd)
+    trans = torch.exp(-torch.cat([torch.zeros_like(sd[:, :, :, :1, :, :]),
+                                  torch.cumsum(sd[:, :, :, :-1, :, :], dim=3)], dim=3))
+    wts = alpha * trans
+    acc = wts.sum(dim=3)
+    bg_depth = (1 - acc) * conf["d_bound"][1]
+    rgb_p = torch.sum(wts * f_rgb, dim=3)
+    seg_p = torch.sum(wts * f_seg, dim=3)
+    dep_p = (wts * buf["camera_mids"][None, None, None, :, None, None]).sum(dim=3) + bg_depth
+
+    vf = F.grid_sample(vol, go, align_corners=True)
+    vf = torch.flip(vf, dims=[2])
+    v_den = laplace_density(vf[:, :1, ...], beta_param, bias)
+    v_seg = vf[:, 1:K + 1, ...]
+    v_rgb = vf[:, K + 1:K + 4, ...]
+    v_out = vf[:, K + 4:, ...]
+    if conf.get("cat_seg", False):
+        v_out = torch.cat((v_out, v_seg), dim=1)
+    v_delta = torch.ones_like(v_den) * conf["z_bound_det"][2]
+    vsd = v_den * v_delta
+    v_alpha = 1 - torch.exp(-vsd)
+    v_trans = torch.exp(-torch.cat([torch.zeros_like(vsd[:, :, :1, :, :]),
+                                    torch.cumsum(vsd[:, :, :-1, :, :], dim=2)], dim=2))
+    v_w = v_alpha * v_trans
+    bev_rgb = torch.sum(v_w * v_rgb, dim=2)
+    bev_seg = torch.sum(v_w * v_seg, dim=2)
+    bev_h = (v_w * buf["bev_mids"][None, None, :, None, None]).sum(dim=2)
+    return rgb_p, seg_p, dep_p, bev_rgb, bev_seg, bev_h, v_den, v_out
+
+
+def render_from_mats(conf, buf, mats, density_feature, semantic_logits, voxel_features, rgb, beta_param):
+    """BV2:554-559 + 612-614: geometry -> nan_to_num -> render (the fused operation)."""
+    geom = get_geometry(buf, mats["sensor2ego_mats"][:, 0], mats["intrin_mats"][:, 0],
+                        mats["ida_mats"][:, 0], mats.get("bda_mat", None))
+    geom = torch.nan_to_num(geom, -1e3)
+    return volume_rendering(conf, buf, geom, density_feature, semantic_logits, voxel_features, rgb, beta_param)

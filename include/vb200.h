@@ -1,0 +1,215 @@
+/*
+ * vb200.h -- C ABI of libvb200.so: the B200-native (sm_100a) 2D->3D feature path of Vampire.
+ *
+ * This is the drop-in boundary.  The reference (cskkxjk/Vampire) has no FFI of its own: its
+ * setup.py registers a BuildExtension with NO ext_modules (/root/reference/setup.py:10-26) and the
+ * path is four methods of the backbone nn.Module plus one inline expression
+ * (/root/reference/src/layers/backbones/base_vampire2.py, "BV2" below).  The entry points here
+ * are what a CUDA extension in that setup.py would bind, one per reference call site:
+ *
+ *   vb200_get_pixel          <- BaseVAMPIRE2.get_pixel                         BV2:351-388
+ *   vb200_get_geometry       <- BaseVAMPIRE2.get_geometry (+ nan_to_num)       BV2:314-349, 612
+ *   vb200_lift_indices       <- the integers behind F.grid_sample in get_voxel_feats   BV2:493-507
+ *   vb200_render_indices     <- the integers behind F.grid_sample in the render        BV2:397-419
+ *   vb200_lift_pool_fwd/bwd  <- depth (x) ctx outer product + get_voxel_feats  BV2:553, 483-516
+ *   vb200_render_fwd/bwd     <- volume_rendering_from_multiple_views           BV2:391-467
+ *                               with ModifyLaplaceDensity        src/utils/render_utils.py:30-46
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, ints and floats only; no C++/torch types; no exceptions.
+ *   - every pointer named d_* is DEVICE memory owned by the caller (the PyTorch caching
+ *     allocator in the Python host); the library allocates nothing and keeps no mutable state.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant and
+ *     thread-safe.
+ *   - return 0 on success, a negative VB200_ERR_* otherwise; vb200_strerror() names it.
+ *   - there is no CPU fallback: on a device that is not sm_100 the compute calls return
+ *     VB200_ERR_ARCH.
+ *   - feature tensors come in `dtype` VB200_F32 / VB200_BF16 / VB200_F16; all arithmetic and all
+ *     geometry is fp32 (the reference runs the geometry under autocast(enabled=False), BV2:485).
+ */
+#ifndef VB200_H_
+#define VB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB200_VERSION 100 /* 0.1.0 */
+
+enum vb200_status {
+  VB200_OK = 0,
+  VB200_ERR_ARG = -1,       /* null pointer / bad size / unsupported channel count */
+  VB200_ERR_DTYPE = -2,     /* unknown dtype code */
+  VB200_ERR_ARCH = -3,      /* current device is not sm_100 */
+  VB200_ERR_WORKSPACE = -4, /* workspace too small */
+  VB200_ERR_CUDA = -5,      /* a CUDA runtime call or launch failed (see cudaGetLastError) */
+  VB200_ERR_ALIGN = -6      /* a pointer is not 16-byte aligned */
+};
+
+enum vb200_dtype { VB200_F32 = 0, VB200_BF16 = 1, VB200_F16 = 2 };
+
+/* memory layout of a (B, C, Z, Y, X) volume */
+enum vb200_layout {
+  VB200_NCDHW = 0, /* the reference's contiguous layout, x fastest           */
+  VB200_NDHWC = 1  /* channels-last (torch.channels_last_3d), channel fastest */
+};
+
+/* Static description of the path: sizes + the fp32 constants the reference derives from its
+ * backbone_conf (base_exp.py:40-92).  Floats are the Python doubles rounded to fp32 exactly as
+ * torch rounds a Python scalar operand. */
+typedef struct VbGrid {
+  int32_t B, N;           /* samples, cameras per sample (6)                                    */
+  int32_t D, fH, fW;      /* depth planes (86), feature rows (64), feature cols (176)           */
+  int32_t vZ, vY, vX;     /* seg voxel grid (20, 256, 256)                                      */
+  int32_t oZ, oY, oX;     /* det / BEV grid (10, 256, 256)                                      */
+  int32_t C, K;           /* context channels (16), semantic classes (18)                       */
+  int32_t has_bda;        /* 0: mats_dict has no 'bda_mat' (BV2:370,343 skip the bda products)  */
+  float img_w_m1, img_h_m1; /* float(W-1), float(H-1)          BV2:499-500                      */
+  float x_hi, y_hi;       /* float(W-0.5), float(H-0.5)        BV2:494-495                      */
+  float d_lo, d_hi;       /* d_bound[0], d_bound[1]            BV2:496                          */
+  float d_ext;            /* d_bound[1]-d_bound[0] in double, then fp32   BV2:501               */
+  float seg_lo[3];        /* x/y/z_bound_seg[0]                BV2:397-399                      */
+  float seg_ext[3];       /* x/y/z_bound_seg[1]-[0]            BV2:400-402                      */
+  float bg_depth;         /* d_bound[1]                        BV2:436                          */
+  float bev_delta;        /* z_bound_det[2]                    BV2:451                          */
+  float sdf_bias;         /* density bias (-1)                 render_utils.py:35               */
+  float beta_min;         /* 1e-4                              render_utils.py:31               */
+  float term_eps;         /* early-termination threshold on transmittance; 0 disables          */
+} VbGrid;
+
+/* Lattice tables, DEVICE pointers to fp32 arrays built on the host with the reference's own torch
+ * calls (BV2:243-293); recomputing them in-kernel is not bit-identical. */
+typedef struct VbTables {
+  const float* us;       /* [fW]  linspace(0, W-1, fW)                       */
+  const float* vs;       /* [fH]  linspace(0, H-1, fH)                       */
+  const float* ds;       /* [D]   arange(*d_bound)                           */
+  const float* xs;       /* [vX]  seg voxel centres                          */
+  const float* ys;       /* [vY]                                             */
+  const float* zs;       /* [vZ]                                             */
+  const float* oxs;      /* [oX]  det voxel centres                          */
+  const float* oys;      /* [oY]                                             */
+  const float* ozs;      /* [oZ]                                             */
+  const float* mids;     /* [D-1] interval mid depths                        */
+  const float* bev_mids; /* [oZ]  BEV level heights, top level first         */
+} VbTables;
+
+/* d_mats: (B, N, 6, 4, 4) fp32 row-major, prepared on the host with the reference's torch calls:
+ *   slot 0 bda^-1 | 1 K.E^-1 | 2 ida | 3 ida^-1 | 4 E.K^-1 | 5 bda      (vampire_b200/matrices.py) */
+#define VB200_MAT_SLOTS 6
+
+int vb200_version(void);
+const char* vb200_strerror(int status);
+/* 0 if the current CUDA device is sm_100, VB200_ERR_ARCH otherwise */
+int vb200_device_check(void);
+
+/* ---- geometry ------------------------------------------------- */
+
+/* G1: d_pix (B, N, vZ, vY, vX, 3) fp32 = get_pixel(...)                          BV2:351-388 */
+int vb200_get_pixel(const VbGrid* g, const VbTables* t, const float* d_mats, float* d_pix, void* stream);
+
+/* G2: d_geom (B, N, D, fH, fW, 3) fp32 = get_geometry(...); nan_to_num != 0 additionally applies
+ * torch.nan_to_num(geom, -1e3)                                                  BV2:314-349, 612 */
+int vb200_get_geometry(const VbGrid* g, const VbTables* t, const float* d_mats, float* d_geom,
+                       int nan_to_num, void* stream);
+
+/* L2: per (b, n, voxel): valid (uint8), base corner (x0, y0, z0) int16 x3, fractions fp32 x3 of the
+ * align_corners=False trilinear lookup into the (D, fH, fW) frustum volume.  Any output may be NULL. */
+int vb200_lift_indices(const VbGrid* g, const VbTables* t, const float* d_mats, uint8_t* d_valid,
+                       int16_t* d_i0, float* d_frac, void* stream);
+
+/* R2: per (b, n, s<D-1, h, w): geom_valid_mask (uint8), base voxel (x0, y0, z0) int16 x3 and fractions
+ * of the align_corners=True lookup into the (vZ, vY, vX) volume.  d_geom may be NULL (geometry is
+ * then recomputed from d_mats + nan_to_num) or a (B, N, D, fH, fW, 3) tensor as passed to the
+ * reference's render.  Any output may be NULL. */
+int vb200_render_indices(const VbGrid* g, const VbTables* t, const float* d_mats, const float* d_geom,
+                         uint8_t* d_mask, int16_t* d_i0, float* d_frac, void* stream);
+
+/* ---- lift + pool (Bk) --------------------------------------------------- */
+
+/* bytes of scratch vb200_lift_pool_fwd / _bwd need for grid g and feature dtype */
+size_t vb200_lift_pool_fwd_workspace(const VbGrid* g, int dtype);
+size_t vb200_lift_pool_bwd_workspace(const VbGrid* g, int dtype);
+
+/* Forward: out[b,c,z,y,x] = sum_n f[n,c] / (sum_n [|f[n,c]|>0] + 1e-6), f = valid * trilinear sample
+ * of depth[b,n] (x) ctx[b,n] at the projected voxel centre -- the frustum tensor is never formed.
+ *   d_depth (B,N,D,fH,fW), d_ctx (B,N,C,fH,fW) in `dtype` (contiguous, reference layout)
+ *   d_out   (B,C,vZ,vY,vX) in `dtype`, memory layout `out_layout`
+ *   d_cnt   optional (B, vZ*vY*vX) uint64: per-channel non-zero camera count, 4 bits per channel
+ *           (saved for the backward); may be NULL for inference. */
+int vb200_lift_pool_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, const void* d_depth,
+                        const void* d_ctx, int dtype, void* d_out, int out_layout, uint64_t* d_cnt,
+                        void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Backward: deterministic (sorted-segment gather, no float atomics).
+ *   d_gout (B,C,vZ,vY,vX) in `dtype`, layout gout_layout; d_cnt from the forward
+ *   d_gdepth (B,N,D,fH,fW), d_gctx (B,N,C,fH,fW) in `dtype` (fully overwritten) */
+int vb200_lift_pool_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const void* d_depth,
+                        const void* d_ctx, int dtype, const void* d_gout, int gout_layout,
+                        const uint64_t* d_cnt, void* d_gdepth, void* d_gctx, void* d_workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* ---- volume rendering (Bk) ------------------------------------------ */
+
+typedef struct VbRenderIn {
+  const void* density;  /* (B, 1, vZ, vY, vX) density_feature, `dtype`, NCDHW */
+  const void* sem;      /* (B, K, vZ, vY, vX) semantic_logits                 */
+  const void* rgb;      /* (B, 3, vZ, vY, vX)                                 */
+  const void* feat;     /* (B, C, vZ, vY, vX) base features                   */
+  const float* beta;    /* device pointer to the learnable density.beta scalar */
+  const float* geom;    /* optional (B, N, D, fH, fW, 3) fp32 geometry as passed to the reference's
+                           render; NULL = recompute from d_mats (+ nan_to_num), no 70 MB/sample read */
+} VbRenderIn;
+
+typedef struct VbRenderOut {
+  float* rgb;           /* (B, N, 3, fH, fW)                                  */
+  float* seg;           /* (B, N, K, fH, fW)                                  */
+  float* depth;         /* (B, N, 1, fH, fW)                                  */
+  float* bev_rgb;       /* (B, 3, oY, oX)                                     */
+  float* bev_seg;       /* (B, K, oY, oX)                                     */
+  float* bev_height;    /* (B, 1, oY, oX)                                     */
+  float* voxel_density; /* (B, 1, oZ, oY, oX)  sigma, top level first         */
+  void* voxel_output;   /* (B, C, oZ, oY, oX)  `dtype`, resampled features    */
+} VbRenderOut;
+
+size_t vb200_render_fwd_workspace(const VbGrid* g, int dtype);
+size_t vb200_render_bwd_workspace(const VbGrid* g, int dtype);
+
+/* branches: bit 0 = camera branch, bit 1 = BEV branch */
+#define VB200_BRANCH_CAM 1
+#define VB200_BRANCH_BEV 2
+
+int vb200_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, const VbRenderIn* in,
+                     int dtype, const VbRenderOut* out, int branches, void* d_workspace,
+                     size_t workspace_bytes, void* stream);
+
+typedef struct VbRenderGrad {
+  /* cotangents of the eight outputs (same shapes/dtypes as VbRenderOut; NULL = zero) */
+  const float* g_rgb;
+  const float* g_seg;
+  const float* g_depth;
+  const float* g_bev_rgb;
+  const float* g_bev_seg;
+  const float* g_bev_height;
+  const float* g_voxel_density;
+  const void* g_voxel_output;
+  /* gradients of the inputs (fully overwritten), `dtype`; g_beta is 1 fp32 */
+  void* g_density;
+  void* g_sem;
+  void* g_rgb_in;
+  void* g_feat;
+  float* g_beta;
+} VbRenderGrad;
+
+/* `out` = the forward's outputs (the compositing backward reuses them: suffix sums are formed
+ * as total - prefix). */
+int vb200_render_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const VbRenderIn* in,
+                     int dtype, const VbRenderOut* out, const VbRenderGrad* grad, int branches,
+                     void* d_workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VB200_H_ */

@@ -1,0 +1,149 @@
+"""GPU: L1-L4 lift+pool and R1-R6 render forward through the C ABI / custom ops, against the
+reference's golden outputs and the live torch oracle."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import CASES, Case, assert_close_scaled, golden_value
+from oracle import torch_path as tp
+
+pytestmark = pytest.mark.gpu
+
+FP32_REL = 1e-5     # north star: 1e-5 relative in fp32
+BF16_REL = 1e-2     # 1e-2 with bf16 features
+NAMES = ["rgb", "seg", "depth", "bev_rgb", "bev_seg", "bev_height", "voxel_density", "voxel_output"]
+
+
+@pytest.fixture(scope="module", params=list(CASES))
+def case(request):
+    return Case(request.param)
+
+
+def _ops(cfg):
+    from vampire_b200 import ops
+    return ops, ops.register_config(cfg)
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_lift_pool_fp32_vs_reference(case, channels_last):
+    if not case.inputs_match_golden:
+        pytest.skip("inputs differ from the fixture's")
+    ops, cid = _ops(case.cfg)
+    out, cnt = ops.lift_pool_fwd(case.depth.cuda(), case.ctx.cuda(), case.prep.cuda(), cid, True, channels_last, True)
+    assert out.shape == (case.batch, case.cfg.C, case.cfg.vZ, case.cfg.vY, case.cfg.vX)
+    assert out.permute(0, 2, 3, 4, 1).is_contiguous() == channels_last
+    exp, got = golden_value(case.gold, "vox", out.contiguous().cpu().numpy())
+    assert_close_scaled(got, exp, FP32_REL, "pooled voxel features")
+
+
+def test_lift_pool_determinism(case):
+    ops, cid = _ops(case.cfg)
+    args = (case.depth.cuda(), case.ctx.cuda(), case.prep.cuda(), cid, True, False, False)
+    a = ops.lift_pool_fwd(*args)[0]
+    for _ in range(3):
+        assert torch.equal(a, ops.lift_pool_fwd(*args)[0])
+
+
+def test_lift_count_matches_oracle():
+    """Per-channel non-zero camera count (BV2:509-512) incl. exact zeros in ctx."""
+    from oracle import strict_np as sn
+    case = Case("mini_stress")
+    ops, cid = _ops(case.cfg)
+    ctx = case.ctx.clone()
+    ctx[:, :, 3] = 0.0           # a dead channel: count must be 0 -> output 0/(0+1e-6) = 0
+    ctx[:, 1, 5] = 0.0           # dead in one camera only
+    out, cnt = ops.lift_pool_fwd(case.depth.cuda(), ctx.cuda(), case.prep.cuda(), cid, True, False, True)
+    lat, cfg = case.lat, case.cfg
+    pix = sn.project_voxels(case.gold["prep"], lat.xs.numpy(), lat.ys.numpy(), lat.zs.numpy())
+    ref, rcnt = sn.lift_pool_factorised(case.depth.numpy(), ctx.numpy(), pix, cfg.final_dim, cfg.d_bound)
+    cnt = cnt.cpu().numpy().astype(np.uint64).reshape(case.batch, cfg.vZ, cfg.vY, cfg.vX)
+    got = np.stack([(cnt >> np.uint64(4 * c)) & np.uint64(0xF) for c in range(cfg.C)], 1).astype(np.int32)
+    assert np.array_equal(got, rcnt)
+    assert_close_scaled(out.cpu().numpy(), ref, FP32_REL, "pooled features with dead channels")
+    assert (out[:, 3] == 0).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_lift_pool_half_features(case, dtype):
+    """bf16/fp16-valued features, fp32 arithmetic; oracle fed the same rounded inputs."""
+    ops, cid = _ops(case.cfg)
+    d, c = case.depth.to(dtype), case.ctx.to(dtype)
+    out, _ = ops.lift_pool_fwd(d.cuda(), c.cuda(), case.prep.cuda(), cid, True, False, False)
+    assert out.dtype == dtype
+    buf = tp.build_buffers(case.conf)
+    with torch.no_grad():
+        ref = tp.lift_pool(case.conf, buf, d.float(), c.float(), case.mats)
+    assert_close_scaled(out.float().cpu().numpy(), ref.numpy(), BF16_REL, f"lift {dtype}")
+
+
+@pytest.mark.parametrize("from_tensor", [False, True])
+def test_render_fp32_vs_reference(case, from_tensor):
+    if not case.inputs_match_golden:
+        pytest.skip("inputs differ from the fixture's")
+    ops, cid = _ops(case.cfg)
+    prep = case.prep.cuda()
+    geom = ops.get_geometry(prep, cid, True, True) if from_tensor else None
+    beta = torch.tensor(0.1, device="cuda")
+    outs = ops.render_fwd(case.den.cuda(), case.sem.cuda(), case.rgb.cuda(), case.feat.cuda(), beta, prep, geom, cid,
+                          True, 3)
+    for n, o in zip(NAMES, outs):
+        exp, got = golden_value(case.gold, "r_" + n, o.cpu().numpy())
+        assert_close_scaled(got, exp, FP32_REL, n)
+
+
+def test_render_early_termination_is_within_tolerance():
+    """term_eps only skips samples whose weight is below 1e-8."""
+    case = Case("mini_val")
+    ops, cid = _ops(case.cfg)
+    st = ops.state(cid)
+    args = (case.den.cuda(), case.sem.cuda(), case.rgb.cuda(), case.feat.cuda(), torch.tensor(0.1, device="cuda"),
+            case.prep.cuda(), None, cid, True, 1)
+    old = st.term_eps
+    try:
+        st.term_eps = 0.0
+        full = [o.clone() for o in ops.render_fwd(*args)]
+        st.term_eps = 1e-8
+        cut = ops.render_fwd(*args)
+    finally:
+        st.term_eps = old
+    for n, a, b in zip(NAMES[:3], full, cut):
+        assert_close_scaled(b.cpu().numpy(), a.cpu().numpy(), 1e-6, n)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_render_half_features(case, dtype):
+    ops, cid = _ops(case.cfg)
+    vols = [t.to(dtype) for t in (case.den, case.sem, case.rgb, case.feat)]
+    beta = torch.tensor(0.1, device="cuda")
+    outs = ops.render_fwd(*[v.cuda() for v in vols], beta, case.prep.cuda(), None, cid, True, 3)
+    buf = tp.build_buffers(case.conf)
+    with torch.no_grad():
+        ref = tp.render_from_mats(case.conf, buf, case.mats, vols[0].float(), vols[1].float(), vols[3].float(),
+                                  vols[2].float(), torch.tensor(0.1))
+    assert outs[7].dtype == dtype
+    for n, o, r in zip(NAMES, outs, ref):
+        assert_close_scaled(o.float().cpu().numpy(), r.numpy(), BF16_REL, f"{n} {dtype}")
+
+
+def test_module_interface_matches_reference_signatures():
+    """LiftRenderB200 mirrors the backbone methods: same arguments, same return shapes/order."""
+    from vampire_b200.view_transform import LiftRenderB200
+    case = Case("mini_val")
+    mod = LiftRenderB200(**case.conf).cuda()
+    assert "density.beta" in mod.state_dict()
+    a = case.mat_args()
+    geom = mod.get_geometry(*a)
+    pix = mod.get_pixel(*a)
+    c = case.cfg
+    assert geom.shape == (case.batch, 6, c.D, c.fH, c.fW, 3) and pix.shape == (case.batch, 6, c.vZ, c.vY, c.vX, 3)
+    vox = mod.lift_pool(case.depth.cuda(), case.ctx.cuda(), case.mats)
+    exp, got = golden_value(case.gold, "vox", vox.cpu().numpy())
+    assert_close_scaled(got, exp, FP32_REL, "module lift_pool")
+    vols = [t.cuda() for t in (case.den, case.sem, case.feat, case.rgb)]
+    fused = mod.render(case.mats, *vols)
+    ref_sig = mod.volume_rendering_from_multiple_views(torch.nan_to_num(geom, -1e3), *vols)
+    assert len(fused) == len(ref_sig) == 8
+    for n, x, y in zip(NAMES, fused, ref_sig):
+        assert torch.equal(x, y), n
+        exp, got = golden_value(case.gold, "r_" + n, x.detach().cpu().numpy())
+        assert_close_scaled(got, exp, FP32_REL, n)

@@ -1,0 +1,55 @@
+"""CPU, build container only: the oracle against the live reference (skipped on the GPU box,
+which has no /root/reference -- there the committed golden fixtures pin the oracle)."""
+import pytest
+import torch
+
+from oracle import torch_path as tp
+from oracle.ref_import import build_reference_backbone, reference_available
+from vampire_b200 import synth
+from vampire_b200.config import MINI
+
+pytestmark = pytest.mark.skipif(not reference_available(), reason="/root/reference not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return build_reference_backbone(MINI.backbone_kwargs())
+
+
+@pytest.mark.parametrize("mode", ["val", "train", "stress"])
+def test_bit_identical_forward_and_backward(ref, mode):
+    cfg, conf = MINI, MINI.backbone_kwargs()
+    buf = tp.build_buffers(conf)
+    for k in ("frustum", "voxel_coords", "output_coords", "camera_mids", "bev_mids"):
+        assert torch.equal(getattr(ref, k), buf[k]), k
+    mats = synth.make_mats(cfg, 2, mode, seed=77)
+    a = (mats["sensor2ego_mats"][:, 0], mats["intrin_mats"][:, 0], mats["ida_mats"][:, 0], mats["bda_mat"])
+    assert torch.equal(ref.get_pixel(*a), tp.get_pixel(buf, *a))
+    assert torch.equal(ref.get_geometry(*a), tp.get_geometry(buf, *a))
+    depth, ctx = synth.make_lift_inputs(cfg, 2, seed=77)
+    den, sem, feat, rgb = synth.make_render_inputs(cfg, 2, seed=77, field="surface")
+    leaves = [depth, ctx, den, sem, feat, rgb]
+    for t in leaves:
+        t.requires_grad_(True)
+    geom = torch.nan_to_num(ref.get_geometry(*a), -1e3)
+    o_ref = [ref.get_voxel_feats(depth.unsqueeze(2) * ctx.unsqueeze(3), 0, mats)] + \
+        list(ref.volume_rendering_from_multiple_views(geom, den, sem, feat, rgb))
+    beta = ref.density.beta.detach().clone().requires_grad_(True)
+    o_me = [tp.lift_pool(conf, buf, depth, ctx, mats)] + \
+        list(tp.volume_rendering(conf, buf, geom, den, sem, feat, rgb, beta))
+    for x, y in zip(o_ref, o_me):
+        assert torch.equal(x, y)
+    cots = synth.make_cotangents([o.shape for o in o_ref], seed=5)
+    g_ref = torch.autograd.grad(sum((o * c).sum() for o, c in zip(o_ref, cots)), leaves + [ref.density.beta])
+    g_me = torch.autograd.grad(sum((o * c).sum() for o, c in zip(o_me, cots)), leaves + [beta])
+    for x, y in zip(g_ref, g_me):
+        assert torch.allclose(x, y, rtol=1e-6, atol=1e-7)
+
+
+def test_no_bda_branch(ref):
+    cfg, conf = MINI, MINI.backbone_kwargs()
+    buf = tp.build_buffers(conf)
+    mats = synth.make_mats(cfg, 1, "val")
+    a = (mats["sensor2ego_mats"][:, 0], mats["intrin_mats"][:, 0], mats["ida_mats"][:, 0], None)
+    assert torch.equal(ref.get_pixel(*a), tp.get_pixel(buf, *a))
+    assert torch.equal(ref.get_geometry(*a), tp.get_geometry(buf, *a))

@@ -1,0 +1,220 @@
+// vb_lift.cu -- L1-L4 (+ backward): depth (x) context lift fused with the camera->voxel gather/pool.
+//
+// Reference semantics (BV2:553 + get_voxel_feats BV2:483-516): build the (B,N,C,D,fH,fW) frustum
+// tensor depth[d,h,w]*ctx[c,h,w] (372 MB/sample), project every voxel centre into every camera
+// (get_pixel), trilinear grid_sample(align_corners=False, zeros padding) the frustum there, mask,
+// and average over the cameras with a per-channel non-zero count.
+//
+// Here the outer product is never formed: trilinear interpolation is linear, and the frustum
+// value factorises, so per (voxel, camera)
+//     f[c] = sum_{4 pixel corners (j,k)} w_j w_k ctx[c,j,k] * (sum_{2 depth bins i} w_i depth[i,j,k])
+// with 16 register accumulators per thread.  Context rows are re-laid out
+// channels-last by a tiny pre-pass so one pixel's C channels are one or two 128-bit loads.
+//
+// HBM roofline: read depth + ctx once (L2-resident afterwards: 27.6 MB fp32 per sample), write the
+// (B,C,vZ,vY,vX) volume once => 111.5 MB/sample fp32, 55.7 MB bf16.
+#include "vb_common.cuh"
+
+namespace {
+
+constexpr int kLiftThreads = 256;
+
+// ---- ctx (B,N,C,fH,fW) -> (B,N,fH,fW,C): one block per (b*n, h) row -------------------------
+template <typename T, int C>
+__global__ void __launch_bounds__(256) ctx_to_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, int fH,
+                                                          int fW) {
+  extern __shared__ unsigned char s_raw[];
+  T* s = reinterpret_cast<T*>(s_raw);  // [C][fW + 1]
+  const int h = blockIdx.x, bn = blockIdx.y;
+  const int ld = fW + 1;
+  for (int i = threadIdx.x; i < C * fW; i += blockDim.x) {
+    const int c = i / fW, w = i % fW;
+    s[c * ld + w] = src[(((size_t)bn * C + c) * fH + h) * fW + w];
+  }
+  __syncthreads();
+  T* out = dst + ((size_t)bn * fH + h) * fW * C;
+  for (int i = threadIdx.x; i < C * fW; i += blockDim.x) {
+    const int w = i / C, c = i % C;
+    out[i] = s[c * ld + w];
+  }
+}
+
+template <typename T, int C> struct CtxLoad;
+template <int C> struct CtxLoad<float, C> {
+  __device__ __forceinline__ static void ld(const float* p, float (&o)[C]) {
+#pragma unroll
+    for (int q = 0; q < C / 4; ++q) VbVec<float, 4>::ld(p + 4 * q, &o[4 * q]);
+  }
+};
+template <int C> struct CtxLoad<__nv_bfloat16, C> {
+  __device__ __forceinline__ static void ld(const __nv_bfloat16* p, float (&o)[C]) {
+#pragma unroll
+    for (int q = 0; q < C / 8; ++q) VbVec<__nv_bfloat16, 8>::ld(p + 8 * q, &o[8 * q]);
+  }
+};
+template <int C> struct CtxLoad<__half, C> {
+  __device__ __forceinline__ static void ld(const __half* p, float (&o)[C]) {
+#pragma unroll
+    for (int q = 0; q < C / 8; ++q) VbVec<__half, 8>::ld(p + 8 * q, &o[8 * q]);
+  }
+};
+
+// Trilinear weights exactly as ATen forms them (GridSampler: corner weight = product of
+// (x_far - ix) terms), in the tolerance zone (FMA allowed).
+struct TriW {
+  float wx0, wx1, wy0, wy1, wz0, wz1;
+};
+__device__ __forceinline__ TriW tri_weights(float ix, float iy, float iz, int x0, int y0, int z0) {
+  TriW w;
+  w.wx1 = ix - (float)x0;
+  w.wx0 = (float)(x0 + 1) - ix;
+  w.wy1 = iy - (float)y0;
+  w.wy0 = (float)(y0 + 1) - iy;
+  w.wz1 = iz - (float)z0;
+  w.wz0 = (float)(z0 + 1) - iz;
+  return w;
+}
+
+// ---- forward: one thread per voxel, loop over cameras ---------------------------------------
+template <typename T, int C, int OUT_LAYOUT>
+__global__ void __launch_bounds__(kLiftThreads) lift_pool_fwd_kernel(VbGrid g, VbTables t,
+                                                                     const float* __restrict__ d_mats,
+                                                                     const T* __restrict__ depth,
+                                                                     const T* __restrict__ ctx_nhwc,
+                                                                     T* __restrict__ out, uint64_t* __restrict__ cnt_out) {
+  static_assert(C <= 16, "per-channel counts are packed 4 bits each into 64 bits");
+  __shared__ float s_m[VB_MAX_CAMS * VB200_MAT_SLOTS * 16];
+  const int b = blockIdx.y;
+  stage_mats(s_m, d_mats, b, g.N);
+  __syncthreads();
+  const int nvox = g.vZ * g.vY * g.vX;
+  const int vox = blockIdx.x * kLiftThreads + threadIdx.x;
+  if (vox >= nvox) return;
+  const int x = vox % g.vX, y = (vox / g.vX) % g.vY, z = vox / (g.vX * g.vY);
+  const float px = __ldg(t.xs + x), py = __ldg(t.ys + y), pz = __ldg(t.zs + z);
+  const bool has_bda = g.has_bda != 0;
+  const int HW = g.fH * g.fW;
+
+  float acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.0f;
+  uint64_t cnt = 0;
+
+  for (int n = 0; n < g.N; ++n) {
+    float pix[3];
+    project_voxel(s_m + n * VB200_MAT_SLOTS * 16, has_bda, px, py, pz, pix);
+    const LiftCoord lc = lift_coord(g, pix);
+    if (!lc.valid) continue;  // f = grid_sample * 0: adds nothing to numer nor to the count
+    const TriW w = tri_weights(lc.ix, lc.iy, lc.iz, lc.x0, lc.y0, lc.z0);
+    const T* dcam = depth + (size_t)(b * g.N + n) * g.D * HW;
+    const T* ccam = ctx_nhwc + (size_t)(b * g.N + n) * HW * C;
+    const bool z0_in = lc.z0 >= 0 && lc.z0 < g.D;
+    const bool z1_in = lc.z0 + 1 >= 0 && lc.z0 + 1 < g.D;
+    float f[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) f[c] = 0.0f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int yy = lc.y0 + dy;
+      if (yy < 0 || yy >= g.fH) continue;
+      const float wy = dy ? w.wy1 : w.wy0;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int xx = lc.x0 + dx;
+        if (xx < 0 || xx >= g.fW) continue;
+        const float wx = dx ? w.wx1 : w.wx0;
+        const int pixel = yy * g.fW + xx;
+        float s = 0.0f;
+        if (z0_in) s = w.wz0 * VbType<T>::ld(dcam + (size_t)lc.z0 * HW + pixel);
+        if (z1_in) s += w.wz1 * VbType<T>::ld(dcam + (size_t)(lc.z0 + 1) * HW + pixel);
+        const float wgt = wx * wy * s;
+        float cv[C];
+        CtxLoad<T, C>::ld(ccam + (size_t)pixel * C, cv);
+#pragma unroll
+        for (int c = 0; c < C; ++c) f[c] = fmaf(cv[c], wgt, f[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      acc[c] += f[c];
+      cnt += (uint64_t)(fabsf(f[c]) > 0.0f ? 1 : 0) << (4 * c);   // voxel_mask  BV2:509
+    }
+  }
+
+  if (cnt_out) cnt_out[(size_t)b * nvox + vox] = cnt;
+  if (OUT_LAYOUT == VB200_NCDHW) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float denom = (float)((cnt >> (4 * c)) & 0xf) + 1e-6f;     // BV2:512
+      out[((size_t)b * C + c) * nvox + vox] = VbType<T>::cvt(acc[c] / denom);
+    }
+  } else {
+    T* o = out + ((size_t)b * nvox + vox) * C;
+    T v[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float denom = (float)((cnt >> (4 * c)) & 0xf) + 1e-6f;
+      v[c] = VbType<T>::cvt(acc[c] / denom);
+    }
+    constexpr int L = VbLanes<T>::n;
+#pragma unroll
+    for (int q = 0; q < C / L; ++q) reinterpret_cast<uint4*>(o)[q] = reinterpret_cast<const uint4*>(v)[q];
+  }
+}
+
+template <typename T>
+int launch_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, const void* d_depth, const void* d_ctx,
+               void* d_out, int out_layout, uint64_t* d_cnt, void* ws, cudaStream_t st) {
+  constexpr int C = 16;
+  if (g->C != C) return VB200_ERR_ARG;
+  T* ctx_nhwc = reinterpret_cast<T*>(ws);
+  {
+    dim3 grid(g->fH, g->B * g->N);
+    const size_t smem = (size_t)C * (g->fW + 1) * sizeof(T);
+    ctx_to_nhwc_kernel<T, C><<<grid, 256, smem, st>>>(reinterpret_cast<const T*>(d_ctx), ctx_nhwc, g->fH, g->fW);
+    VB_LAUNCH_CHECK();
+  }
+  const int nvox = g->vZ * g->vY * g->vX;
+  dim3 grid(vb_ceil_div(nvox, kLiftThreads), g->B);
+  if (out_layout == VB200_NCDHW)
+    lift_pool_fwd_kernel<T, C, VB200_NCDHW><<<grid, kLiftThreads, 0, st>>>(
+        *g, *t, d_mats, reinterpret_cast<const T*>(d_depth), ctx_nhwc, reinterpret_cast<T*>(d_out), d_cnt);
+  else
+    lift_pool_fwd_kernel<T, C, VB200_NDHWC><<<grid, kLiftThreads, 0, st>>>(
+        *g, *t, d_mats, reinterpret_cast<const T*>(d_depth), ctx_nhwc, reinterpret_cast<T*>(d_out), d_cnt);
+  VB_LAUNCH_CHECK();
+  return VB200_OK;
+}
+
+size_t elem_size(int dtype) { return dtype == VB200_F32 ? 4 : 2; }
+
+}  // namespace
+
+extern "C" size_t vb200_lift_pool_fwd_workspace(const VbGrid* g, int dtype) {
+  if (!g) return 0;
+  // channels-last copy of ctx, rounded up to 256 B
+  const size_t n = (size_t)g->B * g->N * g->fH * g->fW * g->C * elem_size(dtype);
+  return (n + 255) & ~(size_t)255;
+}
+
+extern "C" int vb200_lift_pool_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, const void* d_depth,
+                                   const void* d_ctx, int dtype, void* d_out, int out_layout, uint64_t* d_cnt,
+                                   void* d_workspace, size_t workspace_bytes, void* stream) {
+  VB_CHECK_ARG(g && t && d_mats && d_depth && d_ctx && d_out && d_workspace);
+  VB_CHECK_ARG(g->B > 0 && g->N > 0 && g->N <= VB_MAX_CAMS);
+  VB_CHECK_ARG(out_layout == VB200_NCDHW || out_layout == VB200_NDHWC);
+  if (workspace_bytes < vb200_lift_pool_fwd_workspace(g, dtype)) return VB200_ERR_WORKSPACE;
+  if (((uintptr_t)d_workspace | (uintptr_t)d_out | (uintptr_t)d_ctx | (uintptr_t)d_depth) & 15) return VB200_ERR_ALIGN;
+  int rc = vb200_device_check();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case VB200_F32: return launch_fwd<float>(g, t, d_mats, d_depth, d_ctx, d_out, out_layout, d_cnt, d_workspace, st);
+    case VB200_BF16:
+      return launch_fwd<__nv_bfloat16>(g, t, d_mats, d_depth, d_ctx, d_out, out_layout, d_cnt, d_workspace, st);
+    case VB200_F16: return launch_fwd<__half>(g, t, d_mats, d_depth, d_ctx, d_out, out_layout, d_cnt, d_workspace, st);
+    default: return VB200_ERR_DTYPE;
+  }
+}
+
+// ---- backward: implemented in vb_lift_bwd.cu ---------------------------------------------------

@@ -1,0 +1,418 @@
+"""torch.library custom ops over the extern "C" entry points of libvb200.so.
+
+Each op body does nothing but allocate outputs/workspace from the PyTorch caching allocator,
+fetch ``data_ptr()`` / the current CUDA stream and call the C ABI through ctypes
+(``vampire_b200.cabi``).  Autograd is wired with ``register_autograd`` to the matching backward
+entry points.  There is no CPU implementation: a CPU tensor raises.
+
+Static configuration (sizes, fp32 constants, lattice tables) cannot travel through an op schema,
+so a :class:`PathState` is registered once per config and ops receive its integer handle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import cabi
+from .config import PathConfig
+from .lattice import Lattice, build_lattice
+
+Tensor = torch.Tensor
+
+
+class PathState:
+    """Per-config state: the lattice (host) and its per-device copies."""
+
+    def __init__(self, cfg: PathConfig):
+        self.cfg = cfg
+        self.lattice: Lattice = build_lattice(cfg)
+        self._tables: Dict[torch.device, cabi.DeviceTables] = {}
+        self.term_eps = 1e-8
+        # samples packed+marched per round of the render; 1 keeps the packed volume L2-resident
+        self.render_group = 1
+
+    def tables(self, device: torch.device) -> cabi.DeviceTables:
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("vampire_b200 ops run on CUDA (sm_100a) tensors only; there is no CPU path")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        if device not in self._tables:
+            self._tables[device] = cabi.DeviceTables(self.lattice, device)
+        return self._tables[device]
+
+    def grid(self, batch: int, has_bda: bool) -> cabi.VbGrid:
+        return cabi.make_grid(self.cfg, batch, has_bda, self.term_eps)
+
+
+_STATES: List[PathState] = []
+_BY_CFG: Dict[PathConfig, int] = {}
+
+
+def register_config(cfg: PathConfig) -> int:
+    if cfg not in _BY_CFG:
+        _STATES.append(PathState(cfg))
+        _BY_CFG[cfg] = len(_STATES) - 1
+    return _BY_CFG[cfg]
+
+
+def state(handle: int) -> PathState:
+    return _STATES[handle]
+
+
+def _need_cuda(*ts: Optional[Tensor]) -> torch.device:
+    dev = None
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("vampire_b200: expected CUDA tensors (no CPU fallback exists for this path)")
+        dev = t.device if dev is None else dev
+        if t.device != dev:
+            raise RuntimeError("vampire_b200: tensors on different devices")
+    return dev
+
+
+def _mats_ok(mats: Tensor, B: int, N: int) -> Tensor:
+    if mats.shape != (B, N, 6, 4, 4) or mats.dtype != torch.float32:
+        raise ValueError(f"mats must be (B={B}, N={N}, 6, 4, 4) fp32 from prepare_matrices, got {tuple(mats.shape)}")
+    return mats.contiguous()
+
+
+# =============================================================================================
+# geometry (no autograd: the reference computes it from constants and matrices only)
+# =============================================================================================
+@torch.library.custom_op("vampire_b200::get_pixel", mutates_args=())
+def get_pixel(mats: Tensor, cfg_id: int, has_bda: bool) -> Tensor:
+    st = state(cfg_id)
+    cfg = st.cfg
+    dev = _need_cuda(mats)
+    B = mats.shape[0]
+    mats = _mats_ok(mats, B, cfg.num_cams)
+    out = torch.empty(B, cfg.num_cams, cfg.vZ, cfg.vY, cfg.vX, 3, dtype=torch.float32, device=dev)
+    g = st.grid(B, has_bda)
+    with torch.cuda.device(dev):
+        cabi.check(cabi.lib().vb200_get_pixel(C.byref(g), C.byref(st.tables(dev).struct), mats.data_ptr(),
+                                              out.data_ptr(), cabi.stream_ptr(dev)))
+    return out
+
+
+@get_pixel.register_fake
+def _(mats, cfg_id, has_bda):
+    cfg = state(cfg_id).cfg
+    return mats.new_empty(mats.shape[0], cfg.num_cams, cfg.vZ, cfg.vY, cfg.vX, 3)
+
+
+@torch.library.custom_op("vampire_b200::get_geometry", mutates_args=())
+def get_geometry(mats: Tensor, cfg_id: int, has_bda: bool, nan_to_num: bool) -> Tensor:
+    st = state(cfg_id)
+    cfg = st.cfg
+    dev = _need_cuda(mats)
+    B = mats.shape[0]
+    mats = _mats_ok(mats, B, cfg.num_cams)
+    out = torch.empty(B, cfg.num_cams, cfg.D, cfg.fH, cfg.fW, 3, dtype=torch.float32, device=dev)
+    g = st.grid(B, has_bda)
+    with torch.cuda.device(dev):
+        cabi.check(cabi.lib().vb200_get_geometry(C.byref(g), C.byref(st.tables(dev).struct), mats.data_ptr(),
+                                                 out.data_ptr(), int(nan_to_num), cabi.stream_ptr(dev)))
+    return out
+
+
+@get_geometry.register_fake
+def _(mats, cfg_id, has_bda, nan_to_num):
+    cfg = state(cfg_id).cfg
+    return mats.new_empty(mats.shape[0], cfg.num_cams, cfg.D, cfg.fH, cfg.fW, 3)
+
+
+def lift_indices(mats: Tensor, cfg_id: int, has_bda: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """(valid uint8 (B,N,Z,Y,X), i0 int16 (...,3) = (x0,y0,z0), frac fp32 (...,3)) -- parity probe."""
+    st = state(cfg_id)
+    cfg = st.cfg
+    dev = _need_cuda(mats)
+    B = mats.shape[0]
+    mats = _mats_ok(mats, B, cfg.num_cams)
+    shp = (B, cfg.num_cams, cfg.vZ, cfg.vY, cfg.vX)
+    valid = torch.empty(shp, dtype=torch.uint8, device=dev)
+    i0 = torch.empty(shp + (3,), dtype=torch.int16, device=dev)
+    frac = torch.empty(shp + (3,), dtype=torch.float32, device=dev)
+    g = st.grid(B, has_bda)
+    with torch.cuda.device(dev):
+        cabi.check(cabi.lib().vb200_lift_indices(C.byref(g), C.byref(st.tables(dev).struct), mats.data_ptr(),
+                                                 valid.data_ptr(), i0.data_ptr(), frac.data_ptr(),
+                                                 cabi.stream_ptr(dev)))
+    return valid, i0, frac
+
+
+def render_indices(mats: Tensor, cfg_id: int, has_bda: bool, geom: Optional[Tensor] = None):
+    """(mask uint8 (B,N,S,fH,fW), i0 int16 (...,3), frac fp32 (...,3)) -- parity probe."""
+    st = state(cfg_id)
+    cfg = st.cfg
+    dev = _need_cuda(mats, geom)
+    B = mats.shape[0]
+    mats = _mats_ok(mats, B, cfg.num_cams)
+    shp = (B, cfg.num_cams, cfg.S, cfg.fH, cfg.fW)
+    mask = torch.empty(shp, dtype=torch.uint8, device=dev)
+    i0 = torch.empty(shp + (3,), dtype=torch.int16, device=dev)
+    frac = torch.empty(shp + (3,), dtype=torch.float32, device=dev)
+    if geom is not None:
+        geom = geom.float().contiguous()
+    g = st.grid(B, has_bda)
+    with torch.cuda.device(dev):
+        cabi.check(cabi.lib().vb200_render_indices(C.byref(g), C.byref(st.tables(dev).struct), mats.data_ptr(),
+                                                   cabi.ptr(geom), mask.data_ptr(), i0.data_ptr(), frac.data_ptr(),
+                                                   cabi.stream_ptr(dev)))
+    return mask, i0, frac
+
+
+# =============================================================================================
+# lift + pool
+# =============================================================================================
+@torch.library.custom_op("vampire_b200::lift_pool_fwd", mutates_args=())
+def lift_pool_fwd(depth: Tensor, ctx: Tensor, mats: Tensor, cfg_id: int, has_bda: bool, channels_last: bool,
+                  save_cnt: bool) -> Tuple[Tensor, Tensor]:
+    st = state(cfg_id)
+    cfg = st.cfg
+    dev = _need_cuda(depth, ctx, mats)
+    B, N = depth.shape[:2]
+    if depth.shape != (B, N, cfg.D, cfg.fH, cfg.fW) or ctx.shape != (B, N, cfg.C, cfg.fH, cfg.fW):
+        raise ValueError(f"lift_pool: depth {tuple(depth.shape)} / ctx {tuple(ctx.shape)} do not match the config")
+    if ctx.dtype != depth.dtype:
+        raise TypeError("lift_pool: depth and ctx must share a dtype")
+    dt = cabi.dtype_code(depth.dtype)
+    mats = _mats_ok(mats, B, N)
+    depth = depth.contiguous()
+    ctx = ctx.contiguous()
+    nvox = cfg.vZ * cfg.vY * cfg.vX
+    if channels_last:
+        out = torch.empty(B, cfg.vZ, cfg.vY, cfg.vX, cfg.C, dtype=depth.dtype, device=dev).permute(0, 4, 1, 2, 3)
+    else:
+        out = torch.empty(B, cfg.C, cfg.vZ, cfg.vY, cfg.vX, dtype=depth.dtype, device=dev)
+    cnt = torch.empty(B, nvox if save_cnt else 0, dtype=torch.int64, device=dev)
+    g = st.grid(B, has_bda)
+    lib = cabi.lib()
+    ws_bytes = lib.vb200_lift_pool_fwd_workspace(C.byref(g), dt)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        cabi.check(lib.vb200_lift_pool_fwd(C.byref(g), C.byref(st.tables(dev).struct), mats.data_ptr(),
+                                           depth.data_ptr(), ctx.data_ptr(), dt, out.data_ptr(),
+                                           cabi.NDHWC if channels_last else cabi.NCDHW,
+                                           cnt.data_ptr() if save_cnt else None, ws.data_ptr(), ws_bytes,
+                                           cabi.stream_ptr(dev)))
+    return out, cnt
+
+
+@lift_pool_fwd.register_fake
+def _(depth, ctx, mats, cfg_id, has_bda, channels_last, save_cnt):
+    cfg = state(cfg_id).cfg
+    B = depth.shape[0]
+    if channels_last:
+        out = depth.new_empty(B, cfg.vZ, cfg.vY, cfg.vX, cfg.C).permute(0, 4, 1, 2, 3)
+    else:
+        out = depth.new_empty(B, cfg.C, cfg.vZ, cfg.vY, cfg.vX)
+    cnt = depth.new_empty(B, cfg.vZ * cfg.vY * cfg.vX if save_cnt else 0, dtype=torch.int64)
+    return out, cnt
+
+
+@torch.library.custom_op("vampire_b200::lift_pool_bwd", mutates_args=())
+def lift_pool_bwd(gout: Tensor, depth: Tensor, ctx: Tensor, mats: Tensor, cnt: Tensor, cfg_id: int,
+                  has_bda: bool) -> Tuple[Tensor, Tensor]:
+    st = state(cfg_id)
+    cfg = st.cfg
+    dev = _need_cuda(gout, depth, ctx, mats, cnt)
+    B, N = depth.shape[:2]
+    dt = cabi.dtype_code(depth.dtype)
+    mats = _mats_ok(mats, B, N)
+    depth = depth.contiguous()
+    ctx = ctx.contiguous()
+    gout = gout.to(depth.dtype)
+    if gout.permute(0, 2, 3, 4, 1).is_contiguous():
+        layout = cabi.NDHWC
+    else:
+        gout = gout.contiguous()
+        layout = cabi.NCDHW
+    gdepth = torch.empty_like(depth)
+    gctx = torch.empty_like(ctx)
+    g = st.grid(B, has_bda)
+    lib = cabi.lib()
+    ws_bytes = lib.vb200_lift_pool_bwd_workspace(C.byref(g), dt)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        cabi.check(lib.vb200_lift_pool_bwd(C.byref(g), C.byref(st.tables(dev).struct), mats.data_ptr(),
+                                           depth.data_ptr(), ctx.data_ptr(), dt, gout.data_ptr(), layout,
+                                           cnt.data_ptr(), gdepth.data_ptr(), gctx.data_ptr(), ws.data_ptr(),
+                                           ws_bytes, cabi.stream_ptr(dev)))
+    return gdepth, gctx
+
+
+@lift_pool_bwd.register_fake
+def _(gout, depth, ctx, mats, cnt, cfg_id, has_bda):
+    return torch.empty_like(depth), torch.empty_like(ctx)
+
+
+def _lift_setup(ctx_, inputs, output):
+    depth, ctx, mats, cfg_id, has_bda, channels_last, save_cnt = inputs
+    _, cnt = output
+    ctx_.save_for_backward(depth, ctx, mats, cnt)
+    ctx_.cfg_id, ctx_.has_bda, ctx_.save_cnt = cfg_id, has_bda, save_cnt
+
+
+def _lift_backward(ctx_, gout, gcnt):
+    if not ctx_.save_cnt:
+        raise RuntimeError("lift_pool_fwd was called with save_cnt=False: no backward possible")
+    depth, ctx, mats, cnt = ctx_.saved_tensors
+    gdepth, gctx = lift_pool_bwd(gout, depth, ctx, mats, cnt, ctx_.cfg_id, ctx_.has_bda)
+    return gdepth, gctx, None, None, None, None, None
+
+
+torch.library.register_autograd("vampire_b200::lift_pool_fwd", _lift_backward, setup_context=_lift_setup)
+
+
+# =============================================================================================
+# render
+# =============================================================================================
+def _render_out_shapes(cfg: PathConfig, B: int):
+    N, K, Cc = cfg.num_cams, cfg.K, cfg.C
+    return [(B, N, 3, cfg.fH, cfg.fW), (B, N, K, cfg.fH, cfg.fW), (B, N, 1, cfg.fH, cfg.fW),
+            (B, 3, cfg.oY, cfg.oX), (B, K, cfg.oY, cfg.oX), (B, 1, cfg.oY, cfg.oX),
+            (B, 1, cfg.oZ, cfg.oY, cfg.oX), (B, Cc, cfg.oZ, cfg.oY, cfg.oX)]
+
+
+def _render_in_struct(density, sem, rgb, feat, beta, geom):
+    rin = cabi.VbRenderIn()
+    rin.density, rin.sem, rin.rgb, rin.feat = density.data_ptr(), sem.data_ptr(), rgb.data_ptr(), feat.data_ptr()
+    rin.beta = beta.data_ptr()
+    rin.geom = None if geom is None else geom.data_ptr()
+    return rin
+
+
+def _render_out_struct(outs):
+    ro = cabi.VbRenderOut()
+    for name, t in zip(("rgb", "seg", "depth", "bev_rgb", "bev_seg", "bev_height", "voxel_density", "voxel_output"),
+                       outs):
+        setattr(ro, name, t.data_ptr())
+    return ro
+
+
+def _check_render_inputs(cfg, density, sem, rgb, feat, beta):
+    B = density.shape[0]
+    vol = (cfg.vZ, cfg.vY, cfg.vX)
+    exp = {"density_feature": (density, 1), "semantic_logits": (sem, cfg.K), "rgb": (rgb, 3),
+           "voxel_features": (feat, cfg.C)}
+    for name, (t, ch) in exp.items():
+        if t.shape != (B, ch) + vol:
+            raise ValueError(f"render: {name} has shape {tuple(t.shape)}, expected {(B, ch) + vol}")
+        if t.dtype != density.dtype:
+            raise TypeError("render: the four volumes must share a dtype")
+    if beta.numel() != 1:
+        raise ValueError("render: beta must be a scalar tensor")
+    return B
+
+
+@torch.library.custom_op("vampire_b200::render_fwd", mutates_args=())
+def render_fwd(density: Tensor, sem: Tensor, rgb: Tensor, feat: Tensor, beta: Tensor, mats: Tensor,
+               geom: Optional[Tensor], cfg_id: int, has_bda: bool, branches: int) -> List[Tensor]:
+    st = state(cfg_id)
+    cfg = st.cfg
+    dev = _need_cuda(density, sem, rgb, feat, beta, mats, geom)
+    B = _check_render_inputs(cfg, density, sem, rgb, feat, beta)
+    dt = cabi.dtype_code(density.dtype)
+    mats = _mats_ok(mats, B, cfg.num_cams)
+    density, sem, rgb, feat = (t.contiguous() for t in (density, sem, rgb, feat))
+    beta32 = beta.detach().reshape(1).float().contiguous()
+    if geom is not None:
+        if geom.shape != (B, cfg.num_cams, cfg.D, cfg.fH, cfg.fW, 3):
+            raise ValueError(f"render: geom_xyz has shape {tuple(geom.shape)}")
+        geom = geom.float().contiguous()
+    shapes = _render_out_shapes(cfg, B)
+    outs = [torch.empty(s, dtype=torch.float32, device=dev) for s in shapes[:7]]
+    outs.append(torch.empty(shapes[7], dtype=density.dtype, device=dev))
+    g = st.grid(B, has_bda)
+    lib = cabi.lib()
+    per = lib.vb200_render_fwd_workspace(C.byref(g), dt)
+    ws_bytes = per * max(1, min(B, st.render_group))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    rin = _render_in_struct(density, sem, rgb, feat, beta32, geom)
+    ro = _render_out_struct(outs)
+    with torch.cuda.device(dev):
+        cabi.check(lib.vb200_render_fwd(C.byref(g), C.byref(st.tables(dev).struct), mats.data_ptr(), C.byref(rin), dt,
+                                        C.byref(ro), branches, ws.data_ptr(), ws_bytes, cabi.stream_ptr(dev)))
+    if not branches & cabi.BRANCH_CAM:
+        for t in outs[:3]:
+            t.zero_()
+    if not branches & cabi.BRANCH_BEV:
+        for t in outs[3:]:
+            t.zero_()
+    return outs
+
+
+@render_fwd.register_fake
+def _(density, sem, rgb, feat, beta, mats, geom, cfg_id, has_bda, branches):
+    cfg = state(cfg_id).cfg
+    shapes = _render_out_shapes(cfg, density.shape[0])
+    outs = [density.new_empty(s, dtype=torch.float32) for s in shapes[:7]]
+    outs.append(density.new_empty(shapes[7]))
+    return outs
+
+
+@torch.library.custom_op("vampire_b200::render_bwd", mutates_args=())
+def render_bwd(grads: List[Tensor], outs: List[Tensor], density: Tensor, sem: Tensor, rgb: Tensor, feat: Tensor,
+               beta: Tensor, mats: Tensor, geom: Optional[Tensor], cfg_id: int, has_bda: bool,
+               branches: int) -> List[Tensor]:
+    st = state(cfg_id)
+    cfg = st.cfg
+    dev = _need_cuda(density, sem, rgb, feat, beta, mats, geom)
+    B = density.shape[0]
+    dt = cabi.dtype_code(density.dtype)
+    mats = _mats_ok(mats, B, cfg.num_cams)
+    density, sem, rgb, feat = (t.contiguous() for t in (density, sem, rgb, feat))
+    beta32 = beta.detach().reshape(1).float().contiguous()
+    if geom is not None:
+        geom = geom.float().contiguous()
+    grads = [gt.float().contiguous() for gt in grads[:7]] + [grads[7].to(density.dtype).contiguous()]
+    outs = [o.contiguous() for o in outs]
+    g_den, g_sem, g_rgb, g_feat = (torch.empty_like(t) for t in (density, sem, rgb, feat))
+    g_beta = torch.zeros(1, dtype=torch.float32, device=dev)
+    g = st.grid(B, has_bda)
+    lib = cabi.lib()
+    ws_bytes = lib.vb200_render_bwd_workspace(C.byref(g), dt)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    rin = _render_in_struct(density, sem, rgb, feat, beta32, geom)
+    ro = _render_out_struct(outs)
+    rg = cabi.VbRenderGrad()
+    for name, t in zip(("g_rgb", "g_seg", "g_depth", "g_bev_rgb", "g_bev_seg", "g_bev_height", "g_voxel_density",
+                        "g_voxel_output"), grads):
+        setattr(rg, name, t.data_ptr())
+    rg.g_density, rg.g_sem, rg.g_rgb_in, rg.g_feat = (t.data_ptr() for t in (g_den, g_sem, g_rgb, g_feat))
+    rg.g_beta = g_beta.data_ptr()
+    with torch.cuda.device(dev):
+        cabi.check(lib.vb200_render_bwd(C.byref(g), C.byref(st.tables(dev).struct), mats.data_ptr(), C.byref(rin), dt,
+                                        C.byref(ro), C.byref(rg), branches, ws.data_ptr(), ws_bytes,
+                                        cabi.stream_ptr(dev)))
+    return [g_den, g_sem, g_rgb, g_feat, g_beta]
+
+
+@render_bwd.register_fake
+def _(grads, outs, density, sem, rgb, feat, beta, mats, geom, cfg_id, has_bda, branches):
+    return [torch.empty_like(density), torch.empty_like(sem), torch.empty_like(rgb), torch.empty_like(feat),
+            density.new_empty(1, dtype=torch.float32)]
+
+
+def _render_setup(ctx_, inputs, output):
+    density, sem, rgb, feat, beta, mats, geom, cfg_id, has_bda, branches = inputs
+    ctx_.save_for_backward(density, sem, rgb, feat, beta, mats, geom, *output)
+    ctx_.cfg_id, ctx_.has_bda, ctx_.branches = cfg_id, has_bda, branches
+
+
+def _render_backward(ctx_, grads):
+    saved = ctx_.saved_tensors
+    density, sem, rgb, feat, beta, mats, geom = saved[:7]
+    outs = list(saved[7:])
+    grads = [gt if gt is not None else torch.zeros_like(o) for gt, o in zip(grads, outs)]
+    g_den, g_sem, g_rgb, g_feat, g_beta = render_bwd(grads, outs, density, sem, rgb, feat, beta, mats, geom,
+                                                     ctx_.cfg_id, ctx_.has_bda, ctx_.branches)
+    return g_den, g_sem, g_rgb, g_feat, g_beta.reshape(beta.shape).to(beta.dtype), None, None, None, None, None
+
+
+torch.library.register_autograd("vampire_b200::render_fwd", _render_backward, setup_context=_render_setup)

@@ -1,0 +1,125 @@
+"""Host-side mirror of the reference backbone's view-transform + render interface.
+
+``LiftRenderB200`` exposes, with the reference's names, argument meaning and return shapes, the
+methods of ``BaseVAMPIRE2`` that make up the 2D->3D feature path
+(/root/reference/src/layers/backbones/base_vampire2.py):
+
+    get_geometry(sensor2ego_mat, intrin_mat, ida_mat, bda_mat)                       BV2:314
+    get_pixel(sensor2ego_mat, intrin_mat, ida_mat, bda_mat)                          BV2:351
+    get_voxel_feats(frustum_feats, sweep_index, mats_dict)   [materialised frustum]  BV2:483
+    volume_rendering_from_multiple_views(geom_xyz, density_feature, semantic_logits,
+                                         voxel_features, rgb) -> 8-tuple            BV2:391
+
+plus the two fused entry points the drop-in ``_forward_single_sweep`` uses instead of lines
+BV2:553+563 and BV2:554-559+612-614:
+
+    lift_pool(depth_softmax_features, low_channel_source_features, mats_dict)
+    render(mats_dict, density_feature, semantic_logits, voxel_features, rgb)
+
+It owns the one learnable parameter of the path, ``density.beta`` (render_utils.py:7), under the
+reference's state-dict key so published checkpoints load unchanged.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import cabi, ops
+from .config import PathConfig
+from .matrices import prepare_matrices
+
+Tensor = torch.Tensor
+
+
+class LaplaceDensityParam(nn.Module):
+    """Holds ``beta`` exactly like the reference's ``ModifyLaplaceDensity`` (render_utils.py:30-46);
+    the density itself is evaluated inside the render kernels."""
+
+    def __init__(self, beta: float = 0.1, bias: float = -1.0, beta_min: float = 1e-4):
+        super().__init__()
+        self.beta = nn.Parameter(torch.tensor(beta))
+        self.beta_min = beta_min
+        self.bias = bias
+
+    def get_beta(self) -> Tensor:
+        return self.beta.abs() + self.beta_min
+
+
+class LiftRenderB200(nn.Module):
+    def __init__(self, channels_last_volume: bool = False, **backbone_conf):
+        """``backbone_conf``: the reference's dict (base_exp.py:40-92); unknown keys are ignored the
+        way the image-encoder keys are irrelevant here."""
+        super().__init__()
+        self.cfg = PathConfig.from_backbone_conf(backbone_conf, backbone_conf.get("num_cams", 6))
+        if self.cfg.density_mode != "sdf":
+            raise NotImplementedError("only density_mode='sdf' (the target experiment, base_exp.py:51) is built")
+        if self.cfg.cat_seg:
+            raise NotImplementedError("cat_seg=True is not part of the target experiment (base_exp.py:54)")
+        self.cfg_id = ops.register_config(self.cfg)
+        self.density = LaplaceDensityParam(beta=0.1, bias=self.cfg.sdf_bias)
+        self.channels_last_volume = channels_last_volume
+        st = ops.state(self.cfg_id)
+        lat = st.lattice
+        # the reference's buffers (BV2:146-160), rebuilt from the same 1-D axes
+        self.register_buffer("camera_mids", lat.mids.clone(), persistent=False)
+        self.register_buffer("bev_mids", lat.bev_mids.clone(), persistent=False)
+        self.fD, self.fH, self.fW = self.cfg.S, self.cfg.fH, self.cfg.fW
+        self.vZ, self.vY, self.vX = self.cfg.vZ, self.cfg.vY, self.cfg.vX
+
+    # ---- matrices -----------------------------------------------------------------------------
+    @staticmethod
+    def _prep(sensor2ego_mat, intrin_mat, ida_mat, bda_mat, device) -> Tuple[Tensor, bool]:
+        mats = prepare_matrices(sensor2ego_mat, intrin_mat, ida_mat, bda_mat)
+        return mats.to(device, non_blocking=True), bda_mat is not None
+
+    def _prep_dict(self, mats_dict: Dict[str, Tensor], sweep_index: int, device):
+        return self._prep(mats_dict["sensor2ego_mats"][:, sweep_index, ...],
+                          mats_dict["intrin_mats"][:, sweep_index, ...],
+                          mats_dict["ida_mats"][:, sweep_index, ...],
+                          mats_dict.get("bda_mat", None), device)
+
+    def _device(self) -> torch.device:
+        return self.density.beta.device
+
+    # ---- reference-named methods ----------------------------------------------------------------
+    def get_geometry(self, sensor2ego_mat, intrin_mat, ida_mat, bda_mat) -> Tensor:
+        mats, has_bda = self._prep(sensor2ego_mat, intrin_mat, ida_mat, bda_mat, self._device())
+        return ops.get_geometry(mats, self.cfg_id, has_bda, False)
+
+    def get_pixel(self, sensor2ego_mat, intrin_mat, ida_mat, bda_mat) -> Tensor:
+        mats, has_bda = self._prep(sensor2ego_mat, intrin_mat, ida_mat, bda_mat, self._device())
+        return ops.get_pixel(mats, self.cfg_id, has_bda)
+
+    def volume_rendering_from_multiple_views(self, geom_xyz, density_feature, semantic_logits, voxel_features, rgb,
+                                             mats_dict: Optional[Dict[str, Tensor]] = None):
+        """Reference signature (BV2:391).  ``geom_xyz`` is consumed as given (the caller has applied
+        nan_to_num, BV2:612).  Returns the reference's 8-tuple."""
+        B = density_feature.shape[0]
+        dev = density_feature.device
+        # matrices are unused when geom is supplied; an identity block keeps the ABI uniform
+        mats = torch.eye(4, device=dev).expand(B, self.cfg.num_cams, 6, 4, 4).contiguous()
+        outs = ops.render_fwd(density_feature, semantic_logits, rgb, voxel_features, self.density.beta, mats,
+                              geom_xyz, self.cfg_id, True, cabi.BRANCH_CAM | cabi.BRANCH_BEV)
+        return tuple(outs)
+
+    # ---- fused entry points -------------------------------------------------------------------
+    def lift_pool(self, depth_softmax_features: Tensor, low_channel_source_features: Tensor,
+                  mats_dict: Dict[str, Tensor], sweep_index: int = 0) -> Tensor:
+        """BV2:553 + 563 without the (B,N,C,D,fH,fW) tensor.  depth (B,N,D,fH,fW), ctx (B,N,C,fH,fW)."""
+        mats, has_bda = self._prep_dict(mats_dict, sweep_index, depth_softmax_features.device)
+        dt = low_channel_source_features.dtype
+        depth = depth_softmax_features.to(dt) if depth_softmax_features.dtype != dt else depth_softmax_features
+        need_grad = torch.is_grad_enabled() and (depth.requires_grad or low_channel_source_features.requires_grad)
+        out, _ = ops.lift_pool_fwd(depth, low_channel_source_features, mats, self.cfg_id, has_bda,
+                                   self.channels_last_volume, need_grad)
+        return out
+
+    def render(self, mats_dict: Dict[str, Tensor], density_feature: Tensor, semantic_logits: Tensor,
+               voxel_features: Tensor, rgb: Tensor, sweep_index: int = 0, branches: int = 3):
+        """BV2:554-559 + 612-614: geometry recomputed in-kernel from the matrices (never stored)."""
+        mats, has_bda = self._prep_dict(mats_dict, sweep_index, density_feature.device)
+        outs = ops.render_fwd(density_feature, semantic_logits, rgb, voxel_features, self.density.beta, mats,
+                              None, self.cfg_id, has_bda, branches)
+        return tuple(outs)

@@ -105,6 +105,17 @@ const char* vb200_strerror(int status);
 /* 0 if the current CUDA device is sm_100, VB200_ERR_ARCH otherwise */
 int vb200_device_check(void);
 
+/* ---- instrumentation (bench.py: gpu_launches + live per-kernel CUDA-event timing) ----------- */
+int vb200_trace_num_kernels(void);
+const char* vb200_trace_kernel_name(int kernel_id);
+/* launches of kernel family `kernel_id` since load (any id outside the range: all families) */
+long long vb200_launch_count(int kernel_id);
+/* start (1) / stop (0) recording a CUDA-event pair around every kernel launch; clears old records */
+int vb200_trace_enable(int on);
+/* waits for the recorded events; fills per-family device milliseconds and launch counts
+ * (arrays of vb200_trace_num_kernels() entries) and clears the records */
+int vb200_trace_collect(double* total_ms, long long* launches);
+
 /* ---- geometry ------------------------------------------------- */
 
 /* G1: d_pix (B, N, vZ, vY, vX, 3) fp32 = get_pixel(...)                          BV2:351-388 */

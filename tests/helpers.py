@@ -43,7 +43,7 @@ class Case:
         self.depth, self.ctx = synth.make_lift_inputs(self.cfg, self.batch)
         self.den, self.sem, self.feat, self.rgb = synth.make_render_inputs(self.cfg, self.batch, field=self.field)
         chk = np.array([t.double().sum().item() for t in (self.depth, self.ctx, self.den, self.sem, self.feat, self.rgb)])
-        self.inputs_match_golden = bool(np.allclose(chk, self.gold["in_checksum"], rtol=1e-12, atol=0))
+        self.inputs_match_golden = bool(np.allclose(chk, self.gold["in_checksum"], rtol=1e-7, atol=0))
         self.prep = torch.from_numpy(self.gold["prep"])  # the build container's prepared matrices
         self.stride = int(self.gold["meta_stride"])
 

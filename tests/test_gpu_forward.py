@@ -147,3 +147,64 @@ def test_module_interface_matches_reference_signatures():
         assert torch.equal(x, y), n
         exp, got = golden_value(case.gold, "r_" + n, x.detach().cpu().numpy())
         assert_close_scaled(got, exp, FP32_REL, n)
+
+
+ODD_CONFIGS = {
+    # det grid coarser than the seg grid in xy: the BEV window assumption fails -> scalar gathers
+    "coarse_det": dict(x_bound_det=(-51.2, 51.2, 6.4), y_bound_det=(-51.2, 51.2, 6.4)),
+    # vX, oX not multiples of 4 -> the scalar BEV kernel; ragged feature map (fW=44 is not a multiple of 8)
+    "ragged": dict(x_bound_seg=(-48.0, 48.0, 3.2), x_bound_det=(-48.0, 48.0, 3.2)),
+    # det z-range not aligned with seg levels, fewer levels
+    "shifted_z": dict(z_bound_det=(-2.2, 2.6, 1.6)),
+}
+
+
+@pytest.mark.parametrize("name", list(ODD_CONFIGS))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_odd_grids_vs_live_oracle(name, dtype):
+    """Edge geometries the reference supports through its config: every kernel path (vectorised /
+    scalar BEV, ragged ray patches) against the torch oracle."""
+    from dataclasses import replace
+    from vampire_b200 import synth
+    from vampire_b200.config import MINI
+    from vampire_b200.matrices import prepare_matrices
+    cfg = replace(MINI, **ODD_CONFIGS[name])
+    conf = cfg.backbone_kwargs()
+    ops, cid = _ops(cfg)
+    B = 2
+    mats = synth.make_mats(cfg, B, "stress", seed=11)
+    prep = prepare_matrices(mats["sensor2ego_mats"][:, 0], mats["intrin_mats"][:, 0], mats["ida_mats"][:, 0],
+                            mats["bda_mat"])
+    depth, ctx = synth.make_lift_inputs(cfg, B, seed=11, dtype=dtype)
+    den, sem, feat, rgb = synth.make_render_inputs(cfg, B, seed=11, field="surface", dtype=dtype)
+    buf = tp.build_buffers(conf)
+    with torch.no_grad():
+        ref_vox = tp.lift_pool(conf, buf, depth.float(), ctx.float(), mats)
+        ref = tp.render_from_mats(conf, buf, mats, den.float(), sem.float(), feat.float(), rgb.float(),
+                                  torch.tensor(0.1))
+    rel = FP32_REL if dtype == torch.float32 else BF16_REL
+    vox, _ = ops.lift_pool_fwd(depth.cuda(), ctx.cuda(), prep.cuda(), cid, True, False, False)
+    assert_close_scaled(vox.float().cpu().numpy(), ref_vox.numpy(), rel, "vox")
+    outs = ops.render_fwd(den.cuda(), sem.cuda(), rgb.cuda(), feat.cuda(), torch.tensor(0.1, device="cuda"),
+                          prep.cuda(), None, cid, True, 3)
+    for n, o, r in zip(NAMES, outs, ref):
+        assert_close_scaled(o.float().cpu().numpy(), r.numpy(), rel, n)
+
+
+def test_render_group_sizes_agree():
+    """Packing/marching 1 sample per round (L2-resident) or all at once must not change results."""
+    case = Case("mini_stress")
+    ops, cid = _ops(case.cfg)
+    st = ops.state(cid)
+    args = (case.den.cuda(), case.sem.cuda(), case.rgb.cuda(), case.feat.cuda(), torch.tensor(0.1, device="cuda"),
+            case.prep.cuda(), None, cid, True, 3)
+    old = st.render_group
+    try:
+        st.render_group = 1
+        a = [o.clone() for o in ops.render_fwd(*args)]
+        st.render_group = 8
+        b = ops.render_fwd(*args)
+    finally:
+        st.render_group = old
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)

@@ -65,6 +65,11 @@ _PROTOS = {
     "vb200_version": (C.c_int, []),
     "vb200_strerror": (C.c_char_p, [C.c_int]),
     "vb200_device_check": (C.c_int, []),
+    "vb200_trace_num_kernels": (C.c_int, []),
+    "vb200_trace_kernel_name": (C.c_char_p, [C.c_int]),
+    "vb200_launch_count": (C.c_longlong, [C.c_int]),
+    "vb200_trace_enable": (C.c_int, [C.c_int]),
+    "vb200_trace_collect": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "vb200_get_pixel": (C.c_int, [C.POINTER(VbGrid), C.POINTER(VbTables), _P, _P, _P]),
     "vb200_get_geometry": (C.c_int, [C.POINTER(VbGrid), C.POINTER(VbTables), _P, _P, C.c_int, _P]),
     "vb200_lift_indices": (C.c_int, [C.POINTER(VbGrid), C.POINTER(VbTables), _P, _P, _P, _P, _P]),
@@ -168,3 +173,22 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 def stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
+
+
+def launch_count() -> int:
+    """Kernels launched by libvb200 since it was loaded."""
+    return int(lib().vb200_launch_count(-1))
+
+
+def trace_enable(on: bool) -> None:
+    check(lib().vb200_trace_enable(1 if on else 0))
+
+
+def trace_collect():
+    """{kernel family: (device ms total, launches)} for the launches recorded since trace_enable."""
+    l = lib()
+    n = l.vb200_trace_num_kernels()
+    ms = (C.c_double * n)()
+    cnt = (C.c_longlong * n)()
+    check(l.vb200_trace_collect(ms, cnt))
+    return {l.vb200_trace_kernel_name(i).decode(): (ms[i], int(cnt[i])) for i in range(n) if cnt[i]}

@@ -5,6 +5,7 @@
 // fused kernels use.  They exist for the drop-in get_pixel / get_geometry methods and for the
 // index-parity tests.
 #include "vb_common.cuh"
+#include "vb_trace.cuh"
 
 namespace {
 
@@ -112,6 +113,7 @@ extern "C" int vb200_get_pixel(const VbGrid* g, const VbTables* t, const float* 
   if ((rc = vb200_device_check())) return rc;
   const int nvox = g->vZ * g->vY * g->vX;
   dim3 grid(vb_ceil_div(nvox, 256), g->B * g->N);
+  VbTraceScope tr(VB_K_GET_PIXEL, (cudaStream_t)stream);
   get_pixel_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*g, *t, d_mats, d_pix, nullptr, nullptr, nullptr);
   VB_LAUNCH_CHECK();
   return VB200_OK;
@@ -125,6 +127,7 @@ extern "C" int vb200_lift_indices(const VbGrid* g, const VbTables* t, const floa
   if ((rc = vb200_device_check())) return rc;
   const int nvox = g->vZ * g->vY * g->vX;
   dim3 grid(vb_ceil_div(nvox, 256), g->B * g->N);
+  VbTraceScope tr(VB_K_GET_PIXEL, (cudaStream_t)stream);
   get_pixel_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*g, *t, d_mats, nullptr, d_valid, d_i0, d_frac);
   VB_LAUNCH_CHECK();
   return VB200_OK;
@@ -138,6 +141,7 @@ extern "C" int vb200_get_geometry(const VbGrid* g, const VbTables* t, const floa
   if ((rc = vb200_device_check())) return rc;
   const int npts = g->D * g->fH * g->fW;
   dim3 grid(vb_ceil_div(npts, 256), g->B * g->N);
+  VbTraceScope tr(VB_K_GET_GEOMETRY, (cudaStream_t)stream);
   get_geometry_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*g, *t, d_mats, nullptr, d_geom, nan_to_num_flag,
                                                              nullptr, nullptr, nullptr);
   VB_LAUNCH_CHECK();
@@ -152,6 +156,7 @@ extern "C" int vb200_render_indices(const VbGrid* g, const VbTables* t, const fl
   if ((rc = vb200_device_check())) return rc;
   const int npts = g->D * g->fH * g->fW;
   dim3 grid(vb_ceil_div(npts, 256), g->B * g->N);
+  VbTraceScope tr(VB_K_GET_GEOMETRY, (cudaStream_t)stream);
   get_geometry_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*g, *t, d_mats, d_geom, nullptr, 1, d_mask, d_i0,
                                                              d_frac);
   VB_LAUNCH_CHECK();

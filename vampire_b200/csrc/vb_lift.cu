@@ -14,6 +14,7 @@
 // HBM roofline: read depth + ctx once (L2-resident afterwards: 27.6 MB fp32 per sample), write the
 // (B,C,vZ,vY,vX) volume once => 111.5 MB/sample fp32, 55.7 MB bf16.
 #include "vb_common.cuh"
+#include "vb_trace.cuh"
 
 namespace {
 
@@ -84,15 +85,29 @@ __global__ void __launch_bounds__(kLiftThreads) lift_pool_fwd_kernel(VbGrid g, V
                                                                      T* __restrict__ out, uint64_t* __restrict__ cnt_out) {
   static_assert(C <= 16, "per-channel counts are packed 4 bits each into 64 bits");
   __shared__ float s_m[VB_MAX_CAMS * VB200_MAT_SLOTS * 16];
+  __shared__ float s_q[VB_MAX_CAMS * 16];   // fast cull: (K.E^-1)(bda^-1), FMA-composed
   const int b = blockIdx.y;
   stage_mats(s_m, d_mats, b, g.N);
+  __syncthreads();
+  const bool has_bda = g.has_bda != 0;
+  for (int i = threadIdx.x; i < g.N * 16; i += blockDim.x) {
+    const int n = i / 16, r = (i % 16) / 4, c = i % 4;
+    const float* A = s_m + n * VB200_MAT_SLOTS * 16 + 16;   // K.E^-1
+    const float* Bm = s_m + n * VB200_MAT_SLOTS * 16;       // bda^-1
+    float v = A[r * 4 + c];
+    if (has_bda) {
+      v = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v = fmaf(A[r * 4 + k], Bm[k * 4 + c], v);
+    }
+    s_q[i] = v;
+  }
   __syncthreads();
   const int nvox = g.vZ * g.vY * g.vX;
   const int vox = blockIdx.x * kLiftThreads + threadIdx.x;
   if (vox >= nvox) return;
   const int x = vox % g.vX, y = (vox / g.vX) % g.vY, z = vox / (g.vX * g.vY);
   const float px = __ldg(t.xs + x), py = __ldg(t.ys + y), pz = __ldg(t.zs + z);
-  const bool has_bda = g.has_bda != 0;
   const int HW = g.fH * g.fW;
 
   float acc[C];
@@ -101,6 +116,25 @@ __global__ void __launch_bounds__(kLiftThreads) lift_pool_fwd_kernel(VbGrid g, V
   uint64_t cnt = 0;
 
   for (int n = 0; n < g.N; ++n) {
+    // Conservative cull (tolerance zone): 84 % of (voxel, camera) pairs are invisible by a wide
+    // margin, so an FMA/approx-reciprocal projection with a 1 px / 5 cm guard band rejects them
+    // for ~25 instructions.  Everything that survives goes through the strict, bit-exact
+    // projection below, which alone decides `valid` -- the cull can only skip pairs whose strict
+    // result is provably invalid (fp32 rounding differences are < 0.02 px / 1e-4 m here).
+    {
+      const float* q = s_q + n * 16;
+      const float cz = fmaf(q[8], px, fmaf(q[9], py, fmaf(q[10], pz, q[11])));
+      if (!(cz > g.d_lo - 0.05f && cz < g.d_hi + 0.05f)) continue;
+      const float cx = fmaf(q[0], px, fmaf(q[1], py, fmaf(q[2], pz, q[3])));
+      const float cy = fmaf(q[4], px, fmaf(q[5], py, fmaf(q[6], pz, q[7])));
+      const float rz = __frcp_rn(cz);
+      const float ux = cx * rz, uy = cy * rz;
+      const float* I = s_m + n * VB200_MAT_SLOTS * 16 + 2 * 16;   // ida
+      const float cw = fmaf(q[12], px, fmaf(q[13], py, fmaf(q[14], pz, q[15])));
+      const float ax = fmaf(I[0], ux, fmaf(I[1], uy, fmaf(I[2], cz, I[3] * cw)));
+      const float ay = fmaf(I[4], ux, fmaf(I[5], uy, fmaf(I[6], cz, I[7] * cw)));
+      if (!(ax > -1.5f && ax < g.x_hi + 1.0f && ay > -1.5f && ay < g.y_hi + 1.0f)) continue;
+    }
     float pix[3];
     project_voxel(s_m + n * VB200_MAT_SLOTS * 16, has_bda, px, py, pz, pix);
     const LiftCoord lc = lift_coord(g, pix);
@@ -171,11 +205,13 @@ int launch_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, const vo
   {
     dim3 grid(g->fH, g->B * g->N);
     const size_t smem = (size_t)C * (g->fW + 1) * sizeof(T);
+    VbTraceScope tr(VB_K_CTX_NHWC, st);
     ctx_to_nhwc_kernel<T, C><<<grid, 256, smem, st>>>(reinterpret_cast<const T*>(d_ctx), ctx_nhwc, g->fH, g->fW);
     VB_LAUNCH_CHECK();
   }
   const int nvox = g->vZ * g->vY * g->vX;
   dim3 grid(vb_ceil_div(nvox, kLiftThreads), g->B);
+  VbTraceScope tr(VB_K_LIFT_FWD, st);
   if (out_layout == VB200_NCDHW)
     lift_pool_fwd_kernel<T, C, VB200_NCDHW><<<grid, kLiftThreads, 0, st>>>(
         *g, *t, d_mats, reinterpret_cast<const T*>(d_depth), ctx_nhwc, reinterpret_cast<T*>(d_out), d_cnt);

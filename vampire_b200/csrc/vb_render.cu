@@ -20,6 +20,7 @@
 //   bev_fwd          = R5+R6 fused: reads the four NCDHW tensors directly (regular stencil, fully
 //                      coalesced), never materialises the 38-channel cat.
 #include "vb_common.cuh"
+#include "vb_trace.cuh"
 
 namespace {
 
@@ -229,6 +230,11 @@ __device__ __forceinline__ void sample_levels(const VbGrid& g, const VbTables& t
   }
 }
 
+// grid = (column tiles, channel groups, samples).  Every group recomputes the compositing weights
+// from the density plane (11 rows x 4 loads) and then handles kBevGroup of the 37 other channels
+// (18 sem | 3 rgb | 16 feat), so the launch has enough threads to cover the machine.
+constexpr int kBevGroup = 8;
+
 template <typename T, int K, int C>
 __global__ void __launch_bounds__(256) bev_fwd_kernel(VbGrid g, VbTables t, const T* __restrict__ den,
                                                       const T* __restrict__ sem, const T* __restrict__ rgb,
@@ -236,7 +242,8 @@ __global__ void __launch_bounds__(256) bev_fwd_kernel(VbGrid g, VbTables t, cons
                                                       float* __restrict__ o_rgb, float* __restrict__ o_seg,
                                                       float* __restrict__ o_height, float* __restrict__ o_density,
                                                       T* __restrict__ o_feat, int b0) {
-  const int b = b0 + blockIdx.y;
+  const int b = b0 + blockIdx.z;
+  const int grp = blockIdx.y;
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const int ncol = g.oY * g.oX;
   if (col >= ncol) return;
@@ -269,35 +276,229 @@ __global__ void __launch_bounds__(256) bev_fwd_kernel(VbGrid g, VbTables t, cons
   for (int l = 0; l < kMaxLevels; ++l) {
     if (l < g.oZ) {
       const float sigma = laplace_density(vals[l], g.sdf_bias, beta);
-      o_density[((size_t)b * g.oZ + l) * ncol + col] = sigma;
+      if (grp == 0) o_density[((size_t)b * g.oZ + l) * ncol + col] = sigma;
       const float sd = sigma * g.bev_delta;
       wl[l] = (1.0f - expf(-sd)) * expf(-tau);
       tau += sd;
       height = fmaf(wl[l], __ldg(t.bev_mids + l), height);
     }
   }
-  o_height[(size_t)b * ncol + col] = height;
-  for (int k = 0; k < K; ++k) {
-    sample_levels<T>(g, t, bc, sem + ((size_t)b * K + k) * nvox, vals);
-    float a = 0.0f;
+  if (grp == 0) o_height[(size_t)b * ncol + col] = height;
+
+  const int j0 = grp * kBevGroup, j1 = min(K + 3 + C, j0 + kBevGroup);
+  for (int j = j0; j < j1; ++j) {
+    if (j < K + 3) {   // composited channels: semantics then rgb                       BV2:459-460
+      const T* plane = j < K ? sem + ((size_t)b * K + j) * nvox : rgb + ((size_t)b * 3 + (j - K)) * nvox;
+      sample_levels<T>(g, t, bc, plane, vals);
+      float a = 0.0f;
 #pragma unroll
-    for (int l = 0; l < kMaxLevels; ++l)
-      if (l < g.oZ) a = fmaf(wl[l], vals[l], a);
-    o_seg[((size_t)b * K + k) * ncol + col] = a;
+      for (int l = 0; l < kMaxLevels; ++l)
+        if (l < g.oZ) a = fmaf(wl[l], vals[l], a);
+      if (j < K) o_seg[((size_t)b * K + j) * ncol + col] = a;
+      else o_rgb[((size_t)b * 3 + (j - K)) * ncol + col] = a;
+    } else {           // resampled base features, returned unweighted                    BV2:448
+      const int c = j - (K + 3);
+      sample_levels<T>(g, t, bc, feat + ((size_t)b * C + c) * nvox, vals);
+#pragma unroll
+      for (int l = 0; l < kMaxLevels; ++l)
+        if (l < g.oZ) o_feat[(((size_t)b * C + c) * g.oZ + l) * ncol + col] = VbType<T>::cvt(vals[l]);
+    }
   }
-  for (int j = 0; j < 3; ++j) {
-    sample_levels<T>(g, t, bc, rgb + ((size_t)b * 3 + j) * nvox, vals);
-    float a = 0.0f;
-#pragma unroll
-    for (int l = 0; l < kMaxLevels; ++l)
-      if (l < g.oZ) a = fmaf(wl[l], vals[l], a);
-    o_rgb[((size_t)b * 3 + j) * ncol + col] = a;
+}
+
+// ---- R5+R6, vectorised: one thread = 4 consecutive output columns ------------------------------
+// Output column ox samples input columns x0(ox), x0(ox)+1 with x0(ox) in {ox-1, ox} whenever the det
+// grid shares the seg grid's xy lattice (the reference config).  A thread then needs the 6-wide
+// window in[ox0-1 .. ox0+4]: one 64/128-bit load plus one value from each neighbouring lane
+// (shuffles) -- 8x fewer load instructions than the scalar kernel.  Threads whose columns do not
+// satisfy the window assumption fall back to scalar gathers (still exact), so any grid works.
+template <typename T> struct Vec4Load;
+template <> struct Vec4Load<float> {
+  __device__ __forceinline__ static void ld(const float* p, float (&o)[4]) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
   }
-  for (int c = 0; c < C; ++c) {   // resampled base features, returned unweighted   BV2:448
-    sample_levels<T>(g, t, bc, feat + ((size_t)b * C + c) * nvox, vals);
+};
+template <> struct Vec4Load<__nv_bfloat16> {
+  __device__ __forceinline__ static void ld(const __nv_bfloat16* p, float (&o)[4]) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    o[0] = __uint_as_float(v.x << 16); o[1] = __uint_as_float(v.x & 0xffff0000u);
+    o[2] = __uint_as_float(v.y << 16); o[3] = __uint_as_float(v.y & 0xffff0000u);
+  }
+};
+template <> struct Vec4Load<__half> {
+  __device__ __forceinline__ static void ld(const __half* p, float (&o)[4]) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+  }
+};
+
+struct BevQuad {
+  int ox0;            // first output column (multiple of 4)
+  int x0[4];          // base input column of each output column
+  float wx0[4], wx1[4];
+  bool window;        // x0[c] - (ox0 + c - 1) in {0, 1} for all 4 columns
+  int k[4];           // that offset
+  int y0;
+  float wy0, wy1;
+};
+
+// x-interpolated values of one input row (z, y) for the thread's 4 columns
+template <typename T>
+__device__ __forceinline__ void quad_row(const VbGrid& g, const BevQuad& q, const T* __restrict__ row, bool warp_window,
+                                         int lane, float (&out)[4], float wy) {
+  float a[4], b[4];
+  if (warp_window) {
+    float v[4];
+    Vec4Load<T>::ld(row + q.ox0, v);
+    float left = __shfl_up_sync(0xffffffffu, v[3], 1);
+    float right = __shfl_down_sync(0xffffffffu, v[0], 1);
+    if (lane == 0) left = q.ox0 - 1 >= 0 ? VbType<T>::ld(row + q.ox0 - 1) : 0.0f;
+    if (lane == 31) right = q.ox0 + 4 < g.vX ? VbType<T>::ld(row + q.ox0 + 4) : 0.0f;
+    const float w[6] = {left, v[0], v[1], v[2], v[3], right};
 #pragma unroll
-    for (int l = 0; l < kMaxLevels; ++l)
-      if (l < g.oZ) o_feat[(((size_t)b * C + c) * g.oZ + l) * ncol + col] = VbType<T>::cvt(vals[l]);
+    for (int c = 0; c < 4; ++c) {
+      a[c] = q.k[c] ? w[c + 1] : w[c];
+      b[c] = q.k[c] ? w[c + 2] : w[c + 1];
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int xa = q.x0[c], xb = q.x0[c] + 1;
+      a[c] = (xa >= 0 && xa < g.vX) ? VbType<T>::ld(row + xa) : 0.0f;
+      b[c] = (xb >= 0 && xb < g.vX) ? VbType<T>::ld(row + xb) : 0.0f;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) out[c] = fmaf(wy, fmaf(q.wx0[c], a[c], q.wx1[c] * b[c]), out[c]);
+}
+
+// xy-bilinear values of one z-row of a channel plane for the 4 columns (zeros padding)
+template <typename T>
+__device__ __forceinline__ void quad_zrow(const VbGrid& g, const BevQuad& q, const T* __restrict__ plane, int z,
+                                          bool warp_window, int lane, float (&out)[4]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) out[c] = 0.0f;
+  if (z < 0 || z >= g.vZ) return;
+  const T* zr = plane + (size_t)z * g.vY * g.vX;
+  if (q.y0 >= 0 && q.y0 < g.vY) quad_row<T>(g, q, zr + (size_t)q.y0 * g.vX, warp_window, lane, out, q.wy0);
+  if (q.y0 + 1 >= 0 && q.y0 + 1 < g.vY) quad_row<T>(g, q, zr + (size_t)(q.y0 + 1) * g.vX, warp_window, lane, out, q.wy1);
+}
+
+// walk the levels of one plane top-down, calling sink(l, vals[4]) per level
+template <typename T, typename Sink>
+__device__ __forceinline__ void quad_levels(const VbGrid& g, const VbTables& t, const BevQuad& q,
+                                            const T* __restrict__ plane, bool warp_window, int lane, Sink&& sink) {
+  int prev_z0 = -1000000;
+  float prev_lo[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int l = 0; l < kMaxLevels; ++l) {
+    if (l < g.oZ) {
+      int z0;
+      float wz0, wz1;
+      axis_coord(__ldg(t.ozs + (g.oZ - 1 - l)), g.seg_lo[2], g.seg_ext[2], g.vZ, z0, wz0, wz1);
+      float hi[4], lo[4];
+      if (z0 + 1 == prev_z0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) hi[c] = prev_lo[c];
+      } else {
+        quad_zrow<T>(g, q, plane, z0 + 1, warp_window, lane, hi);
+      }
+      quad_zrow<T>(g, q, plane, z0, warp_window, lane, lo);
+      float v[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        v[c] = wz0 * lo[c] + wz1 * hi[c];
+        prev_lo[c] = lo[c];
+      }
+      prev_z0 = z0;
+      sink(l, v);
+    }
+  }
+}
+
+template <typename T, int K, int C>
+__global__ void __launch_bounds__(64) bev_fwd_vec4_kernel(VbGrid g, VbTables t, const T* __restrict__ den,
+                                                          const T* __restrict__ sem, const T* __restrict__ rgb,
+                                                          const T* __restrict__ feat, const float* __restrict__ beta_ptr,
+                                                          float* __restrict__ o_rgb, float* __restrict__ o_seg,
+                                                          float* __restrict__ o_height, float* __restrict__ o_density,
+                                                          T* __restrict__ o_feat) {
+  const int b = blockIdx.z, grp = blockIdx.y;
+  const int tiles_x = (g.oX + 255) / 256;
+  const int oy = blockIdx.x / tiles_x;
+  const int lane = threadIdx.x & 31;
+  const int ox_raw = (blockIdx.x % tiles_x) * 256 + threadIdx.x * 4;
+  const bool live = ox_raw < g.oX;                    // oX % 4 == 0 is guaranteed by the launcher
+  const int ncol = g.oY * g.oX;
+  const size_t nvox = (size_t)g.vZ * g.vY * g.vX;
+  const float beta = fabsf(__ldg(beta_ptr)) + g.beta_min;
+
+  BevQuad q;
+  q.ox0 = live ? ox_raw : 0;
+  q.window = true;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    axis_coord(__ldg(t.oxs + q.ox0 + c), g.seg_lo[0], g.seg_ext[0], g.vX, q.x0[c], q.wx0[c], q.wx1[c]);
+    q.k[c] = q.x0[c] - (q.ox0 + c - 1);
+    q.window = q.window && (q.k[c] == 0 || q.k[c] == 1);
+  }
+  q.window = q.window && (q.ox0 + 3 < g.vX);
+  axis_coord(__ldg(t.oys + oy), g.seg_lo[1], g.seg_ext[1], g.vY, q.y0, q.wy0, q.wy1);
+  const bool warp_window = __all_sync(0xffffffffu, q.window);   // shuffles need the whole warp on one path
+
+  float wl[4][kMaxLevels];
+  {
+    float tau[4] = {0.f, 0.f, 0.f, 0.f}, height[4] = {0.f, 0.f, 0.f, 0.f};
+    quad_levels<T>(g, t, q, den + (size_t)b * nvox, warp_window, lane, [&](int l, const float (&v)[4]) {
+      const float mid = __ldg(t.bev_mids + l);
+      float sig[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        sig[c] = laplace_density(v[c], g.sdf_bias, beta);                      // BV2:445
+        const float sd = sig[c] * g.bev_delta;
+        wl[c][l] = (1.0f - expf(-sd)) * expf(-tau[c]);                          // BV2:454-458
+        tau[c] += sd;
+        height[c] = fmaf(wl[c][l], mid, height[c]);
+      }
+      if (grp == 0 && live)
+        *reinterpret_cast<float4*>(o_density + ((size_t)b * g.oZ + l) * ncol + (size_t)oy * g.oX + q.ox0) =
+            make_float4(sig[0], sig[1], sig[2], sig[3]);
+    });
+    if (grp == 0 && live)
+      *reinterpret_cast<float4*>(o_height + (size_t)b * ncol + (size_t)oy * g.oX + q.ox0) =
+          make_float4(height[0], height[1], height[2], height[3]);
+  }
+
+  const int j0 = grp * kBevGroup, j1 = min(K + 3 + C, j0 + kBevGroup);
+  for (int j = j0; j < j1; ++j) {
+    if (j < K + 3) {
+      const T* plane = j < K ? sem + ((size_t)b * K + j) * nvox : rgb + ((size_t)b * 3 + (j - K)) * nvox;
+      float a[4] = {0.f, 0.f, 0.f, 0.f};
+      quad_levels<T>(g, t, q, plane, warp_window, lane, [&](int l, const float (&v)[4]) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) a[c] = fmaf(wl[c][l], v[c], a[c]);
+      });
+      float* o = (j < K ? o_seg + ((size_t)b * K + j) * ncol : o_rgb + ((size_t)b * 3 + (j - K)) * ncol) +
+                 (size_t)oy * g.oX + q.ox0;
+      if (live) *reinterpret_cast<float4*>(o) = make_float4(a[0], a[1], a[2], a[3]);
+    } else {
+      const int c_ = j - (K + 3);
+      T* obase = o_feat + ((size_t)b * C + c_) * g.oZ * ncol + (size_t)oy * g.oX + q.ox0;
+      quad_levels<T>(g, t, q, feat + ((size_t)b * C + c_) * nvox, warp_window, lane, [&](int l, const float (&v)[4]) {
+        if (live) {
+          T* o = obase + (size_t)l * ncol;
+          if (sizeof(T) == 4) {
+            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+            T h[4] = {VbType<T>::cvt(v[0]), VbType<T>::cvt(v[1]), VbType<T>::cvt(v[2]), VbType<T>::cvt(v[3])};
+            *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(h);
+          }
+        }
+      });
+    }
   }
 }
 
@@ -323,36 +524,46 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
   const T* feat = reinterpret_cast<const T*>(in->feat);
   const int patches = vb_ceil_div(g->fW, kPatchW) * vb_ceil_div(g->fH, kPatchH);
   const int ncol = g->oY * g->oX;
-  const int step = (branches & VB200_BRANCH_CAM) ? group : g->B;
-  for (int b0 = 0; b0 < g->B; b0 += step) {
-    const int nb = (g->B - b0) < step ? (g->B - b0) : step;
-    if (branches & VB200_BRANCH_CAM) {
-      for (int i = 0; i < nb; ++i) {
-        const int b = b0 + i;
-        pack_cam_volume_kernel<T, K><<<vb_ceil_div(nvox, kPackThreads), kPackThreads, 0, st>>>(
-            den + (size_t)b * nvox, sem + (size_t)b * K * nvox, rgb + (size_t)b * 3 * nvox,
-            reinterpret_cast<T*>((char*)ws + (size_t)i * per), (int)nvox);
-        VB_LAUNCH_CHECK();
-      }
-    }
-    if (branches & VB200_BRANCH_BEV) {
-      dim3 grid(vb_ceil_div(ncol, 256), nb);
+  if (branches & VB200_BRANCH_BEV) {
+    dim3 grid(vb_ceil_div(ncol, 256), vb_ceil_div(K + 3 + C, kBevGroup), g->B);
+    VbTraceScope tr(VB_K_BEV_FWD, st);
+    const bool vec_ok = (g->vX % 4 == 0) && (g->oX % 4 == 0) &&
+                        ((((uintptr_t)den | (uintptr_t)sem | (uintptr_t)rgb | (uintptr_t)feat |
+                           (uintptr_t)out->voxel_output | (uintptr_t)out->bev_rgb | (uintptr_t)out->bev_seg |
+                           (uintptr_t)out->bev_height | (uintptr_t)out->voxel_density) & 15) == 0);
+    if (vec_ok) {
+      dim3 vgrid(g->oY * vb_ceil_div(g->oX, 256), vb_ceil_div(K + 3 + C, kBevGroup), g->B);
+      bev_fwd_vec4_kernel<T, K, C><<<vgrid, 64, 0, st>>>(*g, *t, den, sem, rgb, feat, in->beta, out->bev_rgb,
+                                                         out->bev_seg, out->bev_height, out->voxel_density,
+                                                         reinterpret_cast<T*>(out->voxel_output));
+    } else {
       bev_fwd_kernel<T, K, C><<<grid, 256, 0, st>>>(*g, *t, den, sem, rgb, feat, in->beta, out->bev_rgb,
                                                     out->bev_seg, out->bev_height, out->voxel_density,
-                                                    reinterpret_cast<T*>(out->voxel_output), b0);
+                                                    reinterpret_cast<T*>(out->voxel_output), 0);
+    }
+    VB_LAUNCH_CHECK();
+  }
+  if (!(branches & VB200_BRANCH_CAM)) return VB200_OK;
+  if (per != nvox * packed_channels(K) * sizeof(T)) return VB200_ERR_ARG;  // march indexes densely
+  for (int b0 = 0; b0 < g->B; b0 += group) {
+    const int nb = (g->B - b0) < group ? (g->B - b0) : group;
+    for (int i = 0; i < nb; ++i) {
+      const int b = b0 + i;
+      VbTraceScope tr(VB_K_PACK, st);
+      pack_cam_volume_kernel<T, K><<<vb_ceil_div(nvox, kPackThreads), kPackThreads, 0, st>>>(
+          den + (size_t)b * nvox, sem + (size_t)b * K * nvox, rgb + (size_t)b * 3 * nvox,
+          reinterpret_cast<T*>((char*)ws + (size_t)i * per), (int)nvox);
       VB_LAUNCH_CHECK();
     }
-    if (branches & VB200_BRANCH_CAM) {
-      if (per != nvox * packed_channels(K) * sizeof(T)) return VB200_ERR_ARG;  // march indexes densely
-      dim3 grid(vb_ceil_div(patches, kMarchThreads / 32), g->N, nb);
-      if (in->geom)
-        march_fwd_kernel<T, K, false><<<grid, kMarchThreads, 0, st>>>(
-            *g, *t, d_mats, in->geom, reinterpret_cast<const T*>(ws), in->beta, out->rgb, out->seg, out->depth, b0);
-      else
-        march_fwd_kernel<T, K, true><<<grid, kMarchThreads, 0, st>>>(
-            *g, *t, d_mats, nullptr, reinterpret_cast<const T*>(ws), in->beta, out->rgb, out->seg, out->depth, b0);
-      VB_LAUNCH_CHECK();
-    }
+    dim3 grid(vb_ceil_div(patches, kMarchThreads / 32), g->N, nb);
+    VbTraceScope tr(VB_K_MARCH_FWD, st);
+    if (in->geom)
+      march_fwd_kernel<T, K, false><<<grid, kMarchThreads, 0, st>>>(
+          *g, *t, d_mats, in->geom, reinterpret_cast<const T*>(ws), in->beta, out->rgb, out->seg, out->depth, b0);
+    else
+      march_fwd_kernel<T, K, true><<<grid, kMarchThreads, 0, st>>>(
+          *g, *t, d_mats, nullptr, reinterpret_cast<const T*>(ws), in->beta, out->rgb, out->seg, out->depth, b0);
+    VB_LAUNCH_CHECK();
   }
   return VB200_OK;
 }

@@ -251,18 +251,18 @@ def _(gout, depth, ctx, mats, cnt, cfg_id, has_bda):
     return torch.empty_like(depth), torch.empty_like(ctx)
 
 
-def _lift_setup(ctx_, inputs, output):
-    depth, ctx, mats, cfg_id, has_bda, channels_last, save_cnt = inputs
+def _lift_setup(ctx, inputs, output):
+    depth, context, mats, cfg_id, has_bda, channels_last, save_cnt = inputs
     _, cnt = output
-    ctx_.save_for_backward(depth, ctx, mats, cnt)
-    ctx_.cfg_id, ctx_.has_bda, ctx_.save_cnt = cfg_id, has_bda, save_cnt
+    ctx.save_for_backward(depth, context, mats, cnt)
+    ctx.cfg_id, ctx.has_bda, ctx.save_cnt = cfg_id, has_bda, save_cnt
 
 
-def _lift_backward(ctx_, gout, gcnt):
-    if not ctx_.save_cnt:
+def _lift_backward(ctx, gout, gcnt):
+    if not ctx.save_cnt:
         raise RuntimeError("lift_pool_fwd was called with save_cnt=False: no backward possible")
-    depth, ctx, mats, cnt = ctx_.saved_tensors
-    gdepth, gctx = lift_pool_bwd(gout, depth, ctx, mats, cnt, ctx_.cfg_id, ctx_.has_bda)
+    depth, context, mats, cnt = ctx.saved_tensors
+    gdepth, gctx = lift_pool_bwd(gout, depth, context, mats, cnt, ctx.cfg_id, ctx.has_bda)
     return gdepth, gctx, None, None, None, None, None
 
 
@@ -399,19 +399,19 @@ def _(grads, outs, density, sem, rgb, feat, beta, mats, geom, cfg_id, has_bda, b
             density.new_empty(1, dtype=torch.float32)]
 
 
-def _render_setup(ctx_, inputs, output):
+def _render_setup(ctx, inputs, output):
     density, sem, rgb, feat, beta, mats, geom, cfg_id, has_bda, branches = inputs
-    ctx_.save_for_backward(density, sem, rgb, feat, beta, mats, geom, *output)
-    ctx_.cfg_id, ctx_.has_bda, ctx_.branches = cfg_id, has_bda, branches
+    ctx.save_for_backward(density, sem, rgb, feat, beta, mats, geom, *output)
+    ctx.cfg_id, ctx.has_bda, ctx.branches = cfg_id, has_bda, branches
 
 
-def _render_backward(ctx_, grads):
-    saved = ctx_.saved_tensors
+def _render_backward(ctx, grads):
+    saved = ctx.saved_tensors
     density, sem, rgb, feat, beta, mats, geom = saved[:7]
     outs = list(saved[7:])
     grads = [gt if gt is not None else torch.zeros_like(o) for gt, o in zip(grads, outs)]
     g_den, g_sem, g_rgb, g_feat, g_beta = render_bwd(grads, outs, density, sem, rgb, feat, beta, mats, geom,
-                                                     ctx_.cfg_id, ctx_.has_bda, ctx_.branches)
+                                                     ctx.cfg_id, ctx.has_bda, ctx.branches)
     return g_den, g_sem, g_rgb, g_feat, g_beta.reshape(beta.shape).to(beta.dtype), None, None, None, None, None
 
 

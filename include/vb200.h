@@ -185,7 +185,11 @@ typedef struct VbRenderOut {
   void* voxel_output;   /* (B, C, oZ, oY, oX)  `dtype`, resampled features    */
 } VbRenderOut;
 
+/* vb200_render_fwd_workspace = the minimum: BEV compositing weights + ONE packed camera volume (samples
+ * are then packed and marched one at a time, the packed copy staying L2-resident).  Passing
+ * minimum + (n-1) * vb200_render_packed_bytes lets n samples share a pack/march round. */
 size_t vb200_render_fwd_workspace(const VbGrid* g, int dtype);
+size_t vb200_render_packed_bytes(const VbGrid* g, int dtype);
 size_t vb200_render_bwd_workspace(const VbGrid* g, int dtype);
 
 /* branches: bit 0 = camera branch, bit 1 = BEV branch */

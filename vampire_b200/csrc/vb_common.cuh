@@ -91,10 +91,13 @@ __device__ __forceinline__ float sdiv(float a, float b) { return __fdiv_rn(a, b)
 
 // row-major 4x4 (16 floats at M) times 4-vector, ATen native bmm order:
 // acc = 0; acc += M[i][k] * p[k] for k = 0..3, separate multiply / add roundings.
+// SIGNED_ZERO=false drops the leading "0 +" (it only turns a -0 product into +0): value-identical
+// for every compare / floor downstream, used by the fused kernels that never output coordinates.
+template <bool SIGNED_ZERO = true>
 __device__ __forceinline__ void mv_strict(const float* __restrict__ M, const float (&p)[4], float (&r)[4]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float acc = sadd(0.0f, smul(M[i * 4 + 0], p[0]));
+    float acc = SIGNED_ZERO ? sadd(0.0f, smul(M[i * 4 + 0], p[0])) : smul(M[i * 4 + 0], p[0]);
     acc = sadd(acc, smul(M[i * 4 + 1], p[1]));
     acc = sadd(acc, smul(M[i * 4 + 2], p[2]));
     acc = sadd(acc, smul(M[i * 4 + 3], p[3]));
@@ -103,38 +106,40 @@ __device__ __forceinline__ void mv_strict(const float* __restrict__ M, const flo
 }
 
 // G1 get_pixel for one voxel centre (BV2:367-388). M = this camera's 6 prepared matrices.
+template <bool SIGNED_ZERO = true>
 __device__ __forceinline__ void project_voxel(const float* __restrict__ M, bool has_bda, float x, float y,
                                               float z, float (&pix)[3]) {
   float p[4] = {x, y, z, 1.0f}, q[4];
   if (has_bda) {
-    mv_strict(M + 0 * 16, p, q);  // bda^-1                                     BV2:374
+    mv_strict<SIGNED_ZERO>(M + 0 * 16, p, q);  // bda^-1                        BV2:374
 #pragma unroll
     for (int i = 0; i < 4; ++i) p[i] = q[i];
   }
-  mv_strict(M + 1 * 16, p, q);    // K . E^-1                                   BV2:380
+  mv_strict<SIGNED_ZERO>(M + 1 * 16, p, q);    // K . E^-1                      BV2:380
   const float zc = q[2] < 1e-6f ? 1e-6f : q[2];  // torch.clamp(min=eps), NaN-propagating   BV2:385
   p[0] = sdiv(q[0], zc);
   p[1] = sdiv(q[1], zc);
   p[2] = q[2];
   p[3] = q[3];
-  mv_strict(M + 2 * 16, p, q);    // ida                                        BV2:387
+  mv_strict<SIGNED_ZERO>(M + 2 * 16, p, q);    // ida                           BV2:387
   pix[0] = q[0]; pix[1] = q[1]; pix[2] = q[2];
 }
 
 // G2 get_geometry for one frustum lattice point (BV2:332-349).
+template <bool SIGNED_ZERO = true>
 __device__ __forceinline__ void frustum_point(const float* __restrict__ M, bool has_bda, float u, float v,
                                               float d, float (&xyz)[3]) {
   float p[4] = {u, v, d, 1.0f}, q[4];
-  mv_strict(M + 3 * 16, p, q);    // ida^-1                                     BV2:334
+  mv_strict<SIGNED_ZERO>(M + 3 * 16, p, q);    // ida^-1                        BV2:334
   p[0] = smul(q[0], q[2]);        //                                            BV2:336-338
   p[1] = smul(q[1], q[2]);
   p[2] = q[2];
   p[3] = q[3];
-  mv_strict(M + 4 * 16, p, q);    // E . K^-1                                   BV2:341-342
+  mv_strict<SIGNED_ZERO>(M + 4 * 16, p, q);    // E . K^-1                      BV2:341-342
   if (has_bda) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) p[i] = q[i];
-    mv_strict(M + 5 * 16, p, q);  // bda                                        BV2:346
+    mv_strict<SIGNED_ZERO>(M + 5 * 16, p, q);  // bda                           BV2:346
   }
   xyz[0] = q[0]; xyz[1] = q[1]; xyz[2] = q[2];
 }

@@ -21,44 +21,25 @@ namespace {
 constexpr int kLiftThreads = 256;
 
 // ---- ctx (B,N,C,fH,fW) -> (B,N,fH,fW,C): one block per (b*n, h) row -------------------------
+// (the copy is widened to fp32 so the gather needs no per-element unpack: 64 B = 4 x 128-bit per pixel)
 template <typename T, int C>
-__global__ void __launch_bounds__(256) ctx_to_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, int fH,
+__global__ void __launch_bounds__(256) ctx_to_nhwc_kernel(const T* __restrict__ src, float* __restrict__ dst, int fH,
                                                           int fW) {
   extern __shared__ unsigned char s_raw[];
-  T* s = reinterpret_cast<T*>(s_raw);  // [C][fW + 1]
+  float* s = reinterpret_cast<float*>(s_raw);  // [C][fW + 1]
   const int h = blockIdx.x, bn = blockIdx.y;
   const int ld = fW + 1;
   for (int i = threadIdx.x; i < C * fW; i += blockDim.x) {
     const int c = i / fW, w = i % fW;
-    s[c * ld + w] = src[(((size_t)bn * C + c) * fH + h) * fW + w];
+    s[c * ld + w] = VbType<T>::ld(src + (((size_t)bn * C + c) * fH + h) * fW + w);
   }
   __syncthreads();
-  T* out = dst + ((size_t)bn * fH + h) * fW * C;
+  float* out = dst + ((size_t)bn * fH + h) * fW * C;
   for (int i = threadIdx.x; i < C * fW; i += blockDim.x) {
     const int w = i / C, c = i % C;
     out[i] = s[c * ld + w];
   }
 }
-
-template <typename T, int C> struct CtxLoad;
-template <int C> struct CtxLoad<float, C> {
-  __device__ __forceinline__ static void ld(const float* p, float (&o)[C]) {
-#pragma unroll
-    for (int q = 0; q < C / 4; ++q) VbVec<float, 4>::ld(p + 4 * q, &o[4 * q]);
-  }
-};
-template <int C> struct CtxLoad<__nv_bfloat16, C> {
-  __device__ __forceinline__ static void ld(const __nv_bfloat16* p, float (&o)[C]) {
-#pragma unroll
-    for (int q = 0; q < C / 8; ++q) VbVec<__nv_bfloat16, 8>::ld(p + 8 * q, &o[8 * q]);
-  }
-};
-template <int C> struct CtxLoad<__half, C> {
-  __device__ __forceinline__ static void ld(const __half* p, float (&o)[C]) {
-#pragma unroll
-    for (int q = 0; q < C / 8; ++q) VbVec<__half, 8>::ld(p + 8 * q, &o[8 * q]);
-  }
-};
 
 // Trilinear weights exactly as ATen forms them (GridSampler: corner weight = product of
 // (x_far - ix) terms), in the tolerance zone (FMA allowed).
@@ -81,7 +62,7 @@ template <typename T, int C, int OUT_LAYOUT>
 __global__ void __launch_bounds__(kLiftThreads) lift_pool_fwd_kernel(VbGrid g, VbTables t,
                                                                      const float* __restrict__ d_mats,
                                                                      const T* __restrict__ depth,
-                                                                     const T* __restrict__ ctx_nhwc,
+                                                                     const float* __restrict__ ctx_nhwc,
                                                                      T* __restrict__ out, uint64_t* __restrict__ cnt_out) {
   static_assert(C <= 16, "per-channel counts are packed 4 bits each into 64 bits");
   __shared__ float s_m[VB_MAX_CAMS * VB200_MAT_SLOTS * 16];
@@ -110,10 +91,9 @@ __global__ void __launch_bounds__(kLiftThreads) lift_pool_fwd_kernel(VbGrid g, V
   const float px = __ldg(t.xs + x), py = __ldg(t.ys + y), pz = __ldg(t.zs + z);
   const int HW = g.fH * g.fW;
 
-  float acc[C];
+  float acc[C], cntf[C];
 #pragma unroll
-  for (int c = 0; c < C; ++c) acc[c] = 0.0f;
-  uint64_t cnt = 0;
+  for (int c = 0; c < C; ++c) { acc[c] = 0.0f; cntf[c] = 0.0f; }
 
   for (int n = 0; n < g.N; ++n) {
     // Conservative cull (tolerance zone): 84 % of (voxel, camera) pairs are invisible by a wide
@@ -136,60 +116,65 @@ __global__ void __launch_bounds__(kLiftThreads) lift_pool_fwd_kernel(VbGrid g, V
       if (!(ax > -1.5f && ax < g.x_hi + 1.0f && ay > -1.5f && ay < g.y_hi + 1.0f)) continue;
     }
     float pix[3];
-    project_voxel(s_m + n * VB200_MAT_SLOTS * 16, has_bda, px, py, pz, pix);
+    project_voxel<false>(s_m + n * VB200_MAT_SLOTS * 16, has_bda, px, py, pz, pix);
     const LiftCoord lc = lift_coord(g, pix);
     if (!lc.valid) continue;  // f = grid_sample * 0: adds nothing to numer nor to the count
     const TriW w = tri_weights(lc.ix, lc.iy, lc.iz, lc.x0, lc.y0, lc.z0);
     const T* dcam = depth + (size_t)(b * g.N + n) * g.D * HW;
-    const T* ccam = ctx_nhwc + (size_t)(b * g.N + n) * HW * C;
-    const bool z0_in = lc.z0 >= 0 && lc.z0 < g.D;
-    const bool z1_in = lc.z0 + 1 >= 0 && lc.z0 + 1 < g.D;
+    const float* ccam = ctx_nhwc + (size_t)(b * g.N + n) * HW * C;
+    // zeros padding without branches: clamp the address, zero the weight (valid => i0 in [-1, size-1])
+    const int xa = max(lc.x0, 0), xb = min(lc.x0 + 1, g.fW - 1);
+    const int ya = max(lc.y0, 0), yb = min(lc.y0 + 1, g.fH - 1);
+    const int za = max(lc.z0, 0), zb = min(lc.z0 + 1, g.D - 1);
+    const float wxa = lc.x0 >= 0 ? w.wx0 : 0.0f, wxb = lc.x0 + 1 < g.fW ? w.wx1 : 0.0f;
+    const float wya = lc.y0 >= 0 ? w.wy0 : 0.0f, wyb = lc.y0 + 1 < g.fH ? w.wy1 : 0.0f;
+    const float wza = lc.z0 >= 0 ? w.wz0 : 0.0f, wzb = lc.z0 + 1 < g.D ? w.wz1 : 0.0f;
+    const int pxl[4] = {ya * g.fW + xa, ya * g.fW + xb, yb * g.fW + xa, yb * g.fW + xb};
+    const float wxy[4] = {wxa * wya, wxb * wya, wxa * wyb, wxb * wyb};
+    const T* d0 = dcam + (size_t)za * HW;
+    const T* d1 = dcam + (size_t)zb * HW;
+    float wgt[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      wgt[k] = wxy[k] * fmaf(wzb, VbType<T>::ld(d1 + pxl[k]), wza * VbType<T>::ld(d0 + pxl[k]));
     float f[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) f[c] = 0.0f;
 #pragma unroll
-    for (int dy = 0; dy < 2; ++dy) {
-      const int yy = lc.y0 + dy;
-      if (yy < 0 || yy >= g.fH) continue;
-      const float wy = dy ? w.wy1 : w.wy0;
+    for (int k = 0; k < 4; ++k) {
+      const float4* cp = reinterpret_cast<const float4*>(ccam + (size_t)pxl[k] * C);
 #pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const int xx = lc.x0 + dx;
-        if (xx < 0 || xx >= g.fW) continue;
-        const float wx = dx ? w.wx1 : w.wx0;
-        const int pixel = yy * g.fW + xx;
-        float s = 0.0f;
-        if (z0_in) s = w.wz0 * VbType<T>::ld(dcam + (size_t)lc.z0 * HW + pixel);
-        if (z1_in) s += w.wz1 * VbType<T>::ld(dcam + (size_t)(lc.z0 + 1) * HW + pixel);
-        const float wgt = wx * wy * s;
-        float cv[C];
-        CtxLoad<T, C>::ld(ccam + (size_t)pixel * C, cv);
-#pragma unroll
-        for (int c = 0; c < C; ++c) f[c] = fmaf(cv[c], wgt, f[c]);
+      for (int q4 = 0; q4 < C / 4; ++q4) {
+        const float4 cv = __ldg(cp + q4);
+        f[4 * q4 + 0] = fmaf(cv.x, wgt[k], f[4 * q4 + 0]);
+        f[4 * q4 + 1] = fmaf(cv.y, wgt[k], f[4 * q4 + 1]);
+        f[4 * q4 + 2] = fmaf(cv.z, wgt[k], f[4 * q4 + 2]);
+        f[4 * q4 + 3] = fmaf(cv.w, wgt[k], f[4 * q4 + 3]);
       }
     }
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       acc[c] += f[c];
-      cnt += (uint64_t)(fabsf(f[c]) > 0.0f ? 1 : 0) << (4 * c);   // voxel_mask  BV2:509
+      cntf[c] += (fabsf(f[c]) > 0.0f) ? 1.0f : 0.0f;   // voxel_mask  BV2:509
     }
   }
 
-  if (cnt_out) cnt_out[(size_t)b * nvox + vox] = cnt;
-  if (OUT_LAYOUT == VB200_NCDHW) {
+  if (cnt_out) {   // saved for the backward: 4 bits per channel
+    uint64_t cnt = 0;
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float denom = (float)((cnt >> (4 * c)) & 0xf) + 1e-6f;     // BV2:512
-      out[((size_t)b * C + c) * nvox + vox] = VbType<T>::cvt(acc[c] / denom);
-    }
+    for (int c = 0; c < C; ++c) cnt |= (uint64_t)(uint32_t)cntf[c] << (4 * c);
+    cnt_out[(size_t)b * nvox + vox] = cnt;
+  }
+  // mean = numer / (count + 1e-6)  (BV2:512-514); reciprocal-multiply is within 2 ulp of the division
+  if (OUT_LAYOUT == VB200_NCDHW) {
+    T* o = out + (size_t)b * C * nvox + vox;
+#pragma unroll
+    for (int c = 0; c < C; ++c) o[(size_t)c * nvox] = VbType<T>::cvt(__fdividef(acc[c], cntf[c] + 1e-6f));
   } else {
     T* o = out + ((size_t)b * nvox + vox) * C;
     T v[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float denom = (float)((cnt >> (4 * c)) & 0xf) + 1e-6f;
-      v[c] = VbType<T>::cvt(acc[c] / denom);
-    }
+    for (int c = 0; c < C; ++c) v[c] = VbType<T>::cvt(__fdividef(acc[c], cntf[c] + 1e-6f));
     constexpr int L = VbLanes<T>::n;
 #pragma unroll
     for (int q = 0; q < C / L; ++q) reinterpret_cast<uint4*>(o)[q] = reinterpret_cast<const uint4*>(v)[q];
@@ -201,10 +186,10 @@ int launch_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, const vo
                void* d_out, int out_layout, uint64_t* d_cnt, void* ws, cudaStream_t st) {
   constexpr int C = 16;
   if (g->C != C) return VB200_ERR_ARG;
-  T* ctx_nhwc = reinterpret_cast<T*>(ws);
+  float* ctx_nhwc = reinterpret_cast<float*>(ws);
   {
     dim3 grid(g->fH, g->B * g->N);
-    const size_t smem = (size_t)C * (g->fW + 1) * sizeof(T);
+    const size_t smem = (size_t)C * (g->fW + 1) * sizeof(float);
     VbTraceScope tr(VB_K_CTX_NHWC, st);
     ctx_to_nhwc_kernel<T, C><<<grid, 256, smem, st>>>(reinterpret_cast<const T*>(d_ctx), ctx_nhwc, g->fH, g->fW);
     VB_LAUNCH_CHECK();
@@ -228,8 +213,9 @@ size_t elem_size(int dtype) { return dtype == VB200_F32 ? 4 : 2; }
 
 extern "C" size_t vb200_lift_pool_fwd_workspace(const VbGrid* g, int dtype) {
   if (!g) return 0;
-  // channels-last copy of ctx, rounded up to 256 B
-  const size_t n = (size_t)g->B * g->N * g->fH * g->fW * g->C * elem_size(dtype);
+  // channels-last fp32 copy of ctx, rounded up to 256 B
+  (void)dtype;
+  const size_t n = (size_t)g->B * g->N * g->fH * g->fW * g->C * sizeof(float);
   return (n + 255) & ~(size_t)255;
 }
 

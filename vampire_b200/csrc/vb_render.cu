@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kMarchThreads) march_fwd_kernel(VbGrid g, VbTa
 
   auto point = [&](int d, float (&p)[3]) {
     if (FROM_MATS) {
-      frustum_point(s_m, has_bda, u, vv, __ldg(t.ds + d), p);
+      frustum_point<false>(s_m, has_bda, u, vv, __ldg(t.ds + d), p);
 #pragma unroll
       for (int a = 0; a < 3; ++a) p[a] = nan_to_num(p[a], -1e3f);  // BV2:612
     } else {
@@ -176,10 +176,16 @@ __global__ void __launch_bounds__(kMarchThreads) march_fwd_kernel(VbGrid g, VbTa
   for (int j = 0; j < 3; ++j) o_rgb[(bn * 3 + j) * HW + pix] = ch[K + j];
 }
 
-// ---- R5+R6: BEV branch, one thread per (oy, ox) column ---------------------------------------
+// ---- R5+R6: BEV branch ---------------------------------------------------------------------------
 // The sample position of output voxel (oz, oy, ox) is its centre normalised by the SEG bounds
 // (BV2:408-417): the x/y terms are level-independent and the z terms column-independent, so a
-// column needs (oZ + 1) xy-bilinear rows per channel instead of 8 corners x oZ levels.
+// column needs (oZ + 1) xy-bilinear rows per channel instead of 8 corners x oZ levels, and the z
+// terms live in a tiny per-block table.  Two kernels:
+//   bev_weights   one thread per column: density plane -> sigma (= the voxel_density output),
+//                 compositing weights w_l (workspace, 2.6 MB/sample, L2-resident) and bev_height
+//   bev_channels  grid = (column tiles, 37 channels, samples): every other channel plane is read
+//                 exactly once, coalesced along x, straight from the NCDHW tensors -- the 38-channel
+//                 cat of the reference is never materialised.
 __device__ __forceinline__ void axis_coord(float centre, float lo, float ext, int size, int& i0, float& w0,
                                            float& w1) {
   const float gn = ssub(smul(sdiv(ssub(centre, lo), ext), 2.0f), 1.0f);
@@ -190,319 +196,135 @@ __device__ __forceinline__ void axis_coord(float centre, float lo, float ext, in
   w0 = (fl + 1.0f) - i;
 }
 
+struct BevLevel {     // per output level (top first): base z-row and weights -- identical for all columns
+  int z0;
+  float wz0, wz1;
+};
+
 struct BevColumn {
   int o00, o01, o10, o11;      // offsets of the 4 xy corners inside one z-row (clamped)
   float w00, w01, w10, w11;    // their weights (0 where the corner is outside the grid)
 };
 
-// trilinear samples of one channel plane at every level of this column, top level first
-// (torch.flip BV2:443: level l reads output voxel oz = oZ-1-l).
-template <typename T>
-__device__ __forceinline__ void sample_levels(const VbGrid& g, const VbTables& t, const BevColumn& bc,
-                                              const T* __restrict__ plane, float (&vals)[kMaxLevels]) {
-  const int YX = g.vY * g.vX;
-  int prev_z0 = -1000000;
-  float prev_lo = 0.0f;
-#pragma unroll
-  for (int l = 0; l < kMaxLevels; ++l) {
-    if (l < g.oZ) {
-      int z0;
-      float wz0, wz1;
-      axis_coord(__ldg(t.ozs + (g.oZ - 1 - l)), g.seg_lo[2], g.seg_ext[2], g.vZ, z0, wz0, wz1);
-      float rows[2];
-#pragma unroll
-      for (int dz = 1; dz >= 0; --dz) {
-        const int z = z0 + dz;
-        if (dz == 1 && z == prev_z0) {
-          rows[1] = prev_lo;   // the previous (higher) level's lower row
-        } else if (z < 0 || z >= g.vZ) {
-          rows[dz] = 0.0f;
-        } else {
-          const T* r = plane + (size_t)z * YX;
-          rows[dz] = bc.w00 * VbType<T>::ld(r + bc.o00) + bc.w01 * VbType<T>::ld(r + bc.o01) +
-                     bc.w10 * VbType<T>::ld(r + bc.o10) + bc.w11 * VbType<T>::ld(r + bc.o11);
-        }
-      }
-      prev_z0 = z0;
-      prev_lo = rows[0];
-      vals[l] = wz0 * rows[0] + wz1 * rows[1];
-    }
+__device__ __forceinline__ void bev_level_table(const VbGrid& g, const VbTables& t, BevLevel* s_lv) {
+  if (threadIdx.x < g.oZ) {   // level l samples output voxel oz = oZ-1-l (torch.flip BV2:443)
+    BevLevel L;
+    axis_coord(__ldg(t.ozs + (g.oZ - 1 - threadIdx.x)), g.seg_lo[2], g.seg_ext[2], g.vZ, L.z0, L.wz0, L.wz1);
+    s_lv[threadIdx.x] = L;
   }
+  __syncthreads();
 }
 
-// grid = (column tiles, channel groups, samples).  Every group recomputes the compositing weights
-// from the density plane (11 rows x 4 loads) and then handles kBevGroup of the 37 other channels
-// (18 sem | 3 rgb | 16 feat), so the launch has enough threads to cover the machine.
-constexpr int kBevGroup = 8;
+__device__ __forceinline__ BevColumn bev_column(const VbGrid& g, const VbTables& t, int ox, int oy) {
+  BevColumn bc;
+  int x0, y0;
+  float wx0, wx1, wy0, wy1;
+  axis_coord(__ldg(t.oxs + ox), g.seg_lo[0], g.seg_ext[0], g.vX, x0, wx0, wx1);
+  axis_coord(__ldg(t.oys + oy), g.seg_lo[1], g.seg_ext[1], g.vY, y0, wy0, wy1);
+  const bool x0in = x0 >= 0 && x0 < g.vX, x1in = x0 + 1 >= 0 && x0 + 1 < g.vX;
+  const bool y0in = y0 >= 0 && y0 < g.vY, y1in = y0 + 1 >= 0 && y0 + 1 < g.vY;
+  bc.w00 = (x0in && y0in) ? wx0 * wy0 : 0.0f;
+  bc.w01 = (x1in && y0in) ? wx1 * wy0 : 0.0f;
+  bc.w10 = (x0in && y1in) ? wx0 * wy1 : 0.0f;
+  bc.w11 = (x1in && y1in) ? wx1 * wy1 : 0.0f;
+  const int xa = min(max(x0, 0), g.vX - 1), xb = min(max(x0 + 1, 0), g.vX - 1);
+  const int ya = min(max(y0, 0), g.vY - 1), yb = min(max(y0 + 1, 0), g.vY - 1);
+  bc.o00 = ya * g.vX + xa; bc.o01 = ya * g.vX + xb; bc.o10 = yb * g.vX + xa; bc.o11 = yb * g.vX + xb;
+  return bc;
+}
 
-template <typename T, int K, int C>
-__global__ void __launch_bounds__(256) bev_fwd_kernel(VbGrid g, VbTables t, const T* __restrict__ den,
-                                                      const T* __restrict__ sem, const T* __restrict__ rgb,
-                                                      const T* __restrict__ feat, const float* __restrict__ beta_ptr,
-                                                      float* __restrict__ o_rgb, float* __restrict__ o_seg,
-                                                      float* __restrict__ o_height, float* __restrict__ o_density,
-                                                      T* __restrict__ o_feat, int b0) {
-  const int b = b0 + blockIdx.z;
-  const int grp = blockIdx.y;
+template <typename T>
+__device__ __forceinline__ float bev_row(const VbGrid& g, const BevColumn& bc, const T* __restrict__ plane, int z) {
+  if (z < 0 || z >= g.vZ) return 0.0f;   // zeros padding (uniform branch)
+  const T* r = plane + (size_t)z * g.vY * g.vX;
+  return bc.w00 * VbType<T>::ld(r + bc.o00) + bc.w01 * VbType<T>::ld(r + bc.o01) +
+         bc.w10 * VbType<T>::ld(r + bc.o10) + bc.w11 * VbType<T>::ld(r + bc.o11);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bev_weights_kernel(VbGrid g, VbTables t, const T* __restrict__ den,
+                                                          const float* __restrict__ beta_ptr,
+                                                          float* __restrict__ o_height, float* __restrict__ o_density,
+                                                          float* __restrict__ wl_ws) {
+  __shared__ BevLevel s_lv[kMaxLevels];
+  bev_level_table(g, t, s_lv);
+  const int b = blockIdx.y;
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const int ncol = g.oY * g.oX;
   if (col >= ncol) return;
-  const int ox = col % g.oX, oy = col / g.oX;
-  const size_t nvox = (size_t)g.vZ * g.vY * g.vX;
+  const BevColumn bc = bev_column(g, t, col % g.oX, col / g.oX);
+  const T* plane = den + (size_t)b * g.vZ * g.vY * g.vX;
   const float beta = fabsf(__ldg(beta_ptr)) + g.beta_min;
-
-  BevColumn bc;
-  {
-    int x0, y0;
-    float wx0, wx1, wy0, wy1;
-    axis_coord(__ldg(t.oxs + ox), g.seg_lo[0], g.seg_ext[0], g.vX, x0, wx0, wx1);
-    axis_coord(__ldg(t.oys + oy), g.seg_lo[1], g.seg_ext[1], g.vY, y0, wy0, wy1);
-    const bool x0in = x0 >= 0 && x0 < g.vX, x1in = x0 + 1 >= 0 && x0 + 1 < g.vX;
-    const bool y0in = y0 >= 0 && y0 < g.vY, y1in = y0 + 1 >= 0 && y0 + 1 < g.vY;
-    bc.w00 = (x0in && y0in) ? wx0 * wy0 : 0.0f;
-    bc.w01 = (x1in && y0in) ? wx1 * wy0 : 0.0f;
-    bc.w10 = (x0in && y1in) ? wx0 * wy1 : 0.0f;
-    bc.w11 = (x1in && y1in) ? wx1 * wy1 : 0.0f;
-    const int xa = min(max(x0, 0), g.vX - 1), xb = min(max(x0 + 1, 0), g.vX - 1);
-    const int ya = min(max(y0, 0), g.vY - 1), yb = min(max(y0 + 1, 0), g.vY - 1);
-    bc.o00 = ya * g.vX + xa; bc.o01 = ya * g.vX + xb; bc.o10 = yb * g.vX + xa; bc.o11 = yb * g.vX + xb;
-  }
-
-  float vals[kMaxLevels], wl[kMaxLevels];
-  // density pass: sigma per level, compositing weights, height                      BV2:445-461
-  sample_levels<T>(g, t, bc, den + (size_t)b * nvox, vals);
-  float tau = 0.0f, height = 0.0f;
-#pragma unroll
-  for (int l = 0; l < kMaxLevels; ++l) {
-    if (l < g.oZ) {
-      const float sigma = laplace_density(vals[l], g.sdf_bias, beta);
-      if (grp == 0) o_density[((size_t)b * g.oZ + l) * ncol + col] = sigma;
-      const float sd = sigma * g.bev_delta;
-      wl[l] = (1.0f - expf(-sd)) * expf(-tau);
-      tau += sd;
-      height = fmaf(wl[l], __ldg(t.bev_mids + l), height);
-    }
-  }
-  if (grp == 0) o_height[(size_t)b * ncol + col] = height;
-
-  const int j0 = grp * kBevGroup, j1 = min(K + 3 + C, j0 + kBevGroup);
-  for (int j = j0; j < j1; ++j) {
-    if (j < K + 3) {   // composited channels: semantics then rgb                       BV2:459-460
-      const T* plane = j < K ? sem + ((size_t)b * K + j) * nvox : rgb + ((size_t)b * 3 + (j - K)) * nvox;
-      sample_levels<T>(g, t, bc, plane, vals);
-      float a = 0.0f;
-#pragma unroll
-      for (int l = 0; l < kMaxLevels; ++l)
-        if (l < g.oZ) a = fmaf(wl[l], vals[l], a);
-      if (j < K) o_seg[((size_t)b * K + j) * ncol + col] = a;
-      else o_rgb[((size_t)b * 3 + (j - K)) * ncol + col] = a;
-    } else {           // resampled base features, returned unweighted                    BV2:448
-      const int c = j - (K + 3);
-      sample_levels<T>(g, t, bc, feat + ((size_t)b * C + c) * nvox, vals);
-#pragma unroll
-      for (int l = 0; l < kMaxLevels; ++l)
-        if (l < g.oZ) o_feat[(((size_t)b * C + c) * g.oZ + l) * ncol + col] = VbType<T>::cvt(vals[l]);
-    }
-  }
-}
-
-// ---- R5+R6, vectorised: one thread = 4 consecutive output columns ------------------------------
-// Output column ox samples input columns x0(ox), x0(ox)+1 with x0(ox) in {ox-1, ox} whenever the det
-// grid shares the seg grid's xy lattice (the reference config).  A thread then needs the 6-wide
-// window in[ox0-1 .. ox0+4]: one 64/128-bit load plus one value from each neighbouring lane
-// (shuffles) -- 8x fewer load instructions than the scalar kernel.  Threads whose columns do not
-// satisfy the window assumption fall back to scalar gathers (still exact), so any grid works.
-template <typename T> struct Vec4Load;
-template <> struct Vec4Load<float> {
-  __device__ __forceinline__ static void ld(const float* p, float (&o)[4]) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
-    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-  }
-};
-template <> struct Vec4Load<__nv_bfloat16> {
-  __device__ __forceinline__ static void ld(const __nv_bfloat16* p, float (&o)[4]) {
-    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
-    o[0] = __uint_as_float(v.x << 16); o[1] = __uint_as_float(v.x & 0xffff0000u);
-    o[2] = __uint_as_float(v.y << 16); o[3] = __uint_as_float(v.y & 0xffff0000u);
-  }
-};
-template <> struct Vec4Load<__half> {
-  __device__ __forceinline__ static void ld(const __half* p, float (&o)[4]) {
-    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
-    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
-    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
-    o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
-  }
-};
-
-struct BevQuad {
-  int ox0;            // first output column (multiple of 4)
-  int x0[4];          // base input column of each output column
-  float wx0[4], wx1[4];
-  bool window;        // x0[c] - (ox0 + c - 1) in {0, 1} for all 4 columns
-  int k[4];           // that offset
-  int y0;
-  float wy0, wy1;
-};
-
-// x-interpolated values of one input row (z, y) for the thread's 4 columns
-template <typename T>
-__device__ __forceinline__ void quad_row(const VbGrid& g, const BevQuad& q, const T* __restrict__ row, bool warp_window,
-                                         int lane, float (&out)[4], float wy) {
-  float a[4], b[4];
-  if (warp_window) {
-    float v[4];
-    Vec4Load<T>::ld(row + q.ox0, v);
-    float left = __shfl_up_sync(0xffffffffu, v[3], 1);
-    float right = __shfl_down_sync(0xffffffffu, v[0], 1);
-    if (lane == 0) left = q.ox0 - 1 >= 0 ? VbType<T>::ld(row + q.ox0 - 1) : 0.0f;
-    if (lane == 31) right = q.ox0 + 4 < g.vX ? VbType<T>::ld(row + q.ox0 + 4) : 0.0f;
-    const float w[6] = {left, v[0], v[1], v[2], v[3], right};
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      a[c] = q.k[c] ? w[c + 1] : w[c];
-      b[c] = q.k[c] ? w[c + 2] : w[c + 1];
-    }
-  } else {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int xa = q.x0[c], xb = q.x0[c] + 1;
-      a[c] = (xa >= 0 && xa < g.vX) ? VbType<T>::ld(row + xa) : 0.0f;
-      b[c] = (xb >= 0 && xb < g.vX) ? VbType<T>::ld(row + xb) : 0.0f;
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < 4; ++c) out[c] = fmaf(wy, fmaf(q.wx0[c], a[c], q.wx1[c] * b[c]), out[c]);
-}
-
-// xy-bilinear values of one z-row of a channel plane for the 4 columns (zeros padding)
-template <typename T>
-__device__ __forceinline__ void quad_zrow(const VbGrid& g, const BevQuad& q, const T* __restrict__ plane, int z,
-                                          bool warp_window, int lane, float (&out)[4]) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) out[c] = 0.0f;
-  if (z < 0 || z >= g.vZ) return;
-  const T* zr = plane + (size_t)z * g.vY * g.vX;
-  if (q.y0 >= 0 && q.y0 < g.vY) quad_row<T>(g, q, zr + (size_t)q.y0 * g.vX, warp_window, lane, out, q.wy0);
-  if (q.y0 + 1 >= 0 && q.y0 + 1 < g.vY) quad_row<T>(g, q, zr + (size_t)(q.y0 + 1) * g.vX, warp_window, lane, out, q.wy1);
-}
-
-// walk the levels of one plane top-down, calling sink(l, vals[4]) per level
-template <typename T, typename Sink>
-__device__ __forceinline__ void quad_levels(const VbGrid& g, const VbTables& t, const BevQuad& q,
-                                            const T* __restrict__ plane, bool warp_window, int lane, Sink&& sink) {
+  float tau = 0.0f, height = 0.0f, prev_lo = 0.0f;
   int prev_z0 = -1000000;
-  float prev_lo[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int l = 0; l < kMaxLevels; ++l) {
-    if (l < g.oZ) {
-      int z0;
-      float wz0, wz1;
-      axis_coord(__ldg(t.ozs + (g.oZ - 1 - l)), g.seg_lo[2], g.seg_ext[2], g.vZ, z0, wz0, wz1);
-      float hi[4], lo[4];
-      if (z0 + 1 == prev_z0) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) hi[c] = prev_lo[c];
-      } else {
-        quad_zrow<T>(g, q, plane, z0 + 1, warp_window, lane, hi);
-      }
-      quad_zrow<T>(g, q, plane, z0, warp_window, lane, lo);
-      float v[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        v[c] = wz0 * lo[c] + wz1 * hi[c];
-        prev_lo[c] = lo[c];
-      }
-      prev_z0 = z0;
-      sink(l, v);
-    }
+  for (int l = 0; l < g.oZ; ++l) {
+    const BevLevel L = s_lv[l];
+    const float hi = (L.z0 + 1 == prev_z0) ? prev_lo : bev_row<T>(g, bc, plane, L.z0 + 1);
+    const float lo = bev_row<T>(g, bc, plane, L.z0);
+    prev_z0 = L.z0;
+    prev_lo = lo;
+    const float sigma = laplace_density(L.wz0 * lo + L.wz1 * hi, g.sdf_bias, beta);      // BV2:445
+    const float sd = sigma * g.bev_delta;
+    const float w = (1.0f - expf(-sd)) * expf(-tau);                                       // BV2:454-458
+    tau += sd;
+    height = fmaf(w, __ldg(t.bev_mids + l), height);
+    const size_t o = ((size_t)b * g.oZ + l) * ncol + col;
+    o_density[o] = sigma;
+    wl_ws[o] = w;
   }
+  o_height[(size_t)b * ncol + col] = height;                                               // BV2:461
 }
 
 template <typename T, int K, int C>
-__global__ void __launch_bounds__(64) bev_fwd_vec4_kernel(VbGrid g, VbTables t, const T* __restrict__ den,
-                                                          const T* __restrict__ sem, const T* __restrict__ rgb,
-                                                          const T* __restrict__ feat, const float* __restrict__ beta_ptr,
-                                                          float* __restrict__ o_rgb, float* __restrict__ o_seg,
-                                                          float* __restrict__ o_height, float* __restrict__ o_density,
-                                                          T* __restrict__ o_feat) {
-  const int b = blockIdx.z, grp = blockIdx.y;
-  const int tiles_x = (g.oX + 255) / 256;
-  const int oy = blockIdx.x / tiles_x;
-  const int lane = threadIdx.x & 31;
-  const int ox_raw = (blockIdx.x % tiles_x) * 256 + threadIdx.x * 4;
-  const bool live = ox_raw < g.oX;                    // oX % 4 == 0 is guaranteed by the launcher
+__global__ void __launch_bounds__(256) bev_channels_kernel(VbGrid g, VbTables t, const T* __restrict__ sem,
+                                                           const T* __restrict__ rgb, const T* __restrict__ feat,
+                                                           const float* __restrict__ wl_ws, float* __restrict__ o_rgb,
+                                                           float* __restrict__ o_seg, T* __restrict__ o_feat) {
+  __shared__ BevLevel s_lv[kMaxLevels];
+  bev_level_table(g, t, s_lv);
+  const int b = blockIdx.z, j = blockIdx.y;        // j: 0..K-1 sem | K..K+2 rgb | K+3.. feat
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const int ncol = g.oY * g.oX;
+  if (col >= ncol) return;
+  const BevColumn bc = bev_column(g, t, col % g.oX, col / g.oX);
   const size_t nvox = (size_t)g.vZ * g.vY * g.vX;
-  const float beta = fabsf(__ldg(beta_ptr)) + g.beta_min;
-
-  BevQuad q;
-  q.ox0 = live ? ox_raw : 0;
-  q.window = true;
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    axis_coord(__ldg(t.oxs + q.ox0 + c), g.seg_lo[0], g.seg_ext[0], g.vX, q.x0[c], q.wx0[c], q.wx1[c]);
-    q.k[c] = q.x0[c] - (q.ox0 + c - 1);
-    q.window = q.window && (q.k[c] == 0 || q.k[c] == 1);
-  }
-  q.window = q.window && (q.ox0 + 3 < g.vX);
-  axis_coord(__ldg(t.oys + oy), g.seg_lo[1], g.seg_ext[1], g.vY, q.y0, q.wy0, q.wy1);
-  const bool warp_window = __all_sync(0xffffffffu, q.window);   // shuffles need the whole warp on one path
-
-  float wl[4][kMaxLevels];
-  {
-    float tau[4] = {0.f, 0.f, 0.f, 0.f}, height[4] = {0.f, 0.f, 0.f, 0.f};
-    quad_levels<T>(g, t, q, den + (size_t)b * nvox, warp_window, lane, [&](int l, const float (&v)[4]) {
-      const float mid = __ldg(t.bev_mids + l);
-      float sig[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        sig[c] = laplace_density(v[c], g.sdf_bias, beta);                      // BV2:445
-        const float sd = sig[c] * g.bev_delta;
-        wl[c][l] = (1.0f - expf(-sd)) * expf(-tau[c]);                          // BV2:454-458
-        tau[c] += sd;
-        height[c] = fmaf(wl[c][l], mid, height[c]);
-      }
-      if (grp == 0 && live)
-        *reinterpret_cast<float4*>(o_density + ((size_t)b * g.oZ + l) * ncol + (size_t)oy * g.oX + q.ox0) =
-            make_float4(sig[0], sig[1], sig[2], sig[3]);
-    });
-    if (grp == 0 && live)
-      *reinterpret_cast<float4*>(o_height + (size_t)b * ncol + (size_t)oy * g.oX + q.ox0) =
-          make_float4(height[0], height[1], height[2], height[3]);
-  }
-
-  const int j0 = grp * kBevGroup, j1 = min(K + 3 + C, j0 + kBevGroup);
-  for (int j = j0; j < j1; ++j) {
-    if (j < K + 3) {
-      const T* plane = j < K ? sem + ((size_t)b * K + j) * nvox : rgb + ((size_t)b * 3 + (j - K)) * nvox;
-      float a[4] = {0.f, 0.f, 0.f, 0.f};
-      quad_levels<T>(g, t, q, plane, warp_window, lane, [&](int l, const float (&v)[4]) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) a[c] = fmaf(wl[c][l], v[c], a[c]);
-      });
-      float* o = (j < K ? o_seg + ((size_t)b * K + j) * ncol : o_rgb + ((size_t)b * 3 + (j - K)) * ncol) +
-                 (size_t)oy * g.oX + q.ox0;
-      if (live) *reinterpret_cast<float4*>(o) = make_float4(a[0], a[1], a[2], a[3]);
-    } else {
-      const int c_ = j - (K + 3);
-      T* obase = o_feat + ((size_t)b * C + c_) * g.oZ * ncol + (size_t)oy * g.oX + q.ox0;
-      quad_levels<T>(g, t, q, feat + ((size_t)b * C + c_) * nvox, warp_window, lane, [&](int l, const float (&v)[4]) {
-        if (live) {
-          T* o = obase + (size_t)l * ncol;
-          if (sizeof(T) == 4) {
-            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-          } else {
-            T h[4] = {VbType<T>::cvt(v[0]), VbType<T>::cvt(v[1]), VbType<T>::cvt(v[2]), VbType<T>::cvt(v[3])};
-            *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(h);
-          }
-        }
-      });
+  float prev_lo = 0.0f;
+  int prev_z0 = -1000000;
+  if (j < K + 3) {   // composited channels                                                 BV2:459-460
+    const T* plane = j < K ? sem + ((size_t)b * K + j) * nvox : rgb + ((size_t)b * 3 + (j - K)) * nvox;
+    const float* wl = wl_ws + (size_t)b * g.oZ * ncol + col;
+    float a = 0.0f;
+    for (int l = 0; l < g.oZ; ++l) {
+      const BevLevel L = s_lv[l];
+      const float hi = (L.z0 + 1 == prev_z0) ? prev_lo : bev_row<T>(g, bc, plane, L.z0 + 1);
+      const float lo = bev_row<T>(g, bc, plane, L.z0);
+      prev_z0 = L.z0;
+      prev_lo = lo;
+      a = fmaf(__ldg(wl + (size_t)l * ncol), L.wz0 * lo + L.wz1 * hi, a);
+    }
+    if (j < K) o_seg[((size_t)b * K + j) * ncol + col] = a;
+    else o_rgb[((size_t)b * 3 + (j - K)) * ncol + col] = a;
+  } else {           // resampled base features, returned unweighted                        BV2:448
+    const int c = j - (K + 3);
+    const T* plane = feat + ((size_t)b * C + c) * nvox;
+    T* o = o_feat + ((size_t)b * C + c) * g.oZ * ncol + col;
+    for (int l = 0; l < g.oZ; ++l) {
+      const BevLevel L = s_lv[l];
+      const float hi = (L.z0 + 1 == prev_z0) ? prev_lo : bev_row<T>(g, bc, plane, L.z0 + 1);
+      const float lo = bev_row<T>(g, bc, plane, L.z0);
+      prev_z0 = L.z0;
+      prev_lo = lo;
+      o[(size_t)l * ncol] = VbType<T>::cvt(L.wz0 * lo + L.wz1 * hi);
     }
   }
 }
 
 size_t elem_size(int dtype) { return dtype == VB200_F32 ? 4 : 2; }
+
+size_t bev_weight_bytes(const VbGrid* g) {
+  const size_t n = (size_t)g->B * g->oZ * g->oY * g->oX * sizeof(float);
+  return (n + 255) & ~(size_t)255;
+}
 
 size_t packed_bytes_per_sample(const VbGrid* g, int dtype) {
   const size_t n = (size_t)g->vZ * g->vY * g->vX * packed_channels(g->K) * elem_size(dtype);
@@ -516,8 +338,11 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
   if (g->K != K || g->C != C || g->oZ > kMaxLevels) return VB200_ERR_ARG;
   const size_t nvox = (size_t)g->vZ * g->vY * g->vX;
   const size_t per = packed_bytes_per_sample(g, VbType<T>::code);
-  const int group = (int)((ws_bytes / per) < (size_t)g->B ? (ws_bytes / per) : (size_t)g->B);
-  if ((branches & VB200_BRANCH_CAM) && group < 1) return VB200_ERR_WORKSPACE;
+  const size_t bev_bytes = bev_weight_bytes(g);
+  if (ws_bytes < bev_bytes + per) return VB200_ERR_WORKSPACE;
+  // workspace = [packed camera volumes of `group` samples][BEV compositing weights of all samples]
+  const int group = (int)(((ws_bytes - bev_bytes) / per) < (size_t)g->B ? ((ws_bytes - bev_bytes) / per) : (size_t)g->B);
+  const size_t cam_bytes = (size_t)group * per;
   const T* den = reinterpret_cast<const T*>(in->density);
   const T* sem = reinterpret_cast<const T*>(in->sem);
   const T* rgb = reinterpret_cast<const T*>(in->rgb);
@@ -525,22 +350,13 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
   const int patches = vb_ceil_div(g->fW, kPatchW) * vb_ceil_div(g->fH, kPatchH);
   const int ncol = g->oY * g->oX;
   if (branches & VB200_BRANCH_BEV) {
-    dim3 grid(vb_ceil_div(ncol, 256), vb_ceil_div(K + 3 + C, kBevGroup), g->B);
+    float* wl_ws = reinterpret_cast<float*>((char*)ws + cam_bytes);
     VbTraceScope tr(VB_K_BEV_FWD, st);
-    const bool vec_ok = (g->vX % 4 == 0) && (g->oX % 4 == 0) &&
-                        ((((uintptr_t)den | (uintptr_t)sem | (uintptr_t)rgb | (uintptr_t)feat |
-                           (uintptr_t)out->voxel_output | (uintptr_t)out->bev_rgb | (uintptr_t)out->bev_seg |
-                           (uintptr_t)out->bev_height | (uintptr_t)out->voxel_density) & 15) == 0);
-    if (vec_ok) {
-      dim3 vgrid(g->oY * vb_ceil_div(g->oX, 256), vb_ceil_div(K + 3 + C, kBevGroup), g->B);
-      bev_fwd_vec4_kernel<T, K, C><<<vgrid, 64, 0, st>>>(*g, *t, den, sem, rgb, feat, in->beta, out->bev_rgb,
-                                                         out->bev_seg, out->bev_height, out->voxel_density,
-                                                         reinterpret_cast<T*>(out->voxel_output));
-    } else {
-      bev_fwd_kernel<T, K, C><<<grid, 256, 0, st>>>(*g, *t, den, sem, rgb, feat, in->beta, out->bev_rgb,
-                                                    out->bev_seg, out->bev_height, out->voxel_density,
-                                                    reinterpret_cast<T*>(out->voxel_output), 0);
-    }
+    bev_weights_kernel<T><<<dim3(vb_ceil_div(ncol, 256), g->B), 256, 0, st>>>(
+        *g, *t, den, in->beta, out->bev_height, out->voxel_density, wl_ws);
+    VB_LAUNCH_CHECK();
+    bev_channels_kernel<T, K, C><<<dim3(vb_ceil_div(ncol, 256), K + 3 + C, g->B), 256, 0, st>>>(
+        *g, *t, sem, rgb, feat, wl_ws, out->bev_rgb, out->bev_seg, reinterpret_cast<T*>(out->voxel_output));
     VB_LAUNCH_CHECK();
   }
   if (!(branches & VB200_BRANCH_CAM)) return VB200_OK;
@@ -572,7 +388,13 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
 
 extern "C" size_t vb200_render_fwd_workspace(const VbGrid* g, int dtype) {
   if (!g) return 0;
-  return packed_bytes_per_sample(g, dtype);   // minimum (one sample per pack/march round); more = bigger rounds
+  // minimum: BEV weights + one packed sample per pack/march round; every further
+  // vb200_render_packed_bytes() lets one more sample share a round
+  return bev_weight_bytes(g) + packed_bytes_per_sample(g, dtype);
+}
+
+extern "C" size_t vb200_render_packed_bytes(const VbGrid* g, int dtype) {
+  return g ? packed_bytes_per_sample(g, dtype) : 0;
 }
 
 extern "C" int vb200_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, const VbRenderIn* in,

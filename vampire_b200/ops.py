@@ -330,8 +330,8 @@ def render_fwd(density: Tensor, sem: Tensor, rgb: Tensor, feat: Tensor, beta: Te
     outs.append(torch.empty(shapes[7], dtype=density.dtype, device=dev))
     g = st.grid(B, has_bda)
     lib = cabi.lib()
-    per = lib.vb200_render_fwd_workspace(C.byref(g), dt)
-    ws_bytes = per * max(1, min(B, st.render_group))
+    ws_bytes = lib.vb200_render_fwd_workspace(C.byref(g), dt) + \
+        lib.vb200_render_packed_bytes(C.byref(g), dt) * (max(1, min(B, st.render_group)) - 1)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     rin = _render_in_struct(density, sem, rgb, feat, beta32, geom)
     ro = _render_out_struct(outs)

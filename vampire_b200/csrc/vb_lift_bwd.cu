@@ -1,0 +1,486 @@
+// vb_lift_bwd.cu -- Bk for L1-L4: deterministic backward of the fused lift + pool.
+//
+// The forward is a gather (voxel <- 8 frustum cells per seeing camera), so its backward is a
+// scatter into d_depth / d_ctx.  ATen's grid_sampler_3d_backward does that scatter with float
+// atomicAdd into a 372 MB grad-frustum (order-dependent bits); here the scatter is turned back
+// into a gather by SORTING the valid (voxel, camera) pairs by destination pixel cell
+// (SURVEY §7.1 a/d, A.5.6):
+//
+//   plan_pairs<count>   histogram of valid pairs per cell (n, y0, x0)            [int atomics]
+//   scan_cells          exclusive scan -> CSR offsets (one block per sample)
+//   plan_pairs<fill>    records ((z0+1) << 21 | voxel) dropped into their cell's segment
+//   sort_cells          warp per cell: rank-sort the segment => order fixed by (z0, voxel)
+//   lift_bwd<colour>    warp per cell, 4 launches over the 2x2 cell colouring so that concurrently
+//                       processed cells touch disjoint pixels: per-warp shared-memory depth bins and
+//                       register d_ctx accumulators, plain (non-atomic) read-modify-write flush.
+//                       Phase A (lane = pair): bit-exact re-projection, 8 depth loads, 16-channel
+//                       dot products, warp-shuffle segmented reduction over equal depth bins.
+//                       Phase B (lane = channel): serial accumulation of d_ctx in sorted order.
+//   finalize            fp32 accumulators -> the caller's layout / dtype.
+//
+// No float atomics anywhere => bit-reproducible gradients; no grad-frustum is ever formed.
+#include "vb_common.cuh"
+#include "vb_trace.cuh"
+
+namespace {
+
+constexpr int kC = 16;
+constexpr int kThreads = 256;
+constexpr int kVoxBits = 21;   // record = (z0 + 1) << 21 | voxel  (nvox <= 2^21, D + 1 < 2^11)
+
+struct CellDims {
+  int ncy, ncx, nc;   // cells per camera row / col, cells per sample = N * ncy * ncx
+};
+__host__ __device__ inline CellDims cell_dims(const VbGrid& g) {
+  CellDims c;
+  c.ncy = g.fH + 1;   // y0 in [-1, fH-1]
+  c.ncx = g.fW + 1;
+  c.nc = g.N * c.ncy * c.ncx;
+  return c;
+}
+
+// shared by plan + backward: cull + strict projection of (voxel, camera n); returns validity
+__device__ __forceinline__ bool pair_coord(const VbGrid& g, const float* s_m, const float* s_q, bool has_bda, int n,
+                                           float px, float py, float pz, LiftCoord& lc) {
+  const float* q = s_q + n * 16;
+  const float cz = fmaf(q[8], px, fmaf(q[9], py, fmaf(q[10], pz, q[11])));
+  if (!(cz > g.d_lo - 0.05f && cz < g.d_hi + 0.05f)) return false;
+  const float cx = fmaf(q[0], px, fmaf(q[1], py, fmaf(q[2], pz, q[3])));
+  const float cy = fmaf(q[4], px, fmaf(q[5], py, fmaf(q[6], pz, q[7])));
+  const float rz = __frcp_rn(cz);
+  const float ux = cx * rz, uy = cy * rz;
+  const float* I = s_m + n * VB200_MAT_SLOTS * 16 + 2 * 16;
+  const float cw = fmaf(q[12], px, fmaf(q[13], py, fmaf(q[14], pz, q[15])));
+  const float ax = fmaf(I[0], ux, fmaf(I[1], uy, fmaf(I[2], cz, I[3] * cw)));
+  const float ay = fmaf(I[4], ux, fmaf(I[5], uy, fmaf(I[6], cz, I[7] * cw)));
+  if (!(ax > -1.5f && ax < g.x_hi + 1.0f && ay > -1.5f && ay < g.y_hi + 1.0f)) return false;
+  float pix[3];
+  project_voxel<false>(s_m + n * VB200_MAT_SLOTS * 16, has_bda, px, py, pz, pix);
+  lc = lift_coord(g, pix);
+  return lc.valid;
+}
+
+__device__ __forceinline__ void stage_cull(float* s_q, const float* s_m, int N, bool has_bda) {
+  for (int i = threadIdx.x; i < N * 16; i += blockDim.x) {
+    const int n = i / 16, r = (i % 16) / 4, c = i % 4;
+    const float* A = s_m + n * VB200_MAT_SLOTS * 16 + 16;
+    const float* Bm = s_m + n * VB200_MAT_SLOTS * 16;
+    float v = A[r * 4 + c];
+    if (has_bda) {
+      v = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v = fmaf(A[r * 4 + k], Bm[k * 4 + c], v);
+    }
+    s_q[i] = v;
+  }
+}
+
+// ---- plan: count / fill ---------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) plan_pairs_kernel(VbGrid g, VbTables t, const float* __restrict__ d_mats,
+                                                              int* __restrict__ counts, const int* __restrict__ offsets,
+                                                              int* __restrict__ cursor, uint32_t* __restrict__ recs) {
+  __shared__ float s_m[VB_MAX_CAMS * VB200_MAT_SLOTS * 16];
+  __shared__ float s_q[VB_MAX_CAMS * 16];
+  const int b = blockIdx.y;
+  const bool has_bda = g.has_bda != 0;
+  stage_mats(s_m, d_mats, b, g.N);
+  __syncthreads();
+  stage_cull(s_q, s_m, g.N, has_bda);
+  __syncthreads();
+  const int nvox = g.vZ * g.vY * g.vX;
+  const int vox = blockIdx.x * kThreads + threadIdx.x;
+  if (vox >= nvox) return;
+  const int x = vox % g.vX, y = (vox / g.vX) % g.vY, z = vox / (g.vX * g.vY);
+  const float px = __ldg(t.xs + x), py = __ldg(t.ys + y), pz = __ldg(t.zs + z);
+  const CellDims cd = cell_dims(g);
+  for (int n = 0; n < g.N; ++n) {
+    LiftCoord lc;
+    if (!pair_coord(g, s_m, s_q, has_bda, n, px, py, pz, lc)) continue;
+    const int cell = (n * cd.ncy + (lc.y0 + 1)) * cd.ncx + (lc.x0 + 1);
+    if (MODE == 0) {
+      atomicAdd(counts + (size_t)b * cd.nc + cell, 1);
+    } else {
+      const int slot = offsets[(size_t)b * (cd.nc + 1) + cell] + atomicAdd(cursor + (size_t)b * cd.nc + cell, 1);
+      recs[(size_t)b * g.N * nvox + slot] = ((uint32_t)(lc.z0 + 1) << kVoxBits) | (uint32_t)vox;
+    }
+  }
+}
+
+// ---- exclusive scan of the per-cell counts, one block per sample ------------------------------------
+__global__ void __launch_bounds__(1024) scan_cells_kernel(const int* __restrict__ counts, int* __restrict__ offsets,
+                                                          int nc) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const int b = blockIdx.x;
+  const int* in = counts + (size_t)b * nc;
+  int* out = offsets + (size_t)b * (nc + 1);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nc; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < nc ? in[i] : 0;
+    int s = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += u;
+    }
+    if (lane == 31) s_warp[wid] = s;
+    __syncthreads();
+    if (wid == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += u;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int carry = s_carry;
+    const int excl = carry + (wid ? s_warp[wid - 1] : 0) + s - v;
+    if (i < nc) out[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[nc] = s_carry;
+}
+
+// ---- per-cell rank sort: warp per cell -----------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) sort_cells_kernel(const int* __restrict__ offsets,
+                                                              const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+                                                              int nc, size_t pairs_per_sample, int total_cells) {
+  const int cell_g = blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (cell_g >= total_cells) return;
+  const int lane = threadIdx.x & 31;
+  const int b = cell_g / nc, cell = cell_g % nc;
+  const int* off = offsets + (size_t)b * (nc + 1);
+  const int lo = off[cell], L = off[cell + 1] - lo;
+  const uint32_t* s = src + (size_t)b * pairs_per_sample + lo;
+  uint32_t* d = dst + (size_t)b * pairs_per_sample + lo;
+  for (int i = lane; i < L; i += 32) {
+    const uint32_t r = s[i];
+    int rank = 0;
+    for (int j = 0; j < L; ++j) rank += (__ldg(s + j) < r) ? 1 : 0;   // records are distinct (distinct voxels)
+    d[rank] = r;
+  }
+}
+
+// ---- ctx (B,N,C,fH,fW) T -> (B,N,fH,fW,C) fp32 (same pre-pass as the forward) ---------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) ctx_to_nhwc_f32_kernel(const T* __restrict__ src, float* __restrict__ dst, int fH,
+                                                              int fW) {
+  extern __shared__ float s_t[];  // [C][fW + 1]
+  const int h = blockIdx.x, bn = blockIdx.y, ld = fW + 1;
+  for (int i = threadIdx.x; i < kC * fW; i += blockDim.x) {
+    const int c = i / fW, w = i % fW;
+    s_t[c * ld + w] = VbType<T>::ld(src + (((size_t)bn * kC + c) * fH + h) * fW + w);
+  }
+  __syncthreads();
+  float* out = dst + ((size_t)bn * fH + h) * fW * kC;
+  for (int i = threadIdx.x; i < kC * fW; i += blockDim.x) out[i] = s_t[(i % kC) * ld + i / kC];
+}
+
+// ---- the backward proper -------------------------------------------------------------------------------
+template <typename T, int GOUT_LAYOUT>
+__global__ void __launch_bounds__(kThreads) lift_bwd_kernel(VbGrid g, VbTables t, const float* __restrict__ d_mats,
+                                                            const T* __restrict__ depth,
+                                                            const float* __restrict__ ctx_nhwc,
+                                                            const T* __restrict__ gout, const uint64_t* __restrict__ cnt,
+                                                            const int* __restrict__ offsets,
+                                                            const uint32_t* __restrict__ recs, float* __restrict__ gdepth,
+                                                            float* __restrict__ gctx_nhwc, int colour) {
+  extern __shared__ float s_dyn[];
+  __shared__ float s_m[VB200_MAT_SLOTS * 16];
+  const CellDims cd = cell_dims(g);
+  const int py_ = colour >> 1, px_ = colour & 1;
+  const int ny = (cd.ncy - py_ + 1) / 2, nx = (cd.ncx - px_ + 1) / 2;   // cells of this colour per camera
+  // blockIdx.y = b * N + n so that a block shares one camera's matrices
+  const int bn = blockIdx.y, b = bn / g.N, n = bn % g.N;
+  const bool has_bda = g.has_bda != 0;
+  for (int i = threadIdx.x; i < VB200_MAT_SLOTS * 16; i += blockDim.x)
+    s_m[i] = __ldg(d_mats + (size_t)bn * VB200_MAT_SLOTS * 16 + i);
+  __syncthreads();
+
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ci = blockIdx.x * (kThreads / 32) + wid;
+  if (ci >= ny * nx) return;
+  const int cy = 2 * (ci / nx) + py_, cx = 2 * (ci % nx) + px_;
+  const int y0 = cy - 1, x0 = cx - 1;
+  const int cell = (n * cd.ncy + cy) * cd.ncx + cx;
+  const int* off = offsets + (size_t)b * (cd.nc + 1);
+  const int seg_lo = off[cell], L = off[cell + 1] - seg_lo;
+  if (L == 0) return;
+
+  const int D = g.D, HW = g.fH * g.fW;
+  const int nvox = g.vZ * g.vY * g.vX;
+  // per-warp shared memory: bins[4][D] | pa[32][4] | pg[32][17] | cv[4][16]
+  const int per_warp = 4 * D + 32 * 4 + 32 * 17 + 64;
+  float* bins = s_dyn + wid * per_warp;
+  float* pa = bins + 4 * D;
+  float* pg = pa + 32 * 4;
+  float* cv = pg + 32 * 17;
+
+  // the cell's four corner pixels (zeros padding: clamp the address, remember in-bounds)
+  const int xa = max(x0, 0), xb = min(x0 + 1, g.fW - 1);
+  const int ya = max(y0, 0), yb = min(y0 + 1, g.fH - 1);
+  const bool inx0 = x0 >= 0, inx1 = x0 + 1 < g.fW, iny0 = y0 >= 0, iny1 = y0 + 1 < g.fH;
+  const int pxl[4] = {ya * g.fW + xa, ya * g.fW + xb, yb * g.fW + xa, yb * g.fW + xb};
+  const bool pin[4] = {iny0 && inx0, iny0 && inx1, iny1 && inx0, iny1 && inx1};
+  const float* ccam = ctx_nhwc + (size_t)bn * HW * kC;
+  for (int i = lane; i < 64; i += 32) cv[i] = __ldg(ccam + (size_t)pxl[i >> 4] * kC + (i & 15));
+  for (int i = lane; i < 4 * D; i += 32) bins[i] = 0.0f;
+  __syncwarp();
+
+  const T* dcam = depth + (size_t)bn * D * HW;
+  const uint32_t* seg = recs + (size_t)b * g.N * nvox + seg_lo;
+  const int c_ = lane & 15, half = lane >> 4;
+  float accC[4] = {0.f, 0.f, 0.f, 0.f};
+
+  for (int r0 = 0; r0 < L; r0 += 32) {
+    const int np = min(32, L - r0);
+    const bool act = lane < np;
+    // ---- phase A: lane = pair ----
+    int z0 = 100000 + lane;   // inactive lanes: unique keys => single-lane runs of zeros
+    float vA[4] = {0.f, 0.f, 0.f, 0.f}, vB[4] = {0.f, 0.f, 0.f, 0.f};
+    if (act) {
+      const uint32_t rec = seg[r0 + lane];
+      const int vox = (int)(rec & ((1u << kVoxBits) - 1));
+      const int x = vox % g.vX, y = (vox / g.vX) % g.vY, z = vox / (g.vX * g.vY);
+      float pix[3];
+      project_voxel<false>(s_m, has_bda, __ldg(t.xs + x), __ldg(t.ys + y), __ldg(t.zs + z), pix);
+      const LiftCoord lc = lift_coord(g, pix);   // same code as the plan => same (x0, y0, z0)
+      z0 = lc.z0;
+      const float wx0 = inx0 ? (float)(lc.x0 + 1) - lc.ix : 0.0f, wx1 = inx1 ? lc.ix - (float)lc.x0 : 0.0f;
+      const float wy0 = iny0 ? (float)(lc.y0 + 1) - lc.iy : 0.0f, wy1 = iny1 ? lc.iy - (float)lc.y0 : 0.0f;
+      const float wza = lc.z0 >= 0 ? (float)(lc.z0 + 1) - lc.iz : 0.0f;
+      const float wzb = lc.z0 + 1 < D ? lc.iz - (float)lc.z0 : 0.0f;
+      const int za = max(lc.z0, 0), zb = min(lc.z0 + 1, D - 1);
+      const float wxy[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};
+      const T* d0 = dcam + (size_t)za * HW;
+      const T* d1 = dcam + (size_t)zb * HW;
+      // g' = d_out * valid / (count + 1e-6): the non-zero mask is not differentiated
+      const uint64_t cw = cnt[(size_t)b * nvox + vox];
+      float gp[kC];
+      if (GOUT_LAYOUT == VB200_NCDHW) {
+#pragma unroll
+        for (int c = 0; c < kC; ++c) gp[c] = VbType<T>::ld(gout + ((size_t)b * kC + c) * nvox + vox);
+      } else {
+        const T* gv = gout + ((size_t)b * nvox + vox) * kC;
+        constexpr int Ln = VbLanes<T>::n;
+#pragma unroll
+        for (int q4 = 0; q4 < kC / Ln; ++q4) VbVec<T, Ln>::ld(gv + q4 * Ln, &gp[q4 * Ln]);
+      }
+#pragma unroll
+      for (int c = 0; c < kC; ++c) gp[c] = gp[c] / ((float)((cw >> (4 * c)) & 0xf) + 1e-6f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float s = fmaf(wzb, VbType<T>::ld(d1 + pxl[k]), wza * VbType<T>::ld(d0 + pxl[k]));
+        pa[lane * 4 + k] = wxy[k] * s;                       // d_ctx[c] += g'[c] * w_jk * S_jk
+        float dot = 0.0f;
+#pragma unroll
+        for (int c = 0; c < kC; ++c) dot = fmaf(gp[c], cv[k * 16 + c], dot);
+        vA[k] = wza * wxy[k] * dot;                          // d_depth[z0]   += w_z0 * w_jk * sum_c g' ctx
+        vB[k] = wzb * wxy[k] * dot;                          // d_depth[z0+1] += w_z1 * ...
+      }
+#pragma unroll
+      for (int c = 0; c < kC; ++c) pg[lane * 17 + c] = gp[c];
+    }
+    // segmented reduction over runs of equal z0 (contiguous: the segment is sorted by (z0, voxel))
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int zo = __shfl_down_sync(0xffffffffu, z0, o);
+      const bool take = (lane + o < 32) && (zo == z0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float a = __shfl_down_sync(0xffffffffu, vA[k], o);
+        const float bb = __shfl_down_sync(0xffffffffu, vB[k], o);
+        if (take) { vA[k] += a; vB[k] += bb; }
+      }
+    }
+    const int zprev = __shfl_up_sync(0xffffffffu, z0, 1);
+    const bool head = act && (lane == 0 || zprev != z0);
+    // heads of one round have distinct z0 => distinct bins inside each sub-phase
+    if (head && z0 >= 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) bins[k * D + z0] += vA[k];
+    }
+    __syncwarp();
+    if (head && z0 + 1 < D) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) bins[k * D + z0 + 1] += vB[k];
+    }
+    __syncwarp();
+    // ---- phase B: lane = (channel, half); serial over the round's pairs in sorted order ----
+    for (int p = half; p < np; p += 2) {
+      const float gpc = pg[p * 17 + c_];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) accC[k] = fmaf(gpc, pa[p * 4 + k], accC[k]);
+    }
+    __syncwarp();
+  }
+
+  // ---- flush: this colour's cells own disjoint pixels => plain read-modify-write, fixed colour order
+  float* gd = gdepth + (size_t)bn * D * HW;
+  for (int i = lane; i < 4 * D; i += 32) {
+    const int k = i / D, z = i % D;
+    const float v = bins[i];
+    if (v != 0.0f && pin[k]) gd[(size_t)z * HW + pxl[k]] += v;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) accC[k] += __shfl_down_sync(0xffffffffu, accC[k], 16);
+  if (half == 0) {
+    float* gc = gctx_nhwc + (size_t)bn * HW * kC;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (pin[k]) gc[(size_t)pxl[k] * kC + c_] += accC[k];
+  }
+}
+
+// ---- finalize ----------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) gctx_to_nchw_kernel(const float* __restrict__ src, T* __restrict__ dst, int fH,
+                                                           int fW) {
+  extern __shared__ float s_t[];  // [fW][C + 1]
+  const int h = blockIdx.x, bn = blockIdx.y, ld = kC + 1;
+  const float* in = src + ((size_t)bn * fH + h) * fW * kC;
+  for (int i = threadIdx.x; i < kC * fW; i += blockDim.x) s_t[(i / kC) * ld + (i % kC)] = in[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < kC * fW; i += blockDim.x) {
+    const int c = i / fW, w = i % fW;
+    dst[(((size_t)bn * kC + c) * fH + h) * fW + w] = VbType<T>::cvt(s_t[w * ld + c]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ src, T* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = VbType<T>::cvt(src[i]);
+}
+
+size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+
+struct BwdLayout {
+  size_t ctx, counts, offsets, cursor, recs_a, recs_b, gctx, gdepth, total;
+};
+BwdLayout bwd_layout(const VbGrid* g, bool need_gdepth_ws) {
+  const CellDims cd = cell_dims(*g);
+  const size_t nvox = (size_t)g->vZ * g->vY * g->vX, HW = (size_t)g->fH * g->fW;
+  BwdLayout l;
+  size_t o = 0;
+  l.ctx = o;     o += align256((size_t)g->B * g->N * HW * kC * 4);
+  l.counts = o;  o += align256((size_t)g->B * cd.nc * 4);
+  l.offsets = o; o += align256((size_t)g->B * (cd.nc + 1) * 4);
+  l.cursor = o;  o += align256((size_t)g->B * cd.nc * 4);
+  l.recs_a = o;  o += align256((size_t)g->B * g->N * nvox * 4);
+  l.recs_b = o;  o += align256((size_t)g->B * g->N * nvox * 4);
+  l.gctx = o;    o += align256((size_t)g->B * g->N * HW * kC * 4);
+  l.gdepth = o;  o += need_gdepth_ws ? align256((size_t)g->B * g->N * g->D * HW * 4) : 0;
+  l.total = o;
+  return l;
+}
+
+template <typename T>
+int launch_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const void* d_depth, const void* d_ctx,
+               const void* d_gout, int gout_layout, const uint64_t* d_cnt, void* d_gdepth, void* d_gctx, char* ws,
+               cudaStream_t st) {
+  if (g->C != kC) return VB200_ERR_ARG;
+  const size_t nvox = (size_t)g->vZ * g->vY * g->vX, HW = (size_t)g->fH * g->fW;
+  if (nvox > (1u << kVoxBits) || g->D + 1 >= (1 << (32 - kVoxBits))) return VB200_ERR_ARG;
+  constexpr bool kF32 = sizeof(T) == 4;
+  const BwdLayout l = bwd_layout(g, !kF32);
+  const CellDims cd = cell_dims(*g);
+  float* ctx_nhwc = reinterpret_cast<float*>(ws + l.ctx);
+  int* counts = reinterpret_cast<int*>(ws + l.counts);
+  int* offsets = reinterpret_cast<int*>(ws + l.offsets);
+  int* cursor = reinterpret_cast<int*>(ws + l.cursor);
+  uint32_t* recs_a = reinterpret_cast<uint32_t*>(ws + l.recs_a);
+  uint32_t* recs_b = reinterpret_cast<uint32_t*>(ws + l.recs_b);
+  float* gctx_ws = reinterpret_cast<float*>(ws + l.gctx);
+  float* gdepth_acc = kF32 ? reinterpret_cast<float*>(d_gdepth) : reinterpret_cast<float*>(ws + l.gdepth);
+  const size_t n_gdepth = (size_t)g->B * g->N * g->D * HW;
+
+  if (cudaMemsetAsync(counts, 0, (size_t)g->B * cd.nc * 4, st) != cudaSuccess) return VB200_ERR_CUDA;
+  if (cudaMemsetAsync(cursor, 0, (size_t)g->B * cd.nc * 4, st) != cudaSuccess) return VB200_ERR_CUDA;
+  if (cudaMemsetAsync(gctx_ws, 0, (size_t)g->B * g->N * HW * kC * 4, st) != cudaSuccess) return VB200_ERR_CUDA;
+  if (cudaMemsetAsync(gdepth_acc, 0, n_gdepth * 4, st) != cudaSuccess) return VB200_ERR_CUDA;
+  {
+    VbTraceScope tr(VB_K_CTX_NHWC, st);
+    ctx_to_nhwc_f32_kernel<T><<<dim3(g->fH, g->B * g->N), 256, (size_t)kC * (g->fW + 1) * 4, st>>>(
+        reinterpret_cast<const T*>(d_ctx), ctx_nhwc, g->fH, g->fW);
+    VB_LAUNCH_CHECK();
+  }
+  {
+    VbTraceScope tr(VB_K_LIFT_PLAN, st);
+    dim3 vgrid(vb_ceil_div(nvox, kThreads), g->B);
+    plan_pairs_kernel<0><<<vgrid, kThreads, 0, st>>>(*g, *t, d_mats, counts, nullptr, nullptr, nullptr);
+    VB_LAUNCH_CHECK();
+    scan_cells_kernel<<<g->B, 1024, 0, st>>>(counts, offsets, cd.nc);
+    VB_LAUNCH_CHECK();
+    plan_pairs_kernel<1><<<vgrid, kThreads, 0, st>>>(*g, *t, d_mats, nullptr, offsets, cursor, recs_a);
+    VB_LAUNCH_CHECK();
+    const int total_cells = g->B * cd.nc;
+    sort_cells_kernel<<<vb_ceil_div(total_cells, kThreads / 32), kThreads, 0, st>>>(
+        offsets, recs_a, recs_b, cd.nc, (size_t)g->N * nvox, total_cells);
+    VB_LAUNCH_CHECK();
+  }
+  {
+    VbTraceScope tr(VB_K_LIFT_BWD, st);
+    const size_t smem = (size_t)(kThreads / 32) * (4 * g->D + 32 * 4 + 32 * 17 + 64) * sizeof(float);
+    auto kern = gout_layout == VB200_NCDHW ? lift_bwd_kernel<T, VB200_NCDHW> : lift_bwd_kernel<T, VB200_NDHWC>;
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return VB200_ERR_CUDA;
+    for (int colour = 0; colour < 4; ++colour) {
+      const int ny = (cd.ncy - (colour >> 1) + 1) / 2, nx = (cd.ncx - (colour & 1) + 1) / 2;
+      dim3 grid(vb_ceil_div((long long)ny * nx, kThreads / 32), g->B * g->N);
+      kern<<<grid, kThreads, smem, st>>>(*g, *t, d_mats, reinterpret_cast<const T*>(d_depth), ctx_nhwc,
+                                         reinterpret_cast<const T*>(d_gout), d_cnt, offsets, recs_b, gdepth_acc,
+                                         gctx_ws, colour);
+      VB_LAUNCH_CHECK();
+    }
+    gctx_to_nchw_kernel<T><<<dim3(g->fH, g->B * g->N), 256, (size_t)g->fW * (kC + 1) * 4, st>>>(
+        gctx_ws, reinterpret_cast<T*>(d_gctx), g->fH, g->fW);
+    VB_LAUNCH_CHECK();
+    if (!kF32) {
+      cast_kernel<T><<<VB_SM_COUNT_B200 * 8, 256, 0, st>>>(gdepth_acc, reinterpret_cast<T*>(d_gdepth), n_gdepth);
+      VB_LAUNCH_CHECK();
+    }
+  }
+  return VB200_OK;
+}
+
+}  // namespace
+
+extern "C" size_t vb200_lift_pool_bwd_workspace(const VbGrid* g, int dtype) {
+  if (!g) return 0;
+  return bwd_layout(g, dtype != VB200_F32).total;
+}
+
+extern "C" int vb200_lift_pool_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const void* d_depth,
+                                   const void* d_ctx, int dtype, const void* d_gout, int gout_layout,
+                                   const uint64_t* d_cnt, void* d_gdepth, void* d_gctx, void* d_workspace,
+                                   size_t workspace_bytes, void* stream) {
+  VB_CHECK_ARG(g && t && d_mats && d_depth && d_ctx && d_gout && d_cnt && d_gdepth && d_gctx && d_workspace);
+  VB_CHECK_ARG(g->B > 0 && g->N > 0 && g->N <= VB_MAX_CAMS);
+  VB_CHECK_ARG(gout_layout == VB200_NCDHW || gout_layout == VB200_NDHWC);
+  if (workspace_bytes < vb200_lift_pool_bwd_workspace(g, dtype)) return VB200_ERR_WORKSPACE;
+  if (((uintptr_t)d_workspace | (uintptr_t)d_gout | (uintptr_t)d_gctx | (uintptr_t)d_gdepth) & 15) return VB200_ERR_ALIGN;
+  int rc = vb200_device_check();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = reinterpret_cast<char*>(d_workspace);
+  switch (dtype) {
+    case VB200_F32:
+      return launch_bwd<float>(g, t, d_mats, d_depth, d_ctx, d_gout, gout_layout, d_cnt, d_gdepth, d_gctx, ws, st);
+    case VB200_BF16:
+      return launch_bwd<__nv_bfloat16>(g, t, d_mats, d_depth, d_ctx, d_gout, gout_layout, d_cnt, d_gdepth, d_gctx, ws,
+                                       st);
+    case VB200_F16:
+      return launch_bwd<__half>(g, t, d_mats, d_depth, d_ctx, d_gout, gout_layout, d_cnt, d_gdepth, d_gctx, ws, st);
+    default: return VB200_ERR_DTYPE;
+  }
+}

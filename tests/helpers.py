@@ -74,12 +74,13 @@ def golden_value(gold, key, full_array):
     return gold[key + "_strided"], np.asarray(full_array).reshape(-1)[::stride]
 
 
-def assert_close_scaled(got, exp, rel, what=""):
-    """|got - exp| <= rel * max|exp|  (the inf-norm-relative bar of SURVEY B.3) plus elementwise rtol."""
+def assert_close_scaled(got, exp, rel, what="", scale=None):
+    """|got - exp| <= rel * max|exp|  (the inf-norm-relative bar of SURVEY B.3) plus elementwise rtol.
+    `scale` overrides max|exp| when `exp` is only a strided sample of the full tensor."""
     got = np.asarray(got, dtype=np.float64)
     exp = np.asarray(exp, dtype=np.float64)
     assert got.shape == exp.shape, f"{what}: shape {got.shape} vs {exp.shape}"
-    scale = max(np.abs(exp).max(), 1e-30)
+    scale = max(np.abs(exp).max(), 1e-30) if scale is None else float(scale)
     err = np.abs(got - exp)
     bad = err > rel * scale + rel * np.abs(exp)
     assert not bad.any(), (f"{what}: {int(bad.sum())} / {bad.size} elements off; max abs err {err.max():.3e} "

@@ -256,9 +256,16 @@ def main():
     if train:
         for t in dev_in:
             t.requires_grad_(True)
-        from vampire_b200.dp import GradBucket
+        from vampire_b200.dp import GradBucket, train_step
         bucket = GradBucket(dev, world)
-        cots = None
+        c = cfg
+        shapes = [(batch, c.C, c.vZ, c.vY, c.vX), (batch, c.num_cams, 3, c.fH, c.fW),
+                  (batch, c.num_cams, c.K, c.fH, c.fW), (batch, c.num_cams, 1, c.fH, c.fW), (batch, 3, c.oY, c.oX),
+                  (batch, c.K, c.oY, c.oX), (batch, 1, c.oY, c.oX), (batch, 1, c.oZ, c.oY, c.oX),
+                  (batch, c.C, c.oZ, c.oY, c.oX)]
+        cots = [t.to(dev) for t in synth.make_cotangents(shapes, seed)]
+        cots[0] = cots[0].to(tdt)
+        cots[8] = cots[8].to(tdt)
 
     def step_device():
         """hot path with inputs resident in HBM (prepared matrices uploaded once, like a val loop
@@ -269,18 +276,7 @@ def main():
                 vox, _ = ops.lift_pool_fwd(d, c, prep, mod.cfg_id, True, False, False)
                 rend = ops.render_fwd(den, sem, rgb, feat, beta, prep, None, mod.cfg_id, True, 3)
             return vox, rend
-        for t in dev_in:
-            t.grad = None
-        beta.grad = None
-        vox, _ = ops.lift_pool_fwd(d, c, prep, mod.cfg_id, True, False, True)
-        rend = ops.render_fwd(den, sem, rgb, feat, beta, prep, None, mod.cfg_id, True, 3)
-        nonlocal cots
-        if cots is None:
-            g = torch.Generator(device="cpu").manual_seed(4321)
-            cots = [torch.randn(o.shape, generator=g).to(dev, o.dtype) for o in [vox] + list(rend)]
-        torch.autograd.backward([vox] + list(rend), cots)
-        bucket.allreduce([beta.grad])
-        return vox, rend
+        return train_step(mod, d, c, (den, sem, feat, rgb), prep, cots, bucket)
 
     def barrier():
         if world > 1:

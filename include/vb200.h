@@ -18,7 +18,8 @@
  * Conventions
  *   - plain C: pointers, sizes, ints and floats only; no C++/torch types; no exceptions.
  *   - every pointer named d_* is DEVICE memory owned by the caller (the PyTorch caching
- *     allocator in the Python host); the library allocates nothing and keeps no mutable state.
+ *     allocator in the Python host); the library allocates no device memory and keeps no mutable
+ *     state besides the instrumentation counters/events of vb200_trace_*.
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant and
  *     thread-safe.
  *   - return 0 on success, a negative VB200_ERR_* otherwise; vb200_strerror() names it.
@@ -161,6 +162,16 @@ int vb200_lift_pool_bwd(const VbGrid* g, const VbTables* t, const float* d_mats,
                         const void* d_ctx, int dtype, const void* d_gout, int gout_layout,
                         const uint64_t* d_cnt, void* d_gdepth, void* d_gctx, void* d_workspace,
                         size_t workspace_bytes, void* stream);
+
+/* Compatibility path for the reference's get_voxel_feats SIGNATURE (BV2:483), which is handed the
+ * already materialised frustum tensor d_frustum (B,N,C,D,fH,fW) in `dtype`: same semantics, generic
+ * gather (forward) / atomicAdd scatter (backward, like ATen).  Not the benchmarked path. */
+size_t vb200_gather_pool_bwd_workspace(const VbGrid* g, int dtype);
+int vb200_gather_pool_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, const void* d_frustum,
+                          int dtype, void* d_out, uint64_t* d_cnt, void* stream);
+int vb200_gather_pool_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const void* d_gout,
+                          const uint64_t* d_cnt, int dtype, void* d_gfrustum, void* d_workspace,
+                          size_t workspace_bytes, void* stream);
 
 /* ---- volume rendering (Bk) ------------------------------------------ */
 

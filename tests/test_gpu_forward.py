@@ -208,3 +208,24 @@ def test_render_group_sizes_agree():
         st.render_group = old
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+def test_get_voxel_feats_reference_signature():
+    """The compatibility method takes the materialised 6-D frustum tensor like BV2:483 and agrees with
+    both the reference and the fused lift_pool; its autograd matches the oracle's."""
+    from vampire_b200.view_transform import LiftRenderB200
+    case = Case("mini_stress")
+    mod = LiftRenderB200(**case.conf).cuda()
+    depth, ctx = case.depth.cuda(), case.ctx.cuda()
+    fr = (depth.unsqueeze(2) * ctx.unsqueeze(3)).requires_grad_(True)
+    out = mod.get_voxel_feats(fr, 0, case.mats)
+    assert_close_scaled(out.detach().cpu().numpy(), case.gold["vox"], FP32_REL, "get_voxel_feats")
+    fused = mod.lift_pool(depth, ctx, case.mats)
+    assert_close_scaled(out.detach().cpu().numpy(), fused.cpu().numpy(), FP32_REL, "compat vs fused")
+    cot = case.cotangents()[0]
+    g = torch.autograd.grad((out * cot.cuda()).sum(), fr)[0]
+    buf = tp.build_buffers(case.conf)
+    fr_ref = (case.depth.unsqueeze(2) * case.ctx.unsqueeze(3)).requires_grad_(True)
+    ref = tp.get_voxel_feats(case.conf, buf, fr_ref, case.mats)
+    g_ref = torch.autograd.grad((ref * cot).sum(), fr_ref)[0]
+    assert_close_scaled(g.cpu().numpy(), g_ref.numpy(), 2e-5, "d_frustum")

@@ -1,0 +1,92 @@
+"""Data-parallel harness for the path.
+
+The path shards by batch sample -- the six cameras of one sample stay together because the pool
+reduces over cameras (BV2:508-514) and the render samples one sample's volume from its own six
+cameras (BV2:419).  There is no exchange step in the forward or in the data-gradient backward,
+so ranks never talk inside the path.  The only collective is what the reference's DDP does
+(base_cli.py:84,105): one all-reduce (mean) per step over a flat fp32 bucket of parameter
+gradients.  The path itself owns one parameter (``density.beta``); the bucket is sized like the
+parameters adjacent to the path (the two lift convs and the three 3-D heads, 479,543 floats =
+1.9 MB) so the message is representative: latency-bound on NVLink 5 / NVSwitch, launched on
+NCCL's own stream right after the render backward so it overlaps the lift backward.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+# mapping_along_depth 396,288 + channel_lower 73,728 + density_conv 433 + seg_conv 7,794 + rgb_conv 1,299 + beta 1
+# (BV2:171-176, 189-198)
+ADJACENT_PARAM_FLOATS = 396_288 + 73_728 + 433 + 7_794 + 1_299 + 1
+
+
+def shard_samples(global_batch: int, world_size: int, rank: int) -> List[int]:
+    """Sample b lives on rank b mod G."""
+    return [b for b in range(global_batch) if b % world_size == rank]
+
+
+class GradBucket:
+    """Flat fp32 gradient bucket, all-reduced (mean) once per step."""
+
+    def __init__(self, device, world_size: int, numel: int = ADJACENT_PARAM_FLOATS,
+                 group: Optional[dist.ProcessGroup] = None):
+        self.world_size = world_size
+        self.group = group
+        self.flat = torch.zeros(numel, dtype=torch.float32, device=device)
+        self._handle = None
+        self._views: List[torch.Tensor] = []
+        self._targets: List[torch.Tensor] = []
+
+    def pack(self, grads: Sequence[torch.Tensor]) -> None:
+        off = 0
+        self._views, self._targets = [], []
+        for g in grads:
+            n = g.numel()
+            if off + n > self.flat.numel():
+                raise ValueError("GradBucket: gradients exceed the bucket")
+            view = self.flat[off:off + n]
+            view.copy_(g.reshape(-1))
+            self._views.append(view)
+            self._targets.append(g)
+            off += n
+
+    def allreduce_async(self, grads: Sequence[torch.Tensor]) -> None:
+        """Pack + launch the all-reduce without blocking the caller's stream of work."""
+        self.pack(grads)
+        if self.world_size > 1:
+            self._handle = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def wait(self) -> None:
+        """Finish the all-reduce, average, and write the reduced values back into the gradients."""
+        if self._handle is not None:
+            self._handle.wait()
+            self._handle = None
+        if self.world_size > 1:
+            self.flat.div_(self.world_size)
+        for view, tgt in zip(self._views, self._targets):
+            tgt.copy_(view.view_as(tgt))
+
+    def allreduce(self, grads: Sequence[torch.Tensor]) -> None:
+        self.allreduce_async(grads)
+        self.wait()
+
+
+def train_step(mod, depth, ctx, vols, mats_prep, cotangents, bucket: GradBucket, has_bda: bool = True):
+    """One forward+backward of lift+pool+render with fixed cotangents (BASELINE configs[2]).
+
+    Order: render forward/backward first, then launch the bucket all-reduce (beta's gradient is
+    final), then the lift forward/backward underneath it, then wait."""
+    from . import ops
+    den, sem, feat, rgb = vols
+    beta = mod.density.beta
+    for t in (depth, ctx, den, sem, feat, rgb, beta):
+        t.grad = None
+    rend = ops.render_fwd(den, sem, rgb, feat, beta, mats_prep, None, mod.cfg_id, has_bda, 3)
+    torch.autograd.backward(list(rend), list(cotangents[1:]))
+    bucket.allreduce_async([beta.grad])
+    vox, _ = ops.lift_pool_fwd(depth, ctx, mats_prep, mod.cfg_id, has_bda, False, True)
+    torch.autograd.backward([vox], [cotangents[0]])
+    bucket.wait()
+    return vox, rend

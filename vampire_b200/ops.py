@@ -269,6 +269,77 @@ def _lift_backward(ctx, gout, gcnt):
 torch.library.register_autograd("vampire_b200::lift_pool_fwd", _lift_backward, setup_context=_lift_setup)
 
 
+# ---- compatibility: the reference's get_voxel_feats signature (materialised frustum tensor) --------
+@torch.library.custom_op("vampire_b200::gather_pool_fwd", mutates_args=())
+def gather_pool_fwd(frustum: Tensor, mats: Tensor, cfg_id: int, has_bda: bool) -> Tuple[Tensor, Tensor]:
+    st = state(cfg_id)
+    cfg = st.cfg
+    dev = _need_cuda(frustum, mats)
+    B, N = frustum.shape[:2]
+    if frustum.shape != (B, N, cfg.C, cfg.D, cfg.fH, cfg.fW):
+        raise ValueError(f"get_voxel_feats: frustum_feats has shape {tuple(frustum.shape)}")
+    dt = cabi.dtype_code(frustum.dtype)
+    mats = _mats_ok(mats, B, N)
+    frustum = frustum.contiguous()
+    out = torch.empty(B, cfg.C, cfg.vZ, cfg.vY, cfg.vX, dtype=frustum.dtype, device=dev)
+    cnt = torch.empty(B, cfg.vZ * cfg.vY * cfg.vX, dtype=torch.int64, device=dev)
+    g = st.grid(B, has_bda)
+    with torch.cuda.device(dev):
+        cabi.check(cabi.lib().vb200_gather_pool_fwd(C.byref(g), C.byref(st.tables(dev).struct), mats.data_ptr(),
+                                                    frustum.data_ptr(), dt, out.data_ptr(), cnt.data_ptr(),
+                                                    cabi.stream_ptr(dev)))
+    return out, cnt
+
+
+@gather_pool_fwd.register_fake
+def _(frustum, mats, cfg_id, has_bda):
+    cfg = state(cfg_id).cfg
+    B = frustum.shape[0]
+    return (frustum.new_empty(B, cfg.C, cfg.vZ, cfg.vY, cfg.vX),
+            frustum.new_empty(B, cfg.vZ * cfg.vY * cfg.vX, dtype=torch.int64))
+
+
+@torch.library.custom_op("vampire_b200::gather_pool_bwd", mutates_args=())
+def gather_pool_bwd(gout: Tensor, mats: Tensor, cnt: Tensor, cfg_id: int, has_bda: bool) -> Tensor:
+    st = state(cfg_id)
+    cfg = st.cfg
+    dev = _need_cuda(gout, mats, cnt)
+    B, N = gout.shape[0], cfg.num_cams
+    dt = cabi.dtype_code(gout.dtype)
+    mats = _mats_ok(mats, B, N)
+    gout = gout.contiguous()
+    gfr = torch.empty(B, N, cfg.C, cfg.D, cfg.fH, cfg.fW, dtype=gout.dtype, device=dev)
+    g = st.grid(B, has_bda)
+    lib = cabi.lib()
+    ws_bytes = lib.vb200_gather_pool_bwd_workspace(C.byref(g), dt)
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        cabi.check(lib.vb200_gather_pool_bwd(C.byref(g), C.byref(st.tables(dev).struct), mats.data_ptr(),
+                                             gout.data_ptr(), cnt.data_ptr(), dt, gfr.data_ptr(), ws.data_ptr(),
+                                             ws_bytes, cabi.stream_ptr(dev)))
+    return gfr
+
+
+@gather_pool_bwd.register_fake
+def _(gout, mats, cnt, cfg_id, has_bda):
+    cfg = state(cfg_id).cfg
+    return gout.new_empty(gout.shape[0], cfg.num_cams, cfg.C, cfg.D, cfg.fH, cfg.fW)
+
+
+def _gather_setup(ctx, inputs, output):
+    frustum, mats, cfg_id, has_bda = inputs
+    ctx.save_for_backward(mats, output[1])
+    ctx.cfg_id, ctx.has_bda = cfg_id, has_bda
+
+
+def _gather_backward(ctx, gout, gcnt):
+    mats, cnt = ctx.saved_tensors
+    return gather_pool_bwd(gout, mats, cnt, ctx.cfg_id, ctx.has_bda), None, None, None
+
+
+torch.library.register_autograd("vampire_b200::gather_pool_fwd", _gather_backward, setup_context=_gather_setup)
+
+
 # =============================================================================================
 # render
 # =============================================================================================

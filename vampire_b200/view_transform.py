@@ -92,6 +92,16 @@ class LiftRenderB200(nn.Module):
         mats, has_bda = self._prep(sensor2ego_mat, intrin_mat, ida_mat, bda_mat, self._device())
         return ops.get_pixel(mats, self.cfg_id, has_bda)
 
+    def get_voxel_feats(self, frustum_feats: Tensor, sweep_index: int, mats_dict: Dict[str, Tensor],
+                        clamp_extreme: bool = True) -> Tensor:
+        """Reference signature (BV2:483): the caller has already materialised the (B,N,C,D,fH,fW)
+        frustum tensor.  Kept for drop-in compatibility; the fused ``lift_pool`` is the product path."""
+        if not clamp_extreme:
+            raise NotImplementedError("clamp_extreme=False is never used by the reference (BV2:563)")
+        mats, has_bda = self._prep_dict(mats_dict, sweep_index, frustum_feats.device)
+        out, _ = ops.gather_pool_fwd(frustum_feats, mats, self.cfg_id, has_bda)
+        return out
+
     def volume_rendering_from_multiple_views(self, geom_xyz, density_feature, semantic_logits, voxel_features, rgb,
                                              mats_dict: Optional[Dict[str, Tensor]] = None):
         """Reference signature (BV2:391).  ``geom_xyz`` is consumed as given (the caller has applied

@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--field", default="surface", choices=["surface", "random", "empty"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--render-group", type=int, default=1)
+    ap.add_argument("--render-group", type=int, default=0, help="samples per pack/march round (0 = all)")
     return ap.parse_args()
 
 

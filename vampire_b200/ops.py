@@ -30,8 +30,9 @@ class PathState:
         self.lattice: Lattice = build_lattice(cfg)
         self._tables: Dict[torch.device, cabi.DeviceTables] = {}
         self.term_eps = 1e-8
-        # samples packed+marched per round of the render; 1 keeps the packed volume L2-resident
-        self.render_group = 1
+        # samples packed+marched per round of the render: 0 = the whole batch in one round (best
+        # occupancy, measured 1.8x faster at B=8); 1 = sample by sample (packed copy stays L2-resident)
+        self.render_group = 0
 
     def tables(self, device: torch.device) -> cabi.DeviceTables:
         device = torch.device(device)
@@ -402,7 +403,7 @@ def render_fwd(density: Tensor, sem: Tensor, rgb: Tensor, feat: Tensor, beta: Te
     g = st.grid(B, has_bda)
     lib = cabi.lib()
     ws_bytes = lib.vb200_render_fwd_workspace(C.byref(g), dt) + \
-        lib.vb200_render_packed_bytes(C.byref(g), dt) * (max(1, min(B, st.render_group)) - 1)
+        lib.vb200_render_packed_bytes(C.byref(g), dt) * ((B if st.render_group <= 0 else min(B, st.render_group)) - 1)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     rin = _render_in_struct(density, sem, rgb, feat, beta32, geom)
     ro = _render_out_struct(outs)

@@ -207,6 +207,14 @@ __device__ __forceinline__ float laplace_density(float s, float bias, float beta
   return (1.0f / beta) * (0.5f + 0.5f * sgn * expm1f(-fabsf(x) / beta));
 }
 
+// true iff the 4x4 at M is exactly the identity.  mv(I, p) == p for every finite p, so the fused
+// kernels skip the two bda products then (the reference's default bda_aug_conf IS the identity,
+// base_exp.py:113-120) without changing a single compare or floor.  Block-uniform.
+__device__ __forceinline__ bool block_is_identity(const float* M) {
+  const int i = threadIdx.x;
+  return __syncthreads_and(i >= 16 || M[i] == ((i % 5 == 0) ? 1.0f : 0.0f)) != 0;
+}
+
 __device__ __forceinline__ void stage_mats(float* s_m, const float* __restrict__ d_mats, int b, int N) {
   const float* src = d_mats + (size_t)b * N * VB200_MAT_SLOTS * 16;
   for (int i = threadIdx.x; i < N * VB200_MAT_SLOTS * 16; i += blockDim.x) s_m[i] = __ldg(src + i);

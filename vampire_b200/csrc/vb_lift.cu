@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kLiftThreads) lift_pool_fwd_kernel(VbGrid g, V
   const int b = blockIdx.y;
   stage_mats(s_m, d_mats, b, g.N);
   __syncthreads();
-  const bool has_bda = g.has_bda != 0;
+  const bool has_bda = (g.has_bda != 0) && !block_is_identity(s_m);   // slot 0 of camera 0 = bda^-1 (same for all cameras)
   for (int i = threadIdx.x; i < g.N * 16; i += blockDim.x) {
     const int n = i / 16, r = (i % 16) / 4, c = i % 4;
     const float* A = s_m + n * VB200_MAT_SLOTS * 16 + 16;   // K.E^-1
@@ -85,8 +85,9 @@ __global__ void __launch_bounds__(kLiftThreads) lift_pool_fwd_kernel(VbGrid g, V
   }
   __syncthreads();
   const int nvox = g.vZ * g.vY * g.vX;
-  const int vox = blockIdx.x * kLiftThreads + threadIdx.x;
-  if (vox >= nvox) return;
+  const int vox_raw = blockIdx.x * kLiftThreads + threadIdx.x;
+  const bool live = vox_raw < nvox;             // no early return: the warp-level cull below shuffles
+  const int vox = live ? vox_raw : nvox - 1;
   const int x = vox % g.vX, y = (vox / g.vX) % g.vY, z = vox / (g.vX * g.vY);
   const float px = __ldg(t.xs + x), py = __ldg(t.ys + y), pz = __ldg(t.zs + z);
   const int HW = g.fH * g.fW;
@@ -95,26 +96,58 @@ __global__ void __launch_bounds__(kLiftThreads) lift_pool_fwd_kernel(VbGrid g, V
 #pragma unroll
   for (int c = 0; c < C; ++c) { acc[c] = 0.0f; cntf[c] = 0.0f; }
 
-  for (int n = 0; n < g.N; ++n) {
-    // Conservative cull (tolerance zone): 84 % of (voxel, camera) pairs are invisible by a wide
-    // margin, so an FMA/approx-reciprocal projection with a 1 px / 5 cm guard band rejects them
-    // for ~25 instructions.  Everything that survives goes through the strict, bit-exact
-    // projection below, which alone decides `valid` -- the cull can only skip pairs whose strict
-    // result is provably invalid (fp32 rounding differences are < 0.02 px / 1e-4 m here).
-    {
-      const float* q = s_q + n * 16;
-      const float cz = fmaf(q[8], px, fmaf(q[9], py, fmaf(q[10], pz, q[11])));
-      if (!(cz > g.d_lo - 0.05f && cz < g.d_hi + 0.05f)) continue;
-      const float cx = fmaf(q[0], px, fmaf(q[1], py, fmaf(q[2], pz, q[3])));
-      const float cy = fmaf(q[4], px, fmaf(q[5], py, fmaf(q[6], pz, q[7])));
-      const float rz = __frcp_rn(cz);
-      const float ux = cx * rz, uy = cy * rz;
-      const float* I = s_m + n * VB200_MAT_SLOTS * 16 + 2 * 16;   // ida
-      const float cw = fmaf(q[12], px, fmaf(q[13], py, fmaf(q[14], pz, q[15])));
-      const float ax = fmaf(I[0], ux, fmaf(I[1], uy, fmaf(I[2], cz, I[3] * cw)));
-      const float ay = fmaf(I[4], ux, fmaf(I[5], uy, fmaf(I[6], cz, I[7] * cw)));
-      if (!(ax > -1.5f && ax < g.x_hi + 1.0f && ay > -1.5f && ay < g.y_hi + 1.0f)) continue;
+  // ---- conservative camera culling (tolerance zone; the strict projection below alone decides `valid`) ----
+  // 84 % of (voxel, camera) pairs are invisible by a wide margin.  Two levels, both with FMA/approximate
+  // arithmetic and a 1 px / 5 cm guard band (fp32 rounding differences are < 0.02 px / 1e-4 m here):
+  //  (1) per warp: the warp's 32 voxels are a straight 3-D segment; its image in a camera is the
+  //      segment between the endpoint images (projective maps preserve segments in front of the
+  //      camera), so if both endpoints are rejected by the SAME half-space every voxel is.
+  //      Lanes 0..2N-1 test (camera, endpoint); one ballot gives the warp's camera mask (~1.5 of 6 survive).
+  //  (2) per thread, for surviving cameras: the same test on the voxel itself.
+  auto cull_codes = [&](int n, float qx, float qy, float qz) -> unsigned {
+    // bit0 z<lo, bit1 z>hi, bit2 x<min, bit3 x>max, bit4 y<min, bit5 y>max (x/y bits only when z >= lo)
+    const float* q = s_q + n * 16;
+    const float cz = fmaf(q[8], qx, fmaf(q[9], qy, fmaf(q[10], qz, q[11])));
+    if (!(cz >= g.d_lo - 0.05f)) return 1u;            // also catches NaN
+    unsigned code = (cz > g.d_hi + 0.05f) ? 2u : 0u;
+    const float cx = fmaf(q[0], qx, fmaf(q[1], qy, fmaf(q[2], qz, q[3])));
+    const float cy = fmaf(q[4], qx, fmaf(q[5], qy, fmaf(q[6], qz, q[7])));
+    const float cw = fmaf(q[12], qx, fmaf(q[13], qy, fmaf(q[14], qz, q[15])));
+    const float rz = __frcp_rn(cz);
+    const float ux = cx * rz, uy = cy * rz;
+    const float* I = s_m + n * VB200_MAT_SLOTS * 16 + 2 * 16;   // ida
+    const float ax = fmaf(I[0], ux, fmaf(I[1], uy, fmaf(I[2], cz, I[3] * cw)));
+    const float ay = fmaf(I[4], ux, fmaf(I[5], uy, fmaf(I[6], cz, I[7] * cw)));
+    code |= (ax < -1.5f) ? 4u : 0u;
+    code |= (ax > g.x_hi + 1.0f) ? 8u : 0u;
+    code |= (ay < -1.5f) ? 16u : 0u;
+    code |= (ay > g.y_hi + 1.0f) ? 32u : 0u;
+    if (!(ax == ax) || !(ay == ay)) code = 0u;          // NaN: cannot reject here
+    return code;
+  };
+  unsigned cam_mask;
+  {
+    const int lane = threadIdx.x & 31;
+    // endpoints of this warp's voxel run (a warp never spans two rows when vX % 32 == 0; otherwise
+    // the run is not a straight segment and the warp-level test is skipped)
+    const int vox_a = __shfl_sync(0xffffffffu, vox, 0), vox_b = __shfl_sync(0xffffffffu, vox, 31);
+    const bool straight = (vox_b - vox_a == 31) && (vox_a / g.vX == vox_b / g.vX);
+    unsigned code = 0u;
+    if (lane < 2 * g.N) {
+      const float ex = __ldg(t.xs + ((lane & 1) ? (vox_b % g.vX) : (vox_a % g.vX)));
+      code = cull_codes(lane >> 1, ex, py, pz);
     }
+    const unsigned other = __shfl_xor_sync(0xffffffffu, code, 1);
+    const bool rejected = straight && (lane < 2 * g.N) && ((code & other) != 0u);
+    const unsigned rej = __ballot_sync(0xffffffffu, rejected);   // both lanes of a camera's pair agree
+    cam_mask = 0u;
+    for (int n = 0; n < g.N; ++n)
+      if (!((rej >> (2 * n)) & 1u)) cam_mask |= 1u << n;
+  }
+
+  for (int n = 0; n < g.N; ++n) {
+    if (!((cam_mask >> n) & 1u)) continue;
+    if (cull_codes(n, px, py, pz) != 0u) continue;
     float pix[3];
     project_voxel<false>(s_m + n * VB200_MAT_SLOTS * 16, has_bda, px, py, pz, pix);
     const LiftCoord lc = lift_coord(g, pix);
@@ -131,8 +164,8 @@ __global__ void __launch_bounds__(kLiftThreads) lift_pool_fwd_kernel(VbGrid g, V
     const float wza = lc.z0 >= 0 ? w.wz0 : 0.0f, wzb = lc.z0 + 1 < g.D ? w.wz1 : 0.0f;
     const int pxl[4] = {ya * g.fW + xa, ya * g.fW + xb, yb * g.fW + xa, yb * g.fW + xb};
     const float wxy[4] = {wxa * wya, wxb * wya, wxa * wyb, wxb * wyb};
-    const T* d0 = dcam + (size_t)za * HW;
-    const T* d1 = dcam + (size_t)zb * HW;
+    const T* d0 = dcam + za * HW;
+    const T* d1 = dcam + zb * HW;
     float wgt[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
@@ -142,7 +175,7 @@ __global__ void __launch_bounds__(kLiftThreads) lift_pool_fwd_kernel(VbGrid g, V
     for (int c = 0; c < C; ++c) f[c] = 0.0f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float4* cp = reinterpret_cast<const float4*>(ccam + (size_t)pxl[k] * C);
+      const float4* cp = reinterpret_cast<const float4*>(ccam + pxl[k] * C);
 #pragma unroll
       for (int q4 = 0; q4 < C / 4; ++q4) {
         const float4 cv = __ldg(cp + q4);
@@ -159,6 +192,7 @@ __global__ void __launch_bounds__(kLiftThreads) lift_pool_fwd_kernel(VbGrid g, V
     }
   }
 
+  if (!live) return;
   if (cnt_out) {   // saved for the backward: 4 bits per channel
     uint64_t cnt = 0;
 #pragma unroll

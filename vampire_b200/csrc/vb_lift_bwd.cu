@@ -83,9 +83,9 @@ __global__ void __launch_bounds__(kThreads) plan_pairs_kernel(VbGrid g, VbTables
   __shared__ float s_m[VB_MAX_CAMS * VB200_MAT_SLOTS * 16];
   __shared__ float s_q[VB_MAX_CAMS * 16];
   const int b = blockIdx.y;
-  const bool has_bda = g.has_bda != 0;
   stage_mats(s_m, d_mats, b, g.N);
   __syncthreads();
+  const bool has_bda = (g.has_bda != 0) && !block_is_identity(s_m);
   stage_cull(s_q, s_m, g.N, has_bda);
   __syncthreads();
   const int nvox = g.vZ * g.vY * g.vX;
@@ -200,10 +200,10 @@ __global__ void __launch_bounds__(kThreads) lift_bwd_kernel(VbGrid g, VbTables t
   const int ny = (cd.ncy - py_ + 1) / 2, nx = (cd.ncx - px_ + 1) / 2;   // cells of this colour per camera
   // blockIdx.y = b * N + n so that a block shares one camera's matrices
   const int bn = blockIdx.y, b = bn / g.N, n = bn % g.N;
-  const bool has_bda = g.has_bda != 0;
   for (int i = threadIdx.x; i < VB200_MAT_SLOTS * 16; i += blockDim.x)
     s_m[i] = __ldg(d_mats + (size_t)bn * VB200_MAT_SLOTS * 16 + i);
   __syncthreads();
+  const bool has_bda = (g.has_bda != 0) && !block_is_identity(s_m);
 
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ci = blockIdx.x * (kThreads / 32) + wid;

@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(kMarchThreads) march_fwd_kernel(VbGrid g, VbTa
   for (int i = threadIdx.x; i < VB200_MAT_SLOTS * 16; i += blockDim.x)
     s_m[i] = __ldg(d_mats + (size_t)(b * g.N + n) * VB200_MAT_SLOTS * 16 + i);
   __syncthreads();
+  const bool has_bda = (g.has_bda != 0) && !block_is_identity(s_m + 5 * 16);   // slot 5 = bda
 
   const int patches_x = (g.fW + kPatchW - 1) / kPatchW;
   const int patches_y = (g.fH + kPatchH - 1) / kPatchH;
@@ -49,7 +50,6 @@ __global__ void __launch_bounds__(kMarchThreads) march_fwd_kernel(VbGrid g, VbTa
   const bool active = (w < g.fW) && (h < g.fH);
   const int wc = min(w, g.fW - 1), hc = min(h, g.fH - 1);
 
-  const bool has_bda = g.has_bda != 0;
   const int S = g.D - 1, HW = g.fH * g.fW;
   const int nvox = g.vZ * g.vY * g.vX;
   const float beta = fabsf(__ldg(beta_ptr)) + g.beta_min;
@@ -105,10 +105,17 @@ __global__ void __launch_bounds__(kMarchThreads) march_fwd_kernel(VbGrid g, VbTa
 #pragma unroll
           for (int cx = 0; cx < 2; ++cx) {
             const float wgt = wxm[cx] * wym[cy] * wzm[cz];
-            PackedLoad<T, CP>::fma_corner(vol + ((size_t)(zs_[cz] * g.vY + ys_[cy]) * g.vX + xs_[cx]) * CP, wgt, v);
+            PackedLoad<T, CP>::fma_corner(vol + (((zs_[cz] * g.vY + ys_[cy]) * g.vX + xs_[cx]) * CP), wgt, v);
           }
+      // torch.nan_to_num (BV2:421): any NaN/inf channel makes the channel sum non-finite, so one
+      // test guards the per-channel fix-up (volumes are finite in practice)
+      float chk = 0.0f;
 #pragma unroll
-      for (int c = 0; c < K + 4; ++c) v[c] = nan_to_num(v[c], 0.0f);          // BV2:421
+      for (int c = 0; c < K + 4; ++c) chk += v[c];
+      if (!(fabsf(chk) <= 3.402823466e+38f)) {
+#pragma unroll
+        for (int c = 0; c < K + 4; ++c) v[c] = nan_to_num(v[c], 0.0f);
+      }
     }
     const float sigma = laplace_density(v[0], g.sdf_bias, beta);              // BV2:423
     const float sd = sigma * delta;                                           // BV2:429

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(kMarchThreads) march_bwd_kernel(
   for (int i = threadIdx.x; i < VB200_MAT_SLOTS * 16; i += blockDim.x)
     s_m[i] = __ldg(d_mats + (size_t)(b * g.N + n) * VB200_MAT_SLOTS * 16 + i);
   __syncthreads();
+  const bool has_bda = (g.has_bda != 0) && !block_is_identity(s_m + 5 * 16);   // slot 5 = bda
 
   const int patches_x = (g.fW + kPatchW - 1) / kPatchW;
   const int patches_y = (g.fH + kPatchH - 1) / kPatchH;
@@ -77,7 +78,6 @@ __global__ void __launch_bounds__(kMarchThreads) march_bwd_kernel(
   const bool active = warp_live && (w < g.fW) && (h < g.fH);
   const int wc = min(w, g.fW - 1), hc = min(max(h, 0), g.fH - 1);
 
-  const bool has_bda = g.has_bda != 0;
   const int S = g.D - 1, HW = g.fH * g.fW;
   const float beta = fabsf(__ldg(beta_ptr)) + g.beta_min;
   const float u = __ldg(t.us + wc), vv = __ldg(t.vs + hc);
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kMarchThreads) march_bwd_kernel(
       float v[CP];
 #pragma unroll
       for (int c = 0; c < CP; ++c) v[c] = 0.0f;
-      size_t cidx[8];
+      int cidx[8];
       float cw[8];
       if (live) {
         const float wx[2] = {(float)(rc.x0 + 1) - rc.ix, rc.x0 + 1 < g.vX ? rc.ix - (float)rc.x0 : 0.0f};
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kMarchThreads) march_bwd_kernel(
         for (int q = 0; q < 8; ++q) {
           const int cx = q & 1, cy = (q >> 1) & 1, cz = q >> 2;
           cw[q] = wx[cx] * wy[cy] * wz[cz];
-          cidx[q] = ((size_t)(zs_[cz] * g.vY + ys_[cy]) * g.vX + xs_[cx]) * CP;
+          cidx[q] = ((zs_[cz] * g.vY + ys_[cy]) * g.vX + xs_[cx]) * CP;
           PackedLoad<T, CP>::fma_corner(packed + cidx[q], cw[q], v);
         }
 #pragma unroll

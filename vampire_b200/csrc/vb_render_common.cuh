@@ -102,9 +102,9 @@ __device__ __forceinline__ BevColumn bev_column(const VbGrid& g, const VbTables&
 template <typename T>
 __device__ __forceinline__ float bev_row(const VbGrid& g, const BevColumn& bc, const T* __restrict__ plane, int z) {
   if (z < 0 || z >= g.vZ) return 0.0f;   // zeros padding (uniform branch)
-  const T* r = plane + (size_t)z * g.vY * g.vX;
-  return bc.w00 * VbType<T>::ld(r + bc.o00) + bc.w01 * VbType<T>::ld(r + bc.o01) +
-         bc.w10 * VbType<T>::ld(r + bc.o10) + bc.w11 * VbType<T>::ld(r + bc.o11);
+  const int base = z * g.vY * g.vX;      // 32-bit element index: one plane is < 2^31 elements
+  return bc.w00 * VbType<T>::ld(plane + (base + bc.o00)) + bc.w01 * VbType<T>::ld(plane + (base + bc.o01)) +
+         bc.w10 * VbType<T>::ld(plane + (base + bc.o10)) + bc.w11 * VbType<T>::ld(plane + (base + bc.o11));
 }
 
 

@@ -156,6 +156,8 @@ ODD_CONFIGS = {
     "ragged": dict(x_bound_seg=(-48.0, 48.0, 3.2), x_bound_det=(-48.0, 48.0, 3.2)),
     # det z-range not aligned with seg levels, fewer levels
     "shifted_z": dict(z_bound_det=(-2.2, 2.6, 1.6)),
+    # fine seg z (40 rows) under coarse det levels: more than 17 z-rows touched -> BEV direct fallback
+    "fine_seg_z": dict(z_bound_seg=(-5.0, 3.0, 0.2), z_bound_det=(-4.4, 2.8, 1.2)),
 }
 
 

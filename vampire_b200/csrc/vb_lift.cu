@@ -59,7 +59,7 @@ __device__ __forceinline__ TriW tri_weights(float ix, float iy, float iz, int x0
 
 // ---- forward: one thread per voxel, loop over cameras ---------------------------------------
 template <typename T, int C, int OUT_LAYOUT>
-__global__ void __launch_bounds__(kLiftThreads) lift_pool_fwd_kernel(VbGrid g, VbTables t,
+__global__ void __launch_bounds__(kLiftThreads, 4) lift_pool_fwd_kernel(VbGrid g, VbTables t,
                                                                      const float* __restrict__ d_mats,
                                                                      const T* __restrict__ depth,
                                                                      const float* __restrict__ ctx_nhwc,
@@ -92,9 +92,14 @@ __global__ void __launch_bounds__(kLiftThreads) lift_pool_fwd_kernel(VbGrid g, V
   const float px = __ldg(t.xs + x), py = __ldg(t.ys + y), pz = __ldg(t.zs + z);
   const int HW = g.fH * g.fW;
 
-  float acc[C], cntf[C];
+  // per-channel non-zero camera count (BV2:509-512).  A seeing camera almost always contributes to all
+  // C channels, so the common case is one shared counter; exact zeros (dead ctx channel, both depth
+  // bins outside) take the packed per-channel path: 4 bits per channel, count of cameras that were ZERO.
+  float acc[C];
 #pragma unroll
-  for (int c = 0; c < C; ++c) { acc[c] = 0.0f; cntf[c] = 0.0f; }
+  for (int c = 0; c < C; ++c) acc[c] = 0.0f;
+  int cams_seen = 0;
+  uint64_t zero_cnt = 0;
 
   // ---- conservative camera culling (tolerance zone; the strict projection below alone decides `valid`) ----
   // 84 % of (voxel, camera) pairs are invisible by a wide margin.  Two levels, both with FMA/approximate
@@ -185,30 +190,42 @@ __global__ void __launch_bounds__(kLiftThreads) lift_pool_fwd_kernel(VbGrid g, V
         f[4 * q4 + 3] = fmaf(cv.w, wgt[k], f[4 * q4 + 3]);
       }
     }
+    float fmin_abs = fabsf(f[0]);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       acc[c] += f[c];
-      cntf[c] += (fabsf(f[c]) > 0.0f) ? 1.0f : 0.0f;   // voxel_mask  BV2:509
+      fmin_abs = fminf(fmin_abs, fabsf(f[c]));
+    }
+    cams_seen += 1;
+    if (!(fmin_abs > 0.0f)) {   // some channel is exactly 0 (or NaN): voxel_mask = |f| > 0  BV2:509
+#pragma unroll
+      for (int c = 0; c < C; ++c) zero_cnt += (uint64_t)(fabsf(f[c]) > 0.0f ? 0 : 1) << (4 * c);
     }
   }
 
   if (!live) return;
-  if (cnt_out) {   // saved for the backward: 4 bits per channel
-    uint64_t cnt = 0;
-#pragma unroll
-    for (int c = 0; c < C; ++c) cnt |= (uint64_t)(uint32_t)cntf[c] << (4 * c);
-    cnt_out[(size_t)b * nvox + vox] = cnt;
-  }
+  const uint64_t seen_all = 0x1111111111111111ull * (uint64_t)cams_seen;   // cams_seen in every 4-bit field
+  if (cnt_out) cnt_out[(size_t)b * nvox + vox] = seen_all - zero_cnt;      // saved for the backward
   // mean = numer / (count + 1e-6)  (BV2:512-514); reciprocal-multiply is within 2 ulp of the division
+  float inv[C];
+  if (zero_cnt == 0) {
+    const float r = __fdividef(1.0f, (float)cams_seen + 1e-6f);
+#pragma unroll
+    for (int c = 0; c < C; ++c) inv[c] = r;
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      inv[c] = __fdividef(1.0f, (float)(cams_seen - (int)((zero_cnt >> (4 * c)) & 0xf)) + 1e-6f);
+  }
   if (OUT_LAYOUT == VB200_NCDHW) {
     T* o = out + (size_t)b * C * nvox + vox;
 #pragma unroll
-    for (int c = 0; c < C; ++c) o[(size_t)c * nvox] = VbType<T>::cvt(__fdividef(acc[c], cntf[c] + 1e-6f));
+    for (int c = 0; c < C; ++c) o[(size_t)c * nvox] = VbType<T>::cvt(acc[c] * inv[c]);
   } else {
     T* o = out + ((size_t)b * nvox + vox) * C;
     T v[C];
 #pragma unroll
-    for (int c = 0; c < C; ++c) v[c] = VbType<T>::cvt(__fdividef(acc[c], cntf[c] + 1e-6f));
+    for (int c = 0; c < C; ++c) v[c] = VbType<T>::cvt(acc[c] * inv[c]);
     constexpr int L = VbLanes<T>::n;
 #pragma unroll
     for (int q = 0; q < C / L; ++q) reinterpret_cast<uint4*>(o)[q] = reinterpret_cast<const uint4*>(v)[q];

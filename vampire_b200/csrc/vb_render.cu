@@ -22,7 +22,32 @@
 #include "vb_render_common.cuh"
 #include "vb_trace.cuh"
 
+#include <mutex>
+
 namespace {
+
+// The BEV branch and the camera branch of one render call are independent: fork the BEV kernels
+// onto a per-device side stream and join before returning, so the two instruction-bound kernel
+// families fill each other's idle issue slots.  Everything stays stream-ordered w.r.t. the caller's
+// stream (fork event before, join event after), so caller-owned buffers remain valid.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream* side_stream_for_current_device() {
+  static std::mutex mu;
+  static SideStream table[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  SideStream& s = table[dev];
+  if (!s.stream) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  }
+  return &s;
+}
 
 // ---- R2+R3+R4: camera ray march, one sample (blockIdx.z = sample within this launch) ---------
 template <typename T, int K, bool FROM_MATS>
@@ -253,26 +278,38 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
   const T* feat = reinterpret_cast<const T*>(in->feat);
   const int patches = vb_ceil_div(g->fW, kPatchW) * vb_ceil_div(g->fH, kPatchH);
   const int ncol = g->oY * g->oX;
+  bool forked = false;
+  SideStream* side = nullptr;
   if (branches & VB200_BRANCH_BEV) {
     float* wl_ws = reinterpret_cast<float*>((char*)ws + cam_bytes);
-    VbTraceScope tr(VB_K_BEV_FWD, st);
-    bev_weights_kernel<T><<<dim3(vb_ceil_div(ncol, 256), g->B), 256, 0, st>>>(
+    cudaStream_t bst = st;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if ((branches & VB200_BRANCH_CAM) && cap == cudaStreamCaptureStatusNone &&
+        (side = side_stream_for_current_device()) != nullptr) {
+      if (cudaEventRecord(side->fork, st) == cudaSuccess && cudaStreamWaitEvent(side->stream, side->fork, 0) == cudaSuccess) {
+        bst = side->stream;
+        forked = true;
+      }
+    }
+    VbTraceScope tr(VB_K_BEV_FWD, bst);
+    bev_weights_kernel<T><<<dim3(vb_ceil_div(ncol, 256), g->B), 256, 0, bst>>>(
         *g, *t, den, in->beta, out->bev_height, out->voxel_density, wl_ws);
     VB_LAUNCH_CHECK();
-    bev_channels_kernel<T, K, C><<<dim3(vb_ceil_div(ncol, 256), K + 3 + C, g->B), 256, 0, st>>>(
+    bev_channels_kernel<T, K, C><<<dim3(vb_ceil_div(ncol, 256), K + 3 + C, g->B), 256, 0, bst>>>(
         *g, *t, sem, rgb, feat, wl_ws, out->bev_rgb, out->bev_seg, reinterpret_cast<T*>(out->voxel_output));
     VB_LAUNCH_CHECK();
+    if (forked && cudaEventRecord(side->join, bst) != cudaSuccess) return VB200_ERR_CUDA;
   }
   if (!(branches & VB200_BRANCH_CAM)) return VB200_OK;
   if (per != nvox * packed_channels(K) * sizeof(T)) return VB200_ERR_ARG;  // march indexes densely
   for (int b0 = 0; b0 < g->B; b0 += group) {
     const int nb = (g->B - b0) < group ? (g->B - b0) : group;
-    for (int i = 0; i < nb; ++i) {
-      const int b = b0 + i;
+    {
       VbTraceScope tr(VB_K_PACK, st);
-      pack_cam_volume_kernel<T, K><<<vb_ceil_div(nvox, kPackThreads), kPackThreads, 0, st>>>(
-          den + (size_t)b * nvox, sem + (size_t)b * K * nvox, rgb + (size_t)b * 3 * nvox,
-          reinterpret_cast<T*>((char*)ws + (size_t)i * per), (int)nvox);
+      pack_cam_volume_kernel<T, K><<<dim3(vb_ceil_div(nvox, kPackThreads), nb), kPackThreads, 0, st>>>(
+          den + (size_t)b0 * nvox, sem + (size_t)b0 * K * nvox, rgb + (size_t)b0 * 3 * nvox,
+          reinterpret_cast<T*>(ws), (int)nvox, per / sizeof(T));
       VB_LAUNCH_CHECK();
     }
     dim3 grid(vb_ceil_div(patches, kMarchThreads / 32), g->N, nb);
@@ -285,6 +322,7 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
           *g, *t, d_mats, nullptr, reinterpret_cast<const T*>(ws), in->beta, out->rgb, out->seg, out->depth, b0);
     VB_LAUNCH_CHECK();
   }
+  if (forked && cudaStreamWaitEvent(st, side->join, 0) != cudaSuccess) return VB200_ERR_CUDA;
   return VB200_OK;
 }
 

@@ -33,7 +33,7 @@ __device__ __forceinline__ DensityD density_with_grads(float s, float bias, floa
   const float x = s - bias, ax = fabsf(x);
   const float sgn = (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f);
   const float e = expf(-ax / beta);
-  d.sigma = (1.0f / beta) * (0.5f + 0.5f * sgn * expm1f(-ax / beta));
+  d.sigma = (1.0f / beta) * (0.5f + 0.5f * sgn * (e - 1.0f));
   d.ds = (x != 0.0f) ? -e / (2.0f * beta * beta) : 0.0f;
   d.dbeta = -d.sigma / beta + x * e / (2.0f * beta * beta * beta);
   return d;
@@ -456,7 +456,7 @@ int launch_render_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
       {
         VbTraceScope tr(VB_K_PACK, st);
         pack_cam_volume_kernel<T, K><<<vb_ceil_div(nvox, kPackThreads), kPackThreads, 0, st>>>(
-            den + (size_t)b * nvox, sem + (size_t)b * K * nvox, rgb + (size_t)b * 3 * nvox, packed, (int)nvox);
+            den + (size_t)b * nvox, sem + (size_t)b * K * nvox, rgb + (size_t)b * 3 * nvox, packed, (int)nvox, 0);
         VB_LAUNCH_CHECK();
       }
       VbTraceScope tr(VB_K_MARCH_BWD, st);

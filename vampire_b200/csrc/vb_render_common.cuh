@@ -14,13 +14,20 @@ constexpr int kMaxLevels = 16;
 __host__ __device__ constexpr int packed_channels(int K) { return ((K + 4) + 7) / 8 * 8; }
 
 // ---- R1: pack density | sem | rgb of ONE sample into channels-last ----------------------------
+// grid = (voxel tiles, samples of this round).  den/sem/rgb point at the FIRST sample of the round;
+// `packed_stride` = elements between consecutive samples' packed copies.
 template <typename T, int K>
 __global__ void __launch_bounds__(kPackThreads) pack_cam_volume_kernel(const T* __restrict__ den,
                                                                        const T* __restrict__ sem,
                                                                        const T* __restrict__ rgb, T* __restrict__ packed,
-                                                                       int nvox) {
+                                                                       int nvox, size_t packed_stride) {
   constexpr int NCH = K + 4, CP = packed_channels(K), LD = CP + 1;
   __shared__ T s[kPackThreads * LD];
+  const int i_s = blockIdx.y;
+  den += (size_t)i_s * nvox;
+  sem += (size_t)i_s * K * nvox;
+  rgb += (size_t)i_s * 3 * nvox;
+  packed += (size_t)i_s * packed_stride;
   const int v0 = blockIdx.x * kPackThreads;
   const int v = v0 + threadIdx.x;
   if (v < nvox) {
@@ -55,7 +62,7 @@ template <typename T, int CP> struct PackedLoad {
 __device__ __forceinline__ void axis_coord(float centre, float lo, float ext, int size, int& i0, float& w0,
                                            float& w1) {
   const float gn = ssub(smul(sdiv(ssub(centre, lo), ext), 2.0f), 1.0f);
-  const float i = smul(sdiv(sadd(gn, 1.0f), 2.0f), (float)(size - 1));   // align_corners=True
+  const float i = smul(smul(sadd(gn, 1.0f), 0.5f), (float)(size - 1));   // align_corners=True; /2 == *0.5 exactly
   const float fl = floorf(i);
   i0 = (int)fl;
   w1 = i - fl;

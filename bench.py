@@ -320,20 +320,47 @@ def main():
         host_out = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in [vox] + list(rend)]
         del vox, rend
 
-        def step_e2e():
+        # Three streams, double-buffered: step k's H2D overlaps step k-1's kernels and step k-2's D2H
+        # (PCIe is full duplex), the way a prefetching loader feeds the model.  Every step still moves
+        # all of its inputs from pinned host memory and all of its outputs back, inside the timed region.
+        s_in, s_run, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        nbuf = 2
+        dev_bufs = [[torch.empty_like(h, device=dev) for h in host_in] for _ in range(nbuf)]
+        ev_in = [torch.cuda.Event() for _ in range(nbuf)]
+        ev_run = [torch.cuda.Event() for _ in range(nbuf)]
+        ev_out = [torch.cuda.Event() for _ in range(nbuf)]
+
+        def step_e2e(k):
+            i = k % nbuf
             with torch.no_grad():
-                d, c, den, sem, feat, rgb = [h.to(dev, non_blocking=True) for h in host_in]
-                vox = mod.lift_pool(d, c, mats)              # host mats_dict: 4x4 prep on the CPU, as the oracle
-                rend = mod.render(mats, den, sem, feat, rgb)
-                for o, h in zip([vox] + list(rend), host_out):
-                    h.copy_(o, non_blocking=True)
-        for _ in range(2):
-            step_e2e()
+                with torch.cuda.stream(s_in):
+                    s_in.wait_event(ev_run[i])            # buffer i's previous consumer has finished
+                    for dbuf, h in zip(dev_bufs[i], host_in):
+                        dbuf.copy_(h, non_blocking=True)
+                    ev_in[i].record(s_in)
+                with torch.cuda.stream(s_run):
+                    s_run.wait_event(ev_in[i])
+                    d, c, den, sem, feat, rgb = dev_bufs[i]
+                    vox = mod.lift_pool(d, c, mats)       # host mats_dict: 4x4 prep on the CPU, as the oracle
+                    rend = mod.render(mats, den, sem, feat, rgb)
+                    ev_run[i].record(s_run)
+                outs = [vox] + list(rend)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_run[i])
+                    for o, h in zip(outs, host_out):
+                        o.record_stream(s_out)
+                        h.copy_(o, non_blocking=True)
+                    ev_out[i].record(s_out)
+
+        for k in range(2):
+            step_e2e(k)
         barrier()
-        k = max(3, min(args.steps, 10))
+        k = max(4, min(args.steps, 10))
         e0.record()
-        for _ in range(k):
-            step_e2e()
+        for kk in range(k):
+            step_e2e(kk)
+        for s_ in (s_in, s_run, s_out):
+            torch.cuda.current_stream().wait_stream(s_)
         e1.record()
         barrier()
         t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
@@ -342,7 +369,8 @@ def main():
         ms_e2e = t.item() / k
         e2e = {"value": world * pts / (ms_e2e * 1e-3), "unit": "frustum pts/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(sum(h.numel() * h.element_size() for h in host_in) + prep.numel() * 4),
-               "d2h_bytes_per_step": int(sum(h.numel() * h.element_size() for h in host_out)), "steps": k}
+               "d2h_bytes_per_step": int(sum(h.numel() * h.element_size() for h in host_out)), "steps": k,
+               "pipelining": "3 streams, double-buffered inputs"}
 
     if rank != 0:
         if world > 1:

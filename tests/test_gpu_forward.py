@@ -231,3 +231,35 @@ def test_get_voxel_feats_reference_signature():
     ref = tp.get_voxel_feats(case.conf, buf, fr_ref, case.mats)
     g_ref = torch.autograd.grad((ref * cot).sum(), fr_ref)[0]
     assert_close_scaled(g.cpu().numpy(), g_ref.numpy(), 2e-5, "d_frustum")
+
+
+@pytest.mark.parametrize("seed", [200, 201, 202])
+def test_fused_kernels_use_the_exact_indices_random_rigs(seed):
+    """The conservative culls (per warp / per voxel) and the identity-bda shortcut must never drop a pair
+    the strict projection calls valid: pooled features on random stress rigs vs the live oracle."""
+    from vampire_b200 import synth
+    from vampire_b200.config import MINI
+    from vampire_b200.matrices import prepare_matrices
+    cfg, conf = MINI, MINI.backbone_kwargs()
+    ops, cid = _ops(cfg)
+    m = synth.make_mats(cfg, 2, "stress", seed=seed)
+    if seed == 202:
+        m["bda_mat"] = torch.eye(4).expand(2, 4, 4).contiguous()     # identity-bda fast path
+    prep = prepare_matrices(m["sensor2ego_mats"][:, 0], m["intrin_mats"][:, 0], m["ida_mats"][:, 0], m["bda_mat"])
+    depth, ctx = synth.make_lift_inputs(cfg, 2, seed=seed)
+    den, sem, feat, rgb = synth.make_render_inputs(cfg, 2, seed=seed, field="surface")
+    buf = tp.build_buffers(conf)
+    with torch.no_grad():
+        ref_vox = tp.lift_pool(conf, buf, depth, ctx, m)
+        ref = tp.render_from_mats(conf, buf, m, den, sem, feat, rgb, torch.tensor(0.1))
+    vox, cnt = ops.lift_pool_fwd(depth.cuda(), ctx.cuda(), prep.cuda(), cid, True, False, True)
+    assert_close_scaled(vox.cpu().numpy(), ref_vox.numpy(), FP32_REL, "vox")
+    # the saved camera counts equal the number of strictly valid cameras per voxel
+    valid, _, _ = ops.lift_indices(prep.cuda(), cid, True)
+    nvalid = valid.sum(1).reshape(2, -1).cpu().numpy()
+    got = (cnt.cpu().numpy().astype(np.uint64) & np.uint64(0xF)).astype(np.int64)
+    assert np.array_equal(got, nvalid)
+    outs = ops.render_fwd(den.cuda(), sem.cuda(), rgb.cuda(), feat.cuda(), torch.tensor(0.1, device="cuda"),
+                          prep.cuda(), None, cid, True, 3)
+    for n, o, r in zip(NAMES, outs, ref):
+        assert_close_scaled(o.cpu().numpy(), r.numpy(), FP32_REL, n)

@@ -92,3 +92,36 @@ def test_degenerate_geometry_nan_to_num():
     assert (g[0, 0] == -1e3).all()
     raw = ops.get_geometry(prep.cuda(), cid, True, False).cpu()
     assert torch.equal(torch.nan_to_num(raw, -1e3), g)
+
+
+@pytest.mark.parametrize("seed", list(range(100, 112)))
+@pytest.mark.parametrize("mode", ["train", "stress"])
+def test_random_rigs_bit_exact(seed, mode):
+    """Property: for ANY camera rig (random resize/crop, ida rotation + flip, bda rotation/scale/flip)
+    coordinates, masks and corner indices equal the strict oracle bit for bit."""
+    from vampire_b200 import ops, synth
+    from vampire_b200.config import MINI
+    from vampire_b200.lattice import build_lattice
+    from vampire_b200.matrices import prepare_matrices
+    cfg = MINI
+    cid = ops.register_config(cfg)
+    lat = build_lattice(cfg)
+    m = synth.make_mats(cfg, 2, mode, seed=seed)
+    prep = prepare_matrices(m["sensor2ego_mats"][:, 0], m["intrin_mats"][:, 0], m["ida_mats"][:, 0], m["bda_mat"])
+    pn = prep.numpy()
+    dev = prep.cuda()
+    pix = sn.project_voxels(pn, lat.xs.numpy(), lat.ys.numpy(), lat.zs.numpy())
+    assert np.array_equal(ops.get_pixel(dev, cid, True).cpu().numpy().view(np.uint32), pix.view(np.uint32))
+    geom = sn.frustum_points(pn, lat.us.numpy(), lat.vs.numpy(), lat.ds.numpy())
+    assert np.array_equal(ops.get_geometry(dev, cid, True, False).cpu().numpy().view(np.uint32), geom.view(np.uint32))
+    li = sn.lift_indices(pix, cfg.final_dim, cfg.d_bound, (cfg.fW, cfg.fH, cfg.D))
+    valid, i0, frac = ops.lift_indices(dev, cid, True)
+    assert np.array_equal(valid.cpu().numpy().astype(bool), li["valid"])
+    assert np.array_equal(i0.cpu().numpy(), np.stack(li["i0"], -1).astype(np.int16))
+    lo = (cfg.x_bound_seg[0], cfg.y_bound_seg[0], cfg.z_bound_seg[0])
+    ext = (cfg.x_bound_seg[1] - lo[0], cfg.y_bound_seg[1] - lo[1], cfg.z_bound_seg[1] - lo[2])
+    ri = sn.render_indices(sn.nan_to_num(geom, -1e3)[:, :, :-1], lo, ext, (cfg.vX, cfg.vY, cfg.vZ))
+    mask, r0, _ = ops.render_indices(dev, cid, True, None)
+    mask = mask.cpu().numpy().astype(bool)
+    assert np.array_equal(mask, ri["mask"])
+    assert np.array_equal(r0.cpu().numpy()[mask], np.stack(ri["i0"], -1)[ri["mask"]].astype(np.int16))

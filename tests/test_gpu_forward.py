@@ -156,6 +156,10 @@ ODD_CONFIGS = {
     "ragged": dict(x_bound_seg=(-48.0, 48.0, 3.2), x_bound_det=(-48.0, 48.0, 3.2)),
     # det z-range not aligned with seg levels, fewer levels
     "shifted_z": dict(z_bound_det=(-2.2, 2.6, 1.6)),
+    # BASELINE configs[3] in miniature: the frustum scaled 2x (128x352 input -> 32x88 feature map)
+    "scaled_frustum": dict(final_dim=(128, 352)),
+    # BASELINE configs[4] in miniature: more samples per ray (D = 129 planes, 128 samples)
+    "dense_samples": dict(d_bound=(2.0, 58.0, 0.4375)),
     # fine seg z (40 rows) under coarse det levels: more than 17 z-rows touched -> BEV direct fallback
     "fine_seg_z": dict(z_bound_seg=(-5.0, 3.0, 0.2), z_bound_det=(-4.4, 2.8, 1.2)),
 }

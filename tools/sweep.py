@@ -1,0 +1,72 @@
+"""BASELINE.json configs[3] (scaled frustum, fwd+bwd) and configs[4] (render sweep) on one B200.
+
+    python tools/sweep.py > profiles/r01_config_sweep.md
+"""
+import os, sys
+from dataclasses import replace
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from vampire_b200 import cabi, ops, synth
+from vampire_b200.config import R50_256x704, R50_512x1408
+from vampire_b200.matrices import prepare_matrices
+
+
+def timed(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def setup(cfg, B, dtype, field="surface"):
+    cid = ops.register_config(cfg)
+    m = synth.make_mats(cfg, B, "val")
+    prep = prepare_matrices(m["sensor2ego_mats"][:, 0], m["intrin_mats"][:, 0], m["ida_mats"][:, 0], m["bda_mat"]).cuda()
+    depth, ctx = [t.cuda() for t in synth.make_lift_inputs(cfg, B, dtype=dtype)]
+    vols = [t.cuda() for t in synth.make_render_inputs(cfg, B, field=field, dtype=dtype)]
+    return cid, prep, depth, ctx, vols
+
+
+print("# Round 1 -- BASELINE.json configs[3] and configs[4] on 1 x B200 (CUDA events, 10 iterations after 3 warm-ups)\n")
+print("## configs[3]: scaled frustum 6x512x1408, D=86, grid 20x256x256, B=1, fp32, forward+backward\n")
+print("| geometry | lift fwd ms | lift bwd ms | render fwd ms | render bwd ms | frustum pts | lift fwd Gpts/s | render fwd Mrays/s |")
+print("|---|---|---|---|---|---|---|---|")
+for name, cfg in (("256x704", R50_256x704), ("512x1408", R50_512x1408)):
+    cid, prep, depth, ctx, (den, sem, feat, rgb) = setup(cfg, 1, torch.float32)
+    beta = torch.tensor(0.1, device="cuda", requires_grad=True)
+    t_lf = timed(lambda: ops.lift_pool_fwd(depth, ctx, prep, cid, True, False, True))
+    vox, cnt = ops.lift_pool_fwd(depth, ctx, prep, cid, True, False, True)
+    g = torch.randn_like(vox)
+    t_lb = timed(lambda: ops.lift_pool_bwd(g, depth, ctx, prep, cnt, cid, True))
+    t_rf = timed(lambda: ops.render_fwd(den, sem, rgb, feat, beta, prep, None, cid, True, 3))
+    outs = ops.render_fwd(den, sem, rgb, feat, beta, prep, None, cid, True, 3)
+    gr = [torch.randn_like(o) for o in outs]
+    t_rb = timed(lambda: ops.render_bwd(gr, list(outs), den, sem, rgb, feat, beta, prep, None, cid, True, 3))
+    pts = cfg.num_cams * cfg.D * cfg.fH * cfg.fW
+    rays = cfg.num_cams * cfg.fH * cfg.fW
+    print(f"| {name} | {t_lf:.3f} | {t_lb:.3f} | {t_rf:.3f} | {t_rb:.3f} | {pts} | {pts / t_lf / 1e6:.2f} | {rays / t_rf / 1e3:.1f} |")
+
+print("\n## configs[4]: standalone render sweep (camera branch only, B=1, bf16 volume, 'surface' field)\n")
+print("planes d_i = 2.0 + (68.4/S) i; rays per image = fH x fW of the feature map\n")
+print("| rays/image | S=64 | S=85 | S=128 | S=192 | S=256 |   (ms ; Mrays/s ; Gsamples/s)")
+print("|---|---|---|---|---|---|")
+for fd in ((256, 704), (512, 1408), (1024, 2816)):
+    row = []
+    for S in (64, 85, 128, 192, 256):
+        step = 68.4 / S
+        cfg = replace(R50_256x704, final_dim=fd, d_bound=(2.0, 70.4, step))
+        if cfg.S != S:   # arange end-point rounding: nudge the step
+            cfg = replace(cfg, d_bound=(2.0, 70.4 + (S - cfg.S) * step * 0.5, step))
+        cid, prep, depth, ctx, (den, sem, feat, rgb) = setup(cfg, 1, torch.bfloat16)
+        beta = torch.tensor(0.1, device="cuda")
+        t = timed(lambda: ops.render_fwd(den, sem, rgb, feat, beta, prep, None, cid, True, 1))
+        rays = cfg.num_cams * cfg.fH * cfg.fW
+        row.append(f"{t:.3f} ; {rays / t / 1e3:.0f} ; {rays * cfg.S / t / 1e6:.2f} (S={cfg.S})")
+        del depth, ctx, den, sem, feat, rgb
+    print(f"| {fd[0] // 4}x{fd[1] // 4} | " + " | ".join(row) + " |")

@@ -13,6 +13,8 @@
 //
 // HBM roofline: read depth + ctx once (L2-resident afterwards: 27.6 MB fp32 per sample), write the
 // (B,C,vZ,vY,vX) volume once => 111.5 MB/sample fp32, 55.7 MB bf16.
+#include <cstdlib>
+
 #include "vb_common.cuh"
 #include "vb_trace.cuh"
 
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(kLiftThreads, 4) lift_pool_fwd_kernel(VbGrid g
                                                                      const float* __restrict__ d_mats,
                                                                      const T* __restrict__ depth,
                                                                      const float* __restrict__ ctx_nhwc,
-                                                                     T* __restrict__ out, uint64_t* __restrict__ cnt_out) {
+                                                                     T* __restrict__ out, uint64_t* __restrict__ cnt_out, int zrun) {
   static_assert(C <= 16, "per-channel counts are packed 4 bits each into 64 bits");
   __shared__ float s_m[VB_MAX_CAMS * VB200_MAT_SLOTS * 16];
   __shared__ float s_q[VB_MAX_CAMS * 16];   // fast cull: (K.E^-1)(bda^-1), FMA-composed
@@ -85,29 +87,28 @@ __global__ void __launch_bounds__(kLiftThreads, 4) lift_pool_fwd_kernel(VbGrid g
   }
   __syncthreads();
   const int nvox = g.vZ * g.vY * g.vX;
-  const int vox_raw = blockIdx.x * kLiftThreads + threadIdx.x;
-  const bool live = vox_raw < nvox;             // no early return: the warp-level cull below shuffles
-  const int vox = live ? vox_raw : nvox - 1;
-  const int x = vox % g.vX, y = (vox / g.vX) % g.vY, z = vox / (g.vX * g.vY);
-  const float px = __ldg(t.xs + x), py = __ldg(t.ys + y), pz = __ldg(t.zs + z);
+  const int nplane = g.vY * g.vX;
+  // a block owns kLiftThreads consecutive (y, x) positions and walks a run of `zrun` z-levels, so the
+  // prologue above (matrix staging, cull-matrix composition) is paid once per run, not once per voxel
+  const int pos_raw = blockIdx.x * kLiftThreads + threadIdx.x;
+  const bool pos_live = pos_raw < nplane;       // no early return: the warp-level cull below shuffles
+  const int pos = pos_live ? pos_raw : nplane - 1;
+  const int x = pos % g.vX, y = pos / g.vX;
+  const float px = __ldg(t.xs + x), py = __ldg(t.ys + y);
   const int HW = g.fH * g.fW;
+  const int z_begin = blockIdx.z * zrun, z_end = min(g.vZ, z_begin + zrun);
 
   // per-channel non-zero camera count (BV2:509-512).  A seeing camera almost always contributes to all
   // C channels, so the common case is one shared counter; exact zeros (dead ctx channel, both depth
   // bins outside) take the packed per-channel path: 4 bits per channel, count of cameras that were ZERO.
-  float acc[C];
-#pragma unroll
-  for (int c = 0; c < C; ++c) acc[c] = 0.0f;
-  int cams_seen = 0;
-  uint64_t zero_cnt = 0;
 
   // ---- conservative camera culling (tolerance zone; the strict projection below alone decides `valid`) ----
   // 84 % of (voxel, camera) pairs are invisible by a wide margin.  Two levels, both with FMA/approximate
   // arithmetic and a 1 px / 5 cm guard band (fp32 rounding differences are < 0.02 px / 1e-4 m here):
-  //  (1) per warp: the warp's 32 voxels are a straight 3-D segment; its image in a camera is the
-  //      segment between the endpoint images (projective maps preserve segments in front of the
-  //      camera), so if both endpoints are rejected by the SAME half-space every voxel is.
-  //      Lanes 0..2N-1 test (camera, endpoint); one ballot gives the warp's camera mask (~1.5 of 6 survive).
+  //  (1) per warp and z-run: the warp's voxels form a planar rectangle (32 x-positions times the z-run);
+  //      a projective map sends it to a convex quadrilateral when all corners are in front of the
+  //      camera, so if all 4 corners are rejected by the SAME half-space every voxel is.
+  //      Lanes 0..4N-1 test (camera, corner); one ballot gives the camera mask (~1.5 of 6 survive).
   //  (2) per thread, for surviving cameras: the same test on the voxel itself.
   auto cull_codes = [&](int n, float qx, float qy, float qz) -> unsigned {
     // bit0 z<lo, bit1 z>hi, bit2 x<min, bit3 x>max, bit4 y<min, bit5 y>max (x/y bits only when z >= lo)
@@ -130,26 +131,36 @@ __global__ void __launch_bounds__(kLiftThreads, 4) lift_pool_fwd_kernel(VbGrid g
     if (!(ax == ax) || !(ay == ay)) code = 0u;          // NaN: cannot reject here
     return code;
   };
+  // warp-level mask for the whole run: the warp's voxels form a planar rectangle (32 x-positions times
+  // the z-run); it is rejected for a camera when its 4 corners are rejected by the same half-space.
   unsigned cam_mask;
   {
     const int lane = threadIdx.x & 31;
-    // endpoints of this warp's voxel run (a warp never spans two rows when vX % 32 == 0; otherwise
-    // the run is not a straight segment and the warp-level test is skipped)
-    const int vox_a = __shfl_sync(0xffffffffu, vox, 0), vox_b = __shfl_sync(0xffffffffu, vox, 31);
-    const bool straight = (vox_b - vox_a == 31) && (vox_a / g.vX == vox_b / g.vX);
+    const int pos_a = __shfl_sync(0xffffffffu, pos, 0), pos_b = __shfl_sync(0xffffffffu, pos, 31);
+    const bool straight = (pos_b - pos_a == 31) && (pos_a / g.vX == pos_b / g.vX);
     unsigned code = 0u;
-    if (lane < 2 * g.N) {
-      const float ex = __ldg(t.xs + ((lane & 1) ? (vox_b % g.vX) : (vox_a % g.vX)));
-      code = cull_codes(lane >> 1, ex, py, pz);
+    if (lane < 4 * g.N) {
+      const float ex = __ldg(t.xs + ((lane & 1) ? (pos_b % g.vX) : (pos_a % g.vX)));
+      const float ez = __ldg(t.zs + ((lane & 2) ? (z_end - 1) : z_begin));
+      code = cull_codes(lane >> 2, ex, py, ez);
     }
-    const unsigned other = __shfl_xor_sync(0xffffffffu, code, 1);
-    const bool rejected = straight && (lane < 2 * g.N) && ((code & other) != 0u);
-    const unsigned rej = __ballot_sync(0xffffffffu, rejected);   // both lanes of a camera's pair agree
+    code &= __shfl_xor_sync(0xffffffffu, code, 1);
+    code &= __shfl_xor_sync(0xffffffffu, code, 2);
+    const bool rejected = straight && (lane < 4 * g.N) && (code != 0u);
+    const unsigned rej = __ballot_sync(0xffffffffu, rejected);   // all 4 lanes of a camera's quad agree
     cam_mask = 0u;
     for (int n = 0; n < g.N; ++n)
-      if (!((rej >> (2 * n)) & 1u)) cam_mask |= 1u << n;
+      if (!((rej >> (4 * n)) & 1u)) cam_mask |= 1u << n;
   }
 
+  for (int z = z_begin; z < z_end; ++z) {
+  const int vox = z * nplane + pos;
+  const float pz = __ldg(t.zs + z);
+  float acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.0f;
+  int cams_seen = 0;
+  uint64_t zero_cnt = 0;
   for (int n = 0; n < g.N; ++n) {
     if (!((cam_mask >> n) & 1u)) continue;
     if (cull_codes(n, px, py, pz) != 0u) continue;
@@ -203,7 +214,7 @@ __global__ void __launch_bounds__(kLiftThreads, 4) lift_pool_fwd_kernel(VbGrid g
     }
   }
 
-  if (!live) return;
+  if (!pos_live) continue;
   const uint64_t seen_all = 0x1111111111111111ull * (uint64_t)cams_seen;   // cams_seen in every 4-bit field
   if (cnt_out) cnt_out[(size_t)b * nvox + vox] = seen_all - zero_cnt;      // saved for the backward
   // mean = numer / (count + 1e-6)  (BV2:512-514); reciprocal-multiply is within 2 ulp of the division
@@ -230,6 +241,7 @@ __global__ void __launch_bounds__(kLiftThreads, 4) lift_pool_fwd_kernel(VbGrid g
 #pragma unroll
     for (int q = 0; q < C / L; ++q) reinterpret_cast<uint4*>(o)[q] = reinterpret_cast<const uint4*>(v)[q];
   }
+  }   // z-run
 }
 
 template <typename T>
@@ -245,15 +257,22 @@ int launch_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, const vo
     ctx_to_nhwc_kernel<T, C><<<grid, 256, smem, st>>>(reinterpret_cast<const T*>(d_ctx), ctx_nhwc, g->fH, g->fW);
     VB_LAUNCH_CHECK();
   }
-  const int nvox = g->vZ * g->vY * g->vX;
-  dim3 grid(vb_ceil_div(nvox, kLiftThreads), g->B);
+  // z-run per thread: 5 levels measured best on B200 (B=8: 0.54 ms vs 0.66 at 1 and 0.60 at 20 -- longer runs
+  // make the warp-level camera mask less selective); override with VB200_LIFT_ZRUN for experiments
+  const int plane_blocks = vb_ceil_div(g->vY * g->vX, kLiftThreads);
+  int zrun = g->vZ < 5 ? g->vZ : 5;
+  {
+    const char* env = getenv("VB200_LIFT_ZRUN");
+    if (env && atoi(env) > 0) zrun = atoi(env);
+  }
+  dim3 grid(plane_blocks, g->B, vb_ceil_div(g->vZ, zrun));
   VbTraceScope tr(VB_K_LIFT_FWD, st);
   if (out_layout == VB200_NCDHW)
     lift_pool_fwd_kernel<T, C, VB200_NCDHW><<<grid, kLiftThreads, 0, st>>>(
-        *g, *t, d_mats, reinterpret_cast<const T*>(d_depth), ctx_nhwc, reinterpret_cast<T*>(d_out), d_cnt);
+        *g, *t, d_mats, reinterpret_cast<const T*>(d_depth), ctx_nhwc, reinterpret_cast<T*>(d_out), d_cnt, zrun);
   else
     lift_pool_fwd_kernel<T, C, VB200_NDHWC><<<grid, kLiftThreads, 0, st>>>(
-        *g, *t, d_mats, reinterpret_cast<const T*>(d_depth), ctx_nhwc, reinterpret_cast<T*>(d_out), d_cnt);
+        *g, *t, d_mats, reinterpret_cast<const T*>(d_depth), ctx_nhwc, reinterpret_cast<T*>(d_out), d_cnt, zrun);
   VB_LAUNCH_CHECK();
   return VB200_OK;
 }

@@ -171,9 +171,13 @@ __global__ void __launch_bounds__(kMarchThreads) march_bwd_kernel(
           if (cw[q] != 0.0f) {
             float4* dst = reinterpret_cast<float4*>(gpacked + cidx[q]);
 #pragma unroll
-            for (int f = 0; f < CP / 4; ++f)
-              atomicAdd(dst + f, make_float4(cw[q] * dv[4 * f], cw[q] * dv[4 * f + 1], cw[q] * dv[4 * f + 2],
-                                             cw[q] * dv[4 * f + 3]));
+            for (int f = 0; f < CP / 4; ++f) {
+              // exact zeros (e.g. the rgb loss weight is 0 in the target experiment, base_exp.py loss_weights)
+              // need no atomic at all
+              if (dv[4 * f] != 0.0f || dv[4 * f + 1] != 0.0f || dv[4 * f + 2] != 0.0f || dv[4 * f + 3] != 0.0f)
+                atomicAdd(dst + f, make_float4(cw[q] * dv[4 * f], cw[q] * dv[4 * f + 1], cw[q] * dv[4 * f + 2],
+                                               cw[q] * dv[4 * f + 3]));
+            }
           }
         }
       }

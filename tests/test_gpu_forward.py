@@ -144,7 +144,8 @@ def test_module_interface_matches_reference_signatures():
     ref_sig = mod.volume_rendering_from_multiple_views(torch.nan_to_num(geom, -1e3), *vols)
     assert len(fused) == len(ref_sig) == 8
     for n, x, y in zip(NAMES, fused, ref_sig):
-        assert torch.equal(x, y), n
+        # same kernels; the fused path may finish rays that left the volume with a geometry-free tail
+        assert_close_scaled(x.detach().cpu().numpy(), y.detach().cpu().numpy(), 1e-6, n + " fused vs signature")
         exp, got = golden_value(case.gold, "r_" + n, x.detach().cpu().numpy())
         assert_close_scaled(got, exp, FP32_REL, n)
 

@@ -99,57 +99,99 @@ __global__ void __launch_bounds__(kMarchThreads) march_fwd_kernel(VbGrid g, VbTa
 #pragma unroll
   for (int c = 0; c < K + 3; ++c) ch[c] = 0.0f;
 
+  // a masked / out-of-volume sample has feature 0: sigma(0) is a per-launch constant (~2.27e-4)
+  const float sigma_masked = laplace_density(0.0f, g.sdf_bias, beta);
   float p0[3], p1[3];
   point(0, p0);
+  // A ray is a straight line and the volume a convex box, so once a ray has LEFT the box it never
+  // re-enters: every later sample is masked (feature 0, sigma_masked) and only delta_i and mid_i enter
+  // the compositing.  When every ray of the warp has left decisively (outside by > 1 mm on an axis along
+  // which it keeps moving outward -- far beyond fp32 rounding of the per-sample geometry) or is already
+  // opaque, the warp finishes with a geometry-free tail loop (delta_i = the ray's constant step length,
+  // equal to the reference's per-sample norm up to ~1e-7 relative).
+  bool was_valid = false, exited = false;
+  float delta = 0.0f;
   for (int i = 0; i < S; ++i) {
     const float trans = expf(-tau);
-    if (g.term_eps > 0.0f && __all_sync(0xffffffffu, !active || trans < g.term_eps)) break;
+    if (g.term_eps > 0.0f) {
+      const bool done = !active || trans < g.term_eps;
+      if (__all_sync(0xffffffffu, done)) break;
+      if (FROM_MATS && __all_sync(0xffffffffu, done || exited)) {   // a caller-supplied geom tensor need not be straight rays
+        if (exited && !done) {
+          float tr = trans;
+          for (int ii = i; ii < S; ++ii) {
+            const float sd = sigma_masked * delta;
+            const float wgt = (1.0f - expf(-sd)) * tr;
+            acc += wgt;
+            dep = fmaf(wgt, __ldg(t.mids + ii), dep);
+            tau += sd;
+            tr = expf(-tau);
+          }
+        }
+        break;
+      }
+    }
     point(i + 1, p1);
     const float dx = p1[0] - p0[0], dy = p1[1] - p0[1], dz = p1[2] - p0[2];
-    const float delta = sqrtf(dx * dx + dy * dy + dz * dz);                 // BV2:426
+    delta = sqrtf(dx * dx + dy * dy + dz * dz);                             // BV2:426
     const RenderCoord rc = render_coord(g, p0);
-    float v[CP];
+    if (rc.valid) {
+      was_valid = true;
+    } else if (was_valid && !exited) {
 #pragma unroll
-    for (int c = 0; c < CP; ++c) v[c] = 0.0f;
-    if (rc.valid && active) {
-      const float fx = rc.ix - (float)rc.x0, fy = rc.iy - (float)rc.y0, fz = rc.iz - (float)rc.z0;
-      const float wx[2] = {(float)(rc.x0 + 1) - rc.ix, fx};
-      const float wy[2] = {(float)(rc.y0 + 1) - rc.iy, fy};
-      const float wz[2] = {(float)(rc.z0 + 1) - rc.iz, fz};
+      for (int a = 0; a < 3; ++a) {
+        const float hi = g.seg_lo[a] + g.seg_ext[a];
+        exited = exited || (p0[a] > hi + 1e-3f && p1[a] > p0[a]) || (p0[a] < g.seg_lo[a] - 1e-3f && p1[a] < p0[a]);
+      }
+    }
+    float sigma = sigma_masked;
+    int cidx[8];
+    float cw[8];
+    const bool live = rc.valid && active;
+    if (live) {
       // valid => 0 <= i0 <= size-1, so only the far corner can leave the grid; clamp its address and
       // zero its weight instead of branching, so that all 8 corner loads issue back to back
+      const float wx[2] = {(float)(rc.x0 + 1) - rc.ix, rc.x0 + 1 < g.vX ? rc.ix - (float)rc.x0 : 0.0f};
+      const float wy[2] = {(float)(rc.y0 + 1) - rc.iy, rc.y0 + 1 < g.vY ? rc.iy - (float)rc.y0 : 0.0f};
+      const float wz[2] = {(float)(rc.z0 + 1) - rc.iz, rc.z0 + 1 < g.vZ ? rc.iz - (float)rc.z0 : 0.0f};
       const int xs_[2] = {rc.x0, min(rc.x0 + 1, g.vX - 1)};
       const int ys_[2] = {rc.y0, min(rc.y0 + 1, g.vY - 1)};
       const int zs_[2] = {rc.z0, min(rc.z0 + 1, g.vZ - 1)};
-      const float wxm[2] = {wx[0], rc.x0 + 1 < g.vX ? wx[1] : 0.0f};
-      const float wym[2] = {wy[0], rc.y0 + 1 < g.vY ? wy[1] : 0.0f};
-      const float wzm[2] = {wz[0], rc.z0 + 1 < g.vZ ? wz[1] : 0.0f};
+      // phase 1: density channel only (8 scalar loads) -> sigma, alpha
+      float s0 = 0.0f;
 #pragma unroll
-      for (int cz = 0; cz < 2; ++cz)
-#pragma unroll
-        for (int cy = 0; cy < 2; ++cy)
-#pragma unroll
-          for (int cx = 0; cx < 2; ++cx) {
-            const float wgt = wxm[cx] * wym[cy] * wzm[cz];
-            PackedLoad<T, CP>::fma_corner(vol + (((zs_[cz] * g.vY + ys_[cy]) * g.vX + xs_[cx]) * CP), wgt, v);
-          }
-      // torch.nan_to_num (BV2:421): any NaN/inf channel makes the channel sum non-finite, so one
-      // test guards the per-channel fix-up (volumes are finite in practice)
-      float chk = 0.0f;
-#pragma unroll
-      for (int c = 0; c < K + 4; ++c) chk += v[c];
-      if (!(fabsf(chk) <= 3.402823466e+38f)) {
-#pragma unroll
-        for (int c = 0; c < K + 4; ++c) v[c] = nan_to_num(v[c], 0.0f);
+      for (int q = 0; q < 8; ++q) {
+        const int cx = q & 1, cy = (q >> 1) & 1, cz = q >> 2;
+        cw[q] = wx[cx] * wy[cy] * wz[cz];
+        cidx[q] = ((zs_[cz] * g.vY + ys_[cy]) * g.vX + xs_[cx]) * CP;
+        s0 = fmaf(cw[q], VbType<T>::ld(vol + cidx[q]), s0);
       }
+      sigma = laplace_density(nan_to_num(s0, 0.0f), g.sdf_bias, beta);         // BV2:421, 423
     }
-    const float sigma = laplace_density(v[0], g.sdf_bias, beta);              // BV2:423
     const float sd = sigma * delta;                                           // BV2:429
     const float wgt = (1.0f - expf(-sd)) * trans;                           // BV2:430-434
     acc += wgt;
     dep = fmaf(wgt, __ldg(t.mids + i), dep);
+    // phase 2: the 21 value channels, only where they can contribute.  In free space alpha = 1 - exp(-sd)
+    // is exactly 0.0f in fp32 (the reference's too), so w * v == 0 exactly: skipping the fetch is bit-neutral.
+    if (live && wgt != 0.0f) {
+      float v[CP];
 #pragma unroll
-    for (int c = 0; c < K + 3; ++c) ch[c] = fmaf(wgt, v[1 + c], ch[c]);
+      for (int c = 0; c < CP; ++c) v[c] = 0.0f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) PackedLoad<T, CP>::fma_corner(vol + cidx[q], cw[q], v);
+      // torch.nan_to_num (BV2:421): any NaN/inf channel makes the channel sum non-finite, so one
+      // test guards the per-channel fix-up (volumes are finite in practice)
+      float chk = 0.0f;
+#pragma unroll
+      for (int c = 1; c < K + 4; ++c) chk += v[c];
+      if (!(fabsf(chk) <= 3.402823466e+38f)) {
+#pragma unroll
+        for (int c = 1; c < K + 4; ++c) v[c] = nan_to_num(v[c], 0.0f);
+      }
+#pragma unroll
+      for (int c = 0; c < K + 3; ++c) ch[c] = fmaf(wgt, v[1 + c], ch[c]);
+    }
     tau += sd;
     p0[0] = p1[0]; p0[1] = p1[1]; p0[2] = p1[2];
   }

@@ -211,6 +211,12 @@ int vb200_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, co
                      int dtype, const VbRenderOut* out, int branches, void* d_workspace,
                      size_t workspace_bytes, void* stream);
 
+/* When both branches are requested, vb200_render_fwd forks the BEV kernels onto an internal per-device
+ * side stream and joins before returning (the two branches are independent and both issue-bound).
+ * enable = 0 serialises them on the caller's stream (used by bench.py to time kernels in isolation).
+ * One render call per device should be in flight at a time while forking is enabled. */
+int vb200_render_set_fork(int enable);
+
 typedef struct VbRenderGrad {
   /* cotangents of the eight outputs (same shapes/dtypes as VbRenderOut; NULL = zero) */
   const float* g_rgb;

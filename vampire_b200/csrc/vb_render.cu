@@ -22,6 +22,7 @@
 #include "vb_render_common.cuh"
 #include "vb_trace.cuh"
 
+#include <atomic>
 #include <cstdlib>
 #include <mutex>
 
@@ -31,6 +32,8 @@ namespace {
 // onto a per-device side stream and join before returning, so the two instruction-bound kernel
 // families fill each other's idle issue slots.  Everything stays stream-ordered w.r.t. the caller's
 // stream (fork event before, join event after), so caller-owned buffers remain valid.
+std::atomic<int> g_render_fork_disabled{0};
+
 struct SideStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
@@ -52,7 +55,7 @@ SideStream* side_stream_for_current_device() {
 
 // ---- R2+R3+R4: camera ray march, one sample (blockIdx.z = sample within this launch) ---------
 template <typename T, int K, bool FROM_MATS>
-__global__ void __launch_bounds__(kMarchThreads) march_fwd_kernel(VbGrid g, VbTables t, const float* __restrict__ d_mats,
+__global__ void __launch_bounds__(kMarchThreads, 5) march_fwd_kernel(VbGrid g, VbTables t, const float* __restrict__ d_mats,
                                                                   const float* __restrict__ d_geom,
                                                                   const T* __restrict__ packed,
                                                                   const float* __restrict__ beta_ptr,
@@ -502,7 +505,8 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
     cudaStream_t bst = st;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cap);
-    static const bool no_fork = getenv("VB200_NO_FORK") != nullptr;   // measurement aid: serialise the branches
+    static const bool no_fork_env = getenv("VB200_NO_FORK") != nullptr;   // measurement aid: serialise the branches
+    const bool no_fork = no_fork_env || g_render_fork_disabled.load(std::memory_order_relaxed) != 0;
     if (!no_fork && (branches & VB200_BRANCH_CAM) && cap == cudaStreamCaptureStatusNone &&
         (side = side_stream_for_current_device()) != nullptr) {
       if (cudaEventRecord(side->fork, st) == cudaSuccess && cudaStreamWaitEvent(side->stream, side->fork, 0) == cudaSuccess) {
@@ -558,6 +562,11 @@ extern "C" size_t vb200_render_fwd_workspace(const VbGrid* g, int dtype) {
   // minimum: BEV weights + one packed sample per pack/march round; every further
   // vb200_render_packed_bytes() lets one more sample share a round
   return bev_weight_bytes(g) + packed_bytes_per_sample(g, dtype);
+}
+
+extern "C" int vb200_render_set_fork(int enable) {
+  g_render_fork_disabled.store(enable ? 0 : 1);
+  return VB200_OK;
 }
 
 extern "C" size_t vb200_render_packed_bytes(const VbGrid* g, int dtype) {

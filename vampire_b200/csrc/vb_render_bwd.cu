@@ -25,6 +25,9 @@
 
 namespace {
 
+// 64-thread blocks: at B=1 the 65,536 BEV columns are only 256 blocks of 256 threads (0.3 waves)
+constexpr int kBevBwdThreads = 64;
+
 struct DensityD {
   float sigma, ds, dbeta;
 };
@@ -191,16 +194,17 @@ __global__ void __launch_bounds__(kMarchThreads) march_bwd_kernel(
 
 // ---- BEV branch: per-column compositing backward -------------------------------------------------------------
 template <typename T, int K>
-__global__ void __launch_bounds__(256) bev_bwd_columns_kernel(
+__global__ void __launch_bounds__(kBevBwdThreads) bev_bwd_columns_kernel(
     VbGrid g, VbTables t, const T* __restrict__ den, const T* __restrict__ sem, const T* __restrict__ rgb,
     const float* __restrict__ beta_ptr, const float* __restrict__ g_bev_rgb, const float* __restrict__ g_bev_seg,
     const float* __restrict__ g_bev_height, const float* __restrict__ g_vd, float* __restrict__ wl_ws,
     float* __restrict__ ds_ws, float* __restrict__ beta_partials) {
   __shared__ BevLevel s_lv[kMaxLevels];
   __shared__ float s_red[8];
-  extern __shared__ float s_col[];            // G[kMaxLevels][256] | Sf[kMaxLevels][256]
+  extern __shared__ float s_col[];            // G[kMaxLevels][threads] | Sf[kMaxLevels][threads]
+  constexpr int TB = kBevBwdThreads;
   float* sG = s_col;
-  float* sS = s_col + kMaxLevels * 256;
+  float* sS = s_col + kMaxLevels * TB;
   bev_level_table(g, t, s_lv);
   const int b = blockIdx.y;
   const int col_raw = blockIdx.x * blockDim.x + threadIdx.x;
@@ -226,8 +230,8 @@ __global__ void __launch_bounds__(256) bev_bwd_columns_kernel(
   };
   const float gh = g_bev_height ? __ldg(g_bev_height + (size_t)b * ncol + col) : 0.0f;
   walk(den + (size_t)b * nvox, [&](int l, float v) {
-    sS[l * 256 + tid] = v;
-    sG[l * 256 + tid] = gh * __ldg(t.bev_mids + l);
+    sS[l * TB + tid] = v;
+    sG[l * TB + tid] = gh * __ldg(t.bev_mids + l);
   });
   for (int j = 0; j < K + 3; ++j) {
     const float* gsrc = j < K ? g_bev_seg : g_bev_rgb;
@@ -235,26 +239,26 @@ __global__ void __launch_bounds__(256) bev_bwd_columns_kernel(
     const float gcv = j < K ? __ldg(gsrc + ((size_t)b * K + j) * ncol + col)
                             : __ldg(gsrc + ((size_t)b * 3 + (j - K)) * ncol + col);
     const T* plane = j < K ? sem + ((size_t)b * K + j) * nvox : rgb + ((size_t)b * 3 + (j - K)) * nvox;
-    walk(plane, [&](int l, float v) { sG[l * 256 + tid] = fmaf(gcv, v, sG[l * 256 + tid]); });
+    walk(plane, [&](int l, float v) { sG[l * TB + tid] = fmaf(gcv, v, sG[l * TB + tid]); });
   }
   // total = sum_l w_l G_l, then the front-to-back (top-down) recurrences
   float omega = 0.0f, tau = 0.0f;
   for (int l = 0; l < g.oZ; ++l) {
-    const float sigma = laplace_density(sS[l * 256 + tid], g.sdf_bias, beta);
+    const float sigma = laplace_density(sS[l * TB + tid], g.sdf_bias, beta);
     const float sd = sigma * g.bev_delta;
     const float w = (1.0f - expf(-sd)) * expf(-tau);
     tau += sd;
-    omega = fmaf(w, sG[l * 256 + tid], omega);
+    omega = fmaf(w, sG[l * TB + tid], omega);
     if (live) wl_ws[((size_t)b * g.oZ + l) * ncol + col] = w;
   }
   float prefix = 0.0f, dbeta = 0.0f;
   tau = 0.0f;
   for (int l = 0; l < g.oZ; ++l) {
-    const DensityD dd = density_with_grads(sS[l * 256 + tid], g.sdf_bias, beta);
+    const DensityD dd = density_with_grads(sS[l * TB + tid], g.sdf_bias, beta);
     const float sd = dd.sigma * g.bev_delta;
     const float trans = expf(-tau), e_sd = expf(-sd);
     const float w = (1.0f - e_sd) * trans;
-    const float G = sG[l * 256 + tid];
+    const float G = sG[l * TB + tid];
     prefix = fmaf(w, G, prefix);
     const float dsd = G * (trans * e_sd) - (omega - prefix);
     const float dsig = dsd * g.bev_delta + (g_vd ? __ldg(g_vd + ((size_t)b * g.oZ + l) * ncol + col) : 0.0f);
@@ -301,7 +305,7 @@ __global__ void __launch_bounds__(256) bev_tables_kernel(VbGrid g, VbTables t, B
 
 // ---- per input voxel: camera-branch gradient (channels-last) + gathered BEV gradient -> NCDHW outputs ---------
 template <typename T, int K, int C>
-__global__ void __launch_bounds__(256) unpack_gather_kernel(
+__global__ void __launch_bounds__(256, 3) unpack_gather_kernel(
     VbGrid g, BevTables bt, const float* __restrict__ gpacked, const float* __restrict__ wl_ws,
     const float* __restrict__ ds_ws, const float* __restrict__ g_bev_rgb, const float* __restrict__ g_bev_seg,
     const T* __restrict__ g_vo, T* __restrict__ o_den, T* __restrict__ o_sem, T* __restrict__ o_rgb,
@@ -399,7 +403,7 @@ BwdLayout bwd_layout(const VbGrid* g, int dtype) {
   l.wl = o;       o += vb_align256((size_t)g->B * g->oZ * ncol * 4);
   l.ds = o;       o += vb_align256((size_t)g->B * g->oZ * ncol * 4);
   l.tables = o;   o += vb_align256((size_t)(3 * (g->oX + g->oY + g->oZ) + 2 * (g->vX + g->vY + g->vZ)) * 4 + 64);
-  l.n_bev_blocks = vb_ceil_div(ncol, 256) * g->B;
+  l.n_bev_blocks = vb_ceil_div(ncol, kBevBwdThreads) * g->B;
   const int patches = vb_ceil_div(g->fW, kPatchW) * vb_ceil_div(g->fH, kPatchH);
   l.n_march_blocks = vb_ceil_div(patches, kMarchThreads / 32) * g->N;
   l.partials = o; o += vb_align256((size_t)(l.n_bev_blocks + (size_t)l.n_march_blocks * g->B) * 4);
@@ -443,11 +447,11 @@ int launch_render_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
     VbTraceScope tr(VB_K_UNPACK_BEV_BWD, st);
     bev_tables_kernel<<<1, 256, 0, st>>>(*g, *t, bt);
     VB_LAUNCH_CHECK();
-    const size_t smem = (size_t)2 * kMaxLevels * 256 * sizeof(float);
+    const size_t smem = (size_t)2 * kMaxLevels * kBevBwdThreads * sizeof(float);
     auto kern = bev_bwd_columns_kernel<T, K>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return VB200_ERR_CUDA;
-    kern<<<dim3(vb_ceil_div(ncol, 256), g->B), 256, smem, st>>>(*g, *t, den, sem, rgb, in->beta, gr->g_bev_rgb,
+    kern<<<dim3(vb_ceil_div(ncol, kBevBwdThreads), g->B), kBevBwdThreads, smem, st>>>(*g, *t, den, sem, rgb, in->beta, gr->g_bev_rgb,
                                                                 gr->g_bev_seg, gr->g_bev_height, gr->g_voxel_density,
                                                                 wl_ws, ds_ws, partials);
     VB_LAUNCH_CHECK();

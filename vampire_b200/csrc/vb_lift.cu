@@ -23,20 +23,21 @@ namespace {
 constexpr int kLiftThreads = 256;
 
 // ---- ctx (B,N,C,fH,fW) -> (B,N,fH,fW,C): one block per (b*n, h) row -------------------------
-// (the copy is widened to fp32 so the gather needs no per-element unpack: 64 B = 4 x 128-bit per pixel)
+// (the copy keeps the feature dtype: the gather is L1-wavefront bound -- ncu: l1tex 87 % with an fp32 copy --
+//  so a bf16 pixel = one 32-byte sector beats saving the 16 unpack instructions of an fp32 copy)
 template <typename T, int C>
-__global__ void __launch_bounds__(256) ctx_to_nhwc_kernel(const T* __restrict__ src, float* __restrict__ dst, int fH,
+__global__ void __launch_bounds__(256) ctx_to_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, int fH,
                                                           int fW) {
   extern __shared__ unsigned char s_raw[];
-  float* s = reinterpret_cast<float*>(s_raw);  // [C][fW + 1]
+  T* s = reinterpret_cast<T*>(s_raw);  // [C][fW + 1]
   const int h = blockIdx.x, bn = blockIdx.y;
   const int ld = fW + 1;
   for (int i = threadIdx.x; i < C * fW; i += blockDim.x) {
     const int c = i / fW, w = i % fW;
-    s[c * ld + w] = VbType<T>::ld(src + (((size_t)bn * C + c) * fH + h) * fW + w);
+    s[c * ld + w] = src[(((size_t)bn * C + c) * fH + h) * fW + w];
   }
   __syncthreads();
-  float* out = dst + ((size_t)bn * fH + h) * fW * C;
+  T* out = dst + ((size_t)bn * fH + h) * fW * C;
   for (int i = threadIdx.x; i < C * fW; i += blockDim.x) {
     const int w = i / C, c = i % C;
     out[i] = s[c * ld + w];
@@ -64,7 +65,7 @@ template <typename T, int C, int OUT_LAYOUT>
 __global__ void __launch_bounds__(kLiftThreads, 4) lift_pool_fwd_kernel(VbGrid g, VbTables t,
                                                                      const float* __restrict__ d_mats,
                                                                      const T* __restrict__ depth,
-                                                                     const float* __restrict__ ctx_nhwc,
+                                                                     const T* __restrict__ ctx_nhwc,
                                                                      T* __restrict__ out, uint64_t* __restrict__ cnt_out, int zrun) {
   static_assert(C <= 16, "per-channel counts are packed 4 bits each into 64 bits");
   __shared__ float s_m[VB_MAX_CAMS * VB200_MAT_SLOTS * 16];
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(kLiftThreads, 4) lift_pool_fwd_kernel(VbGrid g
     if (!lc.valid) continue;  // f = grid_sample * 0: adds nothing to numer nor to the count
     const TriW w = tri_weights(lc.ix, lc.iy, lc.iz, lc.x0, lc.y0, lc.z0);
     const T* dcam = depth + (size_t)(b * g.N + n) * g.D * HW;
-    const float* ccam = ctx_nhwc + (size_t)(b * g.N + n) * HW * C;
+    const T* ccam = ctx_nhwc + (size_t)(b * g.N + n) * HW * C;
     // zeros padding without branches: clamp the address, zero the weight (valid => i0 in [-1, size-1])
     const int xa = max(lc.x0, 0), xb = min(lc.x0 + 1, g.fW - 1);
     const int ya = max(lc.y0, 0), yb = min(lc.y0 + 1, g.fH - 1);
@@ -191,14 +192,14 @@ __global__ void __launch_bounds__(kLiftThreads, 4) lift_pool_fwd_kernel(VbGrid g
     for (int c = 0; c < C; ++c) f[c] = 0.0f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float4* cp = reinterpret_cast<const float4*>(ccam + pxl[k] * C);
+      constexpr int L = VbLanes<T>::n;
+      const T* cp = ccam + pxl[k] * C;
 #pragma unroll
-      for (int q4 = 0; q4 < C / 4; ++q4) {
-        const float4 cv = __ldg(cp + q4);
-        f[4 * q4 + 0] = fmaf(cv.x, wgt[k], f[4 * q4 + 0]);
-        f[4 * q4 + 1] = fmaf(cv.y, wgt[k], f[4 * q4 + 1]);
-        f[4 * q4 + 2] = fmaf(cv.z, wgt[k], f[4 * q4 + 2]);
-        f[4 * q4 + 3] = fmaf(cv.w, wgt[k], f[4 * q4 + 3]);
+      for (int q4 = 0; q4 < C / L; ++q4) {
+        float cv[L];
+        VbVec<T, L>::ld(cp + q4 * L, cv);
+#pragma unroll
+        for (int e = 0; e < L; ++e) f[q4 * L + e] = fmaf(cv[e], wgt[k], f[q4 * L + e]);
       }
     }
     float fmin_abs = fabsf(f[0]);
@@ -249,10 +250,10 @@ int launch_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, const vo
                void* d_out, int out_layout, uint64_t* d_cnt, void* ws, cudaStream_t st) {
   constexpr int C = 16;
   if (g->C != C) return VB200_ERR_ARG;
-  float* ctx_nhwc = reinterpret_cast<float*>(ws);
+  T* ctx_nhwc = reinterpret_cast<T*>(ws);
   {
     dim3 grid(g->fH, g->B * g->N);
-    const size_t smem = (size_t)C * (g->fW + 1) * sizeof(float);
+    const size_t smem = (size_t)C * (g->fW + 1) * sizeof(T);
     VbTraceScope tr(VB_K_CTX_NHWC, st);
     ctx_to_nhwc_kernel<T, C><<<grid, 256, smem, st>>>(reinterpret_cast<const T*>(d_ctx), ctx_nhwc, g->fH, g->fW);
     VB_LAUNCH_CHECK();
@@ -283,9 +284,8 @@ size_t elem_size(int dtype) { return dtype == VB200_F32 ? 4 : 2; }
 
 extern "C" size_t vb200_lift_pool_fwd_workspace(const VbGrid* g, int dtype) {
   if (!g) return 0;
-  // channels-last fp32 copy of ctx, rounded up to 256 B
-  (void)dtype;
-  const size_t n = (size_t)g->B * g->N * g->fH * g->fW * g->C * sizeof(float);
+  // channels-last copy of ctx (feature dtype), rounded up to 256 B
+  const size_t n = (size_t)g->B * g->N * g->fH * g->fW * g->C * elem_size(dtype);
   return (n + 255) & ~(size_t)255;
 }
 

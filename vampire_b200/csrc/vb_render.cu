@@ -536,7 +536,7 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
     const int nb = (g->B - b0) < group ? (g->B - b0) : group;
     {
       VbTraceScope tr(VB_K_PACK, st);
-      pack_cam_volume_kernel<T, K><<<dim3(vb_ceil_div(nvox, kPackThreads), nb), kPackThreads, 0, st>>>(
+      pack_cam_volume_kernel<T, K><<<dim3(vb_ceil_div(nvox, kPackThreads * PackVox<T>::n), nb), kPackThreads, 0, st>>>(
           den + (size_t)b0 * nvox, sem + (size_t)b0 * K * nvox, rgb + (size_t)b0 * 3 * nvox,
           reinterpret_cast<T*>(ws), (int)nvox, per / sizeof(T));
       VB_LAUNCH_CHECK();

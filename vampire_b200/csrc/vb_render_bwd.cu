@@ -463,7 +463,7 @@ int launch_render_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
       if (cudaMemsetAsync(gpacked, 0, nvox * cp * 4, st) != cudaSuccess) return VB200_ERR_CUDA;
       {
         VbTraceScope tr(VB_K_PACK, st);
-        pack_cam_volume_kernel<T, K><<<vb_ceil_div(nvox, kPackThreads), kPackThreads, 0, st>>>(
+        pack_cam_volume_kernel<T, K><<<dim3(vb_ceil_div(nvox, kPackThreads * PackVox<T>::n), 1), kPackThreads, 0, st>>>(
             den + (size_t)b * nvox, sem + (size_t)b * K * nvox, rgb + (size_t)b * 3 * nvox, packed, (int)nvox, 0);
         VB_LAUNCH_CHECK();
       }

@@ -390,50 +390,77 @@ __device__ __forceinline__ void quad_zrow(const VbGrid& g, const BevQuadX& q, co
   if (y0 + 1 >= 0 && y0 + 1 < g.vY) quad_row<T, MODE>(g, q, zr + (y0 + 1) * g.vX, lane, wy1, out);
 }
 
+// kBevNC channel planes of one kind per thread: their row loads are issued together (the kernel is
+// latency-bound -- ncu: long_scoreboard -- so memory-level parallelism is what buys speed here).
+constexpr int kBevNC = 1;
+
 template <typename T, int K, int C, int MODE>
-__device__ __forceinline__ void bev_quad_channel(const VbGrid& g, const BevLevel* __restrict__ lv, const BevQuadX& q,
-                                                 const T* __restrict__ plane, int y0, float wy0, float wy1, int lane,
-                                                 bool live, const float* __restrict__ wl, float* __restrict__ o_map,
-                                                 T* __restrict__ o_feat, int ncol) {
-  float prev_lo[4] = {0.f, 0.f, 0.f, 0.f}, acc[4] = {0.f, 0.f, 0.f, 0.f};
+__device__ __forceinline__ void bev_quad_channels(const VbGrid& g, const BevLevel* __restrict__ lv, const BevQuadX& q,
+                                                  const T* __restrict__ plane, size_t plane_stride, int nch, int y0,
+                                                  float wy0, float wy1, int lane, bool live,
+                                                  const float* __restrict__ wl, float* __restrict__ o_map,
+                                                  T* __restrict__ o_feat, size_t out_stride, int ncol) {
+  float prev_lo[kBevNC][4], acc[kBevNC][4];
+#pragma unroll
+  for (int k = 0; k < kBevNC; ++k)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { prev_lo[k][c] = 0.0f; acc[k][c] = 0.0f; }
   int prev_z0 = -1000000;
   for (int l = 0; l < g.oZ; ++l) {
     const BevLevel L = lv[l];
-    float hi[4], lo[4];
-    if (L.z0 + 1 == prev_z0) {
+    float hi[kBevNC][4], lo[kBevNC][4];
+    const bool reuse = (L.z0 + 1 == prev_z0);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) hi[c] = prev_lo[c];
-    } else {
-      quad_zrow<T, MODE>(g, q, plane, L.z0 + 1, y0, wy0, wy1, lane, hi);
+    for (int k = 0; k < kBevNC; ++k) {
+      const T* pk = plane + (size_t)(k < nch ? k : 0) * plane_stride;
+      if (reuse) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) hi[k][c] = prev_lo[k][c];
+      } else {
+        quad_zrow<T, MODE>(g, q, pk, L.z0 + 1, y0, wy0, wy1, lane, hi[k]);
+      }
+      quad_zrow<T, MODE>(g, q, pk, L.z0, y0, wy0, wy1, lane, lo[k]);
     }
-    quad_zrow<T, MODE>(g, q, plane, L.z0, y0, wy0, wy1, lane, lo);
     prev_z0 = L.z0;
-    float v[4];
+    float4 w = make_float4(0, 0, 0, 0);
+    if (o_map && live) w = __ldg(reinterpret_cast<const float4*>(wl + (size_t)l * ncol));
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      v[c] = fmaf(L.wz1, hi[c], L.wz0 * lo[c]);
-      prev_lo[c] = lo[c];
-    }
-    if (o_map) {                                                                            // BV2:459-460
-      const float4 w = live ? __ldg(reinterpret_cast<const float4*>(wl + (size_t)l * ncol)) : make_float4(0, 0, 0, 0);
-      acc[0] = fmaf(w.x, v[0], acc[0]); acc[1] = fmaf(w.y, v[1], acc[1]);
-      acc[2] = fmaf(w.z, v[2], acc[2]); acc[3] = fmaf(w.w, v[3], acc[3]);
-    } else if (live) {                                                                      // BV2:448
-      Vec4Load<T>::st(o_feat + (size_t)l * ncol, v);
+    for (int k = 0; k < kBevNC; ++k) {
+      float v[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        v[c] = fmaf(L.wz1, hi[k][c], L.wz0 * lo[k][c]);
+        prev_lo[k][c] = lo[k][c];
+      }
+      if (o_map) {                                                                          // BV2:459-460
+        acc[k][0] = fmaf(w.x, v[0], acc[k][0]); acc[k][1] = fmaf(w.y, v[1], acc[k][1]);
+        acc[k][2] = fmaf(w.z, v[2], acc[k][2]); acc[k][3] = fmaf(w.w, v[3], acc[k][3]);
+      } else if (live && k < nch) {                                                         // BV2:448
+        Vec4Load<T>::st(o_feat + (size_t)k * out_stride + (size_t)l * ncol, v);
+      }
     }
   }
-  if (o_map && live) *reinterpret_cast<float4*>(o_map) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  if (o_map && live) {
+#pragma unroll
+    for (int k = 0; k < kBevNC; ++k)
+      if (k < nch)
+        *reinterpret_cast<float4*>(o_map + (size_t)k * out_stride) = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
+  }
+}
+
+__host__ __device__ constexpr int bev_groups(int K, int C) {
+  return (K + kBevNC - 1) / kBevNC + (3 + kBevNC - 1) / kBevNC + (C + kBevNC - 1) / kBevNC;
 }
 
 template <typename T, int K, int C>
-__global__ void __launch_bounds__(64) bev_channels_vec4_kernel(VbGrid g, VbTables t, const T* __restrict__ sem,
+__global__ void __launch_bounds__(64, 20) bev_channels_vec4_kernel(VbGrid g, VbTables t, const T* __restrict__ sem,
                                                                const T* __restrict__ rgb, const T* __restrict__ feat,
                                                                const float* __restrict__ wl_ws,
                                                                float* __restrict__ o_rgb, float* __restrict__ o_seg,
                                                                T* __restrict__ o_feat) {
   __shared__ BevLevel s_lv[kMaxLevels];
   bev_level_table(g, t, s_lv);
-  const int b = blockIdx.z, j = blockIdx.y;
+  const int b = blockIdx.z, grp = blockIdx.y;
   const int tiles_x = (g.oX + 255) / 256;
   const int oy = blockIdx.x / tiles_x;
   const int lane = threadIdx.x & 31;
@@ -458,16 +485,35 @@ __global__ void __launch_bounds__(64) bev_channels_vec4_kernel(VbGrid g, VbTable
   const int ncol = g.oY * g.oX;
   const size_t nvox = (size_t)g.vZ * g.vY * g.vX;
   const int col0 = oy * g.oX + q.ox0;
+  constexpr int GS = (K + kBevNC - 1) / kBevNC, GR = (3 + kBevNC - 1) / kBevNC;
   const T* plane;
   float* o_map = nullptr;
   T* o_f = nullptr;
-  if (j < K) { plane = sem + ((size_t)b * K + j) * nvox; o_map = o_seg + ((size_t)b * K + j) * ncol + col0; }
-  else if (j < K + 3) { plane = rgb + ((size_t)b * 3 + (j - K)) * nvox; o_map = o_rgb + ((size_t)b * 3 + (j - K)) * ncol + col0; }
-  else { plane = feat + ((size_t)b * C + (j - K - 3)) * nvox; o_f = o_feat + ((size_t)b * C + (j - K - 3)) * g.oZ * ncol + col0; }
+  int nch;
+  size_t out_stride;
+  if (grp < GS) {
+    const int c0 = grp * kBevNC;
+    nch = min(kBevNC, K - c0);
+    plane = sem + ((size_t)b * K + c0) * nvox;
+    o_map = o_seg + ((size_t)b * K + c0) * ncol + col0;
+    out_stride = ncol;
+  } else if (grp < GS + GR) {
+    const int c0 = (grp - GS) * kBevNC;
+    nch = min(kBevNC, 3 - c0);
+    plane = rgb + ((size_t)b * 3 + c0) * nvox;
+    o_map = o_rgb + ((size_t)b * 3 + c0) * ncol + col0;
+    out_stride = ncol;
+  } else {
+    const int c0 = (grp - GS - GR) * kBevNC;
+    nch = min(kBevNC, C - c0);
+    plane = feat + ((size_t)b * C + c0) * nvox;
+    o_f = o_feat + ((size_t)b * C + c0) * g.oZ * ncol + col0;
+    out_stride = (size_t)g.oZ * ncol;
+  }
   const float* wl = wl_ws + (size_t)b * g.oZ * ncol + col0;
-  if (w1) bev_quad_channel<T, K, C, 1>(g, s_lv, q, plane, y0, wy0, wy1, lane, live, wl, o_map, o_f, ncol);
-  else if (w0) bev_quad_channel<T, K, C, 0>(g, s_lv, q, plane, y0, wy0, wy1, lane, live, wl, o_map, o_f, ncol);
-  else bev_quad_channel<T, K, C, 2>(g, s_lv, q, plane, y0, wy0, wy1, lane, live, wl, o_map, o_f, ncol);
+  if (w1) bev_quad_channels<T, K, C, 1>(g, s_lv, q, plane, nvox, nch, y0, wy0, wy1, lane, live, wl, o_map, o_f, out_stride, ncol);
+  else if (w0) bev_quad_channels<T, K, C, 0>(g, s_lv, q, plane, nvox, nch, y0, wy0, wy1, lane, live, wl, o_map, o_f, out_stride, ncol);
+  else bev_quad_channels<T, K, C, 2>(g, s_lv, q, plane, nvox, nch, y0, wy0, wy1, lane, live, wl, o_map, o_f, out_stride, ncol);
 }
 
 size_t bev_weight_bytes(const VbGrid* g) {
@@ -522,7 +568,7 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
                         ((((uintptr_t)sem | (uintptr_t)rgb | (uintptr_t)feat | (uintptr_t)out->voxel_output |
                            (uintptr_t)out->bev_rgb | (uintptr_t)out->bev_seg | (uintptr_t)wl_ws) & 15) == 0);
     if (vec_ok)
-      bev_channels_vec4_kernel<T, K, C><<<dim3(g->oY * vb_ceil_div(g->oX, 256), K + 3 + C, g->B), 64, 0, bst>>>(
+      bev_channels_vec4_kernel<T, K, C><<<dim3(g->oY * vb_ceil_div(g->oX, 256), bev_groups(K, C), g->B), 64, 0, bst>>>(
           *g, *t, sem, rgb, feat, wl_ws, out->bev_rgb, out->bev_seg, reinterpret_cast<T*>(out->voxel_output));
     else
       bev_channels_kernel<T, K, C><<<dim3(vb_ceil_div(ncol, 256), K + 3 + C, g->B), 256, 0, bst>>>(

@@ -46,7 +46,9 @@ SideStream* side_stream_for_current_device() {
   std::lock_guard<std::mutex> lk(mu);
   SideStream& s = table[dev];
   if (!s.stream) {
-    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // lowest priority: never starve the caller's stream
+    if (cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
   }
@@ -546,20 +548,9 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
   const int ncol = g->oY * g->oX;
   bool forked = false;
   SideStream* side = nullptr;
-  if (branches & VB200_BRANCH_BEV) {
+  // BEV branch on stream `bst`
+  auto launch_bev = [&](cudaStream_t bst) -> int {
     float* wl_ws = reinterpret_cast<float*>((char*)ws + cam_bytes);
-    cudaStream_t bst = st;
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(st, &cap);
-    static const bool no_fork_env = getenv("VB200_NO_FORK") != nullptr;   // measurement aid: serialise the branches
-    const bool no_fork = no_fork_env || g_render_fork_disabled.load(std::memory_order_relaxed) != 0;
-    if (!no_fork && (branches & VB200_BRANCH_CAM) && cap == cudaStreamCaptureStatusNone &&
-        (side = side_stream_for_current_device()) != nullptr) {
-      if (cudaEventRecord(side->fork, st) == cudaSuccess && cudaStreamWaitEvent(side->stream, side->fork, 0) == cudaSuccess) {
-        bst = side->stream;
-        forked = true;
-      }
-    }
     VbTraceScope tr(VB_K_BEV_FWD, bst);
     bev_weights_kernel<T><<<dim3(vb_ceil_div(ncol, 256), g->B), 256, 0, bst>>>(
         *g, *t, den, in->beta, out->bev_height, out->voxel_density, wl_ws);
@@ -574,9 +565,9 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
       bev_channels_kernel<T, K, C><<<dim3(vb_ceil_div(ncol, 256), K + 3 + C, g->B), 256, 0, bst>>>(
           *g, *t, sem, rgb, feat, wl_ws, out->bev_rgb, out->bev_seg, reinterpret_cast<T*>(out->voxel_output));
     VB_LAUNCH_CHECK();
-    if (forked && cudaEventRecord(side->join, bst) != cudaSuccess) return VB200_ERR_CUDA;
-  }
-  if (!(branches & VB200_BRANCH_CAM)) return VB200_OK;
+    return VB200_OK;
+  };
+  if (!(branches & VB200_BRANCH_CAM)) return launch_bev(st);
   if (per != nvox * packed_channels(K) * sizeof(T)) return VB200_ERR_ARG;  // march indexes densely
   for (int b0 = 0; b0 < g->B; b0 += group) {
     const int nb = (g->B - b0) < group ? (g->B - b0) : group;
@@ -586,6 +577,25 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
           den + (size_t)b0 * nvox, sem + (size_t)b0 * K * nvox, rgb + (size_t)b0 * 3 * nvox,
           reinterpret_cast<T*>(ws), (int)nvox, per / sizeof(T));
       VB_LAUNCH_CHECK();
+    }
+    if (b0 == 0 && (branches & VB200_BRANCH_BEV)) {
+      // fork AFTER the first pack: the pack is HBM-bound, the march issue-bound -- the BEV kernels
+      // (low-priority side stream) fill the march's idle issue slots instead of fighting the pack for DRAM
+      cudaStream_t bst = st;
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(st, &cap);
+      static const bool no_fork_env = getenv("VB200_NO_FORK") != nullptr;   // measurement aid
+      const bool no_fork = no_fork_env || g_render_fork_disabled.load(std::memory_order_relaxed) != 0;
+      if (!no_fork && cap == cudaStreamCaptureStatusNone && (side = side_stream_for_current_device()) != nullptr) {
+        if (cudaEventRecord(side->fork, st) == cudaSuccess &&
+            cudaStreamWaitEvent(side->stream, side->fork, 0) == cudaSuccess) {
+          bst = side->stream;
+          forked = true;
+        }
+      }
+      const int rc = launch_bev(bst);
+      if (rc) return rc;
+      if (forked && cudaEventRecord(side->join, bst) != cudaSuccess) return VB200_ERR_CUDA;
     }
     dim3 grid(vb_ceil_div(patches, kMarchThreads / 32), g->N, nb);
     VbTraceScope tr(VB_K_MARCH_FWD, st);

@@ -28,15 +28,18 @@ __global__ void __launch_bounds__(kPackThreads) pack_cam_volume_kernel(const T* 
                                                                        const T* __restrict__ rgb, T* __restrict__ packed,
                                                                        int nvox, size_t packed_stride) {
   constexpr int NCH = K + 4, CP = packed_channels(K), V = PackVox<T>::n;
+  __shared__ uint4 s_rec[kPackThreads * 6];
   const int i_s = blockIdx.y;
   den += (size_t)i_s * nvox;
   sem += (size_t)i_s * K * nvox;
   rgb += (size_t)i_s * 3 * nvox;
   packed += (size_t)i_s * packed_stride;
   const int v = (blockIdx.x * kPackThreads + threadIdx.x) * V;
-  if (v >= nvox) return;
-  if (V == 2 && ((nvox & 1) || v + 1 >= nvox)) {   // odd plane size (misaligned 32-bit words) or tail: scalar path
-    for (int vv = v; vv < min(v + 2, nvox); ++vv) {
+  // the vector path needs the whole warp in range (cooperative stores) and, for 16-bit features, an even
+  // plane size (32-bit words of two voxels must be aligned); anything else takes the scalar path
+  const bool vec_ok = (v + V <= nvox) && (V == 1 || !(nvox & 1));
+  if (!__all_sync(0xffffffffu, vec_ok)) {
+    for (int vv = v; vv < min(v + V, nvox); ++vv) {
       T* o = packed + (size_t)vv * CP;
       o[0] = den[vv];
       for (int k = 0; k < K; ++k) o[1 + k] = sem[(size_t)k * nvox + vv];
@@ -53,10 +56,12 @@ __global__ void __launch_bounds__(kPackThreads) pack_cam_volume_kernel(const T* 
   for (int j = 0; j < 3; ++j) w[1 + K + j] = __ldg(reinterpret_cast<const uint32_t*>(rgb + (size_t)j * nvox + v));
 #pragma unroll
   for (int c = NCH; c < CP; ++c) w[c] = 0u;
-  uint4* out = reinterpret_cast<uint4*>(packed + (size_t)v * CP);
+  // assemble this thread's records (96 contiguous bytes) in registers ...
+  uint4 rec[6];
+  static_assert(CP * sizeof(T) * V == 96, "record staging below assumes 96 bytes per thread");
   if (V == 1) {
 #pragma unroll
-    for (int q = 0; q < CP / 4; ++q) out[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    for (int q = 0; q < 6; ++q) rec[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
   } else {
     // record of voxel v: low halves of consecutive channel words; voxel v+1: high halves
     uint32_t r0[CP / 2], r1[CP / 2];
@@ -66,11 +71,20 @@ __global__ void __launch_bounds__(kPackThreads) pack_cam_volume_kernel(const T* 
       r1[q] = __byte_perm(w[2 * q], w[2 * q + 1], 0x7632);
     }
 #pragma unroll
-    for (int q = 0; q < CP / 8; ++q) out[q] = make_uint4(r0[4 * q], r0[4 * q + 1], r0[4 * q + 2], r0[4 * q + 3]);
-#pragma unroll
-    for (int q = 0; q < CP / 8; ++q)
-      out[CP / 8 + q] = make_uint4(r1[4 * q], r1[4 * q + 1], r1[4 * q + 2], r1[4 * q + 3]);
+    for (int q = 0; q < 3; ++q) {
+      rec[q] = make_uint4(r0[4 * q], r0[4 * q + 1], r0[4 * q + 2], r0[4 * q + 3]);
+      rec[3 + q] = make_uint4(r1[4 * q], r1[4 * q + 1], r1[4 * q + 2], r1[4 * q + 3]);
+    }
   }
+  // ... and bounce them through shared memory so that every 128-bit store instruction of a warp covers
+  // 512 contiguous bytes (16 full sectors) instead of 32 half-written sectors at a 96-byte stride
+  s_rec[threadIdx.x * 6 + 0] = rec[0]; s_rec[threadIdx.x * 6 + 1] = rec[1]; s_rec[threadIdx.x * 6 + 2] = rec[2];
+  s_rec[threadIdx.x * 6 + 3] = rec[3]; s_rec[threadIdx.x * 6 + 4] = rec[4]; s_rec[threadIdx.x * 6 + 5] = rec[5];
+  __syncwarp();
+  const int lane = threadIdx.x & 31, warp0 = threadIdx.x - lane;
+  uint4* out = reinterpret_cast<uint4*>(packed + (size_t)(v - lane * V) * CP);   // the warp's first record
+#pragma unroll
+  for (int q = 0; q < 6; ++q) out[q * 32 + lane] = s_rec[warp0 * 6 + q * 32 + lane];
 }
 
 template <typename T, int CP> struct PackedLoad {

@@ -241,6 +241,30 @@ int vb200_render_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, co
                      int dtype, const VbRenderOut* out, const VbRenderGrad* grad, int branches,
                      void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ---- the callers right after the path (SURVEY §8f "next" rows 2-3) ------------------------------ */
+
+/* nn.UpsamplingBilinear2d(scale_factor=factor), align_corners=True, on `planes` fp32 maps of H x W
+ * (the rendered rgb / semantic / depth maps, BV2:210, 616-626).  Backward is a deterministic gather. */
+int vb200_upsample_bilinear_fwd(const float* d_in, float* d_out, int planes, int H, int W, int factor, void* stream);
+int vb200_upsample_bilinear_bwd(const float* d_gout, float* d_gin, int planes, int H, int W, int factor, void* stream);
+
+/* F.grid_sample(volume, normalise(points), align_corners=True) for point / occupancy queries (BV2:576-609).
+ *   d_vol   (B, channels, vZ, vY, vX) in `dtype`;  d_pts (B or 1, P, 3) fp32 EGO coordinates
+ *   d_rot3x3 optional (B, 9): points are first rotated by bda[:3,:3] (the Occ3D grid, BV2:598-601)
+ *   border         1 = padding_mode='border' (semantic logits), 0 = zeros
+ *   apply_density  1 = sample sigma(volume) instead of the volume (occ_density, BV2:609); needs d_beta
+ *   mask_invalid   1 = multiply by the in-range mask (pts_sdf, BV2:595)
+ *   d_out (B, channels, P) fp32;  d_valid optional (B, P) uint8 in-range mask (BV2:587-589)
+ * Backward scatters with atomicAdd (as ATen does); d_gvol (B, channels, vZ, vY, vX) in `dtype`. */
+size_t vb200_query_points_bwd_workspace(const VbGrid* g, int channels, int P, int dtype);
+int vb200_query_points_fwd(const VbGrid* g, const void* d_vol, int dtype, int channels, const float* d_pts, int P,
+                           int pts_batched, const float* d_rot3x3, int border, int apply_density, int mask_invalid,
+                           const float* d_beta, float* d_out, uint8_t* d_valid, void* stream);
+int vb200_query_points_bwd(const VbGrid* g, const void* d_vol, int dtype, int channels, const float* d_pts, int P,
+                           int pts_batched, const float* d_rot3x3, int border, int apply_density, int mask_invalid,
+                           const float* d_beta, const float* d_gout, void* d_gvol, float* d_gbeta,
+                           void* d_workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -228,3 +228,51 @@ def render_from_mats(conf, buf, mats, density_feature, semantic_logits, voxel_fe
                         mats["ida_mats"][:, 0], mats.get("bda_mat", None))
     geom = torch.nan_to_num(geom, -1e3)
     return volume_rendering(conf, buf, geom, density_feature, semantic_logits, voxel_features, rgb, beta_param)
+
+
+# --------------------------------------------------------------------------------------------
+# callers right after the path
+# --------------------------------------------------------------------------------------------
+def upsample(x, factor):
+    """BV2:210, 616-626: nn.UpsamplingBilinear2d(scale_factor) on (B*N, ch, fH, fW)."""
+    lead = x.shape[:-3]
+    y = torch.nn.UpsamplingBilinear2d(scale_factor=factor)(x.reshape(-1, *x.shape[-3:]))
+    return y.reshape(*lead, *y.shape[-3:])
+
+
+def occ_coords(point_cloud_range=(-40.0, -40.0, -1.0, 40.0, 40.0, 5.4), voxel=(0.4, 0.4, 0.4), dims=(200, 200, 16)):
+    """BV2:295-302 ``create_norm_occ_coords(norm=False)`` -> (200,200,16,3)."""
+    mask = torch.ones(dims, dtype=torch.bool)
+    idx = torch.where(mask)
+    c = torch.cat((idx[0][:, None] * voxel[0] + voxel[0] / 2 + point_cloud_range[0],
+                   idx[1][:, None] * voxel[1] + voxel[1] / 2 + point_cloud_range[1],
+                   idx[2][:, None] * voxel[2] + voxel[2] / 2 + point_cloud_range[2]), dim=1)
+    return c.reshape(*dims, 3)
+
+
+def point_queries(conf, semantic_logits, density_feature, pts, i):
+    """BV2:579-596 for sample i: (pts_logits (P,K), pts_sdf (P,))."""
+    lo, ext = _seg_lo_ext(conf)
+    n = (pts - lo) / ext
+    n = n[None, None, None, :, :]
+    n = n * 2. - 1.
+    valid = (n[..., 0] >= -1.) & (n[..., 0] <= 1.) & (n[..., 1] >= -1.) & (n[..., 1] <= 1.) & \
+            (n[..., 2] >= -1.) & (n[..., 2] <= 1.)
+    logits = F.grid_sample(semantic_logits[[i], ...], n, padding_mode='border', align_corners=True)
+    sdf = F.grid_sample(density_feature[[i], ...], n, align_corners=True)
+    sdf = sdf.squeeze(1) * valid
+    return logits[0, :, 0, 0, :].permute(1, 0), sdf[0, 0, 0, :]
+
+
+def occupancy_queries(conf, semantic_logits, density_feature, bda, beta_param, coords=None):
+    """BV2:597-609 + 647-648: (occ_logits (B,X,Y,Z,K), tanh(occ_density) (B,X,Y,Z,1))."""
+    coords = occ_coords() if coords is None else coords
+    B = semantic_logits.shape[0]
+    lo, ext = _seg_lo_ext(conf)
+    rot = bda[:, :3, :3].view(B, 1, 1, 1, 3, 3)
+    c = (rot @ coords[None, ..., None].expand(B, *coords.shape, 1)).squeeze(-1)
+    n = (c - lo) / ext
+    n = n * 2. - 1.
+    logits = F.grid_sample(semantic_logits, n, padding_mode='border', align_corners=True)
+    dens = F.grid_sample(laplace_density(density_feature, beta_param, conf["sdf_bias"]), n, align_corners=True)
+    return logits.permute(0, 2, 3, 4, 1), dens.permute(0, 2, 3, 4, 1).tanh()

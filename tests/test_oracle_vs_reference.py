@@ -53,3 +53,10 @@ def test_no_bda_branch(ref):
     a = (mats["sensor2ego_mats"][:, 0], mats["intrin_mats"][:, 0], mats["ida_mats"][:, 0], None)
     assert torch.equal(ref.get_pixel(*a), tp.get_pixel(buf, *a))
     assert torch.equal(ref.get_geometry(*a), tp.get_geometry(buf, *a))
+
+
+def test_post_path_restatements(ref):
+    """§8f rows 2-3: the Occ3D coordinate buffer and the x4 upsample module equal the reference's own."""
+    assert torch.equal(ref.occ_coords, tp.occ_coords())
+    x = torch.randn(12, 5, MINI.fH, MINI.fW, generator=torch.Generator().manual_seed(1))
+    assert torch.equal(ref.upsample2d(x), tp.upsample(x, MINI.upsample_factor))

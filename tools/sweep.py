@@ -70,3 +70,27 @@ for fd in ((256, 704), (512, 1408), (1024, 2816)):
         row.append(f"{t:.3f} ; {rays / t / 1e3:.0f} ; {rays * cfg.S / t / 1e6:.2f} (S={cfg.S})")
         del depth, ctx, den, sem, feat, rgb
     print(f"| {fd[0] // 4}x{fd[1] // 4} | " + " | ".join(row) + " |")
+
+
+print("\n## next rows (SURVEY 8f 2-3): x4 upsample of the rendered maps and Occ3D queries, R50 256x704, B=1, fp32\n")
+print("| op | ms | algorithmic MB | GB/s | % of 6551 GB/s |")
+print("|---|---|---|---|---|")
+from vampire_b200.view_transform import LiftRenderB200
+from oracle import torch_path as tp   # coordinates of the Occ3D grid only (checker-side helper)
+cfg = R50_256x704
+mod = LiftRenderB200(**cfg.backbone_kwargs()).cuda()
+maps = torch.randn(1, cfg.num_cams, cfg.cam_channels, cfg.fH, cfg.fW, device="cuda")
+t = timed(lambda: mod.upsample2d(maps))
+mb = maps.numel() * 4 * (1 + 16) / 1e6
+print(f"| upsample2d x4 (22 maps x 6 cams) fwd | {t:.3f} | {mb:.1f} | {mb / t:.0f} | {mb / t / 65.51:.1f} |")
+up = mod.upsample2d(maps)
+gup = torch.randn_like(up)
+t = timed(lambda: ops.upsample_bwd(gup, 4))
+print(f"| upsample2d x4 bwd (gather) | {t:.3f} | {mb:.1f} | {mb / t:.0f} | {mb / t / 65.51:.1f} |")
+cid, prep, depth, ctx, (den, sem, feat, rgb) = setup(cfg, 1, torch.float32)
+coords = tp.occ_coords().cuda()
+bda = torch.eye(4, device="cuda")[None]
+t = timed(lambda: mod.occupancy(sem, den, bda, coords))
+P = coords.numel() // 3
+mb = (P * 3 * 4 + (cfg.K + 1) * P * 4 + (cfg.K + 1) * 16 * 200 * 200 * 4 * 0 + (cfg.K + 1) * cfg.vZ * cfg.vY * cfg.vX * 4 * (16.0 * 0.4 / 8.0) * (80.0 / 102.4) ** 2) / 1e6
+print(f"| occupancy queries (640k pts, 18 logits + sigma) fwd | {t:.3f} | {mb:.1f} | {mb / t:.0f} | {mb / t / 65.51:.1f} |")

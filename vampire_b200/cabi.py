@@ -84,6 +84,13 @@ _PROTOS = {
     "vb200_gather_pool_fwd": (C.c_int, [C.POINTER(VbGrid), C.POINTER(VbTables), _P, _P, C.c_int, _P, _P, _P]),
     "vb200_gather_pool_bwd": (C.c_int, [C.POINTER(VbGrid), C.POINTER(VbTables), _P, _P, _P, C.c_int, _P, _P,
                                         C.c_size_t, _P]),
+    "vb200_upsample_bilinear_fwd": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "vb200_upsample_bilinear_bwd": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "vb200_query_points_bwd_workspace": (C.c_size_t, [C.POINTER(VbGrid), C.c_int, C.c_int, C.c_int]),
+    "vb200_query_points_fwd": (C.c_int, [C.POINTER(VbGrid), _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, C.c_int,
+                                         C.c_int, C.c_int, _P, _P, _P, _P]),
+    "vb200_query_points_bwd": (C.c_int, [C.POINTER(VbGrid), _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, C.c_int,
+                                         C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "vb200_render_fwd_workspace": (C.c_size_t, [C.POINTER(VbGrid), C.c_int]),
     "vb200_render_bwd_workspace": (C.c_size_t, [C.POINTER(VbGrid), C.c_int]),
     "vb200_render_packed_bytes": (C.c_size_t, [C.POINTER(VbGrid), C.c_int]),

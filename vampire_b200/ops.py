@@ -488,3 +488,146 @@ def _render_backward(ctx, grads):
 
 
 torch.library.register_autograd("vampire_b200::render_fwd", _render_backward, setup_context=_render_setup)
+
+
+# =============================================================================================
+# callers right after the path: x4 upsample of the rendered maps, point queries
+# =============================================================================================
+@torch.library.custom_op("vampire_b200::upsample_fwd", mutates_args=())
+def upsample_fwd(x: Tensor, factor: int) -> Tensor:
+    dev = _need_cuda(x)
+    if x.dim() < 2:
+        raise ValueError("upsample: need (..., H, W)")
+    H, W = x.shape[-2:]
+    xin = x.float().contiguous()
+    planes = xin.numel() // (H * W)
+    out = torch.empty(x.shape[:-2] + (H * factor, W * factor), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        for p0 in range(0, planes, 65535):
+            n = min(65535, planes - p0)
+            cabi.check(cabi.lib().vb200_upsample_bilinear_fwd(
+                xin.data_ptr() + p0 * H * W * 4, out.data_ptr() + p0 * H * W * factor * factor * 4, n, H, W, factor,
+                cabi.stream_ptr(dev)))
+    return out
+
+
+@upsample_fwd.register_fake
+def _(x, factor):
+    return x.new_empty(x.shape[:-2] + (x.shape[-2] * factor, x.shape[-1] * factor), dtype=torch.float32)
+
+
+@torch.library.custom_op("vampire_b200::upsample_bwd", mutates_args=())
+def upsample_bwd(gout: Tensor, factor: int) -> Tensor:
+    dev = _need_cuda(gout)
+    OH, OW = gout.shape[-2:]
+    H, W = OH // factor, OW // factor
+    g = gout.float().contiguous()
+    planes = g.numel() // (OH * OW)
+    gin = torch.empty(gout.shape[:-2] + (H, W), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        for p0 in range(0, planes, 65535):
+            n = min(65535, planes - p0)
+            cabi.check(cabi.lib().vb200_upsample_bilinear_bwd(
+                g.data_ptr() + p0 * OH * OW * 4, gin.data_ptr() + p0 * H * W * 4, n, H, W, factor,
+                cabi.stream_ptr(dev)))
+    return gin
+
+
+@upsample_bwd.register_fake
+def _(gout, factor):
+    return gout.new_empty(gout.shape[:-2] + (gout.shape[-2] // factor, gout.shape[-1] // factor), dtype=torch.float32)
+
+
+def _up_setup(ctx, inputs, output):
+    ctx.factor = inputs[1]
+    ctx.in_dtype = inputs[0].dtype
+
+
+def _up_backward(ctx, gout):
+    return upsample_bwd(gout, ctx.factor).to(ctx.in_dtype), None
+
+
+torch.library.register_autograd("vampire_b200::upsample_fwd", _up_backward, setup_context=_up_setup)
+
+
+@torch.library.custom_op("vampire_b200::query_points_fwd", mutates_args=())
+def query_points_fwd(vol: Tensor, pts: Tensor, rot: Optional[Tensor], beta: Optional[Tensor], cfg_id: int,
+                     border: bool, apply_density: bool, mask_invalid: bool) -> Tuple[Tensor, Tensor]:
+    """vol (B,CH,Z,Y,X); pts (B,P,3) or (P,3) ego coordinates -> (out (B,CH,P) fp32, valid (B,P) uint8)."""
+    st = state(cfg_id)
+    cfg = st.cfg
+    dev = _need_cuda(vol, pts, rot, beta)
+    B, CH = vol.shape[:2]
+    if vol.shape[2:] != (cfg.vZ, cfg.vY, cfg.vX):
+        raise ValueError(f"query_points: volume {tuple(vol.shape)} does not match the seg grid")
+    batched = pts.dim() == 3
+    P = pts.shape[-2]
+    pts32 = pts.float().contiguous()
+    vol = vol.contiguous()
+    rot32 = None if rot is None else rot.float().reshape(B, 9).contiguous()
+    beta32 = None if beta is None else beta.detach().reshape(1).float().contiguous()
+    out = torch.empty(B, CH, P, dtype=torch.float32, device=dev)
+    valid = torch.empty(B, P, dtype=torch.uint8, device=dev)
+    g = st.grid(B, True)
+    with torch.cuda.device(dev):
+        cabi.check(cabi.lib().vb200_query_points_fwd(
+            C.byref(g), vol.data_ptr(), cabi.dtype_code(vol.dtype), CH, pts32.data_ptr(), P, int(batched),
+            cabi.ptr(rot32), int(border), int(apply_density), int(mask_invalid), cabi.ptr(beta32), out.data_ptr(),
+            valid.data_ptr(), cabi.stream_ptr(dev)))
+    return out, valid
+
+
+@query_points_fwd.register_fake
+def _(vol, pts, rot, beta, cfg_id, border, apply_density, mask_invalid):
+    B, CH = vol.shape[:2]
+    P = pts.shape[-2]
+    return vol.new_empty(B, CH, P, dtype=torch.float32), vol.new_empty(B, P, dtype=torch.uint8)
+
+
+@torch.library.custom_op("vampire_b200::query_points_bwd", mutates_args=())
+def query_points_bwd(gout: Tensor, vol: Tensor, pts: Tensor, rot: Optional[Tensor], beta: Optional[Tensor],
+                     cfg_id: int, border: bool, apply_density: bool, mask_invalid: bool) -> Tuple[Tensor, Tensor]:
+    st = state(cfg_id)
+    dev = _need_cuda(gout, vol, pts, rot, beta)
+    B, CH = vol.shape[:2]
+    batched = pts.dim() == 3
+    P = pts.shape[-2]
+    pts32 = pts.float().contiguous()
+    vol = vol.contiguous()
+    gout = gout.float().contiguous()
+    rot32 = None if rot is None else rot.float().reshape(B, 9).contiguous()
+    beta32 = None if beta is None else beta.detach().reshape(1).float().contiguous()
+    gvol = torch.empty_like(vol)
+    gbeta = torch.zeros(1, dtype=torch.float32, device=dev)
+    g = st.grid(B, True)
+    lib = cabi.lib()
+    dt = cabi.dtype_code(vol.dtype)
+    ws_bytes = lib.vb200_query_points_bwd_workspace(C.byref(g), CH, P, dt)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        cabi.check(lib.vb200_query_points_bwd(
+            C.byref(g), vol.data_ptr(), dt, CH, pts32.data_ptr(), P, int(batched), cabi.ptr(rot32), int(border),
+            int(apply_density), int(mask_invalid), cabi.ptr(beta32), gout.data_ptr(), gvol.data_ptr(), gbeta.data_ptr(),
+            ws.data_ptr(), ws_bytes, cabi.stream_ptr(dev)))
+    return gvol, gbeta
+
+
+@query_points_bwd.register_fake
+def _(gout, vol, pts, rot, beta, cfg_id, border, apply_density, mask_invalid):
+    return torch.empty_like(vol), vol.new_empty(1, dtype=torch.float32)
+
+
+def _query_setup(ctx, inputs, output):
+    vol, pts, rot, beta, cfg_id, border, apply_density, mask_invalid = inputs
+    ctx.save_for_backward(vol, pts, rot, beta)
+    ctx.args = (cfg_id, border, apply_density, mask_invalid)
+
+
+def _query_backward(ctx, gout, gvalid):
+    vol, pts, rot, beta = ctx.saved_tensors
+    gvol, gbeta = query_points_bwd(gout, vol, pts, rot, beta, *ctx.args)
+    gb = None if beta is None else gbeta.reshape(beta.shape).to(beta.dtype)
+    return gvol, None, None, gb, None, None, None, None
+
+
+torch.library.register_autograd("vampire_b200::query_points_fwd", _query_backward, setup_context=_query_setup)

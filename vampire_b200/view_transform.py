@@ -133,3 +133,28 @@ class LiftRenderB200(nn.Module):
         outs = ops.render_fwd(density_feature, semantic_logits, rgb, voxel_features, self.density.beta, mats,
                               None, self.cfg_id, has_bda, branches)
         return tuple(outs)
+
+    # ---- the callers right after the path ------------------------------------
+    def upsample2d(self, x: Tensor) -> Tensor:
+        """``nn.UpsamplingBilinear2d(scale_factor=upsample_factor)`` (BV2:210) on (..., fH, fW) maps."""
+        return ops.upsample_fwd(x, self.cfg.upsample_factor)
+
+    def query_points(self, semantic_logits: Tensor, density_feature: Tensor, inrange_pts: Tensor):
+        """LiDAR-point queries (BV2:578-596) for ONE sample's points (P,3) against every sample in the
+        batch tensors given: returns (pts_logits (B,P,K) border-padded, pts_sdf (B,P) zero-padded * valid)."""
+        logits, _ = ops.query_points_fwd(semantic_logits, inrange_pts, None, None, self.cfg_id, True, False, False)
+        sdf, _ = ops.query_points_fwd(density_feature, inrange_pts, None, None, self.cfg_id, False, False, True)
+        return logits.permute(0, 2, 1), sdf[:, 0]
+
+    def occupancy(self, semantic_logits: Tensor, density_feature: Tensor, bda_mat: Tensor, occ_coords: Tensor):
+        """Occ3D-grid queries (BV2:597-609, 647-648): occ_coords (X,Y,Z,3) ego coordinates of the
+        200x200x16 grid, rotated per sample by bda[:3,:3].  Returns (occ_logits (B,X,Y,Z,K),
+        tanh(occ_density) (B,X,Y,Z,1)) like the reference's return tuple."""
+        shape = occ_coords.shape[:-1]
+        pts = occ_coords.reshape(-1, 3)
+        rot = bda_mat[:, :3, :3]
+        logits, _ = ops.query_points_fwd(semantic_logits, pts, rot, None, self.cfg_id, True, False, False)
+        dens, _ = ops.query_points_fwd(density_feature, pts, rot, self.density.beta, self.cfg_id, False, True, False)
+        B = semantic_logits.shape[0]
+        return (logits.reshape(B, -1, *shape).permute(0, 2, 3, 4, 1),
+                dens.reshape(B, 1, *shape).permute(0, 2, 3, 4, 1).tanh())

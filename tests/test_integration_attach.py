@@ -24,6 +24,8 @@ def test_attach_preserves_interface_and_state_dict():
     assert bb._vb200_path.density.beta is bb.density.beta          # shared parameter, not a copy
     assert PathConfig.from_backbone_conf(backbone_conf_of(bb)) == MINI
     assert hasattr(bb, "lift_pool") and hasattr(bb, "render")
+    from vampire_b200.view_transform import UpsampleB200
+    assert isinstance(bb.upsample2d, UpsampleB200) and bb.upsample2d.scale_factor == MINI.upsample_factor
 
 
 def test_attached_methods_refuse_cpu_tensors():

@@ -21,7 +21,7 @@ import types
 
 import torch.nn as nn
 
-from .view_transform import LiftRenderB200
+from .view_transform import LiftRenderB200, UpsampleB200
 
 _CONF_KEYS = ("x_bound_seg", "y_bound_seg", "z_bound_seg", "x_bound_det", "y_bound_det", "z_bound_det", "d_bound",
               "final_dim", "downsample_factor", "upsample_factor", "mid_channels", "num_classes", "density_mode",
@@ -62,4 +62,7 @@ def attach(backbone: nn.Module, channels_last_volume: bool = False) -> nn.Module
 
     for fn in (get_geometry, get_pixel, get_voxel_feats, volume_rendering_from_multiple_views, lift_pool, render):
         setattr(backbone, fn.__name__, types.MethodType(fn, backbone))
+    # the x4 upsample of the rendered maps right after the path (BV2:210, 616-626): parameter-free module
+    if hasattr(backbone, "upsample2d") and hasattr(backbone, "upsample_factor"):
+        backbone.upsample2d = UpsampleB200(backbone.upsample_factor)
     return backbone

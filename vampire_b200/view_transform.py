@@ -47,6 +47,17 @@ class LaplaceDensityParam(nn.Module):
         return self.beta.abs() + self.beta_min
 
 
+class UpsampleB200(nn.Module):
+    """Drop-in for the reference's ``self.upsample2d = nn.UpsamplingBilinear2d(scale_factor=f)`` (BV2:210)."""
+
+    def __init__(self, scale_factor: int):
+        super().__init__()
+        self.scale_factor = int(scale_factor)
+
+    def forward(self, x: Tensor) -> Tensor:
+        return ops.upsample_fwd(x, self.scale_factor)
+
+
 class LiftRenderB200(nn.Module):
     def __init__(self, channels_last_volume: bool = False, **backbone_conf):
         """``backbone_conf``: the reference's dict (base_exp.py:40-92); unknown keys are ignored the

@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--field", default="surface", choices=["surface", "random", "empty"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--channels-last", action="store_true",
+                    help="emit the pooled volume in torch.channels_last_3d instead of the reference's NCDHW strides")
     ap.add_argument("--render-group", type=int, default=0, help="samples per pack/march round (0 = all)")
     return ap.parse_args()
 
@@ -204,6 +206,7 @@ def workload_config(args, cfg, batch, dtype):
         "voxel_grid": [cfg.vZ, cfg.vY, cfg.vX], "bev_grid": [cfg.oZ, cfg.oY, cfg.oX],
         "context_channels": cfg.C, "classes": cfg.K, "batch_per_gpu": batch, "features": dtype,
         "density_field": args.field, "ida": "val", "l2": "inputs larger than L2 (no flush needed)",
+        "pooled_volume_layout": "channels_last_3d" if args.channels_last else "NCDHW (reference strides)",
     }
 
 
@@ -273,7 +276,7 @@ def main():
         d, c, den, sem, feat, rgb = dev_in
         if not train:
             with torch.no_grad():
-                vox, _ = ops.lift_pool_fwd(d, c, prep, mod.cfg_id, True, False, False)
+                vox, _ = ops.lift_pool_fwd(d, c, prep, mod.cfg_id, True, args.channels_last, False)
                 rend = ops.render_fwd(den, sem, rgb, feat, beta, prep, None, mod.cfg_id, True, 3)
             return vox, rend
         return train_step(mod, d, c, (den, sem, feat, rgb), prep, cots, bucket)

@@ -7,7 +7,7 @@
 // (SURVEY §7.1 a/d, A.5.6):
 //
 //   plan_pairs<count>   histogram of valid pairs per cell (n, y0, x0)            [int atomics]
-//   scan_cells          exclusive scan -> CSR offsets (one block per sample)
+//   scan_chunks/sums/add exclusive scan -> CSR offsets (chunked 3-pass scan)
 //   plan_pairs<fill>    records ((z0+1) << 21 | voxel) dropped into their cell's segment
 //   sort_cells          warp per cell: rank-sort the segment => order fixed by (z0, voxel)
 //   lift_bwd<colour>    warp per cell, 4 launches over the 2x2 cell colouring so that concurrently
@@ -107,46 +107,82 @@ __global__ void __launch_bounds__(kThreads) plan_pairs_kernel(VbGrid g, VbTables
   }
 }
 
-// ---- exclusive scan of the per-cell counts, one block per sample ------------------------------------
-__global__ void __launch_bounds__(1024) scan_cells_kernel(const int* __restrict__ counts, int* __restrict__ offsets,
-                                                          int nc) {
-  __shared__ int s_warp[32];
-  __shared__ int s_carry;
-  const int b = blockIdx.x;
-  const int* in = counts + (size_t)b * nc;
-  int* out = offsets + (size_t)b * (nc + 1);
+// ---- exclusive scan of the per-cell counts: chunked 3-pass scan (a single block per sample took 63 us) ----
+constexpr int kScanThreads = 1024;
+constexpr int kScanPerThread = 4;
+constexpr int kScanChunk = kScanThreads * kScanPerThread;
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (threadIdx.x == 0) s_carry = 0;
+  int s = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, s, o);
+    if (lane >= o) s += u;
+  }
+  if (lane == 31) s_warp[wid] = s;
   __syncthreads();
-  for (int base = 0; base < nc; base += 1024) {
-    const int i = base + threadIdx.x;
-    const int v = i < nc ? in[i] : 0;
-    int s = v;
+  if (wid == 0) {
+    int w = s_warp[lane];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const int u = __shfl_up_sync(0xffffffffu, s, o);
-      if (lane >= o) s += u;
+      const int u = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += u;
     }
-    if (lane == 31) s_warp[wid] = s;
-    __syncthreads();
-    if (wid == 0) {
-      int w = s_warp[lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int u = __shfl_up_sync(0xffffffffu, w, o);
-        if (lane >= o) w += u;
-      }
-      s_warp[lane] = w;
-    }
-    __syncthreads();
-    const int carry = s_carry;
-    const int excl = carry + (wid ? s_warp[wid - 1] : 0) + s - v;
-    if (i < nc) out[i] = excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
-    __syncthreads();
+    s_warp[lane] = w;
   }
-  if (threadIdx.x == 0) out[nc] = s_carry;
+  __syncthreads();
+  total = s_warp[31];
+  return (wid ? s_warp[wid - 1] : 0) + s - v;
+}
+
+// pass 1: per-chunk exclusive scan + chunk totals.  grid = (chunks, B)
+__global__ void __launch_bounds__(kScanThreads) scan_chunks_kernel(const int* __restrict__ counts, int* __restrict__ offsets,
+                                                                   int* __restrict__ chunk_sums, int nc, int nchunks) {
+  __shared__ int s_warp[32];
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int* in = counts + (size_t)b * nc;
+  int* out = offsets + (size_t)b * (nc + 1);
+  const int base = chunk * kScanChunk + threadIdx.x * kScanPerThread;
+  int v[kScanPerThread], sum = 0;
+#pragma unroll
+  for (int k = 0; k < kScanPerThread; ++k) {
+    v[k] = (base + k < nc) ? in[base + k] : 0;
+    sum += v[k];
+  }
+  int total;
+  int excl = block_exclusive_scan(sum, s_warp, total);
+#pragma unroll
+  for (int k = 0; k < kScanPerThread; ++k) {
+    if (base + k < nc) out[base + k] = excl;
+    excl += v[k];
+  }
+  if (threadIdx.x == 0) chunk_sums[(size_t)b * nchunks + chunk] = total;
+}
+
+// pass 2: exclusive scan of the chunk totals (<= 1024 chunks), one block per sample; also the grand total
+__global__ void __launch_bounds__(kScanThreads) scan_sums_kernel(int* __restrict__ chunk_sums, int* __restrict__ offsets,
+                                                                 int nc, int nchunks) {
+  __shared__ int s_warp[32];
+  const int b = blockIdx.x;
+  int* sums = chunk_sums + (size_t)b * nchunks;
+  const int v = threadIdx.x < nchunks ? sums[threadIdx.x] : 0;
+  int total;
+  const int excl = block_exclusive_scan(v, s_warp, total);
+  if (threadIdx.x < nchunks) sums[threadIdx.x] = excl;
+  if (threadIdx.x == 0) offsets[(size_t)b * (nc + 1) + nc] = total;
+}
+
+// pass 3: add the chunk base.  grid = (chunks, B)
+__global__ void __launch_bounds__(kScanThreads) scan_add_kernel(int* __restrict__ offsets, const int* __restrict__ chunk_sums,
+                                                                int nc, int nchunks) {
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int add = chunk_sums[(size_t)b * nchunks + chunk];
+  int* out = offsets + (size_t)b * (nc + 1);
+  const int base = chunk * kScanChunk + threadIdx.x * kScanPerThread;
+#pragma unroll
+  for (int k = 0; k < kScanPerThread; ++k)
+    if (base + k < nc) out[base + k] += add;
 }
 
 // ---- per-cell rank sort: warp per cell -----------------------------------------------------------------
@@ -364,7 +400,7 @@ __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ src
 size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 
 struct BwdLayout {
-  size_t ctx, counts, offsets, cursor, recs_a, recs_b, gctx, gdepth, total;
+  size_t ctx, counts, offsets, cursor, chunk_sums, recs_a, recs_b, gctx, gdepth, total;
 };
 BwdLayout bwd_layout(const VbGrid* g, bool need_gdepth_ws) {
   const CellDims cd = cell_dims(*g);
@@ -375,6 +411,7 @@ BwdLayout bwd_layout(const VbGrid* g, bool need_gdepth_ws) {
   l.counts = o;  o += align256((size_t)g->B * cd.nc * 4);
   l.offsets = o; o += align256((size_t)g->B * (cd.nc + 1) * 4);
   l.cursor = o;  o += align256((size_t)g->B * cd.nc * 4);
+  l.chunk_sums = o; o += align256((size_t)g->B * 1024 * 4);
   l.recs_a = o;  o += align256((size_t)g->B * g->N * nvox * 4);
   l.recs_b = o;  o += align256((size_t)g->B * g->N * nvox * 4);
   l.gctx = o;    o += align256((size_t)g->B * g->N * HW * kC * 4);
@@ -397,6 +434,7 @@ int launch_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const vo
   int* counts = reinterpret_cast<int*>(ws + l.counts);
   int* offsets = reinterpret_cast<int*>(ws + l.offsets);
   int* cursor = reinterpret_cast<int*>(ws + l.cursor);
+  int* chunk_sums = reinterpret_cast<int*>(ws + l.chunk_sums);
   uint32_t* recs_a = reinterpret_cast<uint32_t*>(ws + l.recs_a);
   uint32_t* recs_b = reinterpret_cast<uint32_t*>(ws + l.recs_b);
   float* gctx_ws = reinterpret_cast<float*>(ws + l.gctx);
@@ -418,7 +456,13 @@ int launch_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const vo
     dim3 vgrid(vb_ceil_div(nvox, kThreads), g->B);
     plan_pairs_kernel<0><<<vgrid, kThreads, 0, st>>>(*g, *t, d_mats, counts, nullptr, nullptr, nullptr);
     VB_LAUNCH_CHECK();
-    scan_cells_kernel<<<g->B, 1024, 0, st>>>(counts, offsets, cd.nc);
+    const int nchunks = vb_ceil_div(cd.nc, kScanChunk);
+    if (nchunks > kScanThreads) return VB200_ERR_ARG;   // > 4 M pixel cells per sample: not a camera feature map
+    scan_chunks_kernel<<<dim3(nchunks, g->B), kScanThreads, 0, st>>>(counts, offsets, chunk_sums, cd.nc, nchunks);
+    VB_LAUNCH_CHECK();
+    scan_sums_kernel<<<g->B, kScanThreads, 0, st>>>(chunk_sums, offsets, cd.nc, nchunks);
+    VB_LAUNCH_CHECK();
+    scan_add_kernel<<<dim3(nchunks, g->B), kScanThreads, 0, st>>>(offsets, chunk_sums, cd.nc, nchunks);
     VB_LAUNCH_CHECK();
     plan_pairs_kernel<1><<<vgrid, kThreads, 0, st>>>(*g, *t, d_mats, nullptr, offsets, cursor, recs_a);
     VB_LAUNCH_CHECK();

@@ -14,8 +14,8 @@
 //   march_bwd          camera branch: re-march + trilinear scatter of the 22 channel gradients into a
 //                      channels-last fp32 volume with 128-bit vector atomics (red.global.add.v4.f32;
 //                      order-dependent in the last bits, tolerance-checked -- SURVEY §7.1 d)
-//   bev_bwd_columns    BEV branch, per column: compositing backward -> dL/d(sampled density feature),
-//                      compositing weights, d beta partials
+//   bev_bwd_partials/  BEV branch, per column: channel-group partial sums of g_c * sample, then the compositing
+//   bev_bwd_composite  backward -> dL/d(sampled density feature), compositing weights, d beta partials
 //   unpack_gather      per INPUT voxel: reads the camera-branch gradient (channels-last), GATHERS the BEV
 //                      branch gradient from the <= 2x2x2 output samples whose stencil covers the voxel
 //                      (deterministic, inverse index tables), writes the four NCDHW gradients
@@ -193,29 +193,30 @@ __global__ void __launch_bounds__(kMarchThreads) march_bwd_kernel(
 }
 
 // ---- BEV branch: per-column compositing backward -------------------------------------------------------------
+// Two stages so that the 22 channel planes are walked by 6 thread groups in parallel (a single thread
+// per column walking all of them left the GPU at 0.3 waves / 14 % issue):
+//   bev_bwd_partials   grid.z = channel group: G_part[grp][l] = sum_{c in grp} g_c v_{l,c}; group 0 also
+//                      samples the density plane (-> S, parked in ds_ws) and adds g_height * mid_l
+//   bev_bwd_composite  G = sum of the partials in fixed group order, then the compositing recurrences
+constexpr int kBevBwdGroup = 4;   // composited channels per group
+
 template <typename T, int K>
-__global__ void __launch_bounds__(kBevBwdThreads) bev_bwd_columns_kernel(
+__global__ void __launch_bounds__(kBevBwdThreads) bev_bwd_partials_kernel(
     VbGrid g, VbTables t, const T* __restrict__ den, const T* __restrict__ sem, const T* __restrict__ rgb,
-    const float* __restrict__ beta_ptr, const float* __restrict__ g_bev_rgb, const float* __restrict__ g_bev_seg,
-    const float* __restrict__ g_bev_height, const float* __restrict__ g_vd, float* __restrict__ wl_ws,
-    float* __restrict__ ds_ws, float* __restrict__ beta_partials) {
+    const float* __restrict__ g_bev_rgb, const float* __restrict__ g_bev_seg, const float* __restrict__ g_bev_height,
+    float* __restrict__ gpart_ws, float* __restrict__ s_ws) {
   __shared__ BevLevel s_lv[kMaxLevels];
-  __shared__ float s_red[8];
-  extern __shared__ float s_col[];            // G[kMaxLevels][threads] | Sf[kMaxLevels][threads]
+  extern __shared__ float s_col[];            // G[kMaxLevels][threads]
   constexpr int TB = kBevBwdThreads;
   float* sG = s_col;
-  float* sS = s_col + kMaxLevels * TB;
   bev_level_table(g, t, s_lv);
-  const int b = blockIdx.y;
-  const int col_raw = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y, grp = blockIdx.z;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
   const int ncol = g.oY * g.oX;
-  const bool live = col_raw < ncol;
-  const int col = live ? col_raw : ncol - 1;
+  if (col >= ncol) return;
   const BevColumn bc = bev_column(g, t, col % g.oX, col / g.oX);
   const size_t nvox = (size_t)g.vZ * g.vY * g.vX;
-  const float beta = fabsf(__ldg(beta_ptr)) + g.beta_min;
   const int tid = threadIdx.x;
-
   auto walk = [&](const T* plane, auto&& sink) {
     float prev_lo = 0.0f;
     int prev_z0 = -1000000;
@@ -228,12 +229,17 @@ __global__ void __launch_bounds__(kBevBwdThreads) bev_bwd_columns_kernel(
       sink(l, L.wz0 * lo + L.wz1 * hi);
     }
   };
-  const float gh = g_bev_height ? __ldg(g_bev_height + (size_t)b * ncol + col) : 0.0f;
-  walk(den + (size_t)b * nvox, [&](int l, float v) {
-    sS[l * TB + tid] = v;
-    sG[l * TB + tid] = gh * __ldg(t.bev_mids + l);
-  });
-  for (int j = 0; j < K + 3; ++j) {
+  if (grp == 0) {
+    const float gh = g_bev_height ? __ldg(g_bev_height + (size_t)b * ncol + col) : 0.0f;
+    walk(den + (size_t)b * nvox, [&](int l, float v) {
+      s_ws[((size_t)b * g.oZ + l) * ncol + col] = v;
+      sG[l * TB + tid] = gh * __ldg(t.bev_mids + l);
+    });
+  } else {
+    for (int l = 0; l < g.oZ; ++l) sG[l * TB + tid] = 0.0f;
+  }
+  const int j0 = grp * kBevBwdGroup, j1 = min(K + 3, j0 + kBevBwdGroup);
+  for (int j = j0; j < j1; ++j) {
     const float* gsrc = j < K ? g_bev_seg : g_bev_rgb;
     if (!gsrc) continue;
     const float gcv = j < K ? __ldg(gsrc + ((size_t)b * K + j) * ncol + col)
@@ -241,32 +247,63 @@ __global__ void __launch_bounds__(kBevBwdThreads) bev_bwd_columns_kernel(
     const T* plane = j < K ? sem + ((size_t)b * K + j) * nvox : rgb + ((size_t)b * 3 + (j - K)) * nvox;
     walk(plane, [&](int l, float v) { sG[l * TB + tid] = fmaf(gcv, v, sG[l * TB + tid]); });
   }
+  float* out = gpart_ws + (((size_t)grp * g.B + b) * g.oZ) * ncol + col;
+  for (int l = 0; l < g.oZ; ++l) out[(size_t)l * ncol] = sG[l * TB + tid];
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) bev_bwd_composite_kernel(
+    VbGrid g, const float* __restrict__ beta_ptr, const float* __restrict__ g_vd, const float* __restrict__ gpart_ws,
+    int ngroups, float* __restrict__ wl_ws, float* __restrict__ ds_ws, float* __restrict__ beta_partials) {
+  __shared__ float s_red[8];
+  const int b = blockIdx.y;
+  const int col_raw = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ncol = g.oY * g.oX;
+  const bool live = col_raw < ncol;
+  const int col = live ? col_raw : ncol - 1;
+  const float beta = fabsf(__ldg(beta_ptr)) + g.beta_min;
+  float G[kMaxLevels], S[kMaxLevels];
+#pragma unroll
+  for (int l = 0; l < kMaxLevels; ++l) {
+    G[l] = 0.0f;
+    S[l] = 0.0f;
+    if (l < g.oZ) {
+      const size_t o = ((size_t)b * g.oZ + l) * ncol + col;
+      S[l] = ds_ws[o];                                   // sampled density feature parked by stage 1
+      for (int grp = 0; grp < ngroups; ++grp) G[l] += __ldg(gpart_ws + (size_t)grp * g.B * g.oZ * ncol + o);
+    }
+  }
   // total = sum_l w_l G_l, then the front-to-back (top-down) recurrences
   float omega = 0.0f, tau = 0.0f;
-  for (int l = 0; l < g.oZ; ++l) {
-    const float sigma = laplace_density(sS[l * TB + tid], g.sdf_bias, beta);
-    const float sd = sigma * g.bev_delta;
-    const float w = (1.0f - expf(-sd)) * expf(-tau);
-    tau += sd;
-    omega = fmaf(w, sG[l * TB + tid], omega);
-    if (live) wl_ws[((size_t)b * g.oZ + l) * ncol + col] = w;
+#pragma unroll
+  for (int l = 0; l < kMaxLevels; ++l) {
+    if (l < g.oZ) {
+      const float sigma = laplace_density(S[l], g.sdf_bias, beta);
+      const float sd = sigma * g.bev_delta;
+      const float w = (1.0f - expf(-sd)) * expf(-tau);
+      tau += sd;
+      omega = fmaf(w, G[l], omega);
+      if (live) wl_ws[((size_t)b * g.oZ + l) * ncol + col] = w;
+    }
   }
   float prefix = 0.0f, dbeta = 0.0f;
   tau = 0.0f;
-  for (int l = 0; l < g.oZ; ++l) {
-    const DensityD dd = density_with_grads(sS[l * TB + tid], g.sdf_bias, beta);
-    const float sd = dd.sigma * g.bev_delta;
-    const float trans = expf(-tau), e_sd = expf(-sd);
-    const float w = (1.0f - e_sd) * trans;
-    const float G = sG[l * TB + tid];
-    prefix = fmaf(w, G, prefix);
-    const float dsd = G * (trans * e_sd) - (omega - prefix);
-    const float dsig = dsd * g.bev_delta + (g_vd ? __ldg(g_vd + ((size_t)b * g.oZ + l) * ncol + col) : 0.0f);
-    if (live) {
-      ds_ws[((size_t)b * g.oZ + l) * ncol + col] = dsig * dd.ds;
-      dbeta = fmaf(dsig, dd.dbeta, dbeta);
+#pragma unroll
+  for (int l = 0; l < kMaxLevels; ++l) {
+    if (l < g.oZ) {
+      const DensityD dd = density_with_grads(S[l], g.sdf_bias, beta);
+      const float sd = dd.sigma * g.bev_delta;
+      const float trans = expf(-tau), e_sd = expf(-sd);
+      const float w = (1.0f - e_sd) * trans;
+      prefix = fmaf(w, G[l], prefix);
+      const float dsd = G[l] * (trans * e_sd) - (omega - prefix);
+      const float dsig = dsd * g.bev_delta + (g_vd ? __ldg(g_vd + ((size_t)b * g.oZ + l) * ncol + col) : 0.0f);
+      if (live) {
+        ds_ws[((size_t)b * g.oZ + l) * ncol + col] = dsig * dd.ds;
+        dbeta = fmaf(dsig, dd.dbeta, dbeta);
+      }
+      tau += sd;
     }
-    tau += sd;
   }
   const float tot = block_sum(dbeta, s_red);
   if (threadIdx.x == 0) beta_partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
@@ -390,7 +427,7 @@ __global__ void beta_reduce_kernel(const float* __restrict__ partials, int n, co
 }
 
 struct BwdLayout {
-  size_t packed, gpacked, wl, ds, tables, partials, total;
+  size_t packed, gpacked, wl, ds, gpart, tables, partials, total;
   int n_bev_blocks, n_march_blocks;
 };
 BwdLayout bwd_layout(const VbGrid* g, int dtype) {
@@ -402,8 +439,9 @@ BwdLayout bwd_layout(const VbGrid* g, int dtype) {
   l.gpacked = o;  o += vb_align256(nvox * cp * 4);
   l.wl = o;       o += vb_align256((size_t)g->B * g->oZ * ncol * 4);
   l.ds = o;       o += vb_align256((size_t)g->B * g->oZ * ncol * 4);
+  l.gpart = o;    o += vb_align256((size_t)vb_ceil_div(g->K + 3, kBevBwdGroup) * g->B * g->oZ * ncol * 4);
   l.tables = o;   o += vb_align256((size_t)(3 * (g->oX + g->oY + g->oZ) + 2 * (g->vX + g->vY + g->vZ)) * 4 + 64);
-  l.n_bev_blocks = vb_ceil_div(ncol, kBevBwdThreads) * g->B;
+  l.n_bev_blocks = vb_ceil_div(ncol, 256) * g->B;
   const int patches = vb_ceil_div(g->fW, kPatchW) * vb_ceil_div(g->fH, kPatchH);
   l.n_march_blocks = vb_ceil_div(patches, kMarchThreads / 32) * g->N;
   l.partials = o; o += vb_align256((size_t)(l.n_bev_blocks + (size_t)l.n_march_blocks * g->B) * 4);
@@ -447,13 +485,14 @@ int launch_render_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
     VbTraceScope tr(VB_K_UNPACK_BEV_BWD, st);
     bev_tables_kernel<<<1, 256, 0, st>>>(*g, *t, bt);
     VB_LAUNCH_CHECK();
-    const size_t smem = (size_t)2 * kMaxLevels * kBevBwdThreads * sizeof(float);
-    auto kern = bev_bwd_columns_kernel<T, K>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return VB200_ERR_CUDA;
-    kern<<<dim3(vb_ceil_div(ncol, kBevBwdThreads), g->B), kBevBwdThreads, smem, st>>>(*g, *t, den, sem, rgb, in->beta, gr->g_bev_rgb,
-                                                                gr->g_bev_seg, gr->g_bev_height, gr->g_voxel_density,
-                                                                wl_ws, ds_ws, partials);
+    const size_t smem = (size_t)kMaxLevels * kBevBwdThreads * sizeof(float);
+    const int ngroups = vb_ceil_div(K + 3, kBevBwdGroup);
+    float* gpart_ws = reinterpret_cast<float*>(ws + l.gpart);
+    bev_bwd_partials_kernel<T, K><<<dim3(vb_ceil_div(ncol, kBevBwdThreads), g->B, ngroups), kBevBwdThreads, smem, st>>>(
+        *g, *t, den, sem, rgb, gr->g_bev_rgb, gr->g_bev_seg, gr->g_bev_height, gpart_ws, ds_ws);
+    VB_LAUNCH_CHECK();
+    bev_bwd_composite_kernel<K><<<dim3(vb_ceil_div(ncol, 256), g->B), 256, 0, st>>>(
+        *g, in->beta, gr->g_voxel_density, gpart_ws, ngroups, wl_ws, ds_ws, partials);
     VB_LAUNCH_CHECK();
     n_partials += l.n_bev_blocks;
   }

@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(256) ctx_to_nhwc_f32_kernel(const T* __restric
 
 // ---- the backward proper -------------------------------------------------------------------------------
 template <typename T, int GOUT_LAYOUT>
-__global__ void __launch_bounds__(kThreads, 3) lift_bwd_kernel(VbGrid g, VbTables t, const float* __restrict__ d_mats,
+__global__ void __launch_bounds__(kThreads, 4) lift_bwd_kernel(VbGrid g, VbTables t, const float* __restrict__ d_mats,
                                                             const T* __restrict__ depth,
                                                             const float* __restrict__ ctx_nhwc,
                                                             const T* __restrict__ gout, const uint64_t* __restrict__ cnt,

@@ -1,0 +1,83 @@
+"""GPU: API robustness of the ops / module -- camera counts, non-contiguous inputs, error behaviour."""
+from dataclasses import replace
+
+import pytest
+import torch
+
+from helpers import Case, assert_close_scaled
+from oracle import torch_path as tp
+
+pytestmark = pytest.mark.gpu
+
+
+def test_four_camera_rig_matches_oracle():
+    from vampire_b200 import ops, synth
+    from vampire_b200.config import MINI
+    from vampire_b200.matrices import prepare_matrices
+    cfg = replace(MINI, num_cams=4)
+    conf = cfg.backbone_kwargs()
+    cid = ops.register_config(cfg)
+    m = synth.make_mats(cfg, 2, "stress", seed=31)
+    prep = prepare_matrices(m["sensor2ego_mats"][:, 0], m["intrin_mats"][:, 0], m["ida_mats"][:, 0], m["bda_mat"])
+    depth, ctx = synth.make_lift_inputs(cfg, 2, seed=31)
+    den, sem, feat, rgb = synth.make_render_inputs(cfg, 2, seed=31)
+    buf = tp.build_buffers(conf)
+    with torch.no_grad():
+        ref_vox = tp.lift_pool(conf, buf, depth, ctx, m)
+        ref = tp.render_from_mats(conf, buf, m, den, sem, feat, rgb, torch.tensor(0.1))
+    vox, _ = ops.lift_pool_fwd(depth.cuda(), ctx.cuda(), prep.cuda(), cid, True, False, False)
+    assert_close_scaled(vox.cpu().numpy(), ref_vox.numpy(), 1e-5, "vox, 4 cameras")
+    outs = ops.render_fwd(den.cuda(), sem.cuda(), rgb.cuda(), feat.cuda(), torch.tensor(0.1, device="cuda"),
+                          prep.cuda(), None, cid, True, 3)
+    for o, r in zip(outs, ref):
+        assert_close_scaled(o.cpu().numpy(), r.numpy(), 1e-5, "render, 4 cameras")
+
+
+def test_non_contiguous_inputs_are_accepted():
+    case = Case("mini_val")
+    from vampire_b200 import ops
+    cid = ops.register_config(case.cfg)
+    depth = case.depth.cuda().permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)   # strided view
+    ctx = case.ctx.cuda().flip(-1).flip(-1)
+    assert not depth.is_contiguous()
+    a, _ = ops.lift_pool_fwd(depth, ctx, case.prep.cuda(), cid, True, False, False)
+    b, _ = ops.lift_pool_fwd(case.depth.cuda(), case.ctx.cuda(), case.prep.cuda(), cid, True, False, False)
+    assert torch.equal(a, b)
+
+
+def test_errors_are_loud():
+    case = Case("mini_val")
+    from vampire_b200 import ops
+    cid = ops.register_config(case.cfg)
+    d, c, p = case.depth.cuda(), case.ctx.cuda(), case.prep.cuda()
+    with pytest.raises(ValueError):
+        ops.lift_pool_fwd(d[:, :, :-1], c, p, cid, True, False, False)          # wrong depth planes
+    with pytest.raises(TypeError):
+        ops.lift_pool_fwd(d, c.half(), p, cid, True, False, False)              # dtype mismatch
+    with pytest.raises(ValueError):
+        ops.lift_pool_fwd(d, c, p[:, :, :5], cid, True, False, False)           # not a prepare_matrices block
+    with pytest.raises(TypeError):
+        ops.lift_pool_fwd(d.double(), c.double(), p, cid, True, False, False)   # unsupported dtype
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.lift_pool_fwd(d.cpu(), c.cpu(), p.cpu(), cid, True, False, False)   # no CPU path
+    den, sem, feat, rgb = (t.cuda() for t in (case.den, case.sem, case.feat, case.rgb))
+    with pytest.raises(ValueError):
+        ops.render_fwd(den, sem[:, :-1], rgb, feat, torch.tensor(0.1, device="cuda"), p, None, cid, True, 3)
+    # forward without saved counts cannot be differentiated
+    dd = d.clone().requires_grad_(True)
+    out, _ = ops.lift_pool_fwd(dd, c, p, cid, True, False, False)
+    with pytest.raises(RuntimeError, match="save_cnt"):
+        out.sum().backward()
+
+
+def test_trace_and_launch_counters():
+    from vampire_b200 import cabi, ops
+    case = Case("mini_val")
+    cid = ops.register_config(case.cfg)
+    n0 = cabi.launch_count()
+    cabi.trace_enable(True)
+    ops.lift_pool_fwd(case.depth.cuda(), case.ctx.cuda(), case.prep.cuda(), cid, True, False, False)
+    tr = cabi.trace_collect()
+    cabi.trace_enable(False)
+    assert cabi.launch_count() - n0 == 2
+    assert set(tr) == {"ctx_to_nhwc", "lift_pool_fwd"} and all(ms > 0 and n == 1 for ms, n in tr.values())

@@ -162,8 +162,8 @@ __global__ void __launch_bounds__(kLiftThreads, 4) lift_pool_fwd_kernel(VbGrid g
   for (int c = 0; c < C; ++c) acc[c] = 0.0f;
   int cams_seen = 0;
   uint64_t zero_cnt = 0;
-  for (int n = 0; n < g.N; ++n) {
-    if (!((cam_mask >> n) & 1u)) continue;
+  for (unsigned todo = cam_mask; todo != 0u; todo &= todo - 1u) {   // only the cameras that survived the warp cull
+    const int n = __ffs(todo) - 1;
     if (cull_codes(n, px, py, pz) != 0u) continue;
     float pix[3];
     project_voxel<false>(s_m + n * VB200_MAT_SLOTS * 16, has_bda, px, py, pz, pix);

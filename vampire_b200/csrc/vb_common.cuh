@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/vb200.h"
 
@@ -89,6 +90,34 @@ __device__ __forceinline__ float sadd(float a, float b) { return __fadd_rn(a, b)
 __device__ __forceinline__ float ssub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float sdiv(float a, float b) { return __fdiv_rn(a, b); }
 
+// x / y for a launch-constant divisor y with r = RN(1/y) precomputed on the host: Markstein's
+// two-step FMA correction (the same sequence __fdiv_rn runs after refining its own reciprocal estimate;
+// with an exactly rounded r and a faithful q1 the result is the correctly rounded quotient, Markstein 1990 /
+// Handbook of Floating-Point Arithmetic thm. 4.x).  Preconditions, checked on the host (vb_div_const):
+// y normal, finite, mantissa not all ones.  x must be 0, NaN, or |x| in [2^-100, FLT_MAX]; the callers'
+// operands are differences against / multiples of O(1..1e3) lattice constants.
+struct VbDivConst {
+  float y, r;
+  int ok;      // 0: fall back to __fdiv_rn
+};
+static inline VbDivConst vb_div_const(float y) {
+  VbDivConst d;
+  d.y = y;
+  d.r = 1.0f / y;
+  uint32_t bits;
+  memcpy(&bits, &y, sizeof(bits));
+  const uint32_t ex = (bits >> 23) & 0xffu, man = bits & 0x7fffffu;
+  d.ok = (ex >= 32u && ex <= 222u && man != 0x7fffffu) ? 1 : 0;   // |y| in [2^-95, 2^95], not 2^k (2 - 2^-23)
+  return d;
+}
+template <bool FAST>
+__device__ __forceinline__ float sdiv_const(float x, const VbDivConst& d) {
+  if (!FAST) return __fdiv_rn(x, d.y);
+  const float q0 = __fmul_rn(x, d.r);
+  const float q1 = __fmaf_rn(__fmaf_rn(-q0, d.y, x), d.r, q0);
+  return __fmaf_rn(__fmaf_rn(-q1, d.y, x), d.r, q1);
+}
+
 // row-major 4x4 (16 floats at M) times 4-vector, ATen native bmm order:
 // acc = 0; acc += M[i][k] * p[k] for k = 0..3, separate multiply / add roundings.
 // SIGNED_ZERO=false drops the leading "0 +" (it only turns a -0 product into +0): value-identical
@@ -125,6 +154,48 @@ __device__ __forceinline__ void project_voxel(const float* __restrict__ M, bool 
   pix[0] = q[0]; pix[1] = q[1]; pix[2] = q[2];
 }
 
+// The same collapse for get_pixel: with ida = 2-D affine (rows 2, 3 = e_z, e_w, zero z-column in rows 0, 1)
+// and homogeneous last rows e_w in K.E^-1 (and bda^-1), the w component is exactly 1 and the third mat-vec is
+// pix = ((I00 u + I01 v) + I03, (I10 u + I11 v) + I13, z): every dropped term is a +-0 product or a x*1.
+// (A non-finite z would differ -- NaN instead of a finite pixel -- but then z itself fails the depth test.)
+// Block-uniform test over all N cameras; call from every thread of the block.
+__device__ __forceinline__ bool block_pixel_affine(const float* s_m, int N, bool has_bda) {
+  bool ok = true;
+  for (int i = threadIdx.x; i < N * 16; i += blockDim.x) {
+    const float* M = s_m + (i >> 4) * VB200_MAT_SLOTS * 16;
+    const int e = i & 15;
+    const float ida = M[2 * 16 + e], ke = M[1 * 16 + e], bi = M[e];
+    if (e == 2 || e == 6) ok = ok && (ida == 0.0f);
+    if (e >= 8) ok = ok && (ida == ((e == 10 || e == 15) ? 1.0f : 0.0f));
+    if (e >= 12) ok = ok && (ke == (e == 15 ? 1.0f : 0.0f)) && (!has_bda || bi == (e == 15 ? 1.0f : 0.0f));
+  }
+  return __syncthreads_and(ok) != 0;
+}
+__device__ __forceinline__ void project_voxel_affine(const float* __restrict__ M, bool has_bda, float x, float y,
+                                                     float z, float (&pix)[3]) {
+  float p[3] = {x, y, z};
+  if (has_bda) {
+    const float* B = M;
+    float q[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+      q[i] = sadd(sadd(sadd(smul(B[i * 4], p[0]), smul(B[i * 4 + 1], p[1])), smul(B[i * 4 + 2], p[2])), B[i * 4 + 3]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) p[i] = q[i];
+  }
+  const float* E = M + 16;
+  float q[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    q[i] = sadd(sadd(sadd(smul(E[i * 4], p[0]), smul(E[i * 4 + 1], p[1])), smul(E[i * 4 + 2], p[2])), E[i * 4 + 3]);
+  const float zc = q[2] < 1e-6f ? 1e-6f : q[2];
+  const float u = sdiv(q[0], zc), v = sdiv(q[1], zc);
+  const float* I = M + 32;
+  pix[0] = sadd(sadd(smul(I[0], u), smul(I[1], v)), I[3]);
+  pix[1] = sadd(sadd(smul(I[4], u), smul(I[5], v)), I[7]);
+  pix[2] = q[2];
+}
+
 // G2 get_geometry for one frustum lattice point (BV2:332-349).
 template <bool SIGNED_ZERO = true>
 __device__ __forceinline__ void frustum_point(const float* __restrict__ M, bool has_bda, float u, float v,
@@ -144,6 +215,45 @@ __device__ __forceinline__ void frustum_point(const float* __restrict__ M, bool 
   xyz[0] = q[0]; xyz[1] = q[1]; xyz[2] = q[2];
 }
 
+// ida^-1 (slot 3) as the dataset builds it (nusc_det_seg_dataset.py:118-146: a 2-D rotation/scale/flip plus a
+// translation in column 3) has rows 2, 3 = e_z, e_w and a zero z-column in rows 0, 1.  Then, with finite
+// lattice values, the first mat-vec of get_geometry collapses EXACTLY (every dropped term is a +-0 product
+// or a x*1): q = (A0, A1, d, 1) with A_i = (m_i0 u + m_i1 v) + m_i3 constant along the ray.  Block-uniform.
+__device__ __forceinline__ bool block_ida_inv_affine(const float* M) {
+  const int i = threadIdx.x;
+  bool ok = true;
+  if (i < 16) {
+    const float m = M[i];
+    if (i == 2 || i == 6) ok = (m == 0.0f);
+    else if (i >= 8) ok = (m == ((i == 10 || i == 15) ? 1.0f : 0.0f));
+  }
+  return __syncthreads_and(ok) != 0;
+}
+// ray constants (A0, A1) of the affine case
+__device__ __forceinline__ void frustum_ray_affine(const float* __restrict__ M, float u, float v, float (&A)[2]) {
+  const float* I = M + 3 * 16;
+  A[0] = sadd(sadd(smul(I[0], u), smul(I[1], v)), I[3]);
+  A[1] = sadd(sadd(smul(I[4], u), smul(I[5], v)), I[7]);
+}
+// G2 for the affine case: identical values to frustum_point<false>
+__device__ __forceinline__ void frustum_point_affine(const float* __restrict__ M, bool has_bda, const float (&A)[2],
+                                                     float d, float (&xyz)[3]) {
+  const float p0 = smul(A[0], d), p1 = smul(A[1], d);
+  const float* E = M + 4 * 16;
+  float q[4];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    q[i] = sadd(sadd(sadd(smul(E[i * 4 + 0], p0), smul(E[i * 4 + 1], p1)), smul(E[i * 4 + 2], d)), E[i * 4 + 3]);
+  if (has_bda) {
+    q[3] = sadd(sadd(sadd(smul(E[12], p0), smul(E[13], p1)), smul(E[14], d)), E[15]);
+    float r[4];
+    mv_strict<false>(M + 5 * 16, q, r);
+    xyz[0] = r[0]; xyz[1] = r[1]; xyz[2] = r[2];
+  } else {
+    xyz[0] = q[0]; xyz[1] = q[1]; xyz[2] = q[2];
+  }
+}
+
 // torch.nan_to_num(x, nan) : nan -> `nan`, +-inf -> +-FLT_MAX
 __device__ __forceinline__ float nan_to_num(float x, float nanv) {
   if (isnan(x)) return nanv;
@@ -157,13 +267,30 @@ struct LiftCoord {
   int x0, y0, z0;
   float ix, iy, iz;  // unnormalised sample position
 };
-__device__ __forceinline__ LiftCoord lift_coord(const VbGrid& g, const float (&pix)[3]) {
+struct VbLiftDiv { VbDivConst a[3]; };   // divisions by img_w_m1, img_h_m1, d_ext
+static inline VbLiftDiv vb_lift_div(const VbGrid* g) {
+  VbLiftDiv d;
+  d.a[0] = vb_div_const(g->img_w_m1);
+  d.a[1] = vb_div_const(g->img_h_m1);
+  d.a[2] = vb_div_const(g->d_ext);
+  return d;
+}
+static inline bool vb_lift_div_ok(const VbLiftDiv& d) { return d.a[0].ok && d.a[1].ok && d.a[2].ok; }
+
+// FAST: only for operands that passed the conservative frustum cull of the fused kernels (finite, O(1e3)
+// pixel coordinates or NaN) -- see sdiv_const.  A |quotient| < 2^-100 may be mis-rounded, but it is then
+// absorbed by the "- 1" that follows.
+template <bool FAST = false>
+__device__ __forceinline__ LiftCoord lift_coord(const VbGrid& g, const float (&pix)[3], const VbLiftDiv* dv = nullptr) {
   LiftCoord c;
   const float x = pix[0], y = pix[1], z = pix[2];
   c.valid = (x > -0.5f) && (x < g.x_hi) && (y > -0.5f) && (y < g.y_hi) && (z > g.d_lo) && (z < g.d_hi);
-  float nx = ssub(smul(2.0f, sdiv(x, g.img_w_m1)), 1.0f);
-  float ny = ssub(smul(2.0f, sdiv(y, g.img_h_m1)), 1.0f);
-  float nz = ssub(smul(2.0f, sdiv(ssub(z, g.d_lo), g.d_ext)), 1.0f);
+  const float qx = FAST ? sdiv_const<true>(x, dv->a[0]) : sdiv(x, g.img_w_m1);
+  const float qy = FAST ? sdiv_const<true>(y, dv->a[1]) : sdiv(y, g.img_h_m1);
+  const float qz = FAST ? sdiv_const<true>(ssub(z, g.d_lo), dv->a[2]) : sdiv(ssub(z, g.d_lo), g.d_ext);
+  float nx = ssub(smul(2.0f, qx), 1.0f);
+  float ny = ssub(smul(2.0f, qy), 1.0f);
+  float nz = ssub(smul(2.0f, qz), 1.0f);
   // torch.clamp(min=-2, max=2) propagates NaN; fminf/fmaxf would not, so select explicitly
   nx = nx < -2.0f ? -2.0f : (nx > 2.0f ? 2.0f : nx);
   ny = ny < -2.0f ? -2.0f : (ny > 2.0f ? 2.0f : ny);
@@ -184,11 +311,24 @@ struct RenderCoord {
   int x0, y0, z0;
   float ix, iy, iz;
 };
-__device__ __forceinline__ RenderCoord render_coord(const VbGrid& g, const float (&p)[3]) {
+struct VbRenderDiv { VbDivConst a[3]; };   // divisions by seg_ext[0..2]
+static inline VbRenderDiv vb_render_div(const VbGrid* g) {
+  VbRenderDiv d;
+  for (int a = 0; a < 3; ++a) d.a[a] = vb_div_const(g->seg_ext[a]);
+  return d;
+}
+static inline bool vb_render_div_ok(const VbRenderDiv& d) { return d.a[0].ok && d.a[1].ok && d.a[2].ok; }
+
+template <bool FAST = false>
+__device__ __forceinline__ RenderCoord render_coord(const VbGrid& g, const float (&p)[3],
+                                                    const VbRenderDiv* dv = nullptr) {
   RenderCoord c;
-  const float gx = ssub(smul(sdiv(ssub(p[0], g.seg_lo[0]), g.seg_ext[0]), 2.0f), 1.0f);
-  const float gy = ssub(smul(sdiv(ssub(p[1], g.seg_lo[1]), g.seg_ext[1]), 2.0f), 1.0f);
-  const float gz = ssub(smul(sdiv(ssub(p[2], g.seg_lo[2]), g.seg_ext[2]), 2.0f), 1.0f);
+  const float qx = FAST ? sdiv_const<true>(ssub(p[0], g.seg_lo[0]), dv->a[0]) : sdiv(ssub(p[0], g.seg_lo[0]), g.seg_ext[0]);
+  const float qy = FAST ? sdiv_const<true>(ssub(p[1], g.seg_lo[1]), dv->a[1]) : sdiv(ssub(p[1], g.seg_lo[1]), g.seg_ext[1]);
+  const float qz = FAST ? sdiv_const<true>(ssub(p[2], g.seg_lo[2]), dv->a[2]) : sdiv(ssub(p[2], g.seg_lo[2]), g.seg_ext[2]);
+  const float gx = ssub(smul(qx, 2.0f), 1.0f);
+  const float gy = ssub(smul(qy, 2.0f), 1.0f);
+  const float gz = ssub(smul(qz, 2.0f), 1.0f);
   c.valid = (gx >= -1.0f) && (gx <= 1.0f) && (gy >= -1.0f) && (gy <= 1.0f) && (gz >= -1.0f) && (gz <= 1.0f);
   c.ix = smul(smul(sadd(gx, 1.0f), 0.5f), (float)(g.vX - 1));   // (g + 1) / 2 == (g + 1) * 0.5f exactly
   c.iy = smul(smul(sadd(gy, 1.0f), 0.5f), (float)(g.vY - 1));
@@ -208,6 +348,14 @@ __device__ __forceinline__ float laplace_density(float s, float bias, float beta
   const float x = s - bias;
   const float sgn = (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f);
   return (1.0f / beta) * (0.5f + 0.5f * sgn * (expf(-fabsf(x) / beta) - 1.0f));
+}
+
+// same with a per-launch reciprocal of beta: |x| * (1/beta) differs from |x| / beta by one rounding (2^-24
+// relative on the exponent t), i.e. by <= t e^-t 2^-24 <= 2.2e-8 absolute on a term that is added to 0.5.
+__device__ __forceinline__ float laplace_density_rcp(float s, float bias, float inv_beta) {
+  const float x = s - bias;
+  const float sgn = (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f);
+  return inv_beta * (0.5f + 0.5f * sgn * (expf(-fabsf(x) * inv_beta) - 1.0f));
 }
 
 // true iff the 4x4 at M is exactly the identity.  mv(I, p) == p for every finite p, so the fused

@@ -61,8 +61,8 @@ __device__ __forceinline__ TriW tri_weights(float ix, float iy, float iz, int x0
 }
 
 // ---- forward: one thread per voxel, loop over cameras ---------------------------------------
-template <typename T, int C, int OUT_LAYOUT>
-__global__ void __launch_bounds__(kLiftThreads, 4) lift_pool_fwd_kernel(VbGrid g, VbTables t,
+template <typename T, int C, int OUT_LAYOUT, bool FASTDIV>
+__global__ void __launch_bounds__(kLiftThreads, 4) lift_pool_fwd_kernel(VbGrid g, VbTables t, VbLiftDiv dv,
                                                                      const float* __restrict__ d_mats,
                                                                      const T* __restrict__ depth,
                                                                      const T* __restrict__ ctx_nhwc,
@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(kLiftThreads, 4) lift_pool_fwd_kernel(VbGrid g
   stage_mats(s_m, d_mats, b, g.N);
   __syncthreads();
   const bool has_bda = (g.has_bda != 0) && !block_is_identity(s_m);   // slot 0 of camera 0 = bda^-1 (same for all cameras)
+  const bool affine = block_pixel_affine(s_m, g.N, has_bda);
   for (int i = threadIdx.x; i < g.N * 16; i += blockDim.x) {
     const int n = i / 16, r = (i % 16) / 4, c = i % 4;
     const float* A = s_m + n * VB200_MAT_SLOTS * 16 + 16;   // K.E^-1
@@ -166,8 +167,9 @@ __global__ void __launch_bounds__(kLiftThreads, 4) lift_pool_fwd_kernel(VbGrid g
     const int n = __ffs(todo) - 1;
     if (cull_codes(n, px, py, pz) != 0u) continue;
     float pix[3];
-    project_voxel<false>(s_m + n * VB200_MAT_SLOTS * 16, has_bda, px, py, pz, pix);
-    const LiftCoord lc = lift_coord(g, pix);
+    if (affine) project_voxel_affine(s_m + n * VB200_MAT_SLOTS * 16, has_bda, px, py, pz, pix);
+    else project_voxel<false>(s_m + n * VB200_MAT_SLOTS * 16, has_bda, px, py, pz, pix);
+    const LiftCoord lc = lift_coord<FASTDIV>(g, pix, &dv);
     if (!lc.valid) continue;  // f = grid_sample * 0: adds nothing to numer nor to the count
     const TriW w = tri_weights(lc.ix, lc.iy, lc.iz, lc.x0, lc.y0, lc.z0);
     const T* dcam = depth + (size_t)(b * g.N + n) * g.D * HW;
@@ -268,12 +270,18 @@ int launch_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, const vo
   }
   dim3 grid(plane_blocks, g->B, vb_ceil_div(g->vZ, zrun));
   VbTraceScope tr(VB_K_LIFT_FWD, st);
-  if (out_layout == VB200_NCDHW)
-    lift_pool_fwd_kernel<T, C, VB200_NCDHW><<<grid, kLiftThreads, 0, st>>>(
-        *g, *t, d_mats, reinterpret_cast<const T*>(d_depth), ctx_nhwc, reinterpret_cast<T*>(d_out), d_cnt, zrun);
-  else
-    lift_pool_fwd_kernel<T, C, VB200_NDHWC><<<grid, kLiftThreads, 0, st>>>(
-        *g, *t, d_mats, reinterpret_cast<const T*>(d_depth), ctx_nhwc, reinterpret_cast<T*>(d_out), d_cnt, zrun);
+  const VbLiftDiv dv = vb_lift_div(g);
+#define VB_LIFT(LAYOUT, FD)                                                                                   \
+  lift_pool_fwd_kernel<T, C, LAYOUT, FD><<<grid, kLiftThreads, 0, st>>>(                                       \
+      *g, *t, dv, d_mats, reinterpret_cast<const T*>(d_depth), ctx_nhwc, reinterpret_cast<T*>(d_out), d_cnt, zrun)
+  if (vb_lift_div_ok(dv)) {
+    if (out_layout == VB200_NCDHW) VB_LIFT(VB200_NCDHW, true);
+    else VB_LIFT(VB200_NDHWC, true);
+  } else {
+    if (out_layout == VB200_NCDHW) VB_LIFT(VB200_NCDHW, false);
+    else VB_LIFT(VB200_NDHWC, false);
+  }
+#undef VB_LIFT
   VB_LAUNCH_CHECK();
   return VB200_OK;
 }

@@ -56,20 +56,29 @@ SideStream* side_stream_for_current_device() {
 }
 
 // ---- R2+R3+R4: camera ray march, one sample (blockIdx.z = sample within this launch) ---------
-template <typename T, int K, bool FROM_MATS>
-__global__ void __launch_bounds__(kMarchThreads, 5) march_fwd_kernel(VbGrid g, VbTables t, const float* __restrict__ d_mats,
+// NANSAFE: the packed volume holds a non-finite value somewhere (flag raised by the pack): keep
+// torch.nan_to_num of the interpolated features (BV2:421) per sample.  Otherwise every interpolated value is a
+// convex combination of finite values, nan_to_num is the identity and the corners are accumulated directly
+// into the ray's channel sums (24 fewer live registers, no per-sample finiteness test).  Both variants are
+// launched back to back; the one whose turn it is not returns at once.
+template <typename T, int K, bool FROM_MATS, bool FASTDIV, bool NANSAFE>
+__global__ void __launch_bounds__(kMarchThreads, 5) march_fwd_kernel(VbGrid g, VbTables t, VbRenderDiv dv,
+                                                                  const float* __restrict__ d_mats,
                                                                   const float* __restrict__ d_geom,
                                                                   const T* __restrict__ packed,
+                                                                  const int* __restrict__ nonfinite_flag,
                                                                   const float* __restrict__ beta_ptr,
                                                                   float* __restrict__ o_rgb, float* __restrict__ o_seg,
                                                                   float* __restrict__ o_depth, int b0) {
   constexpr int CP = packed_channels(K);
+  if ((*nonfinite_flag != 0) != NANSAFE) return;
   __shared__ float s_m[VB200_MAT_SLOTS * 16];
   const int b = b0 + blockIdx.z, n = blockIdx.y;
   for (int i = threadIdx.x; i < VB200_MAT_SLOTS * 16; i += blockDim.x)
     s_m[i] = __ldg(d_mats + (size_t)(b * g.N + n) * VB200_MAT_SLOTS * 16 + i);
   __syncthreads();
   const bool has_bda = (g.has_bda != 0) && !block_is_identity(s_m + 5 * 16);   // slot 5 = bda
+  const bool affine = FROM_MATS && block_ida_inv_affine(s_m + 3 * 16);          // slot 3 = ida^-1
 
   const int patches_x = (g.fW + kPatchW - 1) / kPatchW;
   const int patches_y = (g.fH + kPatchH - 1) / kPatchH;
@@ -88,11 +97,18 @@ __global__ void __launch_bounds__(kMarchThreads, 5) march_fwd_kernel(VbGrid g, V
   const float u = __ldg(t.us + wc), vv = __ldg(t.vs + hc);
   const float* gsrc = FROM_MATS ? nullptr : d_geom + ((size_t)(b * g.N + n) * g.D * HW + (size_t)hc * g.fW + wc) * 3;
 
+  float rayA[2] = {0.0f, 0.0f};
+  if (affine) frustum_ray_affine(s_m, u, vv, rayA);
   auto point = [&](int d, float (&p)[3]) {
     if (FROM_MATS) {
-      frustum_point<false>(s_m, has_bda, u, vv, __ldg(t.ds + d), p);
+      if (affine) frustum_point_affine(s_m, has_bda, rayA, __ldg(t.ds + d), p);
+      else frustum_point<false>(s_m, has_bda, u, vv, __ldg(t.ds + d), p);
+      // BV2:612 nan_to_num: one test guards the per-component fix-up (a non-finite component makes the sum
+      // non-finite; a finite sum that overflows only takes the slow, still exact, path)
+      if (!(fabsf(p[0]) + fabsf(p[1]) + fabsf(p[2]) <= 3.402823466e+38f)) {
 #pragma unroll
-      for (int a = 0; a < 3; ++a) p[a] = nan_to_num(p[a], -1e3f);  // BV2:612
+        for (int a = 0; a < 3; ++a) p[a] = nan_to_num(p[a], -1e3f);
+      }
     } else {
       const float* q = gsrc + (size_t)d * HW * 3;
       p[0] = __ldg(q); p[1] = __ldg(q + 1); p[2] = __ldg(q + 2);
@@ -105,7 +121,8 @@ __global__ void __launch_bounds__(kMarchThreads, 5) march_fwd_kernel(VbGrid g, V
   for (int c = 0; c < K + 3; ++c) ch[c] = 0.0f;
 
   // a masked / out-of-volume sample has feature 0: sigma(0) is a per-launch constant (~2.27e-4)
-  const float sigma_masked = laplace_density(0.0f, g.sdf_bias, beta);
+  const float inv_beta = 1.0f / beta;
+  const float sigma_masked = laplace_density_rcp(0.0f, g.sdf_bias, inv_beta);
   float p0[3], p1[3];
   point(0, p0);
   // A ray is a straight line and the volume a convex box, so once a ray has LEFT the box it never
@@ -139,7 +156,7 @@ __global__ void __launch_bounds__(kMarchThreads, 5) march_fwd_kernel(VbGrid g, V
     point(i + 1, p1);
     const float dx = p1[0] - p0[0], dy = p1[1] - p0[1], dz = p1[2] - p0[2];
     delta = sqrtf(dx * dx + dy * dy + dz * dz);                             // BV2:426
-    const RenderCoord rc = render_coord(g, p0);
+    const RenderCoord rc = render_coord<FROM_MATS && FASTDIV>(g, p0, &dv);
     if (rc.valid) {
       was_valid = true;
     } else if (was_valid && !exited) {
@@ -150,28 +167,43 @@ __global__ void __launch_bounds__(kMarchThreads, 5) march_fwd_kernel(VbGrid g, V
       }
     }
     float sigma = sigma_masked;
-    int cidx[8];
+    const T* cp[4];        // corner rows (y, z) in {0,1}^2 at x0; the x1 corner is `xo` elements further
+    int xo = CP;           // (compile-time CP in the fast variant: an immediate offset)
     float cw[8];
     const bool live = rc.valid && active;
     if (live) {
-      // valid => 0 <= i0 <= size-1, so only the far corner can leave the grid; clamp its address and
-      // zero its weight instead of branching, so that all 8 corner loads issue back to back
-      const float wx[2] = {(float)(rc.x0 + 1) - rc.ix, rc.x0 + 1 < g.vX ? rc.ix - (float)rc.x0 : 0.0f};
-      const float wy[2] = {(float)(rc.y0 + 1) - rc.iy, rc.y0 + 1 < g.vY ? rc.iy - (float)rc.y0 : 0.0f};
-      const float wz[2] = {(float)(rc.z0 + 1) - rc.iz, rc.z0 + 1 < g.vZ ? rc.iz - (float)rc.z0 : 0.0f};
-      const int xs_[2] = {rc.x0, min(rc.x0 + 1, g.vX - 1)};
-      const int ys_[2] = {rc.y0, min(rc.y0 + 1, g.vY - 1)};
-      const int zs_[2] = {rc.z0, min(rc.z0 + 1, g.vZ - 1)};
+      // valid => 0 <= i0 <= size-1, so only the far corner can leave the grid (when i == size-1 exactly).
+      int x0 = rc.x0, y0 = rc.y0, z0 = rc.z0;
+      long long sy, sz;
+      float wx[2], wy[2], wz[2];
+      if (!NANSAFE) {
+        // All values are finite here, so a zero-weight corner may be ANY in-grid voxel: shift the base one
+        // voxel inwards instead of clamping the far corner (weights become (0, 1) exactly), which makes the
+        // eight corner offsets launch constants: no clamps, no selects, immediate x offset.  Needs every
+        // grid dimension >= 2 (the launcher routes thinner grids to the NANSAFE variant).
+        x0 = min(x0, g.vX - 2); y0 = min(y0, g.vY - 2); z0 = min(z0, g.vZ - 2);
+        wx[1] = rc.ix - (float)x0; wy[1] = rc.iy - (float)y0; wz[1] = rc.iz - (float)z0;
+        wx[0] = 1.0f - wx[1]; wy[0] = 1.0f - wy[1]; wz[0] = 1.0f - wz[1];
+        sy = (long long)g.vX * CP; sz = (long long)g.vY * g.vX * CP;
+      } else {
+        // clamp the far corner's address and zero its weight instead of branching
+        wx[0] = (float)(x0 + 1) - rc.ix; wx[1] = x0 + 1 < g.vX ? rc.ix - (float)x0 : 0.0f;
+        wy[0] = (float)(y0 + 1) - rc.iy; wy[1] = y0 + 1 < g.vY ? rc.iy - (float)y0 : 0.0f;
+        wz[0] = (float)(z0 + 1) - rc.iz; wz[1] = z0 + 1 < g.vZ ? rc.iz - (float)z0 : 0.0f;
+        xo = x0 + 1 < g.vX ? CP : 0; sy = y0 + 1 < g.vY ? g.vX * CP : 0; sz = z0 + 1 < g.vZ ? g.vY * g.vX * CP : 0;
+      }
+      cp[0] = vol + ((z0 * g.vY + y0) * g.vX + x0) * CP;
+      cp[1] = cp[0] + sy; cp[2] = cp[0] + sz; cp[3] = cp[1] + sz;
       // phase 1: density channel only (8 scalar loads) -> sigma, alpha
       float s0 = 0.0f;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int cx = q & 1, cy = (q >> 1) & 1, cz = q >> 2;
         cw[q] = wx[cx] * wy[cy] * wz[cz];
-        cidx[q] = ((zs_[cz] * g.vY + ys_[cy]) * g.vX + xs_[cx]) * CP;
-        s0 = fmaf(cw[q], VbType<T>::ld(vol + cidx[q]), s0);
+        s0 = fmaf(cw[q], VbType<T>::ld(cp[cy + 2 * cz] + (cx ? xo : 0)), s0);
       }
-      sigma = laplace_density(nan_to_num(s0, 0.0f), g.sdf_bias, beta);         // BV2:421, 423
+      if (NANSAFE) s0 = nan_to_num(s0, 0.0f);                                  // BV2:421
+      sigma = laplace_density_rcp(s0, g.sdf_bias, inv_beta);                   // BV2:423
     }
     const float sd = sigma * delta;                                           // BV2:429
     const float wgt = (1.0f - expf(-sd)) * trans;                           // BV2:430-434
@@ -179,14 +211,20 @@ __global__ void __launch_bounds__(kMarchThreads, 5) march_fwd_kernel(VbGrid g, V
     dep = fmaf(wgt, __ldg(t.mids + i), dep);
     // phase 2: the 21 value channels, only where they can contribute.  In free space alpha = 1 - exp(-sd)
     // is exactly 0.0f in fp32 (the reference's too), so w * v == 0 exactly: skipping the fetch is bit-neutral.
-    if (live && wgt != 0.0f) {
+    if (!NANSAFE) {
+      if (live && wgt != 0.0f) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          PackedLoad<T, CP>::template fma_values<K + 3>(cp[(q >> 1)] + ((q & 1) ? xo : 0), cw[q] * wgt, ch);
+      }
+    } else if (live && wgt != 0.0f) {
       float v[CP];
 #pragma unroll
       for (int c = 0; c < CP; ++c) v[c] = 0.0f;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) PackedLoad<T, CP>::fma_corner(vol + cidx[q], cw[q], v);
+      for (int q = 0; q < 8; ++q) PackedLoad<T, CP>::fma_corner(cp[(q >> 1)] + ((q & 1) ? xo : 0), cw[q], v);
       // torch.nan_to_num (BV2:421): any NaN/inf channel makes the channel sum non-finite, so one
-      // test guards the per-channel fix-up (volumes are finite in practice)
+      // test guards the per-channel fix-up
       float chk = 0.0f;
 #pragma unroll
       for (int c = 1; c < K + 4; ++c) chk += v[c];
@@ -392,76 +430,200 @@ __device__ __forceinline__ void quad_zrow(const VbGrid& g, const BevQuadX& q, co
   if (y0 + 1 >= 0 && y0 + 1 < g.vY) quad_row<T, MODE>(g, q, zr + (y0 + 1) * g.vX, lane, wy1, out);
 }
 
-// kBevNC channel planes of one kind per thread: their row loads are issued together (the kernel is
-// latency-bound -- ncu: long_scoreboard -- so memory-level parallelism is what buys speed here).
-constexpr int kBevNC = 1;
+// ---- fast path (MODE 0 / 1): per input z-row ONE xy-interpolated 4-vector per channel -----------------------
+// A thread owns 4 output columns and loops over a chunk of channel planes, so the coordinate prologue
+// (5 strict axis_coord's with IEEE divisions) is paid once per ~8 channels instead of once per channel.
+// Per channel and level it fetches at most one new z-row: 2 vector loads (rows y0, y0+1) + 2 scalar edge
+// loads (the 5th column), combined with 16 pre-multiplied xy weights (4 FMAs per column).  The row of the
+// NEXT level is requested before the current level is composited, so two rows are always in flight.
+template <typename T> struct Raw4;                       // raw (un-widened) 4 consecutive elements
+template <> struct Raw4<float> { using type = float4; };
+template <> struct Raw4<__nv_bfloat16> { using type = uint2; };
+template <> struct Raw4<__half> { using type = uint2; };
 
-template <typename T, int K, int C, int MODE>
-__device__ __forceinline__ void bev_quad_channels(const VbGrid& g, const BevLevel* __restrict__ lv, const BevQuadX& q,
-                                                  const T* __restrict__ plane, size_t plane_stride, int nch, int y0,
-                                                  float wy0, float wy1, int lane, bool live,
-                                                  const float* __restrict__ wl, float* __restrict__ o_map,
-                                                  T* __restrict__ o_feat, size_t out_stride, int ncol) {
-  float prev_lo[kBevNC][4], acc[kBevNC][4];
+template <typename T> __device__ __forceinline__ void widen4(const typename Raw4<T>::type& r, float (&o)[4]);
+template <> __device__ __forceinline__ void widen4<float>(const float4& r, float (&o)[4]) {
+  o[0] = r.x; o[1] = r.y; o[2] = r.z; o[3] = r.w;
+}
+template <> __device__ __forceinline__ void widen4<__nv_bfloat16>(const uint2& r, float (&o)[4]) {
+  o[0] = __uint_as_float(r.x << 16); o[1] = __uint_as_float(r.x & 0xffff0000u);
+  o[2] = __uint_as_float(r.y << 16); o[3] = __uint_as_float(r.y & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void widen4<__half>(const uint2& r, float (&o)[4]) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
+
+struct BevQuadFast {
+  int off_a, off_b;        // element offsets of (row y0, column ox0) / (row y0+1, column ox0) inside a z-row (rows clamped)
+  int off_ea, off_eb;      // ... of the 5th column (MODE 1: ox0+4, MODE 0: ox0-1; clamped)
+  float w[4][4];           // [column][a0, a1, b0, b1] = wy * wx, zero where the tap leaves the grid
+};
+
+template <typename T> struct RawRow {
+  typename Raw4<T>::type a, b;
+  T ea, eb;
+};
+
+template <typename T>
+__device__ __forceinline__ RawRow<T> bev_load_row(const T* __restrict__ plane, const BevQuadFast& q, int zoff) {
+  RawRow<T> r;
+  using V = typename Raw4<T>::type;
+  r.a = __ldg(reinterpret_cast<const V*>(plane + (zoff + q.off_a)));
+  r.b = __ldg(reinterpret_cast<const V*>(plane + (zoff + q.off_b)));
+  r.ea = __ldg(plane + (zoff + q.off_ea));
+  r.eb = __ldg(plane + (zoff + q.off_eb));
+  return r;
+}
+
+template <typename T> __device__ __forceinline__ float widen1(T v);
+template <> __device__ __forceinline__ float widen1<float>(float v) { return v; }
+template <> __device__ __forceinline__ float widen1<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float widen1<__half>(__half v) { return __half2float(v); }
+
+template <typename T, int MODE>
+__device__ __forceinline__ void bev_finish_row(const RawRow<T>& r, const BevQuadFast& q, float (&out)[4]) {
+  float va[4], vb[4];
+  widen4<T>(r.a, va);
+  widen4<T>(r.b, vb);
+  const float ea = widen1<T>(r.ea), eb = widen1<T>(r.eb);
 #pragma unroll
-  for (int k = 0; k < kBevNC; ++k)
+  for (int c = 0; c < 4; ++c) {
+    const float a0 = MODE == 1 ? va[c] : (c > 0 ? va[c > 0 ? c - 1 : 0] : ea);
+    const float a1 = MODE == 1 ? (c < 3 ? va[c < 3 ? c + 1 : 3] : ea) : va[c];
+    const float b0 = MODE == 1 ? vb[c] : (c > 0 ? vb[c > 0 ? c - 1 : 0] : eb);
+    const float b1 = MODE == 1 ? (c < 3 ? vb[c < 3 ? c + 1 : 3] : eb) : vb[c];
+    out[c] = fmaf(q.w[c][0], a0, fmaf(q.w[c][1], a1, fmaf(q.w[c][2], b0, q.w[c][3] * b1)));
+  }
+}
+
+struct BevLevelX {       // per level: row offsets of z0 / z0+1 inside a plane, their validity, reuse flag
+  int zoff, zoff_hi;     // z * vY * vX (z clamped so the address is always valid)
+  float wz0, wz1;        // zeroed when the row is outside the grid (zeros padding)
+  int flags;             // bit0: row z0+1 of this level == row z0 of the previous level (reuse it)
+                         // bit1: row z0+1 is inside the grid      bit2: row z0 is inside the grid
+};
+
+// One channel plane, all levels, MODE 0/1 (mode1, warp-uniform).  MAP (block-uniform): composite with the
+// level weights into a (oY,oX) map; otherwise store the resampled rows as T.
+template <typename T, bool MAP>
+__device__ __forceinline__ void bev_fast_channel(const BevLevelX* __restrict__ lv, int oZ, const bool mode1,
+                                                 const BevQuadFast& q, const T* __restrict__ plane, bool live,
+                                                 const float* __restrict__ wl, float* __restrict__ o_map,
+                                                 T* __restrict__ o_feat, int ncol) {
+  float prev[4] = {0.0f, 0.0f, 0.0f, 0.0f}, acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  BevLevelX L = lv[0];
+  RawRow<T> nxt = bev_load_row<T>(plane, q, L.zoff);
+  const float4* wp = reinterpret_cast<const float4*>(wl);
+  const int wstep = ncol >> 2;                             // ncol % 4 == 0 (oX % 4 == 0)
+#pragma unroll 2
+  for (int l = 0; l < oZ; ++l, wp += wstep, o_feat += ncol) {
+    float hi[4], lo[4];
+    if (L.flags & 1) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { prev_lo[k][c] = 0.0f; acc[k][c] = 0.0f; }
+      for (int c = 0; c < 4; ++c) hi[c] = prev[c];
+    } else if (L.flags & 2) {
+      const RawRow<T> h = bev_load_row<T>(plane, q, L.zoff_hi);
+      if (mode1) bev_finish_row<T, 1>(h, q, hi);
+      else bev_finish_row<T, 0>(h, q, hi);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) hi[c] = 0.0f;
+    }
+    const RawRow<T> cur = nxt;
+    const BevLevelX Ln = lv[l + 1 < oZ ? l + 1 : l];
+    nxt = bev_load_row<T>(plane, q, Ln.zoff);              // in flight while this level is composited
+    if (mode1) bev_finish_row<T, 1>(cur, q, lo);
+    else bev_finish_row<T, 0>(cur, q, lo);
+    if (!(L.flags & 4)) {                                  // row z0 outside the grid: zeros padding (uniform)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) lo[c] = 0.0f;
+    }
+    float v[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      v[c] = fmaf(L.wz1, hi[c], L.wz0 * lo[c]);
+      prev[c] = lo[c];
+    }
+    if (MAP) {                                                                              // BV2:459-460
+      const float4 w = __ldg(wp);
+      acc[0] = fmaf(w.x, v[0], acc[0]); acc[1] = fmaf(w.y, v[1], acc[1]);
+      acc[2] = fmaf(w.z, v[2], acc[2]); acc[3] = fmaf(w.w, v[3], acc[3]);
+    } else if (live) {                                                                      // BV2:448
+      Vec4Load<T>::st(o_feat, v);
+    }
+    L = Ln;
+  }
+  if (MAP && live) *reinterpret_cast<float4*>(o_map) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
+// generic fallback (MODE 2): scalar gathers, exact for any det grid
+template <typename T, int K, int C>
+__device__ __forceinline__ void bev_quad_channel_generic(const VbGrid& g, const BevLevel* __restrict__ lv,
+                                                         const BevQuadX& q, const T* __restrict__ plane, int y0,
+                                                         float wy0, float wy1, int lane, bool live,
+                                                         const float* __restrict__ wl, float* __restrict__ o_map,
+                                                         T* __restrict__ o_feat, int ncol) {
+  float prev_lo[4] = {0.0f, 0.0f, 0.0f, 0.0f}, acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   int prev_z0 = -1000000;
   for (int l = 0; l < g.oZ; ++l) {
     const BevLevel L = lv[l];
-    float hi[kBevNC][4], lo[kBevNC][4];
-    const bool reuse = (L.z0 + 1 == prev_z0);
+    float hi[4], lo[4];
+    if (L.z0 + 1 == prev_z0) {
 #pragma unroll
-    for (int k = 0; k < kBevNC; ++k) {
-      const T* pk = plane + (size_t)(k < nch ? k : 0) * plane_stride;
-      if (reuse) {
-#pragma unroll
-        for (int c = 0; c < 4; ++c) hi[k][c] = prev_lo[k][c];
-      } else {
-        quad_zrow<T, MODE>(g, q, pk, L.z0 + 1, y0, wy0, wy1, lane, hi[k]);
-      }
-      quad_zrow<T, MODE>(g, q, pk, L.z0, y0, wy0, wy1, lane, lo[k]);
+      for (int c = 0; c < 4; ++c) hi[c] = prev_lo[c];
+    } else {
+      quad_zrow<T, 2>(g, q, plane, L.z0 + 1, y0, wy0, wy1, lane, hi);
     }
+    quad_zrow<T, 2>(g, q, plane, L.z0, y0, wy0, wy1, lane, lo);
     prev_z0 = L.z0;
     float4 w = make_float4(0, 0, 0, 0);
     if (o_map && live) w = __ldg(reinterpret_cast<const float4*>(wl + (size_t)l * ncol));
+    float v[4];
 #pragma unroll
-    for (int k = 0; k < kBevNC; ++k) {
-      float v[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        v[c] = fmaf(L.wz1, hi[k][c], L.wz0 * lo[k][c]);
-        prev_lo[k][c] = lo[k][c];
-      }
-      if (o_map) {                                                                          // BV2:459-460
-        acc[k][0] = fmaf(w.x, v[0], acc[k][0]); acc[k][1] = fmaf(w.y, v[1], acc[k][1]);
-        acc[k][2] = fmaf(w.z, v[2], acc[k][2]); acc[k][3] = fmaf(w.w, v[3], acc[k][3]);
-      } else if (live && k < nch) {                                                         // BV2:448
-        Vec4Load<T>::st(o_feat + (size_t)k * out_stride + (size_t)l * ncol, v);
-      }
+    for (int c = 0; c < 4; ++c) {
+      v[c] = fmaf(L.wz1, hi[c], L.wz0 * lo[c]);
+      prev_lo[c] = lo[c];
+    }
+    if (o_map) {
+      acc[0] = fmaf(w.x, v[0], acc[0]); acc[1] = fmaf(w.y, v[1], acc[1]);
+      acc[2] = fmaf(w.z, v[2], acc[2]); acc[3] = fmaf(w.w, v[3], acc[3]);
+    } else if (live) {
+      Vec4Load<T>::st(o_feat + (size_t)l * ncol, v);
     }
   }
-  if (o_map && live) {
-#pragma unroll
-    for (int k = 0; k < kBevNC; ++k)
-      if (k < nch)
-        *reinterpret_cast<float4*>(o_map + (size_t)k * out_stride) = make_float4(acc[k][0], acc[k][1], acc[k][2], acc[k][3]);
-  }
+  if (o_map && live) *reinterpret_cast<float4*>(o_map) = make_float4(acc[0], acc[1], acc[2], acc[3]);
 }
 
-__host__ __device__ constexpr int bev_groups(int K, int C) {
-  return (K + kBevNC - 1) / kBevNC + (3 + kBevNC - 1) / kBevNC + (C + kBevNC - 1) / kBevNC;
-}
+// channel chunks: the K+3 composited planes and the C feature planes are split into chunks of <= 8 planes,
+// one chunk per blockIdx.y
+__host__ __device__ constexpr int bev_chunks(int n) { return (n + 7) / 8; }
+__host__ __device__ constexpr int bev_chunk_len(int n) { return (n + bev_chunks(n) - 1) / bev_chunks(n); }
+__host__ __device__ constexpr int bev_groups(int K, int C) { return bev_chunks(K + 3) + bev_chunks(C); }
 
 template <typename T, int K, int C>
-__global__ void __launch_bounds__(64, 20) bev_channels_vec4_kernel(VbGrid g, VbTables t, const T* __restrict__ sem,
+__global__ void __launch_bounds__(64, 16) bev_channels_vec4_kernel(VbGrid g, VbTables t, const T* __restrict__ sem,
                                                                const T* __restrict__ rgb, const T* __restrict__ feat,
                                                                const float* __restrict__ wl_ws,
                                                                float* __restrict__ o_rgb, float* __restrict__ o_seg,
                                                                T* __restrict__ o_feat) {
   __shared__ BevLevel s_lv[kMaxLevels];
+  __shared__ BevLevelX s_lx[kMaxLevels];
   bev_level_table(g, t, s_lv);
+  if (threadIdx.x < g.oZ) {
+    const int l = threadIdx.x;
+    const BevLevel L = s_lv[l];
+    BevLevelX X;
+    const bool in0 = L.z0 >= 0 && L.z0 < g.vZ, in1 = L.z0 + 1 >= 0 && L.z0 + 1 < g.vZ;
+    X.zoff = min(max(L.z0, 0), g.vZ - 1) * g.vY * g.vX;
+    X.zoff_hi = min(max(L.z0 + 1, 0), g.vZ - 1) * g.vY * g.vX;
+    X.wz0 = in0 ? L.wz0 : 0.0f;
+    X.wz1 = in1 ? L.wz1 : 0.0f;
+    X.flags = ((l > 0 && L.z0 + 1 == s_lv[l - 1].z0) ? 1 : 0) | (in1 ? 2 : 0) | (in0 ? 4 : 0);
+    s_lx[l] = X;
+  }
+  __syncthreads();
   const int b = blockIdx.z, grp = blockIdx.y;
   const int tiles_x = (g.oX + 255) / 256;
   const int oy = blockIdx.x / tiles_x;
@@ -482,45 +644,63 @@ __global__ void __launch_bounds__(64, 20) bev_channels_vec4_kernel(VbGrid g, VbT
   int y0;
   float wy0, wy1;
   axis_coord(__ldg(t.oys + oy), g.seg_lo[1], g.seg_ext[1], g.vY, y0, wy0, wy1);
-  const bool w1 = __all_sync(0xffffffffu, all1), w0 = __all_sync(0xffffffffu, all0);   // shuffles need one path per warp
+  const bool w1 = __all_sync(0xffffffffu, all1), w0 = __all_sync(0xffffffffu, all0);   // one path per warp
 
   const int ncol = g.oY * g.oX;
   const size_t nvox = (size_t)g.vZ * g.vY * g.vX;
   const int col0 = oy * g.oX + q.ox0;
-  constexpr int GS = (K + kBevNC - 1) / kBevNC, GR = (3 + kBevNC - 1) / kBevNC;
-  const T* plane;
-  float* o_map = nullptr;
-  T* o_f = nullptr;
-  int nch;
-  size_t out_stride;
-  if (grp < GS) {
-    const int c0 = grp * kBevNC;
-    nch = min(kBevNC, K - c0);
-    plane = sem + ((size_t)b * K + c0) * nvox;
-    o_map = o_seg + ((size_t)b * K + c0) * ncol + col0;
-    out_stride = ncol;
-  } else if (grp < GS + GR) {
-    const int c0 = (grp - GS) * kBevNC;
-    nch = min(kBevNC, 3 - c0);
-    plane = rgb + ((size_t)b * 3 + c0) * nvox;
-    o_map = o_rgb + ((size_t)b * 3 + c0) * ncol + col0;
-    out_stride = ncol;
-  } else {
-    const int c0 = (grp - GS - GR) * kBevNC;
-    nch = min(kBevNC, C - c0);
-    plane = feat + ((size_t)b * C + c0) * nvox;
-    o_f = o_feat + ((size_t)b * C + c0) * g.oZ * ncol + col0;
-    out_stride = (size_t)g.oZ * ncol;
-  }
+  constexpr int NM = K + 3, GM = bev_chunks(NM), LM = bev_chunk_len(NM), LF = bev_chunk_len(C);
+  const bool is_map = grp < GM;
+  const int c_begin = is_map ? grp * LM : (grp - GM) * LF;
+  const int c_end = is_map ? min(c_begin + LM, NM) : min(c_begin + LF, C);
   const float* wl = wl_ws + (size_t)b * g.oZ * ncol + col0;
-  if (w1) bev_quad_channels<T, K, C, 1>(g, s_lv, q, plane, nvox, nch, y0, wy0, wy1, lane, live, wl, o_map, o_f, out_stride, ncol);
-  else if (w0) bev_quad_channels<T, K, C, 0>(g, s_lv, q, plane, nvox, nch, y0, wy0, wy1, lane, live, wl, o_map, o_f, out_stride, ncol);
-  else bev_quad_channels<T, K, C, 2>(g, s_lv, q, plane, nvox, nch, y0, wy0, wy1, lane, live, wl, o_map, o_f, out_stride, ncol);
+
+  auto planes = [&](int j, const T*& plane, float*& o_map, T*& o_f) {
+    o_map = nullptr;
+    o_f = nullptr;
+    if (is_map) {
+      plane = j < K ? sem + ((size_t)b * K + j) * nvox : rgb + ((size_t)b * 3 + (j - K)) * nvox;
+      o_map = (j < K ? o_seg + ((size_t)b * K + j) * ncol : o_rgb + ((size_t)b * 3 + (j - K)) * ncol) + col0;
+    } else {
+      plane = feat + ((size_t)b * C + j) * nvox;
+      o_f = o_feat + ((size_t)b * C + j) * g.oZ * ncol + col0;
+    }
+  };
+  if (w1 || w0) {
+    BevQuadFast f;
+    const bool y0in = y0 >= 0 && y0 < g.vY, y1in = y0 + 1 >= 0 && y0 + 1 < g.vY;
+    const int ya = min(max(y0, 0), g.vY - 1), yb = min(max(y0 + 1, 0), g.vY - 1);
+    const int xe = w1 ? min(q.ox0 + 4, g.vX - 1) : max(q.ox0 - 1, 0);
+    f.off_a = ya * g.vX + q.ox0; f.off_b = yb * g.vX + q.ox0;
+    f.off_ea = ya * g.vX + xe;   f.off_eb = yb * g.vX + xe;
+    const float ya_w = y0in ? wy0 : 0.0f, yb_w = y1in ? wy1 : 0.0f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      f.w[c][0] = ya_w * q.wx0[c]; f.w[c][1] = ya_w * q.wx1[c];
+      f.w[c][2] = yb_w * q.wx0[c]; f.w[c][3] = yb_w * q.wx1[c];
+    }
+    for (int j = c_begin; j < c_end; ++j) {
+      const T* plane;
+      float* o_map;
+      T* o_f;
+      planes(j, plane, o_map, o_f);
+      if (is_map) bev_fast_channel<T, true>(s_lx, g.oZ, w1, f, plane, live, wl, o_map, o_f, ncol);
+      else bev_fast_channel<T, false>(s_lx, g.oZ, w1, f, plane, live, wl, o_map, o_f, ncol);
+    }
+  } else {
+    for (int j = c_begin; j < c_end; ++j) {
+      const T* plane;
+      float* o_map;
+      T* o_f;
+      planes(j, plane, o_map, o_f);
+      bev_quad_channel_generic<T, K, C>(g, s_lv, q, plane, y0, wy0, wy1, lane, live, wl, o_map, o_f, ncol);
+    }
+  }
 }
 
-size_t bev_weight_bytes(const VbGrid* g) {
+size_t bev_weight_bytes(const VbGrid* g) {   // + one 256-byte slot at the end: the pack's non-finite flag
   const size_t n = (size_t)g->B * g->oZ * g->oY * g->oX * sizeof(float);
-  return (n + 255) & ~(size_t)255;
+  return ((n + 255) & ~(size_t)255) + 256;
 }
 
 size_t packed_bytes_per_sample(const VbGrid* g, int dtype) {
@@ -551,7 +731,7 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
   // BEV branch on stream `bst`
   auto launch_bev = [&](cudaStream_t bst) -> int {
     float* wl_ws = reinterpret_cast<float*>((char*)ws + cam_bytes);
-    VbTraceScope tr(VB_K_BEV_FWD, bst);
+    VbTraceScope tr(VB_K_BEV_FWD, bst, 2);
     bev_weights_kernel<T><<<dim3(vb_ceil_div(ncol, 256), g->B), 256, 0, bst>>>(
         *g, *t, den, in->beta, out->bev_height, out->voxel_density, wl_ws);
     VB_LAUNCH_CHECK();
@@ -571,11 +751,16 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
   if (per != nvox * packed_channels(K) * sizeof(T)) return VB200_ERR_ARG;  // march indexes densely
   for (int b0 = 0; b0 < g->B; b0 += group) {
     const int nb = (g->B - b0) < group ? (g->B - b0) : group;
+    int* nf_flag = reinterpret_cast<int*>((char*)ws + cam_bytes + bev_bytes - 256);
+    // thin grids (a dimension of one voxel) cannot shift the corner base inwards: raise the flag up front,
+    // the pack never lowers it, and the exact clamp-and-zero variant of the march runs
+    const int flag_init = (g->vX < 2 || g->vY < 2 || g->vZ < 2) ? 1 : 0;
     {
       VbTraceScope tr(VB_K_PACK, st);
+      if (cudaMemsetAsync(nf_flag, flag_init, sizeof(int), st) != cudaSuccess) return VB200_ERR_CUDA;
       pack_cam_volume_kernel<T, K><<<dim3(vb_ceil_div(nvox, kPackThreads * PackVox<T>::n), nb), kPackThreads, 0, st>>>(
           den + (size_t)b0 * nvox, sem + (size_t)b0 * K * nvox, rgb + (size_t)b0 * 3 * nvox,
-          reinterpret_cast<T*>(ws), (int)nvox, per / sizeof(T));
+          reinterpret_cast<T*>(ws), (int)nvox, per / sizeof(T), nf_flag);
       VB_LAUNCH_CHECK();
     }
     if (b0 == 0 && (branches & VB200_BRANCH_BEV)) {
@@ -598,13 +783,23 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
       if (forked && cudaEventRecord(side->join, bst) != cudaSuccess) return VB200_ERR_CUDA;
     }
     dim3 grid(vb_ceil_div(patches, kMarchThreads / 32), g->N, nb);
-    VbTraceScope tr(VB_K_MARCH_FWD, st);
-    if (in->geom)
-      march_fwd_kernel<T, K, false><<<grid, kMarchThreads, 0, st>>>(
-          *g, *t, d_mats, in->geom, reinterpret_cast<const T*>(ws), in->beta, out->rgb, out->seg, out->depth, b0);
-    else
-      march_fwd_kernel<T, K, true><<<grid, kMarchThreads, 0, st>>>(
-          *g, *t, d_mats, nullptr, reinterpret_cast<const T*>(ws), in->beta, out->rgb, out->seg, out->depth, b0);
+    VbTraceScope tr(VB_K_MARCH_FWD, st, 2);
+    const VbRenderDiv dv = vb_render_div(g);
+#define VB_MARCH(FM, FD, NS)                                                                                      \
+  march_fwd_kernel<T, K, FM, FD, NS><<<grid, kMarchThreads, 0, st>>>(*g, *t, dv, d_mats, in->geom,                \
+                                                                     reinterpret_cast<const T*>(ws), nf_flag, in->beta, \
+                                                                     out->rgb, out->seg, out->depth, b0)
+    if (in->geom) {
+      VB_MARCH(false, false, false);
+      VB_MARCH(false, false, true);
+    } else if (vb_render_div_ok(dv)) {
+      VB_MARCH(true, true, false);
+      VB_MARCH(true, true, true);
+    } else {
+      VB_MARCH(true, false, false);
+      VB_MARCH(true, false, true);
+    }
+#undef VB_MARCH
     VB_LAUNCH_CHECK();
   }
   if (forked && cudaStreamWaitEvent(st, side->join, 0) != cudaSuccess) return VB200_ERR_CUDA;

@@ -503,7 +503,7 @@ int launch_render_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
       {
         VbTraceScope tr(VB_K_PACK, st);
         pack_cam_volume_kernel<T, K><<<dim3(vb_ceil_div(nvox, kPackThreads * PackVox<T>::n), 1), kPackThreads, 0, st>>>(
-            den + (size_t)b * nvox, sem + (size_t)b * K * nvox, rgb + (size_t)b * 3 * nvox, packed, (int)nvox, 0);
+            den + (size_t)b * nvox, sem + (size_t)b * K * nvox, rgb + (size_t)b * 3 * nvox, packed, (int)nvox, 0, nullptr);
         VB_LAUNCH_CHECK();
       }
       VbTraceScope tr(VB_K_MARCH_BWD, st);

@@ -21,12 +21,16 @@ __host__ __device__ constexpr int packed_channels(int K) { return ((K + 4) + 7) 
 // records with 128-bit stores -- no shared memory, no barrier, 4x fewer LSU instructions than a
 // scalar shared-memory transpose (ncu showed the LSU pipe, not HBM, limiting the first version).
 template <typename T> struct PackVox { static constexpr int n = 4 / sizeof(T); };   // voxels per thread
+__device__ __forceinline__ float widen_elem(float v) { return v; }
+__device__ __forceinline__ float widen_elem(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float widen_elem(__half v) { return __half2float(v); }
 
 template <typename T, int K>
 __global__ void __launch_bounds__(kPackThreads) pack_cam_volume_kernel(const T* __restrict__ den,
                                                                        const T* __restrict__ sem,
                                                                        const T* __restrict__ rgb, T* __restrict__ packed,
-                                                                       int nvox, size_t packed_stride) {
+                                                                       int nvox, size_t packed_stride,
+                                                                       int* __restrict__ nonfinite_flag) {
   constexpr int NCH = K + 4, CP = packed_channels(K), V = PackVox<T>::n;
   __shared__ uint4 s_rec[kPackThreads * 6];
   const int i_s = blockIdx.y;
@@ -39,13 +43,16 @@ __global__ void __launch_bounds__(kPackThreads) pack_cam_volume_kernel(const T* 
   // plane size (32-bit words of two voxels must be aligned); anything else takes the scalar path
   const bool vec_ok = (v + V <= nvox) && (V == 1 || !(nvox & 1));
   if (!__all_sync(0xffffffffu, vec_ok)) {
+    bool bad = false;
     for (int vv = v; vv < min(v + V, nvox); ++vv) {
       T* o = packed + (size_t)vv * CP;
       o[0] = den[vv];
       for (int k = 0; k < K; ++k) o[1 + k] = sem[(size_t)k * nvox + vv];
       for (int j = 0; j < 3; ++j) o[1 + K + j] = rgb[(size_t)j * nvox + vv];
       for (int c = NCH; c < CP; ++c) o[c] = VbType<T>::cvt(0.0f);
+      for (int c = 0; c < NCH; ++c) bad = bad || !(fabsf(widen_elem(o[c])) <= 3.402823466e+38f);
     }
+    if (bad && nonfinite_flag) *nonfinite_flag = 1;
     return;
   }
   uint32_t w[CP];                          // one 32-bit word per channel: V voxels side by side
@@ -56,6 +63,17 @@ __global__ void __launch_bounds__(kPackThreads) pack_cam_volume_kernel(const T* 
   for (int j = 0; j < 3; ++j) w[1 + K + j] = __ldg(reinterpret_cast<const uint32_t*>(rgb + (size_t)j * nvox + v));
 #pragma unroll
   for (int c = NCH; c < CP; ++c) w[c] = 0u;
+  // non-finite detector for the march (torch.nan_to_num of the sampled features, BV2:421, only matters then):
+  // adding one to an all-ones exponent field carries into the sign position of that element
+  {
+    constexpr uint32_t EXP = sizeof(T) == 4 ? 0x7f800000u : (VbType<T>::code == VB200_BF16 ? 0x7f807f80u : 0x7c007c00u);
+    constexpr uint32_t ONE = sizeof(T) == 4 ? 0x00800000u : (VbType<T>::code == VB200_BF16 ? 0x00800080u : 0x04000400u);
+    constexpr uint32_t SGN = sizeof(T) == 4 ? 0x80000000u : 0x80008000u;
+    uint32_t bad = 0u;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) bad |= ((w[c] & EXP) + ONE) & SGN;
+    if (bad != 0u && nonfinite_flag) *nonfinite_flag = 1;   // benign race: every writer stores 1
+  }
   // assemble this thread's records (96 contiguous bytes) in registers ...
   uint4 rec[6];
   static_assert(CP * sizeof(T) * V == 96, "record staging below assumes 96 bytes per thread");
@@ -87,7 +105,23 @@ __global__ void __launch_bounds__(kPackThreads) pack_cam_volume_kernel(const T* 
   for (int q = 0; q < 6; ++q) out[q * 32 + lane] = s_rec[warp0 * 6 + q * 32 + lane];
 }
 
+template <typename T, int CP> struct PackedLoad;
 template <typename T, int CP> struct PackedLoad {
+  // acc[c] += wgt * p[1 + c] for c < NV (channel 0 = density is skipped)
+  template <int NV>
+  __device__ __forceinline__ static void fma_values(const T* p, float wgt, float (&acc)[NV]) {
+    constexpr int L = VbLanes<T>::n;
+#pragma unroll
+    for (int q = 0; q < CP / L; ++q) {
+      float tmp[L];
+      VbVec<T, L>::ld(p + q * L, tmp);
+#pragma unroll
+      for (int e = 0; e < L; ++e) {
+        const int c = q * L + e - 1;
+        if (c >= 0 && c < NV) acc[c] = fmaf(tmp[e], wgt, acc[c]);
+      }
+    }
+  }
   __device__ __forceinline__ static void fma_corner(const T* p, float wgt, float (&v)[CP]) {
     constexpr int L = VbLanes<T>::n;
 #pragma unroll

@@ -18,8 +18,8 @@ std::vector<Pair> g_pairs;       // completed begin/end pairs awaiting collectio
 std::vector<cudaEvent_t> g_open[VB_K_COUNT];
 }  // namespace
 
-void vb_trace_begin(int id, cudaStream_t st) {
-  g_launches[id].fetch_add(1, std::memory_order_relaxed);
+void vb_trace_begin(int id, cudaStream_t st, int launches) {
+  g_launches[id].fetch_add(launches, std::memory_order_relaxed);
   if (!g_enabled.load(std::memory_order_relaxed)) return;
   cudaEvent_t e;
   if (cudaEventCreate(&e) != cudaSuccess) return;

@@ -23,12 +23,13 @@ enum VbKernelId {
   VB_K_COUNT
 };
 
-void vb_trace_begin(int kernel_id, cudaStream_t st);
+void vb_trace_begin(int kernel_id, cudaStream_t st, int launches = 1);
 void vb_trace_end(int kernel_id, cudaStream_t st);
 
 struct VbTraceScope {
   int id;
   cudaStream_t st;
-  VbTraceScope(int id_, cudaStream_t st_) : id(id_), st(st_) { vb_trace_begin(id, st); }
+  // `launches` = kernels launched inside the scope (the launch counter reports kernels, not scopes)
+  VbTraceScope(int id_, cudaStream_t st_, int launches = 1) : id(id_), st(st_) { vb_trace_begin(id, st, launches); }
   ~VbTraceScope() { vb_trace_end(id, st); }
 };

@@ -268,3 +268,66 @@ def test_fused_kernels_use_the_exact_indices_random_rigs(seed):
                           prep.cuda(), None, cid, True, 3)
     for n, o, r in zip(NAMES, outs, ref):
         assert_close_scaled(o.cpu().numpy(), r.numpy(), FP32_REL, n)
+
+
+_TMA_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+from helpers import Case
+from vampire_b200 import ops
+case = Case(sys.argv[2])
+cid = ops.register_config(case.cfg)
+dt = {"fp32": torch.float32, "bf16": torch.bfloat16}[sys.argv[3]]
+outs = ops.render_fwd(case.den.cuda().to(dt), case.sem.cuda().to(dt), case.rgb.cuda().to(dt), case.feat.cuda().to(dt),
+                      torch.tensor(0.1, device="cuda"), case.prep.cuda(), None, cid, True, 2)
+torch.save([o.cpu() for o in outs], sys.argv[4])
+"""
+
+
+@pytest.mark.parametrize("name,dtype", [("mini_stress", "fp32"), ("r50_val_digest", "bf16")])
+def test_bev_tma_staged_kernel_is_bit_identical(name, dtype, tmp_path):
+    """The opt-in TMA-staged BEV kernel (VB200_BEV_TMA=1: cp.async.bulk + mbarrier ring) does the same arithmetic
+    in the same order as the default direct-load kernel: its outputs must be bit-identical."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for tag, env in (("direct", {}), ("tma", {"VB200_BEV_TMA": "1"})):
+        path = str(tmp_path / (tag + ".pt"))
+        e = dict(os.environ, **env)
+        e.pop("VB200_BEV_TMA", None) if not env else None
+        subprocess.run([sys.executable, "-c", _TMA_SCRIPT, root, name, dtype, path], check=True, env=e, timeout=300)
+        outs[tag] = torch.load(path)
+    for n, a, b in zip(NAMES, outs["direct"], outs["tma"]):
+        if a.numel():
+            assert torch.equal(a, b), n
+
+
+def test_render_nonfinite_volume_takes_the_nan_safe_march():
+    """A NaN / inf anywhere in the camera-branch volume raises the pack's flag and the march keeps
+    torch.nan_to_num of the interpolated features (BV2:421); results must still match the reference ops."""
+    case = Case("mini_val")
+    ops, cid = _ops(case.cfg)
+    den, sem, rgb, feat = case.den.clone(), case.sem.clone(), case.rgb.clone(), case.feat.clone()
+    g = torch.Generator().manual_seed(5)
+    for t, v in ((sem, float("nan")), (rgb, float("inf")), (sem, float("-inf"))):
+        idx = torch.randint(0, t.numel(), (40,), generator=g)
+        t.view(-1)[idx] = v
+    buf = tp.build_buffers(case.conf)
+    ref = tp.render_from_mats(case.conf, buf, case.mats, den, sem, feat, rgb, torch.tensor(0.1))
+    st = ops.state(cid)
+    old = st.term_eps
+    try:
+        st.term_eps = 0.0      # compare every sample: a skipped 1e-9 * FLT_MAX term is not small
+        outs = ops.render_fwd(den.cuda(), sem.cuda(), rgb.cuda(), feat.cuda(), torch.tensor(0.1, device="cuda"),
+                              case.prep.cuda(), None, cid, True, 1)
+    finally:
+        st.term_eps = old
+    for n, o, r in list(zip(NAMES, outs, ref))[:3]:
+        got, exp = o.cpu().numpy(), r.numpy()
+        assert np.array_equal(np.isnan(got), np.isnan(exp)), n
+        ok = ~np.isnan(exp)
+        big = ok & (np.abs(exp) > 1e25)          # weight * +-FLT_MAX sums: compare relatively
+        assert np.allclose(got[big], exp[big], rtol=1e-4, atol=0), n
+        small = ok & ~big
+        assert_close_scaled(got[small], exp[small], FP32_REL, n, scale=max(np.abs(exp[small]).max(), 1e-30))

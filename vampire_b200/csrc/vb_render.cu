@@ -698,6 +698,249 @@ __global__ void __launch_bounds__(64, 16) bev_channels_vec4_kernel(VbGrid g, VbT
   }
 }
 
+// ---- bev_channels, TMA-staged ---------------------------------------------------------------------------------
+// Same arithmetic as the fast path above, but the input rows travel HBM -> shared memory as 1-D bulk copies
+// (cp.async.bulk + mbarrier complete_tx) issued by one thread into a ring of kStages row-pair slots.  The direct-
+// load version keeps one level (512 B per warp) in flight and ncu shows it latency-bound (long scoreboard on the
+// first use of every row, ~2.4 TB/s = bytes in flight / latency); the ring keeps kStages x 1 KB per block in
+// flight without holding registers or issue slots, the 5th column is simply the next shared-memory element,
+// and the 64-bit global address arithmetic disappears from the level loop.
+//   item  = one z-row of one channel plane: its two y-rows [ya, yb] x [cs, ce) (16-byte aligned column range
+//           covering the block's 256 columns +- 8), copied to slot (item % kStages) at element offset 8
+//   order = per channel, per level: the hi row when it is neither reused nor outside the grid, then the lo row
+//           (the same for every channel, tabulated once per block in s_item_z)
+//   sync  = full[slot] mbarrier (producer arrive.expect_tx + 2 copies complete_tx); a slot is refilled right
+//           after the __syncthreads() that ends its consumption, i.e. kStages - 1 items ahead.
+__device__ __forceinline__ uint32_t vb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void vb_mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vb_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void vb_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(vb_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void vb_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   vb_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(vb_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void vb_mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = vb_smem_u32(bar);
+  for (int spin = 0; spin < (1 << 24); ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();   // a lost transaction must fail loudly, never hang the device
+}
+
+constexpr int kBevRowPad = 288;   // 8 zero | up to 272 copied | >= 8 zero  (elements)
+template <typename T> struct BevStages { static constexpr int n = sizeof(T) == 4 ? 6 : 8; };
+
+template <typename T, int K, int C>
+__global__ void __launch_bounds__(64, sizeof(T) == 4 ? 12 : 16) bev_channels_tma_kernel(
+    VbGrid g, VbTables t, const T* __restrict__ sem, const T* __restrict__ rgb, const T* __restrict__ feat,
+    const float* __restrict__ wl_ws, float* __restrict__ o_rgb, float* __restrict__ o_seg, T* __restrict__ o_feat) {
+  constexpr int S = BevStages<T>::n;
+  __shared__ __align__(128) T s_ring[S][2][kBevRowPad];
+  __shared__ __align__(8) uint64_t s_full[S];
+  __shared__ BevLevel s_lv[kMaxLevels];
+  __shared__ BevLevelX s_lx[kMaxLevels];
+  __shared__ int s_item_z[2 * kMaxLevels];
+  __shared__ int s_nitems;
+  bev_level_table(g, t, s_lv);
+  if (threadIdx.x < g.oZ) {
+    const int l = threadIdx.x;
+    const BevLevel L = s_lv[l];
+    BevLevelX X;
+    const bool in0 = L.z0 >= 0 && L.z0 < g.vZ, in1 = L.z0 + 1 >= 0 && L.z0 + 1 < g.vZ;
+    X.zoff = min(max(L.z0, 0), g.vZ - 1) * g.vY * g.vX;
+    X.zoff_hi = min(max(L.z0 + 1, 0), g.vZ - 1) * g.vY * g.vX;
+    X.wz0 = in0 ? L.wz0 : 0.0f;
+    X.wz1 = in1 ? L.wz1 : 0.0f;
+    X.flags = ((l > 0 && L.z0 + 1 == s_lv[l - 1].z0) ? 1 : 0) | (in1 ? 2 : 0) | (in0 ? 4 : 0);
+    s_lx[l] = X;
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) vb_mbar_init(&s_full[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {   // the per-channel item order
+    int n = 0;
+    for (int l = 0; l < g.oZ; ++l) {
+      const BevLevelX L = s_lx[l];
+      if (!(L.flags & 1) && (L.flags & 2)) s_item_z[n++] = L.zoff_hi;
+      s_item_z[n++] = L.zoff;
+    }
+    s_nitems = n;
+  }
+  const int b = blockIdx.z, grp = blockIdx.y;
+  const int tiles_x = (g.oX + 255) / 256;
+  const int oy = blockIdx.x / tiles_x;
+  const int lane = threadIdx.x & 31;
+  const int tile_x0 = (blockIdx.x % tiles_x) * 256;
+  const int ox_raw = tile_x0 + threadIdx.x * 4;
+  const bool live = ox_raw < g.oX;                     // oX % 4 == 0 guaranteed by the launcher
+  BevQuadX q;
+  q.ox0 = live ? ox_raw : 0;
+  bool all1 = q.ox0 + 3 < g.vX, all0 = all1;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    axis_coord(__ldg(t.oxs + q.ox0 + c), g.seg_lo[0], g.seg_ext[0], g.vX, q.x0[c], q.wx0[c], q.wx1[c]);
+    all1 = all1 && (q.x0[c] == q.ox0 + c);
+    all0 = all0 && (q.x0[c] == q.ox0 + c - 1);
+    if (!(q.x0[c] >= 0 && q.x0[c] < g.vX)) q.wx0[c] = 0.0f;
+    if (!(q.x0[c] + 1 >= 0 && q.x0[c] + 1 < g.vX)) q.wx1[c] = 0.0f;
+  }
+  int y0;
+  float wy0, wy1;
+  axis_coord(__ldg(t.oys + oy), g.seg_lo[1], g.seg_ext[1], g.vY, y0, wy0, wy1);
+  const bool w1 = __all_sync(0xffffffffu, all1 || !live), w0 = __all_sync(0xffffffffu, all0 || !live);
+  // the copied column range [cs, ce) must hold every live thread's 4 columns and its 5th (else: zero pad)
+  const int cs = max(tile_x0 - 8, 0), ce = min(tile_x0 + 264, g.vX);
+  const bool fast_block = __syncthreads_and((w1 || w0) && (!live || (q.ox0 >= cs && q.ox0 + 4 <= ce))) != 0;
+
+  const int ncol = g.oY * g.oX;
+  const size_t nvox = (size_t)g.vZ * g.vY * g.vX;
+  const int col0 = oy * g.oX + q.ox0;
+  constexpr int NM = K + 3, GM = bev_chunks(NM), LM = bev_chunk_len(NM), LF = bev_chunk_len(C);
+  const bool is_map = grp < GM;
+  const int c_begin = is_map ? grp * LM : (grp - GM) * LF;
+  const int c_end = is_map ? min(c_begin + LM, NM) : min(c_begin + LF, C);
+  const float* wl = wl_ws + (size_t)b * g.oZ * ncol + col0;
+  auto plane_of = [&](int j) -> const T* {
+    return is_map ? (j < K ? sem + ((size_t)b * K + j) * nvox : rgb + ((size_t)b * 3 + (j - K)) * nvox)
+                  : feat + ((size_t)b * C + j) * nvox;
+  };
+  auto outputs_of = [&](int j, float*& o_map, T*& o_f) {
+    o_map = nullptr;
+    o_f = nullptr;
+    if (is_map) o_map = (j < K ? o_seg + ((size_t)b * K + j) * ncol : o_rgb + ((size_t)b * 3 + (j - K)) * ncol) + col0;
+    else o_f = o_feat + ((size_t)b * C + j) * g.oZ * ncol + col0;
+  };
+  if (!fast_block) {   // irregular det grid: exact scalar gathers, no staging
+    for (int j = c_begin; j < c_end; ++j) {
+      float* o_map;
+      T* o_f;
+      outputs_of(j, o_map, o_f);
+      bev_quad_channel_generic<T, K, C>(g, s_lv, q, plane_of(j), y0, wy0, wy1, lane, live, wl, o_map, o_f, ncol);
+    }
+    return;
+  }
+
+  // ---- staged path ----
+  const bool y0in = y0 >= 0 && y0 < g.vY, y1in = y0 + 1 >= 0 && y0 + 1 < g.vY;
+  const int ya = min(max(y0, 0), g.vY - 1), yb = min(max(y0 + 1, 0), g.vY - 1);
+  float wq[4][4];          // [column][a0, a1, b0, b1] = wy * wx, zero where the tap leaves the grid
+  {
+    const float ya_w = y0in ? wy0 : 0.0f, yb_w = y1in ? wy1 : 0.0f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      wq[c][0] = ya_w * q.wx0[c]; wq[c][1] = ya_w * q.wx1[c];
+      wq[c][2] = yb_w * q.wx0[c]; wq[c][3] = yb_w * q.wx1[c];
+    }
+  }
+  const int ncopy = ce - cs;                                   // elements per row copy, multiple of 16 bytes
+  const uint32_t row_bytes = (uint32_t)ncopy * sizeof(T);
+  // zero the pads the copies never touch: [0, 8) and [8 + ncopy, 8 + ncopy + 8)
+  for (int i = threadIdx.x; i < S * 2 * 16; i += blockDim.x) {
+    const int slot = i / 32, row = (i / 16) & 1, e = i & 15;
+    s_ring[slot][row][e < 8 ? e : 8 + ncopy + (e - 8)] = VbType<T>::cvt(0.0f);
+  }
+  __syncthreads();
+  const int nitems = s_nitems;
+  const int total = (c_end - c_begin) * nitems;
+  int iss_j = c_begin, iss_r = 0;                              // producer cursor (thread 0)
+  auto issue = [&](int it) {
+    const int slot = it % S;
+    const T* src = plane_of(iss_j) + s_item_z[iss_r] + cs;
+    vb_mbar_expect_tx(&s_full[slot], 2u * row_bytes);
+    vb_bulk_load(&s_ring[slot][0][8], src + ya * g.vX, row_bytes, &s_full[slot]);
+    vb_bulk_load(&s_ring[slot][1][8], src + yb * g.vX, row_bytes, &s_full[slot]);
+    if (++iss_r == nitems) { iss_r = 0; ++iss_j; }
+  };
+  if (threadIdx.x == 0)
+    for (int it = 0; it < min(S, total); ++it) issue(it);
+  const int xi = live ? (q.ox0 - cs + 8) : 8;                  // this thread's first column inside a staged row
+  const int xe = w1 ? xi + 4 : xi - 1;                         // its 5th column
+  int consumed = 0;
+  // fetch the next item's rows into registers, then release + refill its slot
+  auto consume = [&](RawRow<T>& r) {
+    const int slot = consumed % S;
+    vb_mbar_wait(&s_full[slot], (uint32_t)(consumed / S) & 1u);
+    using V = typename Raw4<T>::type;
+    r.a = *reinterpret_cast<const V*>(&s_ring[slot][0][xi]);
+    r.b = *reinterpret_cast<const V*>(&s_ring[slot][1][xi]);
+    r.ea = s_ring[slot][0][xe];
+    r.eb = s_ring[slot][1][xe];
+    __syncthreads();
+    if (threadIdx.x == 0 && consumed + S < total) issue(consumed + S);
+    ++consumed;
+  };
+  BevQuadFast f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) f.w[c][k] = wq[c][k];
+  f.off_a = f.off_b = f.off_ea = f.off_eb = 0;
+  const int wstep = ncol >> 2;
+  for (int j = c_begin; j < c_end; ++j) {
+    float* o_map;
+    T* o_f;
+    outputs_of(j, o_map, o_f);
+    const float4* wp = reinterpret_cast<const float4*>(wl);
+    float prev[4] = {0.0f, 0.0f, 0.0f, 0.0f}, acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    float4 wnext = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (is_map) wnext = __ldg(wp);
+    for (int l = 0; l < g.oZ; ++l) {
+      const BevLevelX L = s_lx[l];
+      float hi[4], lo[4];
+      if (L.flags & 1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) hi[c] = prev[c];
+      } else if (L.flags & 2) {
+        RawRow<T> h;
+        consume(h);
+        if (w1) bev_finish_row<T, 1>(h, f, hi);
+        else bev_finish_row<T, 0>(h, f, hi);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) hi[c] = 0.0f;
+      }
+      RawRow<T> cur;
+      consume(cur);
+      const float4 w = wnext;
+      if (is_map && l + 1 < g.oZ) wnext = __ldg(wp + wstep);   // next level's weights, one level ahead
+      if (w1) bev_finish_row<T, 1>(cur, f, lo);
+      else bev_finish_row<T, 0>(cur, f, lo);
+      if (!(L.flags & 4)) {                                    // row z0 outside the grid: zeros padding (uniform)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) lo[c] = 0.0f;
+      }
+      float v[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        v[c] = fmaf(L.wz1, hi[c], L.wz0 * lo[c]);
+        prev[c] = lo[c];
+      }
+      if (is_map) {                                                                         // BV2:459-460
+        acc[0] = fmaf(w.x, v[0], acc[0]); acc[1] = fmaf(w.y, v[1], acc[1]);
+        acc[2] = fmaf(w.z, v[2], acc[2]); acc[3] = fmaf(w.w, v[3], acc[3]);
+      } else if (live) {                                                                    // BV2:448
+        Vec4Load<T>::st(o_f, v);
+      }
+      wp += wstep;
+      if (!is_map) o_f += ncol;
+    }
+    if (is_map && live) *reinterpret_cast<float4*>(o_map) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
+}
+
 size_t bev_weight_bytes(const VbGrid* g) {   // + one 256-byte slot at the end: the pack's non-finite flag
   const size_t n = (size_t)g->B * g->oZ * g->oY * g->oX * sizeof(float);
   return ((n + 255) & ~(size_t)255) + 256;
@@ -738,7 +981,21 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
     const bool vec_ok = (g->vX % 4 == 0) && (g->oX % 4 == 0) &&
                         ((((uintptr_t)sem | (uintptr_t)rgb | (uintptr_t)feat | (uintptr_t)out->voxel_output |
                            (uintptr_t)out->bev_rgb | (uintptr_t)out->bev_seg | (uintptr_t)wl_ws) & 15) == 0);
-    if (vec_ok)
+    // bulk copies need 16-byte aligned rows: vX a multiple of 16 bytes of elements (plane bases are checked above)
+    // Opt-in (VB200_BEV_TMA=1): measured SLOWER than the direct-load kernel on B200 (R50, B=8, bf16: 0.435 vs
+    // 0.291 ms) -- ncu: 2x the warp instructions (mbarrier wait, slot addressing, thread-0 issue path) and a
+    // per-item block barrier, which outweigh the latency it hides.  Kept as a measured alternative, parity-tested.
+    static const bool tma_env = getenv("VB200_BEV_TMA") != nullptr;
+    const bool tma_ok = vec_ok && tma_env && ((size_t)g->vX * sizeof(T)) % 16 == 0 && g->vX >= 8;
+    if (tma_ok) {
+      static std::once_flag carve;
+      std::call_once(carve, [] {
+        cudaFuncSetAttribute(bev_channels_tma_kernel<T, K, C>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+      });
+      bev_channels_tma_kernel<T, K, C><<<dim3(g->oY * vb_ceil_div(g->oX, 256), bev_groups(K, C), g->B), 64, 0, bst>>>(
+          *g, *t, sem, rgb, feat, wl_ws, out->bev_rgb, out->bev_seg, reinterpret_cast<T*>(out->voxel_output));
+    } else if (vec_ok)
       bev_channels_vec4_kernel<T, K, C><<<dim3(g->oY * vb_ceil_div(g->oX, 256), bev_groups(K, C), g->B), 64, 0, bst>>>(
           *g, *t, sem, rgb, feat, wl_ws, out->bev_rgb, out->bev_seg, reinterpret_cast<T*>(out->voxel_output));
     else

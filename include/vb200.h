@@ -265,6 +265,17 @@ int vb200_query_points_bwd(const VbGrid* g, const void* d_vol, int dtype, int ch
                            const float* d_beta, const float* d_gout, void* d_gvol, float* d_gbeta,
                            void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* ---- producer of the lift's depth input (SURVEY §8f "next" row 1) ---------------------------------
+ * Replaces `.softmax(dim=1)` of BV2:551 on the (B*N, D, fH, fW) depth logits: softmax over the D planes
+ * (stride `inner` = fH*fW elements), `outer` = B*N.  fp32 arithmetic; logits fp32 / bf16 / fp16; probabilities in
+ * the logits' dtype or fp32 (the reference's autocast behaviour).  One DRAM read + one write (cp.async staging).
+ * Backward: d_glogits = probs * (d_gprobs - sum_D probs * d_gprobs); probs and d_gprobs share `dtype`;
+ * out_dtype == dtype, or any dtype when dtype is fp32 (fp32 softmax output, fp16 conv gradient under AMP). */
+int vb200_depth_softmax_fwd(const void* d_logits, int in_dtype, void* d_probs, int out_dtype, long long outer, int D,
+                            int inner, void* stream);
+int vb200_depth_softmax_bwd(const void* d_probs, const void* d_gprobs, int dtype, void* d_glogits, int out_dtype,
+                            long long outer, int D, int inner, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

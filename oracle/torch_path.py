@@ -94,6 +94,11 @@ def get_pixel(buf, sensor2ego, intrin, ida, bda):
 # --------------------------------------------------------------------------------------------
 # L1-L4: lift + pool
 # --------------------------------------------------------------------------------------------
+def depth_softmax(logits):
+    """BV2:551 ``.softmax(dim=1)`` on the (B*N, D, fH, fW) depth logits (autocast runs it in fp32)."""
+    return torch.softmax(logits.float(), dim=-3)
+
+
 def lift_outer(depth, ctx):
     """BV2:553: (B,N,D,h,w) x (B,N,C,h,w) -> (B,N,C,D,h,w)."""
     return depth.unsqueeze(2) * ctx.unsqueeze(3)

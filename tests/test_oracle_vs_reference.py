@@ -60,3 +60,6 @@ def test_post_path_restatements(ref):
     assert torch.equal(ref.occ_coords, tp.occ_coords())
     x = torch.randn(12, 5, MINI.fH, MINI.fW, generator=torch.Generator().manual_seed(1))
     assert torch.equal(ref.upsample2d(x), tp.upsample(x, MINI.upsample_factor))
+    # §8f row 1: the reference's inline `.softmax(dim=1)` on the (B*N, D, fH, fW) depth logits (BV2:551)
+    lg = torch.randn(6, MINI.D, MINI.fH, MINI.fW, generator=torch.Generator().manual_seed(2))
+    assert torch.equal(lg.softmax(dim=1), tp.depth_softmax(lg))

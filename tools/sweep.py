@@ -94,3 +94,22 @@ t = timed(lambda: mod.occupancy(sem, den, bda, coords))
 P = coords.numel() // 3
 mb = (P * 3 * 4 + (cfg.K + 1) * P * 4 + (cfg.K + 1) * 16 * 200 * 200 * 4 * 0 + (cfg.K + 1) * cfg.vZ * cfg.vY * cfg.vX * 4 * (16.0 * 0.4 / 8.0) * (80.0 / 102.4) ** 2) / 1e6
 print(f"| occupancy queries (640k pts, 18 logits + sigma) fwd | {t:.3f} | {mb:.1f} | {mb / t:.0f} | {mb / t / 65.51:.1f} |")
+
+print("\n## next row (SURVEY 8f 1): softmax over the 86 depth planes (BV2:551), R50 256x704\n")
+print("| case | ms | algorithmic MB | GB/s | % of 6551 GB/s |")
+print("|---|---|---|---|---|")
+for B, dt, out_fp32 in ((1, torch.float32, True), (8, torch.float32, True), (8, torch.bfloat16, False), (8, torch.float16, True)):
+    lg = (torch.randn(B * cfg.num_cams, cfg.D, cfg.fH, cfg.fW, device="cuda") * 2).to(dt)
+    t = timed(lambda: ops.depth_softmax_fwd(lg, out_fp32))
+    es_in, es_out = lg.element_size(), (4 if out_fp32 else lg.element_size())
+    mb = lg.numel() * (es_in + es_out) / 1e6
+    print(f"| fwd B={B} {str(dt)[6:]} -> {'float32' if out_fp32 else str(dt)[6:]} | {t:.3f} | {mb:.1f} | {mb / t:.0f} | {mb / t / 65.51:.1f} |")
+    y = ops.depth_softmax_fwd(lg, out_fp32)
+    gy = torch.randn_like(y)
+    t = timed(lambda: ops.depth_softmax_bwd(y, gy, lg.dtype))
+    mb = (2 * y.numel() * y.element_size() + lg.numel() * es_in) / 1e6
+    print(f"| bwd B={B} | {t:.3f} | {mb:.1f} | {mb / t:.0f} | {mb / t / 65.51:.1f} |")
+    # same-box comparator: ATen's softmax kernel on the B200
+    t = timed(lambda: torch.softmax(lg.float() if out_fp32 else lg, dim=1))
+    print(f"| (ATen softmax on the same B200, B={B} {str(dt)[6:]}) | {t:.3f} | | | |")
+    del lg, y, gy

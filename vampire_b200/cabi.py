@@ -15,7 +15,8 @@ from .config import PathConfig
 from .lattice import Lattice
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(_HERE, "_lib", "libvb200.so")
+# VB200_LIB: load an alternative build of the same library (kernel-tuning experiments: tools/build_variant.sh)
+LIBPATH = os.environ.get("VB200_LIB") or os.path.join(_HERE, "_lib", "libvb200.so")
 
 F32, BF16, F16 = 0, 1, 2
 NCDHW, NDHWC = 0, 1
@@ -84,6 +85,8 @@ _PROTOS = {
     "vb200_gather_pool_fwd": (C.c_int, [C.POINTER(VbGrid), C.POINTER(VbTables), _P, _P, C.c_int, _P, _P, _P]),
     "vb200_gather_pool_bwd": (C.c_int, [C.POINTER(VbGrid), C.POINTER(VbTables), _P, _P, _P, C.c_int, _P, _P,
                                         C.c_size_t, _P]),
+    "vb200_depth_softmax_fwd": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_longlong, C.c_int, C.c_int, _P]),
+    "vb200_depth_softmax_bwd": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_longlong, C.c_int, C.c_int, _P]),
     "vb200_upsample_bilinear_fwd": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "vb200_upsample_bilinear_bwd": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "vb200_query_points_bwd_workspace": (C.c_size_t, [C.POINTER(VbGrid), C.c_int, C.c_int, C.c_int]),

@@ -20,7 +20,13 @@
 
 namespace {
 
-constexpr int kLiftThreads = 256;
+#ifndef VB_LIFT_THREADS
+#define VB_LIFT_THREADS 256
+#endif
+#ifndef VB_LIFT_MINB
+#define VB_LIFT_MINB 4
+#endif
+constexpr int kLiftThreads = VB_LIFT_THREADS;
 
 // ---- ctx (B,N,C,fH,fW) -> (B,N,fH,fW,C): one block per (b*n, h) row -------------------------
 // (the copy keeps the feature dtype: the gather is L1-wavefront bound -- ncu: l1tex 87 % with an fp32 copy --
@@ -62,7 +68,7 @@ __device__ __forceinline__ TriW tri_weights(float ix, float iy, float iz, int x0
 
 // ---- forward: one thread per voxel, loop over cameras ---------------------------------------
 template <typename T, int C, int OUT_LAYOUT, bool FASTDIV>
-__global__ void __launch_bounds__(kLiftThreads, 4) lift_pool_fwd_kernel(VbGrid g, VbTables t, VbLiftDiv dv,
+__global__ void __launch_bounds__(kLiftThreads, VB_LIFT_MINB) lift_pool_fwd_kernel(VbGrid g, VbTables t, VbLiftDiv dv,
                                                                      const float* __restrict__ d_mats,
                                                                      const T* __restrict__ depth,
                                                                      const T* __restrict__ ctx_nhwc,

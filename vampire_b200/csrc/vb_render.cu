@@ -62,7 +62,7 @@ SideStream* side_stream_for_current_device() {
 // into the ray's channel sums (24 fewer live registers, no per-sample finiteness test).  Both variants are
 // launched back to back; the one whose turn it is not returns at once.
 template <typename T, int K, bool FROM_MATS, bool FASTDIV, bool NANSAFE>
-__global__ void __launch_bounds__(kMarchThreads, 5) march_fwd_kernel(VbGrid g, VbTables t, VbRenderDiv dv,
+__global__ void __launch_bounds__(kMarchThreads, VB_MARCH_MINB) march_fwd_kernel(VbGrid g, VbTables t, VbRenderDiv dv,
                                                                   const float* __restrict__ d_mats,
                                                                   const float* __restrict__ d_geom,
                                                                   const T* __restrict__ packed,
@@ -123,8 +123,58 @@ __global__ void __launch_bounds__(kMarchThreads, 5) march_fwd_kernel(VbGrid g, V
   // a masked / out-of-volume sample has feature 0: sigma(0) is a per-launch constant (~2.27e-4)
   const float inv_beta = 1.0f / beta;
   const float sigma_masked = laplace_density_rcp(0.0f, g.sdf_bias, inv_beta);
-  float p0[3], p1[3];
+  // One sample position, prepared ONE STEP AHEAD of its use: ncu attributed a quarter of all stall samples to
+  // the first use of the eight density gathers (issued and consumed back to back, 5 warps per scheduler cannot
+  // hide an L1-miss).  Now the geometry of sample i+1 is computed and its density loads are issued before
+  // sample i is composited, so they have the whole value phase of sample i to land.
+  struct Smp {
+    bool valid, live;      // inside the volume; and the ray exists
+    int v0;                // voxel index of the base corner
+    int dxo, sy, sz;       // NANSAFE: per-sample corner strides (clamped); otherwise launch constants
+    float fx, fy, fz;      // far-corner weights (near = 1 - far)
+    T raw[8];              // density at the eight corners, not yet widened (widening would wait for the load)
+  };
+  const int c_sy = g.vX, c_sz = g.vY * g.vX;
+  auto prepare = [&](const float (&pp)[3], Smp& sm) {
+    const RenderCoord rc = render_coord<FROM_MATS && FASTDIV>(g, pp, &dv);
+    sm.valid = rc.valid;
+    sm.live = rc.valid && active;
+    if (sm.live) {
+      // valid => 0 <= i0 <= size-1, so only the far corner can leave the grid, and only when i == size-1
+      // exactly, where its weight i - i0 is exactly 0.
+      int x0 = rc.x0, y0 = rc.y0, z0 = rc.z0;
+      int dxo = 1, sy = c_sy, sz = c_sz;
+      if (!NANSAFE) {
+        // All values are finite here, so a zero-weight corner may be ANY in-grid voxel: shift the base one
+        // voxel inwards instead of clamping the far corner (weights become (0, 1) exactly), which makes the
+        // eight corner offsets launch constants: no clamps, no selects, immediate x offset.  Needs every
+        // grid dimension >= 2 (the launcher routes thinner grids to the NANSAFE variant).
+        x0 = min(x0, g.vX - 2); y0 = min(y0, g.vY - 2); z0 = min(z0, g.vZ - 2);
+      } else {
+        // clamp the far corner's address (its weight is 0) instead of branching
+        dxo = x0 + 1 < g.vX ? 1 : 0; sy = y0 + 1 < g.vY ? c_sy : 0; sz = z0 + 1 < g.vZ ? c_sz : 0;
+        sm.dxo = dxo; sm.sy = sy; sm.sz = sz;
+      }
+      sm.fx = rc.ix - (float)x0; sm.fy = rc.iy - (float)y0; sm.fz = rc.iz - (float)z0;
+      sm.v0 = (z0 * g.vY + y0) * g.vX + x0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int cx = q & 1, cy = (q >> 1) & 1, cz = q >> 2;
+        sm.raw[q] = __ldg(vol + (size_t)(sm.v0 + (cy ? sy : 0) + (cz ? sz : 0)) * CP + (cx ? dxo * CP : 0));
+      }
+    }
+  };
+
+  float p0[3], p1[3], p2[3];
   point(0, p0);
+  point(1, p1);
+  Smp nxt;
+  prepare(p0, nxt);
+  float delta_n;
+  {
+    const float dx = p1[0] - p0[0], dy = p1[1] - p0[1], dz = p1[2] - p0[2];
+    delta_n = sqrtf(dx * dx + dy * dy + dz * dz);                           // BV2:426
+  }
   // A ray is a straight line and the volume a convex box, so once a ray has LEFT the box it never
   // re-enters: every later sample is masked (feature 0, sigma_masked) and only delta_i and mid_i enter
   // the compositing.  When every ray of the warp has left decisively (outside by > 1 mm on an axis along
@@ -132,9 +182,9 @@ __global__ void __launch_bounds__(kMarchThreads, 5) march_fwd_kernel(VbGrid g, V
   // opaque, the warp finishes with a geometry-free tail loop (delta_i = the ray's constant step length,
   // equal to the reference's per-sample norm up to ~1e-7 relative).
   bool was_valid = false, exited = false;
-  float delta = 0.0f;
   for (int i = 0; i < S; ++i) {
     const float trans = expf(-tau);
+    const float delta = delta_n;
     if (g.term_eps > 0.0f) {
       const bool done = !active || trans < g.term_eps;
       if (__all_sync(0xffffffffu, done)) break;
@@ -153,11 +203,8 @@ __global__ void __launch_bounds__(kMarchThreads, 5) march_fwd_kernel(VbGrid g, V
         break;
       }
     }
-    point(i + 1, p1);
-    const float dx = p1[0] - p0[0], dy = p1[1] - p0[1], dz = p1[2] - p0[2];
-    delta = sqrtf(dx * dx + dy * dy + dz * dz);                             // BV2:426
-    const RenderCoord rc = render_coord<FROM_MATS && FASTDIV>(g, p0, &dv);
-    if (rc.valid) {
+    const Smp cur = nxt;
+    if (cur.valid) {
       was_valid = true;
     } else if (was_valid && !exited) {
 #pragma unroll
@@ -166,41 +213,25 @@ __global__ void __launch_bounds__(kMarchThreads, 5) march_fwd_kernel(VbGrid g, V
         exited = exited || (p0[a] > hi + 1e-3f && p1[a] > p0[a]) || (p0[a] < g.seg_lo[a] - 1e-3f && p1[a] < p0[a]);
       }
     }
+    if (i + 1 < S) {                        // look ahead: geometry + density gathers of sample i+1
+      point(i + 2, p2);
+      prepare(p1, nxt);
+      const float dx = p2[0] - p1[0], dy = p2[1] - p1[1], dz = p2[2] - p1[2];
+      delta_n = sqrtf(dx * dx + dy * dy + dz * dz);
+    }
     float sigma = sigma_masked;
-    const T* cp[4];        // corner rows (y, z) in {0,1}^2 at x0; the x1 corner is `xo` elements further
-    int xo = CP;           // (compile-time CP in the fast variant: an immediate offset)
     float cw[8];
-    const bool live = rc.valid && active;
+    const bool live = cur.live;
+    const int sy = NANSAFE ? cur.sy : c_sy, sz = NANSAFE ? cur.sz : c_sz, dxo = NANSAFE ? cur.dxo : 1;
     if (live) {
-      // valid => 0 <= i0 <= size-1, so only the far corner can leave the grid (when i == size-1 exactly).
-      int x0 = rc.x0, y0 = rc.y0, z0 = rc.z0;
-      long long sy, sz;
-      float wx[2], wy[2], wz[2];
-      if (!NANSAFE) {
-        // All values are finite here, so a zero-weight corner may be ANY in-grid voxel: shift the base one
-        // voxel inwards instead of clamping the far corner (weights become (0, 1) exactly), which makes the
-        // eight corner offsets launch constants: no clamps, no selects, immediate x offset.  Needs every
-        // grid dimension >= 2 (the launcher routes thinner grids to the NANSAFE variant).
-        x0 = min(x0, g.vX - 2); y0 = min(y0, g.vY - 2); z0 = min(z0, g.vZ - 2);
-        wx[1] = rc.ix - (float)x0; wy[1] = rc.iy - (float)y0; wz[1] = rc.iz - (float)z0;
-        wx[0] = 1.0f - wx[1]; wy[0] = 1.0f - wy[1]; wz[0] = 1.0f - wz[1];
-        sy = (long long)g.vX * CP; sz = (long long)g.vY * g.vX * CP;
-      } else {
-        // clamp the far corner's address and zero its weight instead of branching
-        wx[0] = (float)(x0 + 1) - rc.ix; wx[1] = x0 + 1 < g.vX ? rc.ix - (float)x0 : 0.0f;
-        wy[0] = (float)(y0 + 1) - rc.iy; wy[1] = y0 + 1 < g.vY ? rc.iy - (float)y0 : 0.0f;
-        wz[0] = (float)(z0 + 1) - rc.iz; wz[1] = z0 + 1 < g.vZ ? rc.iz - (float)z0 : 0.0f;
-        xo = x0 + 1 < g.vX ? CP : 0; sy = y0 + 1 < g.vY ? g.vX * CP : 0; sz = z0 + 1 < g.vZ ? g.vY * g.vX * CP : 0;
-      }
-      cp[0] = vol + ((z0 * g.vY + y0) * g.vX + x0) * CP;
-      cp[1] = cp[0] + sy; cp[2] = cp[0] + sz; cp[3] = cp[1] + sz;
-      // phase 1: density channel only (8 scalar loads) -> sigma, alpha
+      const float wx[2] = {1.0f - cur.fx, cur.fx}, wy[2] = {1.0f - cur.fy, cur.fy}, wz[2] = {1.0f - cur.fz, cur.fz};
+      // phase 1: density channel only -> sigma, alpha
       float s0 = 0.0f;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int cx = q & 1, cy = (q >> 1) & 1, cz = q >> 2;
         cw[q] = wx[cx] * wy[cy] * wz[cz];
-        s0 = fmaf(cw[q], VbType<T>::ld(cp[cy + 2 * cz] + (cx ? xo : 0)), s0);
+        s0 = fmaf(cw[q], widen_elem(cur.raw[q]), s0);
       }
       if (NANSAFE) s0 = nan_to_num(s0, 0.0f);                                  // BV2:421
       sigma = laplace_density_rcp(s0, g.sdf_bias, inv_beta);                   // BV2:423
@@ -215,14 +246,18 @@ __global__ void __launch_bounds__(kMarchThreads, 5) march_fwd_kernel(VbGrid g, V
       if (live && wgt != 0.0f) {
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-          PackedLoad<T, CP>::template fma_values<K + 3>(cp[(q >> 1)] + ((q & 1) ? xo : 0), cw[q] * wgt, ch);
+          PackedLoad<T, CP>::template fma_values<K + 3>(
+              vol + (size_t)(cur.v0 + ((q & 2) ? sy : 0) + ((q & 4) ? sz : 0)) * CP + ((q & 1) ? dxo * CP : 0),
+              cw[q] * wgt, ch);
       }
     } else if (live && wgt != 0.0f) {
       float v[CP];
 #pragma unroll
       for (int c = 0; c < CP; ++c) v[c] = 0.0f;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) PackedLoad<T, CP>::fma_corner(cp[(q >> 1)] + ((q & 1) ? xo : 0), cw[q], v);
+      for (int q = 0; q < 8; ++q)
+        PackedLoad<T, CP>::fma_corner(
+            vol + (size_t)(cur.v0 + ((q & 2) ? sy : 0) + ((q & 4) ? sz : 0)) * CP + ((q & 1) ? dxo * CP : 0), cw[q], v);
       // torch.nan_to_num (BV2:421): any NaN/inf channel makes the channel sum non-finite, so one
       // test guards the per-channel fix-up
       float chk = 0.0f;
@@ -236,7 +271,8 @@ __global__ void __launch_bounds__(kMarchThreads, 5) march_fwd_kernel(VbGrid g, V
       for (int c = 0; c < K + 3; ++c) ch[c] = fmaf(wgt, v[1 + c], ch[c]);
     }
     tau += sd;
-    p0[0] = p1[0]; p0[1] = p1[1]; p0[2] = p1[2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { p0[a] = p1[a]; p1[a] = p2[a]; }
   }
   if (!active) return;
   const size_t pix = (size_t)h * g.fW + w;

@@ -8,6 +8,9 @@ namespace {
 
 constexpr int kPackThreads = 256;
 constexpr int kMarchThreads = 128;
+#ifndef VB_MARCH_MINB
+#define VB_MARCH_MINB 5
+#endif
 constexpr int kPatchW = 8, kPatchH = 4;  // a warp marches an 8x4 patch of feature-map pixels
 constexpr int kMaxLevels = 16;
 

@@ -491,6 +491,67 @@ torch.library.register_autograd("vampire_b200::render_fwd", _render_backward, se
 
 
 # =============================================================================================
+# producer right before the path: softmax over the depth planes, BV2:551
+@torch.library.custom_op("vampire_b200::depth_softmax_fwd", mutates_args=())
+def depth_softmax_fwd(logits: Tensor, out_fp32: bool) -> Tensor:
+    """logits (..., D, fH, fW) -> softmax over D (dim=-3), fp32 arithmetic; output in fp32 or the logits' dtype."""
+    dev = _need_cuda(logits)
+    if logits.dim() < 3:
+        raise ValueError("depth_softmax: need (..., D, fH, fW)")
+    x = logits.contiguous()
+    D, inner = x.shape[-3], x.shape[-2] * x.shape[-1]
+    outer = x.numel() // (D * inner) if x.numel() else 0
+    out = torch.empty_like(x, dtype=torch.float32 if out_fp32 else x.dtype)
+    if x.numel():
+        with torch.cuda.device(dev):
+            cabi.check(cabi.lib().vb200_depth_softmax_fwd(
+                x.data_ptr(), cabi.dtype_code(x.dtype), out.data_ptr(), cabi.dtype_code(out.dtype), outer, D, inner,
+                cabi.stream_ptr(dev)))
+    return out
+
+
+@depth_softmax_fwd.register_fake
+def _(logits, out_fp32):
+    return torch.empty_like(logits, dtype=torch.float32 if out_fp32 else logits.dtype,
+                            memory_format=torch.contiguous_format)
+
+
+@torch.library.custom_op("vampire_b200::depth_softmax_bwd", mutates_args=())
+def depth_softmax_bwd(probs: Tensor, gprobs: Tensor, out_dtype: torch.dtype) -> Tensor:
+    dev = _need_cuda(probs, gprobs)
+    y = probs.contiguous()
+    g = gprobs.to(y.dtype).contiguous()
+    D, inner = y.shape[-3], y.shape[-2] * y.shape[-1]
+    outer = y.numel() // (D * inner) if y.numel() else 0
+    if y.dtype != torch.float32 and out_dtype != y.dtype:
+        raise TypeError("depth_softmax_bwd: a 16-bit probability tensor yields gradients of the same dtype")
+    out = torch.empty_like(y, dtype=out_dtype)
+    if y.numel():
+        with torch.cuda.device(dev):
+            cabi.check(cabi.lib().vb200_depth_softmax_bwd(
+                y.data_ptr(), g.data_ptr(), cabi.dtype_code(y.dtype), out.data_ptr(), cabi.dtype_code(out_dtype),
+                outer, D, inner, cabi.stream_ptr(dev)))
+    return out
+
+
+@depth_softmax_bwd.register_fake
+def _(probs, gprobs, out_dtype):
+    return torch.empty_like(probs, dtype=out_dtype, memory_format=torch.contiguous_format)
+
+
+def _smx_setup(ctx, inputs, output):
+    ctx.in_dtype = inputs[0].dtype
+    ctx.save_for_backward(output)
+
+
+def _smx_backward(ctx, gout):
+    (y,) = ctx.saved_tensors
+    return depth_softmax_bwd(y, gout, ctx.in_dtype), None
+
+
+torch.library.register_autograd("vampire_b200::depth_softmax_fwd", _smx_backward, setup_context=_smx_setup)
+
+
 # callers right after the path (SURVEY §8f rows 2-3): x4 upsample of the rendered maps, point queries
 # =============================================================================================
 @torch.library.custom_op("vampire_b200::upsample_fwd", mutates_args=())

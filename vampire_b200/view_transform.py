@@ -146,6 +146,13 @@ class LiftRenderB200(nn.Module):
         return tuple(outs)
 
     # ---- the callers right after the path ------------------------------------
+    def depth_softmax(self, depth_logits: Tensor, out_fp32: bool = True) -> Tensor:
+        """``mapping_along_depth(source_features).softmax(dim=1)`` (BV2:551) on (B*N, D, fH, fW) -- or
+        (B, N, D, fH, fW) -- logits: softmax over the D depth planes in fp32.  ``out_fp32=True`` mirrors the
+        reference under AMP (softmax is an autocast-to-fp32 op); ``False`` keeps the logits' dtype, which is what
+        the bf16-feature lift consumes."""
+        return ops.depth_softmax_fwd(depth_logits, out_fp32)
+
     def upsample2d(self, x: Tensor) -> Tensor:
         """``nn.UpsamplingBilinear2d(scale_factor=upsample_factor)`` (BV2:210) on (..., fH, fW) maps."""
         return ops.upsample_fwd(x, self.cfg.upsample_factor)

@@ -34,9 +34,12 @@ namespace {
 // stream (fork event before, join event after), so caller-owned buffers remain valid.
 std::atomic<int> g_render_fork_disabled{0};
 
+constexpr int kMaxSplit = 8;
 struct SideStream {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaStream_t stream = nullptr;      // low priority: BEV branch
+  cudaStream_t stream_hi = nullptr;   // high priority: packs of the later sample groups (see launch_render_fwd)
+  cudaEvent_t fork = nullptr, join = nullptr, first_pack = nullptr;
+  cudaEvent_t packed[kMaxSplit] = {};
 };
 SideStream* side_stream_for_current_device() {
   static std::mutex mu;
@@ -49,8 +52,12 @@ SideStream* side_stream_for_current_device() {
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);   // lowest priority: never starve the caller's stream
     if (cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithPriority(&s.stream_hi, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&s.first_pack, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    for (auto& e : s.packed)
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
   }
   return &s;
 }
@@ -1042,46 +1049,32 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
   };
   if (!(branches & VB200_BRANCH_CAM)) return launch_bev(st);
   if (per != nvox * packed_channels(K) * sizeof(T)) return VB200_ERR_ARG;  // march indexes densely
-  for (int b0 = 0; b0 < g->B; b0 += group) {
-    const int nb = (g->B - b0) < group ? (g->B - b0) : group;
-    int* nf_flag = reinterpret_cast<int*>((char*)ws + cam_bytes + bev_bytes - 256);
-    // thin grids (a dimension of one voxel) cannot shift the corner base inwards: raise the flag up front,
-    // the pack never lowers it, and the exact clamp-and-zero variant of the march runs
-    const int flag_init = (g->vX < 2 || g->vY < 2 || g->vZ < 2) ? 1 : 0;
-    {
-      VbTraceScope tr(VB_K_PACK, st);
-      if (cudaMemsetAsync(nf_flag, flag_init, sizeof(int), st) != cudaSuccess) return VB200_ERR_CUDA;
-      pack_cam_volume_kernel<T, K><<<dim3(vb_ceil_div(nvox, kPackThreads * PackVox<T>::n), nb), kPackThreads, 0, st>>>(
-          den + (size_t)b0 * nvox, sem + (size_t)b0 * K * nvox, rgb + (size_t)b0 * 3 * nvox,
-          reinterpret_cast<T*>(ws), (int)nvox, per / sizeof(T), nf_flag);
-      VB_LAUNCH_CHECK();
-    }
-    if (b0 == 0 && (branches & VB200_BRANCH_BEV)) {
-      // fork AFTER the first pack: the pack is HBM-bound, the march issue-bound -- the BEV kernels
-      // (low-priority side stream) fill the march's idle issue slots instead of fighting the pack for DRAM
-      cudaStream_t bst = st;
-      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-      cudaStreamIsCapturing(st, &cap);
-      static const bool no_fork_env = getenv("VB200_NO_FORK") != nullptr;   // measurement aid
-      const bool no_fork = no_fork_env || g_render_fork_disabled.load(std::memory_order_relaxed) != 0;
-      if (!no_fork && cap == cudaStreamCaptureStatusNone && (side = side_stream_for_current_device()) != nullptr) {
-        if (cudaEventRecord(side->fork, st) == cudaSuccess &&
-            cudaStreamWaitEvent(side->stream, side->fork, 0) == cudaSuccess) {
-          bst = side->stream;
-          forked = true;
-        }
-      }
-      const int rc = launch_bev(bst);
-      if (rc) return rc;
-      if (forked && cudaEventRecord(side->join, bst) != cudaSuccess) return VB200_ERR_CUDA;
-    }
+  // thin grids (a dimension of one voxel) cannot shift the corner base inwards: raise the flag up front,
+  // the pack never lowers it, and the exact clamp-and-zero variant of the march runs
+  const int flag_init = (g->vX < 2 || g->vY < 2 || g->vZ < 2) ? 1 : 0;
+  int* nf_flags = reinterpret_cast<int*>((char*)ws + cam_bytes + bev_bytes - 256);   // one int per sub-round
+  const VbRenderDiv dv = vb_render_div(g);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap);
+  static const bool no_fork_env = getenv("VB200_NO_FORK") != nullptr;   // measurement aid
+  const bool no_fork = no_fork_env || g_render_fork_disabled.load(std::memory_order_relaxed) != 0;
+  const bool may_fork = !no_fork && cap == cudaStreamCaptureStatusNone;
+
+  auto pack_round = [&](int b0, int nb, T* region, int* flag, cudaStream_t ps) -> int {
+    VbTraceScope tr(VB_K_PACK, ps);
+    if (cudaMemsetAsync(flag, flag_init, sizeof(int), ps) != cudaSuccess) return VB200_ERR_CUDA;
+    pack_cam_volume_kernel<T, K><<<dim3(vb_ceil_div(nvox, kPackThreads * PackVox<T>::n), nb), kPackThreads, 0, ps>>>(
+        den + (size_t)b0 * nvox, sem + (size_t)b0 * K * nvox, rgb + (size_t)b0 * 3 * nvox, region, (int)nvox,
+        per / sizeof(T), flag);
+    VB_LAUNCH_CHECK();
+    return VB200_OK;
+  };
+  auto march_round = [&](int b0, int nb, const T* region, const int* flag) -> int {
     dim3 grid(vb_ceil_div(patches, kMarchThreads / 32), g->N, nb);
     VbTraceScope tr(VB_K_MARCH_FWD, st, 2);
-    const VbRenderDiv dv = vb_render_div(g);
-#define VB_MARCH(FM, FD, NS)                                                                                      \
-  march_fwd_kernel<T, K, FM, FD, NS><<<grid, kMarchThreads, 0, st>>>(*g, *t, dv, d_mats, in->geom,                \
-                                                                     reinterpret_cast<const T*>(ws), nf_flag, in->beta, \
-                                                                     out->rgb, out->seg, out->depth, b0)
+#define VB_MARCH(FM, FD, NS)                                                                                        \
+  march_fwd_kernel<T, K, FM, FD, NS><<<grid, kMarchThreads, 0, st>>>(*g, *t, dv, d_mats, in->geom, region, flag,    \
+                                                                     in->beta, out->rgb, out->seg, out->depth, b0)
     if (in->geom) {
       VB_MARCH(false, false, false);
       VB_MARCH(false, false, true);
@@ -1094,6 +1087,72 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
     }
 #undef VB_MARCH
     VB_LAUNCH_CHECK();
+    return VB200_OK;
+  };
+  auto fork_bev = [&]() -> int {
+    // fork AFTER the first pack: the pack is HBM-bound, the march issue-bound -- the BEV kernels
+    // (low-priority side stream) fill the march's idle issue slots instead of fighting the pack for DRAM
+    cudaStream_t bst = st;
+    if (may_fork && (side = side_stream_for_current_device()) != nullptr) {
+      if (cudaEventRecord(side->fork, st) == cudaSuccess && cudaStreamWaitEvent(side->stream, side->fork, 0) == cudaSuccess) {
+        bst = side->stream;
+        forked = true;
+      }
+    }
+    const int rc = launch_bev(bst);
+    if (rc) return rc;
+    if (forked && cudaEventRecord(side->join, bst) != cudaSuccess) return VB200_ERR_CUDA;
+    return VB200_OK;
+  };
+
+  // Sample groups.  Optional experiment (VB200_RENDER_SPLIT=n, default off): when the workspace holds every
+  // sample's packed volume, split the batch into n sub-rounds whose packs (HBM-bound) run on a high-priority side
+  // stream under the march of the previous sub-round (L1 / issue-bound, 8 % DRAM).  Measured on B200 (R50, B=8,
+  // bf16): 1.26 ms/step unsplit, 1.34 (n=2), 1.57 (n=4), 2.15 (n=8) -- a march over fewer samples loses more to
+  // partial waves and to the co-running pack than hiding the pack gains, so one round over the whole batch stays
+  // the default.  Everything stays stream-ordered for the caller either way.
+  int nsplit = 1;
+  if (group >= g->B && may_fork && g->B >= 4 && (side || (side = side_stream_for_current_device()) != nullptr)) {
+    static const int split_env = getenv("VB200_RENDER_SPLIT") ? atoi(getenv("VB200_RENDER_SPLIT")) : 0;
+    nsplit = split_env > 0 ? split_env : 1;
+    if (nsplit > kMaxSplit) nsplit = kMaxSplit;
+    if (nsplit > g->B) nsplit = g->B;
+  }
+  if (nsplit > 1) {
+    const int sub = vb_ceil_div(g->B, nsplit);
+    int rc = pack_round(0, sub < g->B ? sub : g->B, reinterpret_cast<T*>(ws), nf_flags, st);
+    if (rc) return rc;
+    if (cudaEventRecord(side->first_pack, st) != cudaSuccess ||
+        cudaStreamWaitEvent(side->stream_hi, side->first_pack, 0) != cudaSuccess)
+      return VB200_ERR_CUDA;
+    for (int k = 1; k * sub < g->B; ++k) {
+      const int b0 = k * sub, nb = (g->B - b0) < sub ? (g->B - b0) : sub;
+      rc = pack_round(b0, nb, reinterpret_cast<T*>((char*)ws + (size_t)b0 * per), nf_flags + k, side->stream_hi);
+      if (rc) return rc;
+      if (cudaEventRecord(side->packed[k], side->stream_hi) != cudaSuccess) return VB200_ERR_CUDA;
+    }
+    if (branches & VB200_BRANCH_BEV) {
+      rc = fork_bev();
+      if (rc) return rc;
+    }
+    for (int k = 0; k * sub < g->B; ++k) {
+      const int b0 = k * sub, nb = (g->B - b0) < sub ? (g->B - b0) : sub;
+      if (k > 0 && cudaStreamWaitEvent(st, side->packed[k], 0) != cudaSuccess) return VB200_ERR_CUDA;
+      rc = march_round(b0, nb, reinterpret_cast<const T*>((char*)ws + (size_t)b0 * per), nf_flags + k);
+      if (rc) return rc;
+    }
+  } else {
+    for (int b0 = 0; b0 < g->B; b0 += group) {
+      const int nb = (g->B - b0) < group ? (g->B - b0) : group;
+      int rc = pack_round(b0, nb, reinterpret_cast<T*>(ws), nf_flags, st);
+      if (rc) return rc;
+      if (b0 == 0 && (branches & VB200_BRANCH_BEV)) {
+        rc = fork_bev();
+        if (rc) return rc;
+      }
+      rc = march_round(b0, nb, reinterpret_cast<const T*>(ws), nf_flags);
+      if (rc) return rc;
+    }
   }
   if (forked && cudaStreamWaitEvent(st, side->join, 0) != cudaSuccess) return VB200_ERR_CUDA;
   return VB200_OK;

@@ -79,6 +79,9 @@ typedef struct VbGrid {
   float sdf_bias;         /* density bias (-1)                 render_utils.py:35               */
   float beta_min;         /* 1e-4                              render_utils.py:31               */
   float term_eps;         /* early-termination threshold on transmittance; 0 disables          */
+  int32_t lift_2d;        /* 1: the BaseBiLinear 2-D lift (base_bilinear.py:471-517): no depth
+                           * distribution -- D must be 1, the depth test is z > 0 (set d_lo = 0, d_hi = +inf),
+                           * the z sample position is the single plane (iz = 0); pass a depth tensor of ones    */
 } VbGrid;
 
 /* Lattice tables, DEVICE pointers to fp32 arrays built on the host with the reference's own torch

@@ -40,6 +40,19 @@ def load_reference_module():
     return mod
 
 
+def reference_bilinear_get_voxel_feats():
+    """The unbound ``BaseBiLinear.get_voxel_feats`` (base_bilinear.py:471): it only touches ``self.get_pixel``,
+    ``self.final_dim`` and ``self.vZ/vY/vX``, all of which a ``BaseVAMPIRE2`` instance provides identically."""
+    load_reference_module()          # installs the import stubs
+    path = os.path.join(REFERENCE_ROOT, "src/layers/backbones/base_bilinear.py")
+    spec = importlib.util.spec_from_file_location("ref_bilinear", path)
+    mod = importlib.util.module_from_spec(spec)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        spec.loader.exec_module(mod)
+    return mod.BaseBiLinear.get_voxel_feats
+
+
 def build_reference_backbone(conf: dict):
     """Instantiate ``BaseVAMPIRE2`` with dummy image encoder (never executed)."""
     mod = load_reference_module()

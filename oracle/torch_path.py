@@ -138,6 +138,28 @@ def get_voxel_feats(conf, buf, frustum_feats, mats):
     return numer / denom
 
 
+def get_voxel_feats_2d(conf, buf, img_feats, mats):
+    """base_bilinear.py:471-517 ``BaseBiLinear.get_voxel_feats``: bilinear sampling of the (B,N,C,h,w) image
+    features on a depth-1 volume at z = 0, z_valid = z > 0, non-zero mean over cameras."""
+    B, N, C, h, w = img_feats.shape
+    H, W = conf["final_dim"]
+    pix = get_pixel(buf, mats["sensor2ego_mats"][:, 0], mats["intrin_mats"][:, 0],
+                    mats["ida_mats"][:, 0], mats.get("bda_mat", None))
+    Z, Y, X = buf["voxel_coords"].shape[:3]
+    x, y, z = pix[..., 0], pix[..., 1], pix[..., 2]
+    xv = (x > -0.5).bool() & (x < float(W - 0.5)).bool()
+    yv = (y > -0.5).bool() & (y < float(H - 0.5)).bool()
+    zv = (z > 0.).bool()
+    valid = (xv & yv & zv).float()
+    nx = torch.clamp(2.0 * (x / float(W - 1)) - 1.0, min=-2.0, max=2.0)
+    ny = torch.clamp(2.0 * (y / float(H - 1)) - 1.0, min=-2.0, max=2.0)
+    nxyz = torch.stack([nx, ny, torch.zeros_like(nx)], dim=-1).reshape(-1, Z, Y, X, 3)
+    vf = F.grid_sample(img_feats.reshape(-1, C, 1, h, w), nxyz, align_corners=False)
+    vf = vf.reshape(B, N, C, Z, Y, X) * valid.unsqueeze(2)
+    mask = (torch.abs(vf) > 0).float()
+    return torch.sum(vf, dim=1) / (torch.sum(mask, dim=1) + 1e-6)
+
+
 def lift_pool(conf, buf, depth, ctx, mats):
     """BV2:553 + 563: the fused operation the product implements."""
     return get_voxel_feats(conf, buf, lift_outer(depth, ctx), mats)

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import torch_path as tp
-from oracle.ref_import import build_reference_backbone, reference_available
+from oracle.ref_import import build_reference_backbone, reference_available, reference_bilinear_get_voxel_feats
 from vampire_b200 import synth
 from vampire_b200.config import MINI
 
@@ -63,3 +63,21 @@ def test_post_path_restatements(ref):
     # §8f row 1: the reference's inline `.softmax(dim=1)` on the (B*N, D, fH, fW) depth logits (BV2:551)
     lg = torch.randn(6, MINI.D, MINI.fH, MINI.fW, generator=torch.Generator().manual_seed(2))
     assert torch.equal(lg.softmax(dim=1), tp.depth_softmax(lg))
+
+
+@pytest.mark.parametrize("mode", ["val", "stress"])
+def test_bilinear_2d_lift_restatement(ref, mode):
+    """§8f row 4: ``BaseBiLinear.get_voxel_feats`` (base_bilinear.py:471-517), bit for bit incl. its autograd."""
+    cfg, conf = MINI, MINI.backbone_kwargs()
+    buf = tp.build_buffers(conf)
+    mats = synth.make_mats(cfg, 2, mode, seed=31)
+    _, ctx = synth.make_lift_inputs(cfg, 2, seed=31)
+    a = ctx.clone().requires_grad_(True)
+    b = ctx.clone().requires_grad_(True)
+    o_ref = reference_bilinear_get_voxel_feats()(ref, a, 0, mats)
+    o_me = tp.get_voxel_feats_2d(conf, buf, b, mats)
+    assert torch.equal(o_ref, o_me)
+    cot = synth.make_cotangents([o_ref.shape], seed=6)[0]
+    g_ref, = torch.autograd.grad((o_ref * cot).sum(), a)
+    g_me, = torch.autograd.grad((o_me * cot).sum(), b)
+    assert torch.allclose(g_ref, g_me, rtol=1e-6, atol=1e-7)

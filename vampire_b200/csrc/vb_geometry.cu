@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) get_geometry_kernel(VbGrid g, VbTables t,
 int check_grid(const VbGrid* g) {
   if (!g) return VB200_ERR_ARG;
   if (g->B <= 0 || g->N <= 0 || g->N > VB_MAX_CAMS) return VB200_ERR_ARG;
-  if (g->D < 2 || g->fH <= 0 || g->fW <= 0 || g->vZ <= 0 || g->vY <= 0 || g->vX <= 0) return VB200_ERR_ARG;
+  if ((g->lift_2d ? g->D != 1 : g->D < 2) || g->fH <= 0 || g->fW <= 0 || g->vZ <= 0 || g->vY <= 0 || g->vX <= 0) return VB200_ERR_ARG;
   return VB200_OK;
 }
 

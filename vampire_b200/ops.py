@@ -25,8 +25,10 @@ Tensor = torch.Tensor
 class PathState:
     """Per-config state: the lattice (host) and its per-device copies."""
 
-    def __init__(self, cfg: PathConfig):
+    def __init__(self, cfg: PathConfig, lift_2d: bool = False):
         self.cfg = cfg
+        # the BaseBiLinear ablation's 2-D lift (base_bilinear.py:471-517): same kernels, one depth plane of ones
+        self.lift_2d = lift_2d
         self.lattice: Lattice = build_lattice(cfg)
         self._tables: Dict[torch.device, cabi.DeviceTables] = {}
         self.term_eps = 1e-8
@@ -44,19 +46,27 @@ class PathState:
             self._tables[device] = cabi.DeviceTables(self.lattice, device)
         return self._tables[device]
 
+    @property
+    def lift_D(self) -> int:
+        """Depth planes of the lift input: the config's D, or 1 for the 2-D lift."""
+        return 1 if self.lift_2d else self.cfg.D
+
     def grid(self, batch: int, has_bda: bool) -> cabi.VbGrid:
-        return cabi.make_grid(self.cfg, batch, has_bda, self.term_eps)
+        return cabi.make_grid(self.cfg, batch, has_bda, self.term_eps, self.lift_2d)
 
 
 _STATES: List[PathState] = []
-_BY_CFG: Dict[PathConfig, int] = {}
+_BY_CFG: Dict[Tuple[PathConfig, bool], int] = {}
 
 
-def register_config(cfg: PathConfig) -> int:
-    if cfg not in _BY_CFG:
-        _STATES.append(PathState(cfg))
-        _BY_CFG[cfg] = len(_STATES) - 1
-    return _BY_CFG[cfg]
+def register_config(cfg: PathConfig, lift_2d: bool = False) -> int:
+    """Handle of a path configuration.  ``lift_2d=True`` registers the variant whose lift ops implement the
+    BaseBiLinear 2-D lift (only ``lift_pool_fwd/bwd`` and ``lift_indices`` are meaningful on it)."""
+    key = (cfg, bool(lift_2d))
+    if key not in _BY_CFG:
+        _STATES.append(PathState(cfg, bool(lift_2d)))
+        _BY_CFG[key] = len(_STATES) - 1
+    return _BY_CFG[key]
 
 
 def state(handle: int) -> PathState:
@@ -177,7 +187,7 @@ def lift_pool_fwd(depth: Tensor, ctx: Tensor, mats: Tensor, cfg_id: int, has_bda
     cfg = st.cfg
     dev = _need_cuda(depth, ctx, mats)
     B, N = depth.shape[:2]
-    if depth.shape != (B, N, cfg.D, cfg.fH, cfg.fW) or ctx.shape != (B, N, cfg.C, cfg.fH, cfg.fW):
+    if depth.shape != (B, N, st.lift_D, cfg.fH, cfg.fW) or ctx.shape != (B, N, cfg.C, cfg.fH, cfg.fW):
         raise ValueError(f"lift_pool: depth {tuple(depth.shape)} / ctx {tuple(ctx.shape)} do not match the config")
     if ctx.dtype != depth.dtype:
         raise TypeError("lift_pool: depth and ctx must share a dtype")

@@ -137,6 +137,21 @@ class LiftRenderB200(nn.Module):
                                    self.channels_last_volume, need_grad)
         return out
 
+    def lift_pool_2d(self, img_feats: Tensor, mats_dict: Dict[str, Tensor], sweep_index: int = 0) -> Tensor:
+        """The ``BaseBiLinear`` ablation's lift (base_bilinear.py:471-517 ``get_voxel_feats``):
+        no depth distribution -- every voxel centre with z > 0 bilinearly samples the (B,N,C,fH,fW) image
+        features of each camera it projects into, non-zero mean over cameras.  It is the D = 1 case of the lift
+        kernels (one depth plane of ones, depth test z > 0); gradients flow to ``img_feats``."""
+        mats, has_bda = self._prep_dict(mats_dict, sweep_index, img_feats.device)
+        if not hasattr(self, "_cfg_id_2d"):
+            self._cfg_id_2d = ops.register_config(self.cfg, lift_2d=True)
+        B, N, _, h, w = img_feats.shape
+        ones = torch.ones(B, N, 1, h, w, dtype=img_feats.dtype, device=img_feats.device)
+        need_grad = torch.is_grad_enabled() and img_feats.requires_grad
+        out, _ = ops.lift_pool_fwd(ones, img_feats, mats, self._cfg_id_2d, has_bda, self.channels_last_volume,
+                                   need_grad)
+        return out
+
     def render(self, mats_dict: Dict[str, Tensor], density_feature: Tensor, semantic_logits: Tensor,
                voxel_features: Tensor, rgb: Tensor, sweep_index: int = 0, branches: int = 3):
         """BV2:554-559 + 612-614: geometry recomputed in-kernel from the matrices (never stored)."""

@@ -63,7 +63,10 @@ enum vb200_layout {
  * torch rounds a Python scalar operand. */
 typedef struct VbGrid {
   int32_t B, N;           /* samples, cameras per sample (6)                                    */
-  int32_t D, fH, fW;      /* depth planes (86), feature rows (64), feature cols (176)           */
+  int32_t D, fH, fW;      /* depth planes (86), feature rows (64), feature cols (176).  D == 1 selects the 2-D
+                           * lift of the BaseBiLinear ablation (base_bilinear.py:471-517) in
+                           * the lift entry points: no depth distribution, depth test z > 0 (pass d_lo = 0,
+                           * d_hi = +inf), the single plane sampled at iz = 0; pass a depth tensor of ones     */
   int32_t vZ, vY, vX;     /* seg voxel grid (20, 256, 256)                                      */
   int32_t oZ, oY, oX;     /* det / BEV grid (10, 256, 256)                                      */
   int32_t C, K;           /* context channels (16), semantic classes (18)                       */
@@ -79,9 +82,6 @@ typedef struct VbGrid {
   float sdf_bias;         /* density bias (-1)                 render_utils.py:35               */
   float beta_min;         /* 1e-4                              render_utils.py:31               */
   float term_eps;         /* early-termination threshold on transmittance; 0 disables          */
-  int32_t lift_2d;        /* 1: the BaseBiLinear 2-D lift (base_bilinear.py:471-517): no depth
-                           * distribution -- D must be 1, the depth test is z > 0 (set d_lo = 0, d_hi = +inf),
-                           * the z sample position is the single plane (iz = 0); pass a depth tensor of ones    */
 } VbGrid;
 
 /* Lattice tables, DEVICE pointers to fp32 arrays built on the host with the reference's own torch

@@ -38,7 +38,6 @@ class VbGrid(C.Structure):
         ("seg_lo", C.c_float * 3), ("seg_ext", C.c_float * 3),
         ("bg_depth", C.c_float), ("bev_delta", C.c_float),
         ("sdf_bias", C.c_float), ("beta_min", C.c_float), ("term_eps", C.c_float),
-        ("lift_2d", C.c_int32),
     ]
 
 
@@ -169,10 +168,9 @@ def make_grid(cfg: PathConfig, batch: int, has_bda: bool = True, term_eps: float
     g.sdf_bias = cfg.sdf_bias
     g.beta_min = 1e-4                                            # render_utils.py:31
     g.term_eps = term_eps
-    g.lift_2d = 0
     if lift_2d:
-        # BaseBiLinear's 2-D lift (base_bilinear.py:471-517): one depth plane, depth test z > 0
-        g.lift_2d, g.D = 1, 1
+        # BaseBiLinear's 2-D lift (base_bilinear.py:471-517): D == 1 selects it -- one depth plane, test z > 0
+        g.D = 1
         g.d_lo, g.d_hi, g.d_ext = 0.0, float("inf"), 1.0
     return g
 

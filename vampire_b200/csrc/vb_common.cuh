@@ -302,7 +302,7 @@ __device__ __forceinline__ LiftCoord lift_coord(const VbGrid& g, const float (&p
   c.x0 = (int)floorf(c.ix);
   c.y0 = (int)floorf(c.iy);
   c.z0 = (int)floorf(c.iz);
-  if (g.lift_2d) {
+  if (g.D == 1) {
     // BaseBiLinear (base_bilinear.py:484, 505-507): z_valid = z > 0, and the sampled volume has ONE depth plane
     // addressed at normalised z = 0, i.e. iz = ((0 + 1) * 1 - 1) / 2 = 0: plane 0 with weight 1 (launch-uniform)
     c.valid = (x > -0.5f) && (x < g.x_hi) && (y > -0.5f) && (y < g.y_hi) && (z > 0.0f);

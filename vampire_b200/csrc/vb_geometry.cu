@@ -96,10 +96,11 @@ __global__ void __launch_bounds__(256) get_geometry_kernel(VbGrid g, VbTables t,
   }
 }
 
-int check_grid(const VbGrid* g) {
+// min_D: 1 for the voxel-side entry points (D == 1 = the 2-D lift), 2 for the frustum-side ones (rays need 2 planes)
+int check_grid(const VbGrid* g, int min_D = 2) {
   if (!g) return VB200_ERR_ARG;
   if (g->B <= 0 || g->N <= 0 || g->N > VB_MAX_CAMS) return VB200_ERR_ARG;
-  if ((g->lift_2d ? g->D != 1 : g->D < 2) || g->fH <= 0 || g->fW <= 0 || g->vZ <= 0 || g->vY <= 0 || g->vX <= 0) return VB200_ERR_ARG;
+  if (g->D < min_D || g->fH <= 0 || g->fW <= 0 || g->vZ <= 0 || g->vY <= 0 || g->vX <= 0) return VB200_ERR_ARG;
   return VB200_OK;
 }
 
@@ -107,7 +108,7 @@ int check_grid(const VbGrid* g) {
 
 extern "C" int vb200_get_pixel(const VbGrid* g, const VbTables* t, const float* d_mats, float* d_pix,
                                void* stream) {
-  int rc = check_grid(g);
+  int rc = check_grid(g, 1);
   if (rc) return rc;
   VB_CHECK_ARG(t && d_mats && d_pix);
   if ((rc = vb200_device_check())) return rc;
@@ -121,7 +122,7 @@ extern "C" int vb200_get_pixel(const VbGrid* g, const VbTables* t, const float* 
 
 extern "C" int vb200_lift_indices(const VbGrid* g, const VbTables* t, const float* d_mats, uint8_t* d_valid,
                                   int16_t* d_i0, float* d_frac, void* stream) {
-  int rc = check_grid(g);
+  int rc = check_grid(g, 1);
   if (rc) return rc;
   VB_CHECK_ARG(t && d_mats);
   if ((rc = vb200_device_check())) return rc;

@@ -308,7 +308,7 @@ extern "C" int vb200_lift_pool_fwd(const VbGrid* g, const VbTables* t, const flo
                                    void* d_workspace, size_t workspace_bytes, void* stream) {
   VB_CHECK_ARG(g && t && d_mats && d_depth && d_ctx && d_out && d_workspace);
   VB_CHECK_ARG(g->B > 0 && g->N > 0 && g->N <= VB_MAX_CAMS);
-  VB_CHECK_ARG(!g->lift_2d || g->D == 1);
+  VB_CHECK_ARG(g->D >= 1);
   VB_CHECK_ARG(out_layout == VB200_NCDHW || out_layout == VB200_NDHWC);
   if (workspace_bytes < vb200_lift_pool_fwd_workspace(g, dtype)) return VB200_ERR_WORKSPACE;
   if (((uintptr_t)d_workspace | (uintptr_t)d_out | (uintptr_t)d_ctx | (uintptr_t)d_depth) & 15) return VB200_ERR_ALIGN;

@@ -510,7 +510,7 @@ extern "C" int vb200_lift_pool_bwd(const VbGrid* g, const VbTables* t, const flo
                                    size_t workspace_bytes, void* stream) {
   VB_CHECK_ARG(g && t && d_mats && d_depth && d_ctx && d_gout && d_cnt && d_gdepth && d_gctx && d_workspace);
   VB_CHECK_ARG(g->B > 0 && g->N > 0 && g->N <= VB_MAX_CAMS);
-  VB_CHECK_ARG(!g->lift_2d || g->D == 1);
+  VB_CHECK_ARG(g->D >= 1);
   VB_CHECK_ARG(gout_layout == VB200_NCDHW || gout_layout == VB200_NDHWC);
   if (workspace_bytes < vb200_lift_pool_bwd_workspace(g, dtype)) return VB200_ERR_WORKSPACE;
   if (((uintptr_t)d_workspace | (uintptr_t)d_gout | (uintptr_t)d_gctx | (uintptr_t)d_gdepth) & 15) return VB200_ERR_ALIGN;

@@ -11,7 +11,10 @@ constexpr int kMarchThreads = 128;
 #ifndef VB_MARCH_MINB
 #define VB_MARCH_MINB 5
 #endif
-constexpr int kPatchW = 8, kPatchH = 4;  // a warp marches an 8x4 patch of feature-map pixels
+#ifndef VB_PATCH_W
+#define VB_PATCH_W 8
+#endif
+constexpr int kPatchW = VB_PATCH_W, kPatchH = 32 / VB_PATCH_W;  // a warp marches an 8x4 patch of feature-map pixels
 constexpr int kMaxLevels = 16;
 
 __host__ __device__ constexpr int packed_channels(int K) { return ((K + 4) + 7) / 8 * 8; }

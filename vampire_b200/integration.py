@@ -48,6 +48,11 @@ def attach(backbone: nn.Module, channels_last_volume: bool = False) -> nn.Module
         return self._vb200_path.get_pixel(sensor2ego_mat, intrin_mat, ida_mat, bda_mat)
 
     def get_voxel_feats(self, frustum_feats, sweep_index, mats_dict, clamp_extreme=True):
+        if frustum_feats.dim() == 5:
+            # BaseBiLinear.get_voxel_feats (base_bilinear.py:471): (B,N,C,h,w) image features, 2-D lift
+            if not clamp_extreme:
+                raise NotImplementedError("clamp_extreme=False is never used by the reference")
+            return self._vb200_path.lift_pool_2d(frustum_feats, mats_dict, sweep_index)
         return self._vb200_path.get_voxel_feats(frustum_feats, sweep_index, mats_dict, clamp_extreme)
 
     def volume_rendering_from_multiple_views(self, geom_xyz, density_feature, semantic_logits, voxel_features, rgb):
@@ -60,7 +65,11 @@ def attach(backbone: nn.Module, channels_last_volume: bool = False) -> nn.Module
     def render(self, mats_dict, density_feature, semantic_logits, voxel_features, rgb, sweep_index=0):
         return self._vb200_path.render(mats_dict, density_feature, semantic_logits, voxel_features, rgb, sweep_index)
 
-    for fn in (get_geometry, get_pixel, get_voxel_feats, volume_rendering_from_multiple_views, lift_pool, render):
+    def depth_softmax(self, depth_logits, out_fp32=True):
+        return self._vb200_path.depth_softmax(depth_logits, out_fp32)
+
+    for fn in (get_geometry, get_pixel, get_voxel_feats, volume_rendering_from_multiple_views, lift_pool, render,
+               depth_softmax):
         setattr(backbone, fn.__name__, types.MethodType(fn, backbone))
     # the x4 upsample of the rendered maps right after the path (BV2:210, 616-626): parameter-free module
     if hasattr(backbone, "upsample2d") and hasattr(backbone, "upsample_factor"):

@@ -21,10 +21,10 @@
 namespace {
 
 #ifndef VB_LIFT_THREADS
-#define VB_LIFT_THREADS 256
+#define VB_LIFT_THREADS 128
 #endif
 #ifndef VB_LIFT_MINB
-#define VB_LIFT_MINB 4
+#define VB_LIFT_MINB 8
 #endif
 constexpr int kLiftThreads = VB_LIFT_THREADS;
 
@@ -266,10 +266,11 @@ int launch_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, const vo
     ctx_to_nhwc_kernel<T, C><<<grid, 256, smem, st>>>(reinterpret_cast<const T*>(d_ctx), ctx_nhwc, g->fH, g->fW);
     VB_LAUNCH_CHECK();
   }
-  // z-run per thread: 5 levels measured best on B200 (B=8: 0.54 ms vs 0.66 at 1 and 0.60 at 20 -- longer runs
-  // make the warp-level camera mask less selective); override with VB200_LIFT_ZRUN for experiments
+  // z-run per thread: longer runs amortise the prologue, shorter ones keep the warp-level camera mask selective.
+  // Measured on B200 (R50, B=8, bf16) with 128-thread blocks at 8 blocks/SM: 0.349 ms at 10 levels, 0.355 at 5
+  // (256-thread blocks: 0.356 / 0.362); override with VB200_LIFT_ZRUN for experiments
   const int plane_blocks = vb_ceil_div(g->vY * g->vX, kLiftThreads);
-  int zrun = g->vZ < 5 ? g->vZ : 5;
+  int zrun = g->vZ < 10 ? g->vZ : 10;
   {
     const char* env = getenv("VB200_LIFT_ZRUN");
     if (env && atoi(env) > 0) zrun = atoi(env);

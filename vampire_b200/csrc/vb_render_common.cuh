@@ -7,7 +7,10 @@
 namespace {
 
 constexpr int kPackThreads = 256;
-constexpr int kMarchThreads = 128;
+#ifndef VB_MARCH_THREADS
+#define VB_MARCH_THREADS 128
+#endif
+constexpr int kMarchThreads = VB_MARCH_THREADS;
 #ifndef VB_MARCH_MINB
 #define VB_MARCH_MINB 5
 #endif

@@ -190,7 +190,10 @@ def run_reference_arm(args, cfg):
         "impl": "reference", "metric": "lifted_frustum_pts_per_s", "value": value, "unit": "frustum pts/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, cfg, 1, "fp32"),
+        # the SAME workload description as this repo's arm (the driver compares the two lines); what one timed
+        # step actually ran -- a bounded sample of it, fp32 like the reference -- is stated in cpu_baseline.sample
+        "config": workload_config(args, cfg, args.batch or (1 if args.workload == "train" else 8),
+                                  args.dtype or ("fp32" if args.workload == "train" else "bf16")),
         "cpu_baseline": {"value": value, "unit": "frustum pts/s", "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "frustum pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

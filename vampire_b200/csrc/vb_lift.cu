@@ -38,15 +38,23 @@ __global__ void __launch_bounds__(256) ctx_to_nhwc_kernel(const T* __restrict__ 
   T* s = reinterpret_cast<T*>(s_raw);  // [C][fW + 1]
   const int h = blockIdx.x, bn = blockIdx.y;
   const int ld = fW + 1;
-  for (int i = threadIdx.x; i < C * fW; i += blockDim.x) {
-    const int c = i / fW, w = i % fW;
-    s[c * ld + w] = src[(((size_t)bn * C + c) * fH + h) * fW + w];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // read: a warp per channel row, lanes along w (coalesced, no integer division)
+  for (int c = wid; c < C; c += nw) {
+    const T* row = src + (((size_t)bn * C + c) * fH + h) * fW;
+    for (int w = lane; w < fW; w += 32) s[c * ld + w] = row[w];
   }
   __syncthreads();
-  T* out = dst + ((size_t)bn * fH + h) * fW * C;
-  for (int i = threadIdx.x; i < C * fW; i += blockDim.x) {
-    const int w = i / C, c = i % C;
-    out[i] = s[c * ld + w];
+  // write: one 128-bit store per thread = 16 / sizeof(T) consecutive channels of one pixel
+  constexpr int L = 16 / sizeof(T), PARTS = C / L;
+  static_assert(C % L == 0, "a pixel's channels must be whole 128-bit groups");
+  uint4* out = reinterpret_cast<uint4*>(dst + ((size_t)bn * fH + h) * fW * C);
+  for (int p = threadIdx.x; p < fW * PARTS; p += blockDim.x) {
+    const int w = p / PARTS, c0 = (p % PARTS) * L;   // PARTS is a compile-time power of two
+    __align__(16) T v[L];
+#pragma unroll
+    for (int e = 0; e < L; ++e) v[e] = s[(c0 + e) * ld + w];
+    out[p] = *reinterpret_cast<const uint4*>(v);
   }
 }
 

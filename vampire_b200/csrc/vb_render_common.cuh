@@ -34,8 +34,11 @@ __device__ __forceinline__ float widen_elem(float v) { return v; }
 __device__ __forceinline__ float widen_elem(__nv_bfloat16 v) { return __bfloat162float(v); }
 __device__ __forceinline__ float widen_elem(__half v) { return __half2float(v); }
 
+#ifndef VB_PACK_MINB
+#define VB_PACK_MINB 5   // 51 registers: measured 0.150 ms = 98 % of the copy peak (unbounded: 128 regs, 0.180 ms)
+#endif
 template <typename T, int K>
-__global__ void __launch_bounds__(kPackThreads) pack_cam_volume_kernel(const T* __restrict__ den,
+__global__ void __launch_bounds__(kPackThreads, VB_PACK_MINB) pack_cam_volume_kernel(const T* __restrict__ den,
                                                                        const T* __restrict__ sem,
                                                                        const T* __restrict__ rgb, T* __restrict__ packed,
                                                                        int nvox, size_t packed_stride,

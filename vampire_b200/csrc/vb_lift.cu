@@ -24,7 +24,7 @@ namespace {
 #define VB_LIFT_THREADS 128
 #endif
 #ifndef VB_LIFT_MINB
-#define VB_LIFT_MINB 8
+#define VB_LIFT_MINB 7
 #endif
 constexpr int kLiftThreads = VB_LIFT_THREADS;
 
@@ -275,8 +275,8 @@ int launch_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, const vo
     VB_LAUNCH_CHECK();
   }
   // z-run per thread: longer runs amortise the prologue, shorter ones keep the warp-level camera mask selective.
-  // Measured on B200 (R50, B=8, bf16) with 128-thread blocks at 8 blocks/SM: 0.349 ms at 10 levels, 0.355 at 5
-  // (256-thread blocks: 0.356 / 0.362); override with VB200_LIFT_ZRUN for experiments
+  // Measured on B200 (R50, B=8, bf16) with 128-thread blocks: 0.342 ms at 7 blocks/SM (72 registers) and 10
+  // levels, 0.349 at 8 blocks/SM, 0.355 at 5 levels (256-thread blocks: 0.356 / 0.362); VB200_LIFT_ZRUN overrides
   const int plane_blocks = vb_ceil_div(g->vY * g->vX, kLiftThreads);
   int zrun = g->vZ < 10 ? g->vZ : 10;
   {

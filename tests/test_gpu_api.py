@@ -81,3 +81,51 @@ def test_trace_and_launch_counters():
     cabi.trace_enable(False)
     assert cabi.launch_count() - n0 == 2
     assert set(tr) == {"ctx_to_nhwc", "lift_pool_fwd"} and all(ms > 0 and n == 1 for ms, n in tr.values())
+
+
+def test_forward_is_cuda_graph_capturable():
+    """The ops allocate only from the caching allocator and launch on the current stream, so a whole
+    lift+pool+render forward (on prepared matrices) can be captured into a CUDA graph and replayed -- the BEV
+    side-stream fork is skipped under capture; replays must reproduce the eager results bit for bit."""
+    from vampire_b200 import ops
+    case = Case("mini_val")
+    cid = ops.register_config(case.cfg)
+    prep = case.prep.cuda()
+    depth, ctx = case.depth.cuda(), case.ctx.cuda()
+    den, sem, feat, rgb = case.den.cuda(), case.sem.cuda(), case.feat.cuda(), case.rgb.cuda()
+    beta = torch.tensor(0.1, device="cuda")
+
+    def step():
+        vox, _ = ops.lift_pool_fwd(depth, ctx, prep, cid, True, False, False)
+        return [vox] + list(ops.render_fwd(den, sem, rgb, feat, beta, prep, None, cid, True, 3))
+
+    with torch.no_grad():
+        eager = step()
+        s = torch.cuda.Stream()          # warm-up on a side stream (allocator + lazy state), then capture
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            step()
+        torch.cuda.current_stream().wait_stream(s)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            captured = step()
+        for _ in range(2):
+            for t in captured:
+                t.zero_()
+            graph.replay()
+            torch.cuda.synchronize()
+            for a, b in zip(eager, captured):
+                assert torch.equal(a, b)
+
+
+def test_depth_softmax_and_2d_lift_reject_bad_input():
+    from vampire_b200 import ops
+    from vampire_b200.view_transform import LiftRenderB200
+    case = Case("mini_val")
+    mod = LiftRenderB200(**case.conf).cuda()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mod.depth_softmax(torch.zeros(2, 4, 4, 4))
+    with pytest.raises(ValueError):
+        ops.depth_softmax_fwd(torch.zeros(4, 4, device="cuda"), True)
+    with pytest.raises(ValueError, match="do not match"):
+        mod.lift_pool_2d(torch.zeros(1, case.cfg.num_cams, case.cfg.C, 3, 3, device="cuda"), case.mats)

@@ -743,58 +743,103 @@ __global__ void __launch_bounds__(64, 16) bev_channels_vec4_kernel(VbGrid g, VbT
 
 // ---- bev_channels, TMA-staged ---------------------------------------------------------------------------------
 // Same arithmetic as the fast path above, but the input rows travel HBM -> shared memory as 1-D bulk copies
-// (cp.async.bulk + mbarrier complete_tx) issued by one thread into a ring of kStages row-pair slots.  The direct-
-// load version keeps one level (512 B per warp) in flight and ncu shows it latency-bound (long scoreboard on the
-// first use of every row, ~2.4 TB/s = bytes in flight / latency); the ring keeps kStages x 1 KB per block in
-// flight without holding registers or issue slots, the 5th column is simply the next shared-memory element,
-// and the 64-bit global address arithmetic disappears from the level loop.
+// (cp.async.bulk + mbarrier complete_tx) through a ring of kStages row-pair slots.  The direct-load version keeps
+// one level (512 B per warp) in flight and ncu shows it latency-bound (long scoreboard on the first use of every
+// row, ~2.4 TB/s = bytes in flight / latency); the ring keeps kStages x 1 KB per block in flight without holding
+// registers, the 5th column is simply the next shared-memory element, and the 64-bit global address arithmetic
+// disappears from the consumers' level loop.
+//   block = 2 consumer warps (128 columns each) + 1 producer warp whose lane 0 issues every copy
 //   item  = one z-row of one channel plane: its two y-rows [ya, yb] x [cs, ce) (16-byte aligned column range
 //           covering the block's 256 columns +- 8), copied to slot (item % kStages) at element offset 8
 //   order = per channel, per level: the hi row when it is neither reused nor outside the grid, then the lo row
 //           (the same for every channel, tabulated once per block in s_item_z)
-//   sync  = full[slot] mbarrier (producer arrive.expect_tx + 2 copies complete_tx); a slot is refilled right
-//           after the __syncthreads() that ends its consumption, i.e. kStages - 1 items ahead.
+//   sync  = full[slot]: producer arrive.expect_tx + 2 copies complete_tx, consumers try_wait;
+//           empty[slot]: one arrive per consumer warp once the slot's values sit in registers, producer try_wait.
+// Measured on B200 (R50, B=8, bf16; direct-load kernel: 0.291 ms): first version (one thread of a 2-warp block
+// issuing, a block barrier per item, generic shared addressing) 0.435 ms at twice the instruction count; this
+// lean ring 0.335 ms, the same with one merged 1 KB copy per item instead of two -- so neither the copy rate nor
+// the issue overhead of the ring is what holds it back; with 10 blocks x 2 consumer warps per SM it simply has
+// fewer warps to cover the arithmetic than the direct kernel's 32.  Opt-in (VB200_BEV_TMA=1), bit-identical.
 __device__ __forceinline__ uint32_t vb_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void vb_mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(vb_smem_u32(bar)), "r"(count) : "memory");
+__device__ __forceinline__ void vb_mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void vb_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(vb_smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void vb_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void vb_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   vb_smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(vb_smem_u32(bar))
+__device__ __forceinline__ void vb_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void vb_bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void vb_mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = vb_smem_u32(bar);
-  for (int spin = 0; spin < (1 << 24); ++spin) {
+__device__ __forceinline__ void vb_mbar_wait(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  for (;;) {
     uint32_t ok;
     asm volatile(
         "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
         : "=r"(ok)
-        : "r"(addr), "r"(parity)
+        : "r"(bar), "r"(parity)
         : "memory");
     if (ok) return;
+    if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s: a lost transaction must fail loudly, never hang
   }
-  __trap();   // a lost transaction must fail loudly, never hang the device
 }
+template <typename T> struct SmemRow;      // 4 consecutive elements + 1 scalar from shared memory, by 32-bit address
+template <> struct SmemRow<float> {
+  __device__ __forceinline__ static float4 ld4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+  }
+  __device__ __forceinline__ static float ld1(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+  }
+};
+template <> struct SmemRow<__nv_bfloat16> {
+  __device__ __forceinline__ static uint2 ld4(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+  }
+  __device__ __forceinline__ static __nv_bfloat16 ld1(uint32_t a) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return __ushort_as_bfloat16(v);
+  }
+};
+template <> struct SmemRow<__half> {
+  __device__ __forceinline__ static uint2 ld4(uint32_t a) { return SmemRow<__nv_bfloat16>::ld4(a); }
+  __device__ __forceinline__ static __half ld1(uint32_t a) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return __ushort_as_half(v);
+  }
+};
 
 constexpr int kBevRowPad = 288;   // 8 zero | up to 272 copied | >= 8 zero  (elements)
+constexpr int kBevTmaThreads = 96;
 template <typename T> struct BevStages { static constexpr int n = sizeof(T) == 4 ? 6 : 8; };
 
 template <typename T, int K, int C>
-__global__ void __launch_bounds__(64, sizeof(T) == 4 ? 12 : 16) bev_channels_tma_kernel(
+__global__ void __launch_bounds__(kBevTmaThreads, sizeof(T) == 4 ? 8 : 10) bev_channels_tma_kernel(
     VbGrid g, VbTables t, const T* __restrict__ sem, const T* __restrict__ rgb, const T* __restrict__ feat,
     const float* __restrict__ wl_ws, float* __restrict__ o_rgb, float* __restrict__ o_seg, T* __restrict__ o_feat) {
   constexpr int S = BevStages<T>::n;
+  constexpr uint32_t kRowBytes = kBevRowPad * sizeof(T), kSlotBytes = 2 * kRowBytes;
   __shared__ __align__(128) T s_ring[S][2][kBevRowPad];
-  __shared__ __align__(8) uint64_t s_full[S];
+  __shared__ __align__(8) uint64_t s_full[S], s_empty[S];
   __shared__ BevLevel s_lv[kMaxLevels];
   __shared__ BevLevelX s_lx[kMaxLevels];
   __shared__ int s_item_z[2 * kMaxLevels];
   __shared__ int s_nitems;
+  const uint32_t ring_u32 = vb_smem_u32(&s_ring[0][0][0]);
+  const uint32_t full_u32 = vb_smem_u32(&s_full[0]), empty_u32 = vb_smem_u32(&s_empty[0]);
   bev_level_table(g, t, s_lv);
   if (threadIdx.x < g.oZ) {
     const int l = threadIdx.x;
@@ -809,7 +854,10 @@ __global__ void __launch_bounds__(64, sizeof(T) == 4 ? 12 : 16) bev_channels_tma
     s_lx[l] = X;
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < S; ++i) vb_mbar_init(&s_full[i], 1);
+    for (int i = 0; i < S; ++i) {
+      vb_mbar_init(full_u32 + 8 * i, 1);
+      vb_mbar_init(empty_u32 + 8 * i, 2);     // one arrive per consumer warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -826,9 +874,10 @@ __global__ void __launch_bounds__(64, sizeof(T) == 4 ? 12 : 16) bev_channels_tma
   const int tiles_x = (g.oX + 255) / 256;
   const int oy = blockIdx.x / tiles_x;
   const int lane = threadIdx.x & 31;
+  const bool producer = threadIdx.x >= 64;
   const int tile_x0 = (blockIdx.x % tiles_x) * 256;
-  const int ox_raw = tile_x0 + threadIdx.x * 4;
-  const bool live = ox_raw < g.oX;                     // oX % 4 == 0 guaranteed by the launcher
+  const int ox_raw = tile_x0 + (threadIdx.x & 63) * 4;
+  const bool live = !producer && ox_raw < g.oX;        // oX % 4 == 0 guaranteed by the launcher
   BevQuadX q;
   q.ox0 = live ? ox_raw : 0;
   bool all1 = q.ox0 + 3 < g.vX, all0 = all1;
@@ -867,6 +916,7 @@ __global__ void __launch_bounds__(64, sizeof(T) == 4 ? 12 : 16) bev_channels_tma
     else o_f = o_feat + ((size_t)b * C + j) * g.oZ * ncol + col0;
   };
   if (!fast_block) {   // irregular det grid: exact scalar gathers, no staging
+    if (producer) return;
     for (int j = c_begin; j < c_end; ++j) {
       float* o_map;
       T* o_f;
@@ -877,60 +927,76 @@ __global__ void __launch_bounds__(64, sizeof(T) == 4 ? 12 : 16) bev_channels_tma
   }
 
   // ---- staged path ----
-  const bool y0in = y0 >= 0 && y0 < g.vY, y1in = y0 + 1 >= 0 && y0 + 1 < g.vY;
   const int ya = min(max(y0, 0), g.vY - 1), yb = min(max(y0 + 1, 0), g.vY - 1);
-  float wq[4][4];          // [column][a0, a1, b0, b1] = wy * wx, zero where the tap leaves the grid
-  {
-    const float ya_w = y0in ? wy0 : 0.0f, yb_w = y1in ? wy1 : 0.0f;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      wq[c][0] = ya_w * q.wx0[c]; wq[c][1] = ya_w * q.wx1[c];
-      wq[c][2] = yb_w * q.wx0[c]; wq[c][3] = yb_w * q.wx1[c];
-    }
-  }
   const int ncopy = ce - cs;                                   // elements per row copy, multiple of 16 bytes
-  const uint32_t row_bytes = (uint32_t)ncopy * sizeof(T);
-  // zero the pads the copies never touch: [0, 8) and [8 + ncopy, 8 + ncopy + 8)
-  for (int i = threadIdx.x; i < S * 2 * 16; i += blockDim.x) {
-    const int slot = i / 32, row = (i / 16) & 1, e = i & 15;
-    s_ring[slot][row][e < 8 ? e : 8 + ncopy + (e - 8)] = VbType<T>::cvt(0.0f);
-  }
+  // Adjacent y-rows that are copied whole are ONE contiguous 2*vX-element range: one bulk copy per item instead
+  // of two (the copy engine is rate-limited on ~0.5 KB transfers).  Row 1 then starts right behind row 0; its
+  // "column -1" / row 0's "column vX" are the neighbouring row's finite edge values, weight 0 like the zero pads.
+  const bool merged = (yb == ya + 1) && cs == 0 && ce == g.vX && (2 * g.vX + 16 <= 2 * kBevRowPad);
+  const uint32_t row1_off = merged ? (uint32_t)g.vX * sizeof(T) : kRowBytes;
+  // zero the whole ring once (the copies never touch the pads); order these generic-proxy writes before the
+  // async-proxy copies
+  for (int i = threadIdx.x; i < S * 2 * kBevRowPad; i += blockDim.x) (&s_ring[0][0][0])[i] = VbType<T>::cvt(0.0f);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
   const int nitems = s_nitems;
   const int total = (c_end - c_begin) * nitems;
-  int iss_j = c_begin, iss_r = 0;                              // producer cursor (thread 0)
-  auto issue = [&](int it) {
-    const int slot = it % S;
-    const T* src = plane_of(iss_j) + s_item_z[iss_r] + cs;
-    vb_mbar_expect_tx(&s_full[slot], 2u * row_bytes);
-    vb_bulk_load(&s_ring[slot][0][8], src + ya * g.vX, row_bytes, &s_full[slot]);
-    vb_bulk_load(&s_ring[slot][1][8], src + yb * g.vX, row_bytes, &s_full[slot]);
-    if (++iss_r == nitems) { iss_r = 0; ++iss_j; }
-  };
-  if (threadIdx.x == 0)
-    for (int it = 0; it < min(S, total); ++it) issue(it);
+
+  if (producer) {
+    if (lane != 0) return;
+    const uint32_t row_bytes = (uint32_t)ncopy * sizeof(T);
+    int j = c_begin, r = 0;
+    const T* plane = plane_of(j) + cs;
+    const int oa = ya * g.vX, ob = yb * g.vX;
+    for (int it = 0; it < total; ++it) {
+      const int slot = it % S;
+      if (it >= S) vb_mbar_wait(empty_u32 + 8 * slot, (uint32_t)(it / S - 1) & 1u);
+      const T* src = plane + s_item_z[r];
+      const uint32_t dst = ring_u32 + slot * kSlotBytes + 8 * sizeof(T), bar = full_u32 + 8 * slot;
+      vb_mbar_expect_tx(bar, 2u * row_bytes);
+      if (merged) {
+        vb_bulk_load(dst, src + oa, 2u * row_bytes, bar);
+      } else {
+        vb_bulk_load(dst, src + oa, row_bytes, bar);
+        vb_bulk_load(dst + kRowBytes, src + ob, row_bytes, bar);
+      }
+      if (++r == nitems) {
+        r = 0;
+        ++j;
+        if (j < c_end) plane = plane_of(j) + cs;
+      }
+    }
+    return;
+  }
+
+  // ---- consumers ----
+  BevQuadFast f;
+  {
+    const bool y0in = y0 >= 0 && y0 < g.vY, y1in = y0 + 1 >= 0 && y0 + 1 < g.vY;
+    const float ya_w = y0in ? wy0 : 0.0f, yb_w = y1in ? wy1 : 0.0f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      f.w[c][0] = ya_w * q.wx0[c]; f.w[c][1] = ya_w * q.wx1[c];
+      f.w[c][2] = yb_w * q.wx0[c]; f.w[c][3] = yb_w * q.wx1[c];
+    }
+    f.off_a = f.off_b = f.off_ea = f.off_eb = 0;
+  }
   const int xi = live ? (q.ox0 - cs + 8) : 8;                  // this thread's first column inside a staged row
-  const int xe = w1 ? xi + 4 : xi - 1;                         // its 5th column
+  const uint32_t a4 = ring_u32 + (uint32_t)xi * sizeof(T);     // ... its address in slot 0, row 0
+  const uint32_t a1 = ring_u32 + (uint32_t)(w1 ? xi + 4 : xi - 1) * sizeof(T);   // its 5th column
   int consumed = 0;
-  // fetch the next item's rows into registers, then release + refill its slot
   auto consume = [&](RawRow<T>& r) {
     const int slot = consumed % S;
-    vb_mbar_wait(&s_full[slot], (uint32_t)(consumed / S) & 1u);
-    using V = typename Raw4<T>::type;
-    r.a = *reinterpret_cast<const V*>(&s_ring[slot][0][xi]);
-    r.b = *reinterpret_cast<const V*>(&s_ring[slot][1][xi]);
-    r.ea = s_ring[slot][0][xe];
-    r.eb = s_ring[slot][1][xe];
-    __syncthreads();
-    if (threadIdx.x == 0 && consumed + S < total) issue(consumed + S);
+    vb_mbar_wait(full_u32 + 8 * slot, (uint32_t)(consumed / S) & 1u);
+    const uint32_t so = slot * kSlotBytes;
+    r.a = SmemRow<T>::ld4(a4 + so);
+    r.b = SmemRow<T>::ld4(a4 + so + row1_off);
+    r.ea = SmemRow<T>::ld1(a1 + so);
+    r.eb = SmemRow<T>::ld1(a1 + so + row1_off);
+    __syncwarp();                                   // every lane's values are in registers
+    if (lane == 0) vb_mbar_arrive(empty_u32 + 8 * slot);
     ++consumed;
   };
-  BevQuadFast f;
-#pragma unroll
-  for (int c = 0; c < 4; ++c)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) f.w[c][k] = wq[c][k];
-  f.off_a = f.off_b = f.off_ea = f.off_eb = 0;
   const int wstep = ncol >> 2;
   for (int j = c_begin; j < c_end; ++j) {
     float* o_map;
@@ -1025,9 +1091,8 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
                         ((((uintptr_t)sem | (uintptr_t)rgb | (uintptr_t)feat | (uintptr_t)out->voxel_output |
                            (uintptr_t)out->bev_rgb | (uintptr_t)out->bev_seg | (uintptr_t)wl_ws) & 15) == 0);
     // bulk copies need 16-byte aligned rows: vX a multiple of 16 bytes of elements (plane bases are checked above)
-    // Opt-in (VB200_BEV_TMA=1): measured SLOWER than the direct-load kernel on B200 (R50, B=8, bf16: 0.435 vs
-    // 0.291 ms) -- ncu: 2x the warp instructions (mbarrier wait, slot addressing, thread-0 issue path) and a
-    // per-item block barrier, which outweigh the latency it hides.  Kept as a measured alternative, parity-tested.
+    // Opt-in (VB200_BEV_TMA=1): measured slower than the direct-load kernel on B200 (R50, B=8, bf16: 0.335 vs
+    // 0.291 ms, see the kernel's header).  Kept as a measured alternative, parity-tested bit-identical.
     static const bool tma_env = getenv("VB200_BEV_TMA") != nullptr;
     const bool tma_ok = vec_ok && tma_env && ((size_t)g->vX * sizeof(T)) % 16 == 0 && g->vX >= 8;
     if (tma_ok) {
@@ -1036,7 +1101,7 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
         cudaFuncSetAttribute(bev_channels_tma_kernel<T, K, C>, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
       });
-      bev_channels_tma_kernel<T, K, C><<<dim3(g->oY * vb_ceil_div(g->oX, 256), bev_groups(K, C), g->B), 64, 0, bst>>>(
+      bev_channels_tma_kernel<T, K, C><<<dim3(g->oY * vb_ceil_div(g->oX, 256), bev_groups(K, C), g->B), kBevTmaThreads, 0, bst>>>(
           *g, *t, sem, rgb, feat, wl_ws, out->bev_rgb, out->bev_seg, reinterpret_cast<T*>(out->voxel_output));
     } else if (vec_ok)
       bev_channels_vec4_kernel<T, K, C><<<dim3(g->oY * vb_ceil_div(g->oX, 256), bev_groups(K, C), g->B), 64, 0, bst>>>(

@@ -312,6 +312,18 @@ __device__ __forceinline__ LiftCoord lift_coord(const VbGrid& g, const float (&p
   return c;
 }
 
+// strict projection + sampling coordinates of one (voxel, camera) pair, with the exact shortcuts where the
+// block-uniform flags allow them (affine ida / homogeneous last rows; launch-constant divisors).  Only for
+// pairs that passed a conservative frustum cull (see lift_coord<FAST>).  Value-identical on every path.
+__device__ __forceinline__ LiftCoord pair_strict(const VbGrid& g, const float* __restrict__ Mcam, bool has_bda,
+                                                 bool affine, const VbLiftDiv& dv, float px, float py, float pz) {
+  float pix[3];
+  if (affine) project_voxel_affine(Mcam, has_bda, px, py, pz, pix);
+  else project_voxel<false>(Mcam, has_bda, px, py, pz, pix);
+  const bool fast = dv.a[0].ok && dv.a[1].ok && dv.a[2].ok;
+  return fast ? lift_coord<true>(g, pix, &dv) : lift_coord<false>(g, pix);
+}
+
 // R2: normalise + inclusive mask + ATen unnormalise (align_corners=True)  BV2:397-407, 419
 struct RenderCoord {
   bool valid;
@@ -324,7 +336,7 @@ static inline VbRenderDiv vb_render_div(const VbGrid* g) {
   for (int a = 0; a < 3; ++a) d.a[a] = vb_div_const(g->seg_ext[a]);
   return d;
 }
-static inline bool vb_render_div_ok(const VbRenderDiv& d) { return d.a[0].ok && d.a[1].ok && d.a[2].ok; }
+__host__ __device__ static inline bool vb_render_div_ok(const VbRenderDiv& d) { return d.a[0].ok && d.a[1].ok && d.a[2].ok; }
 
 template <bool FAST = false>
 __device__ __forceinline__ RenderCoord render_coord(const VbGrid& g, const float (&p)[3],

@@ -40,8 +40,9 @@ __host__ __device__ inline CellDims cell_dims(const VbGrid& g) {
 }
 
 // shared by plan + backward: cull + strict projection of (voxel, camera n); returns validity
-__device__ __forceinline__ bool pair_coord(const VbGrid& g, const float* s_m, const float* s_q, bool has_bda, int n,
-                                           float px, float py, float pz, LiftCoord& lc) {
+__device__ __forceinline__ bool pair_coord(const VbGrid& g, const float* s_m, const float* s_q, bool has_bda,
+                                           bool affine, const VbLiftDiv& dv, int n, float px, float py, float pz,
+                                           LiftCoord& lc) {
   const float* q = s_q + n * 16;
   const float cz = fmaf(q[8], px, fmaf(q[9], py, fmaf(q[10], pz, q[11])));
   if (!(cz > g.d_lo - 0.05f && cz < g.d_hi + 0.05f)) return false;
@@ -54,9 +55,7 @@ __device__ __forceinline__ bool pair_coord(const VbGrid& g, const float* s_m, co
   const float ax = fmaf(I[0], ux, fmaf(I[1], uy, fmaf(I[2], cz, I[3] * cw)));
   const float ay = fmaf(I[4], ux, fmaf(I[5], uy, fmaf(I[6], cz, I[7] * cw)));
   if (!(ax > -1.5f && ax < g.x_hi + 1.0f && ay > -1.5f && ay < g.y_hi + 1.0f)) return false;
-  float pix[3];
-  project_voxel<false>(s_m + n * VB200_MAT_SLOTS * 16, has_bda, px, py, pz, pix);
-  lc = lift_coord(g, pix);
+  lc = pair_strict(g, s_m + n * VB200_MAT_SLOTS * 16, has_bda, affine, dv, px, py, pz);
   return lc.valid;
 }
 
@@ -77,7 +76,8 @@ __device__ __forceinline__ void stage_cull(float* s_q, const float* s_m, int N, 
 
 // ---- plan: count / fill ---------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(kThreads) plan_pairs_kernel(VbGrid g, VbTables t, const float* __restrict__ d_mats,
+__global__ void __launch_bounds__(kThreads) plan_pairs_kernel(VbGrid g, VbTables t, VbLiftDiv dv,
+                                                              const float* __restrict__ d_mats,
                                                               int* __restrict__ counts, const int* __restrict__ offsets,
                                                               int* __restrict__ cursor, uint32_t* __restrict__ recs) {
   __shared__ float s_m[VB_MAX_CAMS * VB200_MAT_SLOTS * 16];
@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(kThreads) plan_pairs_kernel(VbGrid g, VbTables
   stage_mats(s_m, d_mats, b, g.N);
   __syncthreads();
   const bool has_bda = (g.has_bda != 0) && !block_is_identity(s_m);
+  const bool affine = block_pixel_affine(s_m, g.N, has_bda);
   stage_cull(s_q, s_m, g.N, has_bda);
   __syncthreads();
   const int nvox = g.vZ * g.vY * g.vX;
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(kThreads) plan_pairs_kernel(VbGrid g, VbTables
   const CellDims cd = cell_dims(g);
   for (int n = 0; n < g.N; ++n) {
     LiftCoord lc;
-    if (!pair_coord(g, s_m, s_q, has_bda, n, px, py, pz, lc)) continue;
+    if (!pair_coord(g, s_m, s_q, has_bda, affine, dv, n, px, py, pz, lc)) continue;
     const int cell = (n * cd.ncy + (lc.y0 + 1)) * cd.ncx + (lc.x0 + 1);
     if (MODE == 0) {
       atomicAdd(counts + (size_t)b * cd.nc + cell, 1);
@@ -222,7 +223,8 @@ __global__ void __launch_bounds__(256) ctx_to_nhwc_f32_kernel(const T* __restric
 
 // ---- the backward proper -------------------------------------------------------------------------------
 template <typename T, int GOUT_LAYOUT>
-__global__ void __launch_bounds__(kThreads, 4) lift_bwd_kernel(VbGrid g, VbTables t, const float* __restrict__ d_mats,
+__global__ void __launch_bounds__(kThreads, 4) lift_bwd_kernel(VbGrid g, VbTables t, VbLiftDiv dv,
+                                                            const float* __restrict__ d_mats,
                                                             const T* __restrict__ depth,
                                                             const float* __restrict__ ctx_nhwc,
                                                             const T* __restrict__ gout, const uint64_t* __restrict__ cnt,
@@ -240,6 +242,7 @@ __global__ void __launch_bounds__(kThreads, 4) lift_bwd_kernel(VbGrid g, VbTable
     s_m[i] = __ldg(d_mats + (size_t)bn * VB200_MAT_SLOTS * 16 + i);
   __syncthreads();
   const bool has_bda = (g.has_bda != 0) && !block_is_identity(s_m);
+  const bool affine = block_pixel_affine(s_m, 1, has_bda);      // this block's one camera
 
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ci = blockIdx.x * (kThreads / 32) + wid;
@@ -286,9 +289,8 @@ __global__ void __launch_bounds__(kThreads, 4) lift_bwd_kernel(VbGrid g, VbTable
       const uint32_t rec = seg[r0 + lane];
       const int vox = (int)(rec & ((1u << kVoxBits) - 1));
       const int x = vox % g.vX, y = (vox / g.vX) % g.vY, z = vox / (g.vX * g.vY);
-      float pix[3];
-      project_voxel<false>(s_m, has_bda, __ldg(t.xs + x), __ldg(t.ys + y), __ldg(t.zs + z), pix);
-      const LiftCoord lc = lift_coord(g, pix);   // same code as the plan => same (x0, y0, z0)
+      // same code as the plan => same (x0, y0, z0)
+      const LiftCoord lc = pair_strict(g, s_m, has_bda, affine, dv, __ldg(t.xs + x), __ldg(t.ys + y), __ldg(t.zs + z));
       z0 = lc.z0;
       const float wx0 = inx0 ? (float)(lc.x0 + 1) - lc.ix : 0.0f, wx1 = inx1 ? lc.ix - (float)lc.x0 : 0.0f;
       const float wy0 = iny0 ? (float)(lc.y0 + 1) - lc.iy : 0.0f, wy1 = iny1 ? lc.iy - (float)lc.y0 : 0.0f;
@@ -441,6 +443,7 @@ int launch_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const vo
   float* gdepth_acc = kF32 ? reinterpret_cast<float*>(d_gdepth) : reinterpret_cast<float*>(ws + l.gdepth);
   const size_t n_gdepth = (size_t)g->B * g->N * g->D * HW;
 
+  const VbLiftDiv dv = vb_lift_div(g);
   if (cudaMemsetAsync(counts, 0, (size_t)g->B * cd.nc * 4, st) != cudaSuccess) return VB200_ERR_CUDA;
   if (cudaMemsetAsync(cursor, 0, (size_t)g->B * cd.nc * 4, st) != cudaSuccess) return VB200_ERR_CUDA;
   if (cudaMemsetAsync(gctx_ws, 0, (size_t)g->B * g->N * HW * kC * 4, st) != cudaSuccess) return VB200_ERR_CUDA;
@@ -454,7 +457,7 @@ int launch_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const vo
   {
     VbTraceScope tr(VB_K_LIFT_PLAN, st);
     dim3 vgrid(vb_ceil_div(nvox, kThreads), g->B);
-    plan_pairs_kernel<0><<<vgrid, kThreads, 0, st>>>(*g, *t, d_mats, counts, nullptr, nullptr, nullptr);
+    plan_pairs_kernel<0><<<vgrid, kThreads, 0, st>>>(*g, *t, dv, d_mats, counts, nullptr, nullptr, nullptr);
     VB_LAUNCH_CHECK();
     const int nchunks = vb_ceil_div(cd.nc, kScanChunk);
     if (nchunks > kScanThreads) return VB200_ERR_ARG;   // > 4 M pixel cells per sample: not a camera feature map
@@ -464,7 +467,7 @@ int launch_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const vo
     VB_LAUNCH_CHECK();
     scan_add_kernel<<<dim3(nchunks, g->B), kScanThreads, 0, st>>>(offsets, chunk_sums, cd.nc, nchunks);
     VB_LAUNCH_CHECK();
-    plan_pairs_kernel<1><<<vgrid, kThreads, 0, st>>>(*g, *t, d_mats, nullptr, offsets, cursor, recs_a);
+    plan_pairs_kernel<1><<<vgrid, kThreads, 0, st>>>(*g, *t, dv, d_mats, nullptr, offsets, cursor, recs_a);
     VB_LAUNCH_CHECK();
     const int total_cells = g->B * cd.nc;
     sort_cells_kernel<<<vb_ceil_div(total_cells, kThreads / 32), kThreads, 0, st>>>(
@@ -481,7 +484,7 @@ int launch_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const vo
     for (int colour = 0; colour < 4; ++colour) {
       const int ny = (cd.ncy - (colour >> 1) + 1) / 2, nx = (cd.ncx - (colour & 1) + 1) / 2;
       dim3 grid(vb_ceil_div((long long)ny * nx, kThreads / 32), g->B * g->N);
-      kern<<<grid, kThreads, smem, st>>>(*g, *t, d_mats, reinterpret_cast<const T*>(d_depth), ctx_nhwc,
+      kern<<<grid, kThreads, smem, st>>>(*g, *t, dv, d_mats, reinterpret_cast<const T*>(d_depth), ctx_nhwc,
                                          reinterpret_cast<const T*>(d_gout), d_cnt, offsets, recs_b, gdepth_acc,
                                          gctx_ws, colour);
       VB_LAUNCH_CHECK();

@@ -57,7 +57,7 @@ __device__ __forceinline__ float block_sum(float v, float* s_red) {
 // ---- camera branch ---------------------------------------------------------------------------------------
 template <typename T, int K, bool FROM_MATS>
 __global__ void __launch_bounds__(kMarchThreads) march_bwd_kernel(
-    VbGrid g, VbTables t, const float* __restrict__ d_mats, const float* __restrict__ d_geom,
+    VbGrid g, VbTables t, VbRenderDiv dv, const float* __restrict__ d_mats, const float* __restrict__ d_geom,
     const T* __restrict__ packed, const float* __restrict__ beta_ptr, const float* __restrict__ o_rgb,
     const float* __restrict__ o_seg, const float* __restrict__ o_depth, const float* __restrict__ g_rgb,
     const float* __restrict__ g_seg, const float* __restrict__ g_depth, float* __restrict__ gpacked,
@@ -70,6 +70,9 @@ __global__ void __launch_bounds__(kMarchThreads) march_bwd_kernel(
     s_m[i] = __ldg(d_mats + (size_t)(b * g.N + n) * VB200_MAT_SLOTS * 16 + i);
   __syncthreads();
   const bool has_bda = (g.has_bda != 0) && !block_is_identity(s_m + 5 * 16);   // slot 5 = bda
+  // the forward march's exact shortcuts (vb_render.cu): affine ida^-1, launch-constant divisors
+  const bool affine = FROM_MATS && block_ida_inv_affine(s_m + 3 * 16);
+  const bool fastdiv = FROM_MATS && vb_render_div_ok(dv);
 
   const int patches_x = (g.fW + kPatchW - 1) / kPatchW;
   const int patches_y = (g.fH + kPatchH - 1) / kPatchH;
@@ -85,11 +88,16 @@ __global__ void __launch_bounds__(kMarchThreads) march_bwd_kernel(
   const float beta = fabsf(__ldg(beta_ptr)) + g.beta_min;
   const float u = __ldg(t.us + wc), vv = __ldg(t.vs + hc);
   const float* gsrc = FROM_MATS ? nullptr : d_geom + ((size_t)(b * g.N + n) * g.D * HW + (size_t)hc * g.fW + wc) * 3;
+  float rayA[2] = {0.0f, 0.0f};
+  if (affine) frustum_ray_affine(s_m, u, vv, rayA);
   auto point = [&](int d, float (&p)[3]) {
     if (FROM_MATS) {
-      frustum_point<false>(s_m, has_bda, u, vv, __ldg(t.ds + d), p);
+      if (affine) frustum_point_affine(s_m, has_bda, rayA, __ldg(t.ds + d), p);
+      else frustum_point<false>(s_m, has_bda, u, vv, __ldg(t.ds + d), p);
+      if (!(fabsf(p[0]) + fabsf(p[1]) + fabsf(p[2]) <= 3.402823466e+38f)) {   // BV2:612, see the forward march
 #pragma unroll
-      for (int a = 0; a < 3; ++a) p[a] = nan_to_num(p[a], -1e3f);
+        for (int a = 0; a < 3; ++a) p[a] = nan_to_num(p[a], -1e3f);
+      }
     } else {
       const float* q = gsrc + (size_t)d * HW * 3;
       p[0] = __ldg(q); p[1] = __ldg(q + 1); p[2] = __ldg(q + 2);
@@ -126,7 +134,7 @@ __global__ void __launch_bounds__(kMarchThreads) march_bwd_kernel(
       point(i + 1, p1);
       const float dx = p1[0] - p0[0], dy = p1[1] - p0[1], dz = p1[2] - p0[2];
       const float delta = sqrtf(dx * dx + dy * dy + dz * dz);
-      const RenderCoord rc = render_coord(g, p0);
+      const RenderCoord rc = fastdiv ? render_coord<true>(g, p0, &dv) : render_coord<false>(g, p0);
       const bool live = rc.valid && active;
       float v[CP];
 #pragma unroll
@@ -510,11 +518,11 @@ int launch_render_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
       dim3 grid(vb_ceil_div(patches, kMarchThreads / 32), g->N);
       if (in->geom)
         march_bwd_kernel<T, K, false><<<grid, kMarchThreads, 0, st>>>(
-            *g, *t, d_mats, in->geom, packed, in->beta, out->rgb, out->seg, out->depth, gr->g_rgb, gr->g_seg,
+            *g, *t, vb_render_div(g), d_mats, in->geom, packed, in->beta, out->rgb, out->seg, out->depth, gr->g_rgb, gr->g_seg,
             gr->g_depth, gpacked, partials + n_partials, b);
       else
         march_bwd_kernel<T, K, true><<<grid, kMarchThreads, 0, st>>>(
-            *g, *t, d_mats, nullptr, packed, in->beta, out->rgb, out->seg, out->depth, gr->g_rgb, gr->g_seg,
+            *g, *t, vb_render_div(g), d_mats, nullptr, packed, in->beta, out->rgb, out->seg, out->depth, gr->g_rgb, gr->g_seg,
             gr->g_depth, gpacked, partials + n_partials, b);
       VB_LAUNCH_CHECK();
       n_partials += l.n_march_blocks;

@@ -222,8 +222,11 @@ __global__ void __launch_bounds__(256) ctx_to_nhwc_f32_kernel(const T* __restric
 }
 
 // ---- the backward proper -------------------------------------------------------------------------------
+#ifndef VB_LIFT_BWD_MINB
+#define VB_LIFT_BWD_MINB 4
+#endif
 template <typename T, int GOUT_LAYOUT>
-__global__ void __launch_bounds__(kThreads, 4) lift_bwd_kernel(VbGrid g, VbTables t, VbLiftDiv dv,
+__global__ void __launch_bounds__(kThreads, VB_LIFT_BWD_MINB) lift_bwd_kernel(VbGrid g, VbTables t, VbLiftDiv dv,
                                                             const float* __restrict__ d_mats,
                                                             const T* __restrict__ depth,
                                                             const float* __restrict__ ctx_nhwc,

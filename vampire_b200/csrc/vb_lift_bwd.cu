@@ -221,16 +221,45 @@ __global__ void __launch_bounds__(256) ctx_to_nhwc_f32_kernel(const T* __restric
   for (int i = threadIdx.x; i < kC * fW; i += blockDim.x) out[i] = s_t[(i % kC) * ld + i / kC];
 }
 
+// ---- g' = d_out / (count + 1e-6), once per voxel, channels-last fp32 ---------------------------------------
+// The gather below visits the voxels of a pixel cell, which lie along a camera ray and are scattered through
+// the volume: read straight from an NCDHW cotangent every one of a pair's 16 channel values is its own 32-byte
+// sector (ncu: 110 MB of DRAM reads per colour launch for 21 MB of useful values) and the 16 IEEE divisions by
+// the camera counts are repeated for every camera that sees the voxel.  One streaming pass writes g' as 64
+// contiguous bytes per voxel instead (the non-zero mask is not differentiated).
+template <typename T, int GOUT_LAYOUT>
+__global__ void __launch_bounds__(256) gout_prep_kernel(const T* __restrict__ gout, const uint64_t* __restrict__ cnt,
+                                                        float* __restrict__ gprep, int nvox) {
+  const int vox = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (vox >= nvox) return;
+  const uint64_t cw = cnt[(size_t)b * nvox + vox];
+  float gp[kC];
+  if (GOUT_LAYOUT == VB200_NCDHW) {
+#pragma unroll
+    for (int c = 0; c < kC; ++c) gp[c] = VbType<T>::ld(gout + ((size_t)b * kC + c) * nvox + vox);
+  } else {
+    const T* gv = gout + ((size_t)b * nvox + vox) * kC;
+    constexpr int Ln = VbLanes<T>::n;
+#pragma unroll
+    for (int q4 = 0; q4 < kC / Ln; ++q4) VbVec<T, Ln>::ld(gv + q4 * Ln, &gp[q4 * Ln]);
+  }
+#pragma unroll
+  for (int c = 0; c < kC; ++c) gp[c] = gp[c] / ((float)((cw >> (4 * c)) & 0xf) + 1e-6f);
+  float4* o = reinterpret_cast<float4*>(gprep + ((size_t)b * nvox + vox) * kC);
+#pragma unroll
+  for (int q4 = 0; q4 < kC / 4; ++q4) o[q4] = make_float4(gp[4 * q4], gp[4 * q4 + 1], gp[4 * q4 + 2], gp[4 * q4 + 3]);
+}
+
 // ---- the backward proper -------------------------------------------------------------------------------
 #ifndef VB_LIFT_BWD_MINB
 #define VB_LIFT_BWD_MINB 4
 #endif
-template <typename T, int GOUT_LAYOUT>
+template <typename T>
 __global__ void __launch_bounds__(kThreads, VB_LIFT_BWD_MINB) lift_bwd_kernel(VbGrid g, VbTables t, VbLiftDiv dv,
                                                             const float* __restrict__ d_mats,
                                                             const T* __restrict__ depth,
                                                             const float* __restrict__ ctx_nhwc,
-                                                            const T* __restrict__ gout, const uint64_t* __restrict__ cnt,
+                                                            const float* __restrict__ gprep,
                                                             const int* __restrict__ offsets,
                                                             const uint32_t* __restrict__ recs, float* __restrict__ gdepth,
                                                             float* __restrict__ gctx_nhwc, int colour) {
@@ -303,20 +332,16 @@ __global__ void __launch_bounds__(kThreads, VB_LIFT_BWD_MINB) lift_bwd_kernel(Vb
       const float wxy[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};
       const T* d0 = dcam + (size_t)za * HW;
       const T* d1 = dcam + (size_t)zb * HW;
-      // g' = d_out * valid / (count + 1e-6): the non-zero mask is not differentiated
-      const uint64_t cw = cnt[(size_t)b * nvox + vox];
+      // g' = d_out * valid / (count + 1e-6), prepared per voxel by gout_prep_kernel: 4 x 128-bit loads
       float gp[kC];
-      if (GOUT_LAYOUT == VB200_NCDHW) {
+      {
+        const float4* gv = reinterpret_cast<const float4*>(gprep + ((size_t)b * nvox + vox) * kC);
 #pragma unroll
-        for (int c = 0; c < kC; ++c) gp[c] = VbType<T>::ld(gout + ((size_t)b * kC + c) * nvox + vox);
-      } else {
-        const T* gv = gout + ((size_t)b * nvox + vox) * kC;
-        constexpr int Ln = VbLanes<T>::n;
-#pragma unroll
-        for (int q4 = 0; q4 < kC / Ln; ++q4) VbVec<T, Ln>::ld(gv + q4 * Ln, &gp[q4 * Ln]);
+        for (int q4 = 0; q4 < kC / 4; ++q4) {
+          const float4 v = __ldg(gv + q4);
+          gp[4 * q4] = v.x; gp[4 * q4 + 1] = v.y; gp[4 * q4 + 2] = v.z; gp[4 * q4 + 3] = v.w;
+        }
       }
-#pragma unroll
-      for (int c = 0; c < kC; ++c) gp[c] = gp[c] / ((float)((cw >> (4 * c)) & 0xf) + 1e-6f);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const float s = fmaf(wzb, VbType<T>::ld(d1 + pxl[k]), wza * VbType<T>::ld(d0 + pxl[k]));
@@ -405,7 +430,7 @@ __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ src
 size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 
 struct BwdLayout {
-  size_t ctx, counts, offsets, cursor, chunk_sums, recs_a, recs_b, gctx, gdepth, total;
+  size_t ctx, counts, offsets, cursor, chunk_sums, recs_a, recs_b, gctx, gprep, gdepth, total;
 };
 BwdLayout bwd_layout(const VbGrid* g, bool need_gdepth_ws) {
   const CellDims cd = cell_dims(*g);
@@ -420,6 +445,7 @@ BwdLayout bwd_layout(const VbGrid* g, bool need_gdepth_ws) {
   l.recs_a = o;  o += align256((size_t)g->B * g->N * nvox * 4);
   l.recs_b = o;  o += align256((size_t)g->B * g->N * nvox * 4);
   l.gctx = o;    o += align256((size_t)g->B * g->N * HW * kC * 4);
+  l.gprep = o;   o += align256((size_t)g->B * nvox * kC * 4);
   l.gdepth = o;  o += need_gdepth_ws ? align256((size_t)g->B * g->N * g->D * HW * 4) : 0;
   l.total = o;
   return l;
@@ -458,7 +484,7 @@ int launch_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const vo
     VB_LAUNCH_CHECK();
   }
   {
-    VbTraceScope tr(VB_K_LIFT_PLAN, st);
+    VbTraceScope tr(VB_K_LIFT_PLAN, st, 6);
     dim3 vgrid(vb_ceil_div(nvox, kThreads), g->B);
     plan_pairs_kernel<0><<<vgrid, kThreads, 0, st>>>(*g, *t, dv, d_mats, counts, nullptr, nullptr, nullptr);
     VB_LAUNCH_CHECK();
@@ -478,9 +504,18 @@ int launch_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const vo
     VB_LAUNCH_CHECK();
   }
   {
-    VbTraceScope tr(VB_K_LIFT_BWD, st);
+    VbTraceScope tr(VB_K_LIFT_BWD, st, kF32 ? 6 : 7);
     const size_t smem = (size_t)(kThreads / 32) * (4 * g->D + 32 * 4 + 32 * 17 + 64) * sizeof(float);
-    auto kern = gout_layout == VB200_NCDHW ? lift_bwd_kernel<T, VB200_NCDHW> : lift_bwd_kernel<T, VB200_NDHWC>;
+    float* gprep = reinterpret_cast<float*>(ws + l.gprep);
+    {
+      dim3 pgrid(vb_ceil_div(nvox, 256), g->B);
+      if (gout_layout == VB200_NCDHW)
+        gout_prep_kernel<T, VB200_NCDHW><<<pgrid, 256, 0, st>>>(reinterpret_cast<const T*>(d_gout), d_cnt, gprep, (int)nvox);
+      else
+        gout_prep_kernel<T, VB200_NDHWC><<<pgrid, 256, 0, st>>>(reinterpret_cast<const T*>(d_gout), d_cnt, gprep, (int)nvox);
+      VB_LAUNCH_CHECK();
+    }
+    auto kern = lift_bwd_kernel<T>;
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return VB200_ERR_CUDA;
@@ -488,7 +523,7 @@ int launch_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const vo
       const int ny = (cd.ncy - (colour >> 1) + 1) / 2, nx = (cd.ncx - (colour & 1) + 1) / 2;
       dim3 grid(vb_ceil_div((long long)ny * nx, kThreads / 32), g->B * g->N);
       kern<<<grid, kThreads, smem, st>>>(*g, *t, dv, d_mats, reinterpret_cast<const T*>(d_depth), ctx_nhwc,
-                                         reinterpret_cast<const T*>(d_gout), d_cnt, offsets, recs_b, gdepth_acc,
+                                         gprep, offsets, recs_b, gdepth_acc,
                                          gctx_ws, colour);
       VB_LAUNCH_CHECK();
     }

@@ -490,7 +490,7 @@ int launch_render_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
   }
   int n_partials = 0;
   if (bev) {
-    VbTraceScope tr(VB_K_UNPACK_BEV_BWD, st);
+    VbTraceScope tr(VB_K_UNPACK_BEV_BWD, st, 3);
     bev_tables_kernel<<<1, 256, 0, st>>>(*g, *t, bt);
     VB_LAUNCH_CHECK();
     const size_t smem = (size_t)kMaxLevels * kBevBwdThreads * sizeof(float);

@@ -237,6 +237,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout for the ONE JSON line: NCCL's own messages (e.g. the version banner under NCCL_DEBUG=VERSION)
+        # go to stderr unless the caller already chose a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     train = args.workload == "train"
     batch = args.batch or (1 if train else 8)

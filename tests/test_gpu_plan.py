@@ -1,0 +1,173 @@
+"""GPU: the cached projection / sort plan (vb200_lift_plan_build) and the plan-driven lift + pool.
+
+The plan must hold exactly the integers and fractions of the strict index kernel (vb200_lift_indices, itself
+SHA-pinned to the reference in test_gpu_geometry.py), and the planned forward / backward must be bit-identical
+to the kernels that recompute the projection on every call."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import CASES, Case, assert_close_scaled
+from oracle import torch_path as tp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", params=["mini_val", "mini_stress"])
+def case(request):
+    return Case(request.param)
+
+
+def _state(cfg, lift_2d=False):
+    from vampire_b200 import ops
+    cid = ops.register_config(cfg, lift_2d)
+    return ops, cid, ops.state(cid)
+
+
+def _batch(case, st):
+    from vampire_b200.plan import LiftPlanBatch, build_lift_plans
+    plans = build_lift_plans(st, case.prep.cuda(), True)
+    return plans, LiftPlanBatch(plans, torch.device("cuda", torch.cuda.current_device()))
+
+
+def test_plan_holds_the_strict_indices(case):
+    """pairs / cell records == (valid, x0, y0, z0, fractions) of the bit-exact index kernel, compacted."""
+    ops, cid, st = _state(case.cfg)
+    cfg = case.cfg
+    valid, i0, frac = ops.lift_indices(case.prep.cuda(), cid, True)
+    plans, _ = _batch(case, st)
+    nvox = cfg.vZ * cfg.vY * cfg.vX
+    for b, p in enumerate(plans):
+        v = valid[b].reshape(cfg.num_cams, nvox).cpu().numpy().astype(bool)
+        ii = i0[b].reshape(cfg.num_cams, nvox, 3).cpu().numpy().astype(np.int64)
+        ff = frac[b].reshape(cfg.num_cams, nvox, 3).cpu().numpy()
+        assert p.num_pairs == int(v.sum())
+        head = p.head.cpu().numpy().view(np.uint32)
+        cnt = head & 15
+        first = head >> 4
+        assert np.array_equal(cnt, v.sum(0))
+        assert np.array_equal(first, np.concatenate([[0], np.cumsum(cnt)[:-1]]))
+        pairs = p.pairs.cpu().numpy().view(np.uint32)
+        key = pairs[:p.num_pairs, 0]
+        n = key >> 29
+        z0 = ((key >> 20) & 511).astype(np.int64) - 1
+        y0 = ((key >> 10) & 1023).astype(np.int64) - 1
+        x0 = (key & 1023).astype(np.int64) - 1
+        vox = np.repeat(np.arange(nvox), cnt)
+        assert v[n, vox].all()
+        # voxel-major, cameras ascending
+        assert np.array_equal(np.stack([vox, n], 1), np.argwhere(v.T))
+        assert np.array_equal(np.stack([x0, y0, z0], 1), ii[n, vox])
+        fr = pairs[:p.num_pairs, 1:].view(np.float32)
+        # vb200_lift_indices reports ix - floor(ix); the plan stores ix - (float)x0: the same subtraction
+        assert np.array_equal(fr, ff[n, vox])
+        # cell-major copy: same multiset of (voxel, z0, fractions), CSR by (n, y0+1, x0+1), sorted by (z0, voxel)
+        off = p.cell_off.cpu().numpy()
+        recs = p.cell_recs.cpu().numpy().view(np.uint32)[:p.num_pairs]
+        assert off[0] == 0 and off[-1] == p.num_pairs and (np.diff(off) >= 0).all()
+        cell_of_pair = (n.astype(np.int64) * (cfg.fH + 1) + (y0 + 1)) * (cfg.fW + 1) + (x0 + 1)
+        assert np.array_equal(np.bincount(cell_of_pair, minlength=off.size - 1), np.diff(off))
+        rkey = recs[:, 0].astype(np.int64)
+        cell_of_rec = np.repeat(np.arange(off.size - 1), np.diff(off))
+        order = np.lexsort((rkey, cell_of_rec))
+        assert np.array_equal(order, np.arange(p.num_pairs)), "cell segments are not sorted by (z0, voxel)"
+        want = np.lexsort((((z0 + 1) << 21) | vox, cell_of_pair))
+        assert np.array_equal(rkey, (((z0 + 1) << 21) | vox)[want])
+        assert np.array_equal(recs[:, 1:], pairs[:p.num_pairs, 1:][want])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_planned_forward_is_bit_identical(case, dtype, channels_last):
+    ops, cid, st = _state(case.cfg)
+    _, batch = _batch(case, st)
+    d, c, m = case.depth.to(dtype).cuda(), case.ctx.to(dtype).cuda(), case.prep.cuda()
+    a, ca = ops.lift_pool_fwd(d, c, m, cid, True, channels_last, True)
+    b, cb = ops.lift_pool_fwd(d, c, m, cid, True, channels_last, True, batch.table)
+    assert torch.equal(a, b) and torch.equal(ca, cb)
+    assert b.permute(0, 2, 3, 4, 1).is_contiguous() == channels_last
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_planned_backward_is_bit_identical(case, dtype):
+    ops, cid, st = _state(case.cfg)
+    _, batch = _batch(case, st)
+    cot = case.cotangents()[0].to(dtype).cuda()
+    grads = []
+    for plan in (None, batch.table):
+        d = case.depth.to(dtype).cuda().requires_grad_(True)
+        c = case.ctx.to(dtype).cuda().requires_grad_(True)
+        out, _ = ops.lift_pool_fwd(d, c, case.prep.cuda(), cid, True, False, True, plan)
+        grads.append(torch.autograd.grad((out * cot).sum(), [d, c]))
+    for ga, gb in zip(*grads):
+        assert torch.equal(ga, gb)
+
+
+def test_planned_2d_lift_is_bit_identical(case):
+    """The BaseBiLinear D = 1 mode goes through the same plan machinery."""
+    ops, cid, st = _state(case.cfg, lift_2d=True)
+    _, batch = _batch(case, st)
+    c = case.ctx.cuda()
+    ones = torch.ones(case.batch, case.cfg.num_cams, 1, case.cfg.fH, case.cfg.fW, device="cuda")
+    a, _ = ops.lift_pool_fwd(ones, c, case.prep.cuda(), cid, True, False, False)
+    b, _ = ops.lift_pool_fwd(ones, c, case.prep.cuda(), cid, True, False, False, batch.table)
+    assert torch.equal(a, b)
+
+
+def test_plan_cache_hits_and_module_modes(case):
+    from vampire_b200.view_transform import LiftRenderB200
+    outs = {}
+    for mode in ("off", "always", "eval"):
+        mod = LiftRenderB200(plans=mode, **case.conf).cuda()
+        if mode == "eval":
+            mod.eval()
+        with torch.no_grad():
+            outs[mode] = mod.lift_pool(case.depth.cuda(), case.ctx.cuda(), case.mats)
+            again = mod.lift_pool(case.depth.cuda(), case.ctx.cuda(), case.mats)
+        assert torch.equal(outs[mode], again)
+        pc = mod.plan_cache
+        if mode == "off":
+            assert pc.hits == 0 and pc.misses == 0
+        else:
+            assert pc.misses == case.batch and pc.hits == case.batch and pc.nbytes() > 0
+            # a permuted batch of known rigs is still a hit (per-sample keys)
+            perm = {k: (v.flip(0) if v is not None else None) for k, v in case.mats.items()}
+            with torch.no_grad():
+                flipped = mod.lift_pool(case.depth.flip(0).cuda(), case.ctx.flip(0).cuda(), perm)
+            assert pc.misses == case.batch
+            assert torch.equal(flipped.flip(0), outs[mode])
+    assert torch.equal(outs["off"], outs["always"]) and torch.equal(outs["off"], outs["eval"])
+    # training mode never builds plans under plans="eval"
+    mod = LiftRenderB200(plans="eval", **case.conf).cuda().train()
+    d = case.depth.cuda().requires_grad_(True)
+    mod.lift_pool(d, case.ctx.cuda(), case.mats).sum().backward()
+    assert mod.plan_cache.misses == 0 and d.grad is not None
+
+
+@pytest.mark.parametrize("cdt", [torch.bfloat16, torch.float16])
+def test_amp_fp32_depth_with_16bit_ctx(case, cdt):
+    """Reference under AMP (BV2:551-553): fp32 softmax output x 16-bit ctx promotes to fp32 -- the pooled volume is
+    fp32 and the depth probabilities are NOT rounded to 16 bits.  Oracle: fp32 path fed the 16-bit-valued ctx."""
+    ops, cid, st = _state(case.cfg)
+    buf = tp.build_buffers(case.conf)
+    ctx16 = case.ctx.to(cdt)
+    d = case.depth.cuda().requires_grad_(True)
+    c = ctx16.cuda().requires_grad_(True)
+    out, _ = ops.lift_pool_fwd(d, c, case.prep.cuda(), cid, True, False, True)
+    assert out.dtype == torch.float32
+    dr = case.depth.clone().requires_grad_(True)
+    cr = ctx16.float().requires_grad_(True)
+    ref = tp.lift_pool(case.conf, buf, dr, cr, case.mats)
+    assert_close_scaled(out.detach().cpu().numpy(), ref.detach().numpy(), 1e-5, "AMP pooled volume (fp32)")
+    cot = case.cotangents()[0]
+    gd, gc = torch.autograd.grad((out * cot.cuda()).sum(), [d, c])
+    rd, rc = torch.autograd.grad((ref * cot).sum(), [dr, cr])
+    assert gd.dtype == torch.float32 and gc.dtype == cdt
+    assert_close_scaled(gd.cpu().numpy(), rd.numpy(), 2e-5, "AMP d_depth (fp32)")
+    assert_close_scaled(gc.float().cpu().numpy(), rc.numpy(), 1e-2, "AMP d_ctx (16-bit)")
+    # the module keeps the mix instead of rounding the probabilities down
+    from vampire_b200.view_transform import LiftRenderB200
+    mod = LiftRenderB200(plans="off", **case.conf).cuda()
+    with torch.no_grad():
+        got = mod.lift_pool(case.depth.cuda(), ctx16.cuda(), case.mats)
+    assert got.dtype == torch.float32 and torch.equal(got, out.detach())

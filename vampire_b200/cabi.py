@@ -46,6 +46,11 @@ class VbTables(C.Structure):
                 ("us", "vs", "ds", "xs", "ys", "zs", "oxs", "oys", "ozs", "mids", "bev_mids")]
 
 
+class VbLiftPlan(C.Structure):
+    """One sample's cached lift plan (device pointers); see include/vb200.h."""
+    _fields_ = [(n, C.c_void_p) for n in ("head", "pairs", "cell_off", "cell_recs")]
+
+
 class VbRenderIn(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("density", "sem", "rgb", "feat", "beta", "geom")]
 
@@ -77,10 +82,18 @@ _PROTOS = {
     "vb200_render_indices": (C.c_int, [C.POINTER(VbGrid), C.POINTER(VbTables), _P, _P, _P, _P, _P, _P]),
     "vb200_lift_pool_fwd_workspace": (C.c_size_t, [C.POINTER(VbGrid), C.c_int]),
     "vb200_lift_pool_bwd_workspace": (C.c_size_t, [C.POINTER(VbGrid), C.c_int]),
-    "vb200_lift_pool_fwd": (C.c_int, [C.POINTER(VbGrid), C.POINTER(VbTables), _P, _P, _P, C.c_int, _P, C.c_int,
-                                      _P, _P, C.c_size_t, _P]),
-    "vb200_lift_pool_bwd": (C.c_int, [C.POINTER(VbGrid), C.POINTER(VbTables), _P, _P, _P, C.c_int, _P, C.c_int,
-                                      _P, _P, _P, _P, C.c_size_t, _P]),
+    "vb200_lift_pool_fwd": (C.c_int, [C.POINTER(VbGrid), C.POINTER(VbTables), _P, _P, _P, C.c_int, C.c_int, _P,
+                                      C.c_int, _P, _P, C.c_size_t, _P]),
+    "vb200_lift_pool_bwd": (C.c_int, [C.POINTER(VbGrid), C.POINTER(VbTables), _P, _P, _P, C.c_int, C.c_int, _P,
+                                      C.c_int, _P, _P, _P, _P, C.c_size_t, _P]),
+    "vb200_lift_plan_workspace": (C.c_size_t, [C.POINTER(VbGrid), C.c_longlong]),
+    "vb200_lift_plan_build": (C.c_int, [C.POINTER(VbGrid), C.POINTER(VbTables), _P, _P, _P, _P, _P, C.c_longlong, _P,
+                                        _P, C.c_size_t, _P]),
+    "vb200_lift_pool_bwd_planned_workspace": (C.c_size_t, [C.POINTER(VbGrid), C.c_int]),
+    "vb200_lift_pool_fwd_planned": (C.c_int, [C.POINTER(VbGrid), _P, _P, _P, C.c_int, C.c_int, _P, C.c_int, _P, _P,
+                                              C.c_size_t, _P]),
+    "vb200_lift_pool_bwd_planned": (C.c_int, [C.POINTER(VbGrid), _P, _P, _P, C.c_int, C.c_int, _P, C.c_int, _P, _P,
+                                              _P, _P, C.c_size_t, _P]),
     "vb200_gather_pool_bwd_workspace": (C.c_size_t, [C.POINTER(VbGrid), C.c_int]),
     "vb200_gather_pool_fwd": (C.c_int, [C.POINTER(VbGrid), C.POINTER(VbTables), _P, _P, C.c_int, _P, _P, _P]),
     "vb200_gather_pool_bwd": (C.c_int, [C.POINTER(VbGrid), C.POINTER(VbTables), _P, _P, _P, C.c_int, _P, _P,

@@ -15,7 +15,7 @@
 // (B,C,vZ,vY,vX) volume once => 111.5 MB/sample fp32, 55.7 MB bf16.
 #include <cstdlib>
 
-#include "vb_common.cuh"
+#include "vb_lift_common.cuh"
 #include "vb_trace.cuh"
 
 namespace {
@@ -27,36 +27,6 @@ namespace {
 #define VB_LIFT_MINB 7
 #endif
 constexpr int kLiftThreads = VB_LIFT_THREADS;
-
-// ---- ctx (B,N,C,fH,fW) -> (B,N,fH,fW,C): one block per (b*n, h) row -------------------------
-// (the copy keeps the feature dtype: the gather is L1-wavefront bound -- ncu: l1tex 87 % with an fp32 copy --
-//  so a bf16 pixel = one 32-byte sector beats saving the 16 unpack instructions of an fp32 copy)
-template <typename T, int C>
-__global__ void __launch_bounds__(256) ctx_to_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, int fH,
-                                                          int fW) {
-  extern __shared__ unsigned char s_raw[];
-  T* s = reinterpret_cast<T*>(s_raw);  // [C][fW + 1]
-  const int h = blockIdx.x, bn = blockIdx.y;
-  const int ld = fW + 1;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  // read: a warp per channel row, lanes along w (coalesced, no integer division)
-  for (int c = wid; c < C; c += nw) {
-    const T* row = src + (((size_t)bn * C + c) * fH + h) * fW;
-    for (int w = lane; w < fW; w += 32) s[c * ld + w] = row[w];
-  }
-  __syncthreads();
-  // write: one 128-bit store per thread = 16 / sizeof(T) consecutive channels of one pixel
-  constexpr int L = 16 / sizeof(T), PARTS = C / L;
-  static_assert(C % L == 0, "a pixel's channels must be whole 128-bit groups");
-  uint4* out = reinterpret_cast<uint4*>(dst + ((size_t)bn * fH + h) * fW * C);
-  for (int p = threadIdx.x; p < fW * PARTS; p += blockDim.x) {
-    const int w = p / PARTS, c0 = (p % PARTS) * L;   // PARTS is a compile-time power of two
-    __align__(16) T v[L];
-#pragma unroll
-    for (int e = 0; e < L; ++e) v[e] = s[(c0 + e) * ld + w];
-    out[p] = *reinterpret_cast<const uint4*>(v);
-  }
-}
 
 // Trilinear weights exactly as ATen forms them (GridSampler: corner weight = product of
 // (x_far - ix) terms), in the tolerance zone (FMA allowed).
@@ -75,12 +45,12 @@ __device__ __forceinline__ TriW tri_weights(float ix, float iy, float iz, int x0
 }
 
 // ---- forward: one thread per voxel, loop over cameras ---------------------------------------
-template <typename T, int C, int OUT_LAYOUT, bool FASTDIV>
+template <typename TD, typename TC, int C, int OUT_LAYOUT, bool FASTDIV>
 __global__ void __launch_bounds__(kLiftThreads, VB_LIFT_MINB) lift_pool_fwd_kernel(VbGrid g, VbTables t, VbLiftDiv dv,
                                                                      const float* __restrict__ d_mats,
-                                                                     const T* __restrict__ depth,
-                                                                     const T* __restrict__ ctx_nhwc,
-                                                                     T* __restrict__ out, uint64_t* __restrict__ cnt_out, int zrun) {
+                                                                     const TD* __restrict__ depth,
+                                                                     const TC* __restrict__ ctx_nhwc,
+                                                                     TD* __restrict__ out, uint64_t* __restrict__ cnt_out, int zrun) {
   static_assert(C <= 16, "per-channel counts are packed 4 bits each into 64 bits");
   __shared__ float s_m[VB_MAX_CAMS * VB200_MAT_SLOTS * 16];
   __shared__ float s_q[VB_MAX_CAMS * 16];   // fast cull: (K.E^-1)(bda^-1), FMA-composed
@@ -186,92 +156,29 @@ __global__ void __launch_bounds__(kLiftThreads, VB_LIFT_MINB) lift_pool_fwd_kern
     const LiftCoord lc = lift_coord<FASTDIV>(g, pix, &dv);
     if (!lc.valid) continue;  // f = grid_sample * 0: adds nothing to numer nor to the count
     const TriW w = tri_weights(lc.ix, lc.iy, lc.iz, lc.x0, lc.y0, lc.z0);
-    const T* dcam = depth + (size_t)(b * g.N + n) * g.D * HW;
-    const T* ccam = ctx_nhwc + (size_t)(b * g.N + n) * HW * C;
-    // zeros padding without branches: clamp the address, zero the weight (valid => i0 in [-1, size-1])
-    const int xa = max(lc.x0, 0), xb = min(lc.x0 + 1, g.fW - 1);
-    const int ya = max(lc.y0, 0), yb = min(lc.y0 + 1, g.fH - 1);
-    const int za = max(lc.z0, 0), zb = min(lc.z0 + 1, g.D - 1);
-    const float wxa = lc.x0 >= 0 ? w.wx0 : 0.0f, wxb = lc.x0 + 1 < g.fW ? w.wx1 : 0.0f;
-    const float wya = lc.y0 >= 0 ? w.wy0 : 0.0f, wyb = lc.y0 + 1 < g.fH ? w.wy1 : 0.0f;
-    const float wza = lc.z0 >= 0 ? w.wz0 : 0.0f, wzb = lc.z0 + 1 < g.D ? w.wz1 : 0.0f;
-    const int pxl[4] = {ya * g.fW + xa, ya * g.fW + xb, yb * g.fW + xa, yb * g.fW + xb};
-    const float wxy[4] = {wxa * wya, wxb * wya, wxa * wyb, wxb * wyb};
-    const T* d0 = dcam + za * HW;
-    const T* d1 = dcam + zb * HW;
-    float wgt[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      wgt[k] = wxy[k] * fmaf(wzb, VbType<T>::ld(d1 + pxl[k]), wza * VbType<T>::ld(d0 + pxl[k]));
+    const TD* dcam = depth + (size_t)(b * g.N + n) * g.D * HW;
+    const TC* ccam = ctx_nhwc + (size_t)(b * g.N + n) * HW * C;
     float f[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) f[c] = 0.0f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      constexpr int L = VbLanes<T>::n;
-      const T* cp = ccam + pxl[k] * C;
-#pragma unroll
-      for (int q4 = 0; q4 < C / L; ++q4) {
-        float cv[L];
-        VbVec<T, L>::ld(cp + q4 * L, cv);
-#pragma unroll
-        for (int e = 0; e < L; ++e) f[q4 * L + e] = fmaf(cv[e], wgt[k], f[q4 * L + e]);
-      }
-    }
-    float fmin_abs = fabsf(f[0]);
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-      acc[c] += f[c];
-      fmin_abs = fminf(fmin_abs, fabsf(f[c]));
-    }
-    cams_seen += 1;
-    if (!(fmin_abs > 0.0f)) {   // some channel is exactly 0 (or NaN): voxel_mask = |f| > 0  BV2:509
-#pragma unroll
-      for (int c = 0; c < C; ++c) zero_cnt += (uint64_t)(fabsf(f[c]) > 0.0f ? 0 : 1) << (4 * c);
-    }
+    lift_pair_gather<TD, TC, C>(g, dcam, ccam, HW, lc.x0, lc.y0, lc.z0, w.wx0, w.wx1, w.wy0, w.wy1, w.wz0, w.wz1, f);
+    lift_accumulate<C>(f, acc, cams_seen, zero_cnt);
   }
 
   if (!pos_live) continue;
-  const uint64_t seen_all = 0x1111111111111111ull * (uint64_t)cams_seen;   // cams_seen in every 4-bit field
-  if (cnt_out) cnt_out[(size_t)b * nvox + vox] = seen_all - zero_cnt;      // saved for the backward
-  // mean = numer / (count + 1e-6)  (BV2:512-514); reciprocal-multiply is within 2 ulp of the division
-  float inv[C];
-  if (zero_cnt == 0) {
-    const float r = __fdividef(1.0f, (float)cams_seen + 1e-6f);
-#pragma unroll
-    for (int c = 0; c < C; ++c) inv[c] = r;
-  } else {
-#pragma unroll
-    for (int c = 0; c < C; ++c)
-      inv[c] = __fdividef(1.0f, (float)(cams_seen - (int)((zero_cnt >> (4 * c)) & 0xf)) + 1e-6f);
-  }
-  if (OUT_LAYOUT == VB200_NCDHW) {
-    T* o = out + (size_t)b * C * nvox + vox;
-#pragma unroll
-    for (int c = 0; c < C; ++c) o[(size_t)c * nvox] = VbType<T>::cvt(acc[c] * inv[c]);
-  } else {
-    T* o = out + ((size_t)b * nvox + vox) * C;
-    T v[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) v[c] = VbType<T>::cvt(acc[c] * inv[c]);
-    constexpr int L = VbLanes<T>::n;
-#pragma unroll
-    for (int q = 0; q < C / L; ++q) reinterpret_cast<uint4*>(o)[q] = reinterpret_cast<const uint4*>(v)[q];
-  }
+  lift_store<TD, C, OUT_LAYOUT>(out, cnt_out, b, nvox, vox, acc, cams_seen, zero_cnt);
   }   // z-run
 }
 
-template <typename T>
+template <typename TD, typename TC>
 int launch_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, const void* d_depth, const void* d_ctx,
                void* d_out, int out_layout, uint64_t* d_cnt, void* ws, cudaStream_t st) {
   constexpr int C = 16;
   if (g->C != C) return VB200_ERR_ARG;
-  T* ctx_nhwc = reinterpret_cast<T*>(ws);
+  TC* ctx_nhwc = reinterpret_cast<TC*>(ws);
   {
     dim3 grid(g->fH, g->B * g->N);
-    const size_t smem = (size_t)C * (g->fW + 1) * sizeof(T);
+    const size_t smem = (size_t)C * (g->fW + 1) * sizeof(TC);
     VbTraceScope tr(VB_K_CTX_NHWC, st);
-    ctx_to_nhwc_kernel<T, C><<<grid, 256, smem, st>>>(reinterpret_cast<const T*>(d_ctx), ctx_nhwc, g->fH, g->fW);
+    ctx_to_nhwc_kernel<TC, C><<<grid, 256, smem, st>>>(reinterpret_cast<const TC*>(d_ctx), ctx_nhwc, g->fH, g->fW);
     VB_LAUNCH_CHECK();
   }
   // z-run per thread: longer runs amortise the prologue, shorter ones keep the warp-level camera mask selective.
@@ -287,8 +194,8 @@ int launch_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, const vo
   VbTraceScope tr(VB_K_LIFT_FWD, st);
   const VbLiftDiv dv = vb_lift_div(g);
 #define VB_LIFT(LAYOUT, FD)                                                                                   \
-  lift_pool_fwd_kernel<T, C, LAYOUT, FD><<<grid, kLiftThreads, 0, st>>>(                                       \
-      *g, *t, dv, d_mats, reinterpret_cast<const T*>(d_depth), ctx_nhwc, reinterpret_cast<T*>(d_out), d_cnt, zrun)
+  lift_pool_fwd_kernel<TD, TC, C, LAYOUT, FD><<<grid, kLiftThreads, 0, st>>>(                                  \
+      *g, *t, dv, d_mats, reinterpret_cast<const TD*>(d_depth), ctx_nhwc, reinterpret_cast<TD*>(d_out), d_cnt, zrun)
   if (vb_lift_div_ok(dv)) {
     if (out_layout == VB200_NCDHW) VB_LIFT(VB200_NCDHW, true);
     else VB_LIFT(VB200_NDHWC, true);
@@ -301,36 +208,30 @@ int launch_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, const vo
   return VB200_OK;
 }
 
-size_t elem_size(int dtype) { return dtype == VB200_F32 ? 4 : 2; }
-
 }  // namespace
 
-extern "C" size_t vb200_lift_pool_fwd_workspace(const VbGrid* g, int dtype) {
+extern "C" size_t vb200_lift_pool_fwd_workspace(const VbGrid* g, int ctx_dtype) {
   if (!g) return 0;
-  // channels-last copy of ctx (feature dtype), rounded up to 256 B
-  const size_t n = (size_t)g->B * g->N * g->fH * g->fW * g->C * elem_size(dtype);
+  // channels-last copy of ctx (its own dtype), rounded up to 256 B
+  const size_t n = (size_t)g->B * g->N * g->fH * g->fW * g->C * vb_lift_elem_size(ctx_dtype);
   return (n + 255) & ~(size_t)255;
 }
 
 extern "C" int vb200_lift_pool_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, const void* d_depth,
-                                   const void* d_ctx, int dtype, void* d_out, int out_layout, uint64_t* d_cnt,
-                                   void* d_workspace, size_t workspace_bytes, void* stream) {
+                                   const void* d_ctx, int dtype, int ctx_dtype, void* d_out, int out_layout,
+                                   uint64_t* d_cnt, void* d_workspace, size_t workspace_bytes, void* stream) {
   VB_CHECK_ARG(g && t && d_mats && d_depth && d_ctx && d_out && d_workspace);
   VB_CHECK_ARG(g->B > 0 && g->N > 0 && g->N <= VB_MAX_CAMS);
   VB_CHECK_ARG(g->D >= 1);
   VB_CHECK_ARG(out_layout == VB200_NCDHW || out_layout == VB200_NDHWC);
-  if (workspace_bytes < vb200_lift_pool_fwd_workspace(g, dtype)) return VB200_ERR_WORKSPACE;
+  if (workspace_bytes < vb200_lift_pool_fwd_workspace(g, ctx_dtype)) return VB200_ERR_WORKSPACE;
   if (((uintptr_t)d_workspace | (uintptr_t)d_out | (uintptr_t)d_ctx | (uintptr_t)d_depth) & 15) return VB200_ERR_ALIGN;
   int rc = vb200_device_check();
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  switch (dtype) {
-    case VB200_F32: return launch_fwd<float>(g, t, d_mats, d_depth, d_ctx, d_out, out_layout, d_cnt, d_workspace, st);
-    case VB200_BF16:
-      return launch_fwd<__nv_bfloat16>(g, t, d_mats, d_depth, d_ctx, d_out, out_layout, d_cnt, d_workspace, st);
-    case VB200_F16: return launch_fwd<__half>(g, t, d_mats, d_depth, d_ctx, d_out, out_layout, d_cnt, d_workspace, st);
-    default: return VB200_ERR_DTYPE;
-  }
+#define VB_CALL(TD, TC) launch_fwd<TD, TC>(g, t, d_mats, d_depth, d_ctx, d_out, out_layout, d_cnt, d_workspace, st)
+  VB_LIFT_DISPATCH(dtype, ctx_dtype, VB_CALL);
+#undef VB_CALL
 }
 
-// ---- backward: implemented in vb_lift_bwd.cu ---------------------------------------------------
+// ---- backward: implemented in vb_lift_bwd.cu; plan-driven variants in vb_lift_plan.cu ------------

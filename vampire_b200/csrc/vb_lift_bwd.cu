@@ -19,60 +19,15 @@
 //   finalize            fp32 accumulators -> the caller's layout / dtype.
 //
 // No float atomics anywhere => bit-reproducible gradients; no grad-frustum is ever formed.
-#include "vb_common.cuh"
+#include "vb_lift_common.cuh"
+#include "vb_lift_pairs.cuh"
+#include "vb_scan.cuh"
 #include "vb_trace.cuh"
 
 namespace {
 
 constexpr int kC = 16;
 constexpr int kThreads = 256;
-constexpr int kVoxBits = 21;   // record = (z0 + 1) << 21 | voxel  (nvox <= 2^21, D + 1 < 2^11)
-
-struct CellDims {
-  int ncy, ncx, nc;   // cells per camera row / col, cells per sample = N * ncy * ncx
-};
-__host__ __device__ inline CellDims cell_dims(const VbGrid& g) {
-  CellDims c;
-  c.ncy = g.fH + 1;   // y0 in [-1, fH-1]
-  c.ncx = g.fW + 1;
-  c.nc = g.N * c.ncy * c.ncx;
-  return c;
-}
-
-// shared by plan + backward: cull + strict projection of (voxel, camera n); returns validity
-__device__ __forceinline__ bool pair_coord(const VbGrid& g, const float* s_m, const float* s_q, bool has_bda,
-                                           bool affine, const VbLiftDiv& dv, int n, float px, float py, float pz,
-                                           LiftCoord& lc) {
-  const float* q = s_q + n * 16;
-  const float cz = fmaf(q[8], px, fmaf(q[9], py, fmaf(q[10], pz, q[11])));
-  if (!(cz > g.d_lo - 0.05f && cz < g.d_hi + 0.05f)) return false;
-  const float cx = fmaf(q[0], px, fmaf(q[1], py, fmaf(q[2], pz, q[3])));
-  const float cy = fmaf(q[4], px, fmaf(q[5], py, fmaf(q[6], pz, q[7])));
-  const float rz = __frcp_rn(cz);
-  const float ux = cx * rz, uy = cy * rz;
-  const float* I = s_m + n * VB200_MAT_SLOTS * 16 + 2 * 16;
-  const float cw = fmaf(q[12], px, fmaf(q[13], py, fmaf(q[14], pz, q[15])));
-  const float ax = fmaf(I[0], ux, fmaf(I[1], uy, fmaf(I[2], cz, I[3] * cw)));
-  const float ay = fmaf(I[4], ux, fmaf(I[5], uy, fmaf(I[6], cz, I[7] * cw)));
-  if (!(ax > -1.5f && ax < g.x_hi + 1.0f && ay > -1.5f && ay < g.y_hi + 1.0f)) return false;
-  lc = pair_strict(g, s_m + n * VB200_MAT_SLOTS * 16, has_bda, affine, dv, px, py, pz);
-  return lc.valid;
-}
-
-__device__ __forceinline__ void stage_cull(float* s_q, const float* s_m, int N, bool has_bda) {
-  for (int i = threadIdx.x; i < N * 16; i += blockDim.x) {
-    const int n = i / 16, r = (i % 16) / 4, c = i % 4;
-    const float* A = s_m + n * VB200_MAT_SLOTS * 16 + 16;
-    const float* Bm = s_m + n * VB200_MAT_SLOTS * 16;
-    float v = A[r * 4 + c];
-    if (has_bda) {
-      v = 0.0f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) v = fmaf(A[r * 4 + k], Bm[k * 4 + c], v);
-    }
-    s_q[i] = v;
-  }
-}
 
 // ---- plan: count / fill ---------------------------------------------------------------------------
 template <int MODE>
@@ -106,84 +61,6 @@ __global__ void __launch_bounds__(kThreads) plan_pairs_kernel(VbGrid g, VbTables
       recs[(size_t)b * g.N * nvox + slot] = ((uint32_t)(lc.z0 + 1) << kVoxBits) | (uint32_t)vox;
     }
   }
-}
-
-// ---- exclusive scan of the per-cell counts: chunked 3-pass scan (a single block per sample took 63 us) ----
-constexpr int kScanThreads = 1024;
-constexpr int kScanPerThread = 4;
-constexpr int kScanChunk = kScanThreads * kScanPerThread;
-
-__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int& total) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int s = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int u = __shfl_up_sync(0xffffffffu, s, o);
-    if (lane >= o) s += u;
-  }
-  if (lane == 31) s_warp[wid] = s;
-  __syncthreads();
-  if (wid == 0) {
-    int w = s_warp[lane];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int u = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w += u;
-    }
-    s_warp[lane] = w;
-  }
-  __syncthreads();
-  total = s_warp[31];
-  return (wid ? s_warp[wid - 1] : 0) + s - v;
-}
-
-// pass 1: per-chunk exclusive scan + chunk totals.  grid = (chunks, B)
-__global__ void __launch_bounds__(kScanThreads) scan_chunks_kernel(const int* __restrict__ counts, int* __restrict__ offsets,
-                                                                   int* __restrict__ chunk_sums, int nc, int nchunks) {
-  __shared__ int s_warp[32];
-  const int b = blockIdx.y, chunk = blockIdx.x;
-  const int* in = counts + (size_t)b * nc;
-  int* out = offsets + (size_t)b * (nc + 1);
-  const int base = chunk * kScanChunk + threadIdx.x * kScanPerThread;
-  int v[kScanPerThread], sum = 0;
-#pragma unroll
-  for (int k = 0; k < kScanPerThread; ++k) {
-    v[k] = (base + k < nc) ? in[base + k] : 0;
-    sum += v[k];
-  }
-  int total;
-  int excl = block_exclusive_scan(sum, s_warp, total);
-#pragma unroll
-  for (int k = 0; k < kScanPerThread; ++k) {
-    if (base + k < nc) out[base + k] = excl;
-    excl += v[k];
-  }
-  if (threadIdx.x == 0) chunk_sums[(size_t)b * nchunks + chunk] = total;
-}
-
-// pass 2: exclusive scan of the chunk totals (<= 1024 chunks), one block per sample; also the grand total
-__global__ void __launch_bounds__(kScanThreads) scan_sums_kernel(int* __restrict__ chunk_sums, int* __restrict__ offsets,
-                                                                 int nc, int nchunks) {
-  __shared__ int s_warp[32];
-  const int b = blockIdx.x;
-  int* sums = chunk_sums + (size_t)b * nchunks;
-  const int v = threadIdx.x < nchunks ? sums[threadIdx.x] : 0;
-  int total;
-  const int excl = block_exclusive_scan(v, s_warp, total);
-  if (threadIdx.x < nchunks) sums[threadIdx.x] = excl;
-  if (threadIdx.x == 0) offsets[(size_t)b * (nc + 1) + nc] = total;
-}
-
-// pass 3: add the chunk base.  grid = (chunks, B)
-__global__ void __launch_bounds__(kScanThreads) scan_add_kernel(int* __restrict__ offsets, const int* __restrict__ chunk_sums,
-                                                                int nc, int nchunks) {
-  const int b = blockIdx.y, chunk = blockIdx.x;
-  const int add = chunk_sums[(size_t)b * nchunks + chunk];
-  int* out = offsets + (size_t)b * (nc + 1);
-  const int base = chunk * kScanChunk + threadIdx.x * kScanPerThread;
-#pragma unroll
-  for (int k = 0; k < kScanPerThread; ++k)
-    if (base + k < nc) out[base + k] += add;
 }
 
 // ---- per-cell rank sort: warp per cell -----------------------------------------------------------------
@@ -254,9 +131,12 @@ __global__ void __launch_bounds__(256) gout_prep_kernel(const T* __restrict__ go
 #ifndef VB_LIFT_BWD_MINB
 #define VB_LIFT_BWD_MINB 4
 #endif
-template <typename T>
+// PLANNED: the cell segments come from a cached VbLiftPlan (one per sample): 16-byte records
+// {(z0+1) << 21 | voxel, fx, fy, fz} already sorted by (z0, voxel) -- no re-projection, no per-call plan.
+template <typename T, bool PLANNED>
 __global__ void __launch_bounds__(kThreads, VB_LIFT_BWD_MINB) lift_bwd_kernel(VbGrid g, VbTables t, VbLiftDiv dv,
                                                             const float* __restrict__ d_mats,
+                                                            const VbLiftPlan* __restrict__ plans,
                                                             const T* __restrict__ depth,
                                                             const float* __restrict__ ctx_nhwc,
                                                             const float* __restrict__ gprep,
@@ -270,11 +150,14 @@ __global__ void __launch_bounds__(kThreads, VB_LIFT_BWD_MINB) lift_bwd_kernel(Vb
   const int ny = (cd.ncy - py_ + 1) / 2, nx = (cd.ncx - px_ + 1) / 2;   // cells of this colour per camera
   // blockIdx.y = b * N + n so that a block shares one camera's matrices
   const int bn = blockIdx.y, b = bn / g.N, n = bn % g.N;
-  for (int i = threadIdx.x; i < VB200_MAT_SLOTS * 16; i += blockDim.x)
-    s_m[i] = __ldg(d_mats + (size_t)bn * VB200_MAT_SLOTS * 16 + i);
-  __syncthreads();
-  const bool has_bda = (g.has_bda != 0) && !block_is_identity(s_m);
-  const bool affine = block_pixel_affine(s_m, 1, has_bda);      // this block's one camera
+  bool has_bda = false, affine = false;
+  if (!PLANNED) {
+    for (int i = threadIdx.x; i < VB200_MAT_SLOTS * 16; i += blockDim.x)
+      s_m[i] = __ldg(d_mats + (size_t)bn * VB200_MAT_SLOTS * 16 + i);
+    __syncthreads();
+    has_bda = (g.has_bda != 0) && !block_is_identity(s_m);
+    affine = block_pixel_affine(s_m, 1, has_bda);      // this block's one camera
+  }
 
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ci = blockIdx.x * (kThreads / 32) + wid;
@@ -282,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, VB_LIFT_BWD_MINB) lift_bwd_kernel(Vb
   const int cy = 2 * (ci / nx) + py_, cx = 2 * (ci % nx) + px_;
   const int y0 = cy - 1, x0 = cx - 1;
   const int cell = (n * cd.ncy + cy) * cd.ncx + cx;
-  const int* off = offsets + (size_t)b * (cd.nc + 1);
+  const int* off = PLANNED ? plans[b].cell_off : offsets + (size_t)b * (cd.nc + 1);
   const int seg_lo = off[cell], L = off[cell + 1] - seg_lo;
   if (L == 0) return;
 
@@ -307,7 +190,8 @@ __global__ void __launch_bounds__(kThreads, VB_LIFT_BWD_MINB) lift_bwd_kernel(Vb
   __syncwarp();
 
   const T* dcam = depth + (size_t)bn * D * HW;
-  const uint32_t* seg = recs + (size_t)b * g.N * nvox + seg_lo;
+  const uint32_t* seg = PLANNED ? nullptr : recs + (size_t)b * g.N * nvox + seg_lo;
+  const uint4* pseg = PLANNED ? reinterpret_cast<const uint4*>(plans[b].cell_recs) + seg_lo : nullptr;
   const int c_ = lane & 15, half = lane >> 4;
   float accC[4] = {0.f, 0.f, 0.f, 0.f};
 
@@ -318,17 +202,30 @@ __global__ void __launch_bounds__(kThreads, VB_LIFT_BWD_MINB) lift_bwd_kernel(Vb
     int z0 = 100000 + lane;   // inactive lanes: unique keys => single-lane runs of zeros
     float vA[4] = {0.f, 0.f, 0.f, 0.f}, vB[4] = {0.f, 0.f, 0.f, 0.f};
     if (act) {
-      const uint32_t rec = seg[r0 + lane];
-      const int vox = (int)(rec & ((1u << kVoxBits) - 1));
-      const int x = vox % g.vX, y = (vox / g.vX) % g.vY, z = vox / (g.vX * g.vY);
-      // same code as the plan => same (x0, y0, z0)
-      const LiftCoord lc = pair_strict(g, s_m, has_bda, affine, dv, __ldg(t.xs + x), __ldg(t.ys + y), __ldg(t.zs + z));
-      z0 = lc.z0;
-      const float wx0 = inx0 ? (float)(lc.x0 + 1) - lc.ix : 0.0f, wx1 = inx1 ? lc.ix - (float)lc.x0 : 0.0f;
-      const float wy0 = iny0 ? (float)(lc.y0 + 1) - lc.iy : 0.0f, wy1 = iny1 ? lc.iy - (float)lc.y0 : 0.0f;
-      const float wza = lc.z0 >= 0 ? (float)(lc.z0 + 1) - lc.iz : 0.0f;
-      const float wzb = lc.z0 + 1 < D ? lc.iz - (float)lc.z0 : 0.0f;
-      const int za = max(lc.z0, 0), zb = min(lc.z0 + 1, D - 1);
+      int vox;
+      float wx0, wx1, wy0, wy1, wza, wzb;
+      if (PLANNED) {
+        const uint4 pr = __ldg(pseg + r0 + lane);
+        vox = (int)(pr.x & ((1u << kVoxBits) - 1));
+        z0 = (int)(pr.x >> kVoxBits) - 1;
+        const float fx = __uint_as_float(pr.y), fy = __uint_as_float(pr.z), fz = __uint_as_float(pr.w);
+        wx0 = inx0 ? 1.0f - fx : 0.0f; wx1 = inx1 ? fx : 0.0f;
+        wy0 = iny0 ? 1.0f - fy : 0.0f; wy1 = iny1 ? fy : 0.0f;
+        wza = z0 >= 0 ? 1.0f - fz : 0.0f;
+        wzb = z0 + 1 < D ? fz : 0.0f;
+      } else {
+        const uint32_t rec = seg[r0 + lane];
+        vox = (int)(rec & ((1u << kVoxBits) - 1));
+        const int x = vox % g.vX, y = (vox / g.vX) % g.vY, z = vox / (g.vX * g.vY);
+        // same code as the plan => same (x0, y0, z0)
+        const LiftCoord lc = pair_strict(g, s_m, has_bda, affine, dv, __ldg(t.xs + x), __ldg(t.ys + y), __ldg(t.zs + z));
+        z0 = lc.z0;
+        wx0 = inx0 ? (float)(lc.x0 + 1) - lc.ix : 0.0f; wx1 = inx1 ? lc.ix - (float)lc.x0 : 0.0f;
+        wy0 = iny0 ? (float)(lc.y0 + 1) - lc.iy : 0.0f; wy1 = iny1 ? lc.iy - (float)lc.y0 : 0.0f;
+        wza = lc.z0 >= 0 ? (float)(lc.z0 + 1) - lc.iz : 0.0f;
+        wzb = lc.z0 + 1 < D ? lc.iz - (float)lc.z0 : 0.0f;
+      }
+      const int za = max(z0, 0), zb = min(z0 + 1, D - 1);
       const float wxy[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};
       const T* d0 = dcam + (size_t)za * HW;
       const T* d1 = dcam + (size_t)zb * HW;
@@ -432,18 +329,19 @@ size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 struct BwdLayout {
   size_t ctx, counts, offsets, cursor, chunk_sums, recs_a, recs_b, gctx, gprep, gdepth, total;
 };
-BwdLayout bwd_layout(const VbGrid* g, bool need_gdepth_ws) {
+// planned: the per-call plan buffers (counts / offsets / cursor / records) are not needed
+BwdLayout bwd_layout(const VbGrid* g, bool need_gdepth_ws, bool planned) {
   const CellDims cd = cell_dims(*g);
   const size_t nvox = (size_t)g->vZ * g->vY * g->vX, HW = (size_t)g->fH * g->fW;
   BwdLayout l;
   size_t o = 0;
   l.ctx = o;     o += align256((size_t)g->B * g->N * HW * kC * 4);
-  l.counts = o;  o += align256((size_t)g->B * cd.nc * 4);
-  l.offsets = o; o += align256((size_t)g->B * (cd.nc + 1) * 4);
-  l.cursor = o;  o += align256((size_t)g->B * cd.nc * 4);
-  l.chunk_sums = o; o += align256((size_t)g->B * 1024 * 4);
-  l.recs_a = o;  o += align256((size_t)g->B * g->N * nvox * 4);
-  l.recs_b = o;  o += align256((size_t)g->B * g->N * nvox * 4);
+  l.counts = o;  o += planned ? 0 : align256((size_t)g->B * cd.nc * 4);
+  l.offsets = o; o += planned ? 0 : align256((size_t)g->B * (cd.nc + 1) * 4);
+  l.cursor = o;  o += planned ? 0 : align256((size_t)g->B * cd.nc * 4);
+  l.chunk_sums = o; o += planned ? 0 : align256((size_t)g->B * 1024 * 4);
+  l.recs_a = o;  o += planned ? 0 : align256((size_t)g->B * g->N * nvox * 4);
+  l.recs_b = o;  o += planned ? 0 : align256((size_t)g->B * g->N * nvox * 4);
   l.gctx = o;    o += align256((size_t)g->B * g->N * HW * kC * 4);
   l.gprep = o;   o += align256((size_t)g->B * nvox * kC * 4);
   l.gdepth = o;  o += need_gdepth_ws ? align256((size_t)g->B * g->N * g->D * HW * 4) : 0;
@@ -451,15 +349,18 @@ BwdLayout bwd_layout(const VbGrid* g, bool need_gdepth_ws) {
   return l;
 }
 
-template <typename T>
-int launch_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const void* d_depth, const void* d_ctx,
-               const void* d_gout, int gout_layout, const uint64_t* d_cnt, void* d_gdepth, void* d_gctx, char* ws,
-               cudaStream_t st) {
+// TD: dtype of depth / d_gout / d_gdepth; TC: dtype of ctx / d_gctx (see vb_lift_common.cuh).
+// d_plans != nullptr: cached plans (device array of B VbLiftPlan), no per-call plan.
+template <typename TD, typename TC>
+int launch_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const VbLiftPlan* d_plans, const void* d_depth,
+               const void* d_ctx, const void* d_gout, int gout_layout, const uint64_t* d_cnt, void* d_gdepth,
+               void* d_gctx, char* ws, cudaStream_t st) {
   if (g->C != kC) return VB200_ERR_ARG;
   const size_t nvox = (size_t)g->vZ * g->vY * g->vX, HW = (size_t)g->fH * g->fW;
   if (nvox > (1u << kVoxBits) || g->D + 1 >= (1 << (32 - kVoxBits))) return VB200_ERR_ARG;
-  constexpr bool kF32 = sizeof(T) == 4;
-  const BwdLayout l = bwd_layout(g, !kF32);
+  constexpr bool kF32 = sizeof(TD) == 4;
+  const bool planned = d_plans != nullptr;
+  const BwdLayout l = bwd_layout(g, !kF32, planned);
   const CellDims cd = cell_dims(*g);
   float* ctx_nhwc = reinterpret_cast<float*>(ws + l.ctx);
   int* counts = reinterpret_cast<int*>(ws + l.counts);
@@ -472,30 +373,28 @@ int launch_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const vo
   float* gdepth_acc = kF32 ? reinterpret_cast<float*>(d_gdepth) : reinterpret_cast<float*>(ws + l.gdepth);
   const size_t n_gdepth = (size_t)g->B * g->N * g->D * HW;
 
-  const VbLiftDiv dv = vb_lift_div(g);
-  if (cudaMemsetAsync(counts, 0, (size_t)g->B * cd.nc * 4, st) != cudaSuccess) return VB200_ERR_CUDA;
-  if (cudaMemsetAsync(cursor, 0, (size_t)g->B * cd.nc * 4, st) != cudaSuccess) return VB200_ERR_CUDA;
+  VbLiftDiv dv = {};
+  VbTables no_tables = {};
+  if (!planned) dv = vb_lift_div(g);
   if (cudaMemsetAsync(gctx_ws, 0, (size_t)g->B * g->N * HW * kC * 4, st) != cudaSuccess) return VB200_ERR_CUDA;
   if (cudaMemsetAsync(gdepth_acc, 0, n_gdepth * 4, st) != cudaSuccess) return VB200_ERR_CUDA;
   {
     VbTraceScope tr(VB_K_CTX_NHWC, st);
-    ctx_to_nhwc_f32_kernel<T><<<dim3(g->fH, g->B * g->N), 256, (size_t)kC * (g->fW + 1) * 4, st>>>(
-        reinterpret_cast<const T*>(d_ctx), ctx_nhwc, g->fH, g->fW);
+    ctx_to_nhwc_f32_kernel<TC><<<dim3(g->fH, g->B * g->N), 256, (size_t)kC * (g->fW + 1) * 4, st>>>(
+        reinterpret_cast<const TC*>(d_ctx), ctx_nhwc, g->fH, g->fW);
     VB_LAUNCH_CHECK();
   }
-  {
+  if (!planned) {
+    if (cudaMemsetAsync(counts, 0, (size_t)g->B * cd.nc * 4, st) != cudaSuccess) return VB200_ERR_CUDA;
+    if (cudaMemsetAsync(cursor, 0, (size_t)g->B * cd.nc * 4, st) != cudaSuccess) return VB200_ERR_CUDA;
     VbTraceScope tr(VB_K_LIFT_PLAN, st, 6);
     dim3 vgrid(vb_ceil_div(nvox, kThreads), g->B);
     plan_pairs_kernel<0><<<vgrid, kThreads, 0, st>>>(*g, *t, dv, d_mats, counts, nullptr, nullptr, nullptr);
     VB_LAUNCH_CHECK();
-    const int nchunks = vb_ceil_div(cd.nc, kScanChunk);
-    if (nchunks > kScanThreads) return VB200_ERR_ARG;   // > 4 M pixel cells per sample: not a camera feature map
-    scan_chunks_kernel<<<dim3(nchunks, g->B), kScanThreads, 0, st>>>(counts, offsets, chunk_sums, cd.nc, nchunks);
-    VB_LAUNCH_CHECK();
-    scan_sums_kernel<<<g->B, kScanThreads, 0, st>>>(chunk_sums, offsets, cd.nc, nchunks);
-    VB_LAUNCH_CHECK();
-    scan_add_kernel<<<dim3(nchunks, g->B), kScanThreads, 0, st>>>(offsets, chunk_sums, cd.nc, nchunks);
-    VB_LAUNCH_CHECK();
+    {
+      const int rc = vb_exclusive_scan(counts, offsets, chunk_sums, cd.nc, g->B, st);   // > 4 M pixel cells per sample: not a camera feature map
+      if (rc) return rc;
+    }
     plan_pairs_kernel<1><<<vgrid, kThreads, 0, st>>>(*g, *t, dv, d_mats, nullptr, offsets, cursor, recs_a);
     VB_LAUNCH_CHECK();
     const int total_cells = g->B * cd.nc;
@@ -510,63 +409,80 @@ int launch_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const vo
     {
       dim3 pgrid(vb_ceil_div(nvox, 256), g->B);
       if (gout_layout == VB200_NCDHW)
-        gout_prep_kernel<T, VB200_NCDHW><<<pgrid, 256, 0, st>>>(reinterpret_cast<const T*>(d_gout), d_cnt, gprep, (int)nvox);
+        gout_prep_kernel<TD, VB200_NCDHW><<<pgrid, 256, 0, st>>>(reinterpret_cast<const TD*>(d_gout), d_cnt, gprep, (int)nvox);
       else
-        gout_prep_kernel<T, VB200_NDHWC><<<pgrid, 256, 0, st>>>(reinterpret_cast<const T*>(d_gout), d_cnt, gprep, (int)nvox);
+        gout_prep_kernel<TD, VB200_NDHWC><<<pgrid, 256, 0, st>>>(reinterpret_cast<const TD*>(d_gout), d_cnt, gprep, (int)nvox);
       VB_LAUNCH_CHECK();
     }
-    auto kern = lift_bwd_kernel<T>;
+    auto kern = planned ? lift_bwd_kernel<TD, true> : lift_bwd_kernel<TD, false>;
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return VB200_ERR_CUDA;
     for (int colour = 0; colour < 4; ++colour) {
       const int ny = (cd.ncy - (colour >> 1) + 1) / 2, nx = (cd.ncx - (colour & 1) + 1) / 2;
       dim3 grid(vb_ceil_div((long long)ny * nx, kThreads / 32), g->B * g->N);
-      kern<<<grid, kThreads, smem, st>>>(*g, *t, dv, d_mats, reinterpret_cast<const T*>(d_depth), ctx_nhwc,
-                                         gprep, offsets, recs_b, gdepth_acc,
-                                         gctx_ws, colour);
+      kern<<<grid, kThreads, smem, st>>>(*g, planned ? no_tables : *t, dv, d_mats, d_plans,
+                                         reinterpret_cast<const TD*>(d_depth), ctx_nhwc, gprep, offsets, recs_b,
+                                         gdepth_acc, gctx_ws, colour);
       VB_LAUNCH_CHECK();
     }
-    gctx_to_nchw_kernel<T><<<dim3(g->fH, g->B * g->N), 256, (size_t)g->fW * (kC + 1) * 4, st>>>(
-        gctx_ws, reinterpret_cast<T*>(d_gctx), g->fH, g->fW);
+    gctx_to_nchw_kernel<TC><<<dim3(g->fH, g->B * g->N), 256, (size_t)g->fW * (kC + 1) * 4, st>>>(
+        gctx_ws, reinterpret_cast<TC*>(d_gctx), g->fH, g->fW);
     VB_LAUNCH_CHECK();
     if (!kF32) {
-      cast_kernel<T><<<VB_SM_COUNT_B200 * 8, 256, 0, st>>>(gdepth_acc, reinterpret_cast<T*>(d_gdepth), n_gdepth);
+      cast_kernel<TD><<<VB_SM_COUNT_B200 * 8, 256, 0, st>>>(gdepth_acc, reinterpret_cast<TD*>(d_gdepth), n_gdepth);
       VB_LAUNCH_CHECK();
     }
   }
   return VB200_OK;
 }
 
-}  // namespace
-
-extern "C" size_t vb200_lift_pool_bwd_workspace(const VbGrid* g, int dtype) {
-  if (!g) return 0;
-  return bwd_layout(g, dtype != VB200_F32).total;
-}
-
-extern "C" int vb200_lift_pool_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const void* d_depth,
-                                   const void* d_ctx, int dtype, const void* d_gout, int gout_layout,
-                                   const uint64_t* d_cnt, void* d_gdepth, void* d_gctx, void* d_workspace,
-                                   size_t workspace_bytes, void* stream) {
-  VB_CHECK_ARG(g && t && d_mats && d_depth && d_ctx && d_gout && d_cnt && d_gdepth && d_gctx && d_workspace);
+int bwd_entry(const VbGrid* g, const VbTables* t, const float* d_mats, const VbLiftPlan* d_plans, const void* d_depth,
+              const void* d_ctx, int dtype, int ctx_dtype, const void* d_gout, int gout_layout, const uint64_t* d_cnt,
+              void* d_gdepth, void* d_gctx, void* d_workspace, size_t workspace_bytes, void* stream) {
+  VB_CHECK_ARG(g && d_depth && d_ctx && d_gout && d_cnt && d_gdepth && d_gctx && d_workspace);
+  VB_CHECK_ARG(d_plans || (t && d_mats));
   VB_CHECK_ARG(g->B > 0 && g->N > 0 && g->N <= VB_MAX_CAMS);
   VB_CHECK_ARG(g->D >= 1);
   VB_CHECK_ARG(gout_layout == VB200_NCDHW || gout_layout == VB200_NDHWC);
-  if (workspace_bytes < vb200_lift_pool_bwd_workspace(g, dtype)) return VB200_ERR_WORKSPACE;
+  if (workspace_bytes < bwd_layout(g, dtype != VB200_F32, d_plans != nullptr).total) return VB200_ERR_WORKSPACE;
   if (((uintptr_t)d_workspace | (uintptr_t)d_gout | (uintptr_t)d_gctx | (uintptr_t)d_gdepth) & 15) return VB200_ERR_ALIGN;
   int rc = vb200_device_check();
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   char* ws = reinterpret_cast<char*>(d_workspace);
-  switch (dtype) {
-    case VB200_F32:
-      return launch_bwd<float>(g, t, d_mats, d_depth, d_ctx, d_gout, gout_layout, d_cnt, d_gdepth, d_gctx, ws, st);
-    case VB200_BF16:
-      return launch_bwd<__nv_bfloat16>(g, t, d_mats, d_depth, d_ctx, d_gout, gout_layout, d_cnt, d_gdepth, d_gctx, ws,
-                                       st);
-    case VB200_F16:
-      return launch_bwd<__half>(g, t, d_mats, d_depth, d_ctx, d_gout, gout_layout, d_cnt, d_gdepth, d_gctx, ws, st);
-    default: return VB200_ERR_DTYPE;
-  }
+#define VB_CALL(TD, TC) \
+  launch_bwd<TD, TC>(g, t, d_mats, d_plans, d_depth, d_ctx, d_gout, gout_layout, d_cnt, d_gdepth, d_gctx, ws, st)
+  VB_LIFT_DISPATCH(dtype, ctx_dtype, VB_CALL);
+#undef VB_CALL
+}
+
+}  // namespace
+
+extern "C" size_t vb200_lift_pool_bwd_workspace(const VbGrid* g, int dtype) {
+  if (!g) return 0;
+  return bwd_layout(g, dtype != VB200_F32, false).total;
+}
+
+extern "C" size_t vb200_lift_pool_bwd_planned_workspace(const VbGrid* g, int dtype) {
+  if (!g) return 0;
+  return bwd_layout(g, dtype != VB200_F32, true).total;
+}
+
+extern "C" int vb200_lift_pool_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const void* d_depth,
+                                   const void* d_ctx, int dtype, int ctx_dtype, const void* d_gout, int gout_layout,
+                                   const uint64_t* d_cnt, void* d_gdepth, void* d_gctx, void* d_workspace,
+                                   size_t workspace_bytes, void* stream) {
+  VB_CHECK_ARG(t && d_mats);
+  return bwd_entry(g, t, d_mats, nullptr, d_depth, d_ctx, dtype, ctx_dtype, d_gout, gout_layout, d_cnt, d_gdepth,
+                   d_gctx, d_workspace, workspace_bytes, stream);
+}
+
+extern "C" int vb200_lift_pool_bwd_planned(const VbGrid* g, const VbLiftPlan* d_plans, const void* d_depth,
+                                           const void* d_ctx, int dtype, int ctx_dtype, const void* d_gout,
+                                           int gout_layout, const uint64_t* d_cnt, void* d_gdepth, void* d_gctx,
+                                           void* d_workspace, size_t workspace_bytes, void* stream) {
+  VB_CHECK_ARG(d_plans);
+  return bwd_entry(g, nullptr, nullptr, d_plans, d_depth, d_ctx, dtype, ctx_dtype, d_gout, gout_layout, d_cnt,
+                   d_gdepth, d_gctx, d_workspace, workspace_bytes, stream);
 }

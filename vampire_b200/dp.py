@@ -73,7 +73,7 @@ class GradBucket:
         self.wait()
 
 
-def train_step(mod, depth, ctx, vols, mats_prep, cotangents, bucket: GradBucket, has_bda: bool = True):
+def train_step(mod, depth, ctx, vols, mats_prep, cotangents, bucket: GradBucket, has_bda: bool = True, plan=None):
     """One forward+backward of lift+pool+render with fixed cotangents (BASELINE configs[2]).
 
     Order: render forward/backward first, then launch the bucket all-reduce (beta's gradient is
@@ -86,7 +86,7 @@ def train_step(mod, depth, ctx, vols, mats_prep, cotangents, bucket: GradBucket,
     rend = ops.render_fwd(den, sem, rgb, feat, beta, mats_prep, None, mod.cfg_id, has_bda, 3)
     torch.autograd.backward(list(rend), list(cotangents[1:]))
     bucket.allreduce_async([beta.grad])
-    vox, _ = ops.lift_pool_fwd(depth, ctx, mats_prep, mod.cfg_id, has_bda, False, True)
+    vox, _ = ops.lift_pool_fwd(depth, ctx, mats_prep, mod.cfg_id, has_bda, False, True, plan)
     torch.autograd.backward([vox], [cotangents[0]])
     bucket.wait()
     return vox, rend

@@ -180,19 +180,37 @@ def render_indices(mats: Tensor, cfg_id: int, has_bda: bool, geom: Optional[Tens
 # =============================================================================================
 # lift + pool
 # =============================================================================================
+def _lift_dtypes(depth: Tensor, ctx: Tensor) -> Tuple[int, int]:
+    """(dtype, ctx_dtype) codes: equal dtypes, or fp32 depth with 16-bit ctx -- the reference under AMP, where the
+    fp32 softmax output promotes the frustum, the grid_sample and the pooled volume to fp32 (BV2:551-553)."""
+    if depth.dtype != ctx.dtype and not (depth.dtype == torch.float32 and ctx.dtype in (torch.bfloat16, torch.float16)):
+        raise TypeError(f"lift_pool: depth {depth.dtype} / ctx {ctx.dtype}: dtypes must match, or depth fp32 with "
+                        f"16-bit ctx (AMP)")
+    return cabi.dtype_code(depth.dtype), cabi.dtype_code(ctx.dtype)
+
+
+def _plan_ok(plan: Optional[Tensor], B: int, dev) -> Optional[Tensor]:
+    if plan is None:
+        return None
+    if plan.dtype != torch.int64 or plan.shape != (B, 4) or plan.device != dev or not plan.is_contiguous():
+        raise ValueError("lift_pool: plan must be the (B, 4) int64 device table of a LiftPlanBatch")
+    return plan
+
+
 @torch.library.custom_op("vampire_b200::lift_pool_fwd", mutates_args=())
 def lift_pool_fwd(depth: Tensor, ctx: Tensor, mats: Tensor, cfg_id: int, has_bda: bool, channels_last: bool,
-                  save_cnt: bool) -> Tuple[Tensor, Tensor]:
+                  save_cnt: bool, plan: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """``plan``: the device table of a :class:`vampire_b200.plan.LiftPlanBatch` built for these matrices; the
+    projection is then read from the cached plan instead of being recomputed (bit-identical result)."""
     st = state(cfg_id)
     cfg = st.cfg
-    dev = _need_cuda(depth, ctx, mats)
+    dev = _need_cuda(depth, ctx, mats, plan)
     B, N = depth.shape[:2]
     if depth.shape != (B, N, st.lift_D, cfg.fH, cfg.fW) or ctx.shape != (B, N, cfg.C, cfg.fH, cfg.fW):
         raise ValueError(f"lift_pool: depth {tuple(depth.shape)} / ctx {tuple(ctx.shape)} do not match the config")
-    if ctx.dtype != depth.dtype:
-        raise TypeError("lift_pool: depth and ctx must share a dtype")
-    dt = cabi.dtype_code(depth.dtype)
+    dt, cdt = _lift_dtypes(depth, ctx)
     mats = _mats_ok(mats, B, N)
+    plan = _plan_ok(plan, B, dev)
     depth = depth.contiguous()
     ctx = ctx.contiguous()
     nvox = cfg.vZ * cfg.vY * cfg.vX
@@ -203,19 +221,25 @@ def lift_pool_fwd(depth: Tensor, ctx: Tensor, mats: Tensor, cfg_id: int, has_bda
     cnt = torch.empty(B, nvox if save_cnt else 0, dtype=torch.int64, device=dev)
     g = st.grid(B, has_bda)
     lib = cabi.lib()
-    ws_bytes = lib.vb200_lift_pool_fwd_workspace(C.byref(g), dt)
+    ws_bytes = lib.vb200_lift_pool_fwd_workspace(C.byref(g), cdt)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    layout = cabi.NDHWC if channels_last else cabi.NCDHW
     with torch.cuda.device(dev):
-        cabi.check(lib.vb200_lift_pool_fwd(C.byref(g), C.byref(st.tables(dev).struct), mats.data_ptr(),
-                                           depth.data_ptr(), ctx.data_ptr(), dt, out.data_ptr(),
-                                           cabi.NDHWC if channels_last else cabi.NCDHW,
-                                           cnt.data_ptr() if save_cnt else None, ws.data_ptr(), ws_bytes,
-                                           cabi.stream_ptr(dev)))
+        if plan is None:
+            cabi.check(lib.vb200_lift_pool_fwd(C.byref(g), C.byref(st.tables(dev).struct), mats.data_ptr(),
+                                               depth.data_ptr(), ctx.data_ptr(), dt, cdt, out.data_ptr(), layout,
+                                               cnt.data_ptr() if save_cnt else None, ws.data_ptr(), ws_bytes,
+                                               cabi.stream_ptr(dev)))
+        else:
+            cabi.check(lib.vb200_lift_pool_fwd_planned(C.byref(g), plan.data_ptr(), depth.data_ptr(), ctx.data_ptr(),
+                                                       dt, cdt, out.data_ptr(), layout,
+                                                       cnt.data_ptr() if save_cnt else None, ws.data_ptr(), ws_bytes,
+                                                       cabi.stream_ptr(dev)))
     return out, cnt
 
 
 @lift_pool_fwd.register_fake
-def _(depth, ctx, mats, cfg_id, has_bda, channels_last, save_cnt):
+def _(depth, ctx, mats, cfg_id, has_bda, channels_last, save_cnt, plan=None):
     cfg = state(cfg_id).cfg
     B = depth.shape[0]
     if channels_last:
@@ -228,13 +252,14 @@ def _(depth, ctx, mats, cfg_id, has_bda, channels_last, save_cnt):
 
 @torch.library.custom_op("vampire_b200::lift_pool_bwd", mutates_args=())
 def lift_pool_bwd(gout: Tensor, depth: Tensor, ctx: Tensor, mats: Tensor, cnt: Tensor, cfg_id: int,
-                  has_bda: bool) -> Tuple[Tensor, Tensor]:
+                  has_bda: bool, plan: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     st = state(cfg_id)
     cfg = st.cfg
-    dev = _need_cuda(gout, depth, ctx, mats, cnt)
+    dev = _need_cuda(gout, depth, ctx, mats, cnt, plan)
     B, N = depth.shape[:2]
-    dt = cabi.dtype_code(depth.dtype)
+    dt, cdt = _lift_dtypes(depth, ctx)
     mats = _mats_ok(mats, B, N)
+    plan = _plan_ok(plan, B, dev)
     depth = depth.contiguous()
     ctx = ctx.contiguous()
     gout = gout.to(depth.dtype)
@@ -247,34 +272,45 @@ def lift_pool_bwd(gout: Tensor, depth: Tensor, ctx: Tensor, mats: Tensor, cnt: T
     gctx = torch.empty_like(ctx)
     g = st.grid(B, has_bda)
     lib = cabi.lib()
-    ws_bytes = lib.vb200_lift_pool_bwd_workspace(C.byref(g), dt)
+    if plan is None:
+        ws_bytes = lib.vb200_lift_pool_bwd_workspace(C.byref(g), dt)
+    else:
+        ws_bytes = lib.vb200_lift_pool_bwd_planned_workspace(C.byref(g), dt)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        cabi.check(lib.vb200_lift_pool_bwd(C.byref(g), C.byref(st.tables(dev).struct), mats.data_ptr(),
-                                           depth.data_ptr(), ctx.data_ptr(), dt, gout.data_ptr(), layout,
-                                           cnt.data_ptr(), gdepth.data_ptr(), gctx.data_ptr(), ws.data_ptr(),
-                                           ws_bytes, cabi.stream_ptr(dev)))
+        if plan is None:
+            cabi.check(lib.vb200_lift_pool_bwd(C.byref(g), C.byref(st.tables(dev).struct), mats.data_ptr(),
+                                               depth.data_ptr(), ctx.data_ptr(), dt, cdt, gout.data_ptr(), layout,
+                                               cnt.data_ptr(), gdepth.data_ptr(), gctx.data_ptr(), ws.data_ptr(),
+                                               ws_bytes, cabi.stream_ptr(dev)))
+        else:
+            cabi.check(lib.vb200_lift_pool_bwd_planned(C.byref(g), plan.data_ptr(), depth.data_ptr(), ctx.data_ptr(),
+                                                       dt, cdt, gout.data_ptr(), layout, cnt.data_ptr(),
+                                                       gdepth.data_ptr(), gctx.data_ptr(), ws.data_ptr(), ws_bytes,
+                                                       cabi.stream_ptr(dev)))
     return gdepth, gctx
 
 
 @lift_pool_bwd.register_fake
-def _(gout, depth, ctx, mats, cnt, cfg_id, has_bda):
+def _(gout, depth, ctx, mats, cnt, cfg_id, has_bda, plan=None):
     return torch.empty_like(depth), torch.empty_like(ctx)
 
 
 def _lift_setup(ctx, inputs, output):
-    depth, context, mats, cfg_id, has_bda, channels_last, save_cnt = inputs
+    depth, context, mats, cfg_id, has_bda, channels_last, save_cnt, plan = inputs
     _, cnt = output
-    ctx.save_for_backward(depth, context, mats, cnt)
+    ctx.save_for_backward(depth, context, mats, cnt, plan)
     ctx.cfg_id, ctx.has_bda, ctx.save_cnt = cfg_id, has_bda, save_cnt
+    # the plan table holds raw pointers: keep the buffers they point into alive until the backward has run
+    ctx.plan_keepalive = getattr(plan, "_vb200_keepalive", None) if plan is not None else None
 
 
 def _lift_backward(ctx, gout, gcnt):
     if not ctx.save_cnt:
         raise RuntimeError("lift_pool_fwd was called with save_cnt=False: no backward possible")
-    depth, context, mats, cnt = ctx.saved_tensors
-    gdepth, gctx = lift_pool_bwd(gout, depth, context, mats, cnt, ctx.cfg_id, ctx.has_bda)
-    return gdepth, gctx, None, None, None, None, None
+    depth, context, mats, cnt, plan = ctx.saved_tensors
+    gdepth, gctx = lift_pool_bwd(gout, depth, context, mats, cnt, ctx.cfg_id, ctx.has_bda, plan)
+    return gdepth, gctx, None, None, None, None, None, None
 
 
 torch.library.register_autograd("vampire_b200::lift_pool_fwd", _lift_backward, setup_context=_lift_setup)

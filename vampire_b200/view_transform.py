@@ -29,6 +29,7 @@ import torch.nn as nn
 from . import cabi, ops
 from .config import PathConfig
 from .matrices import prepare_matrices
+from .plan import PlanCache
 
 Tensor = torch.Tensor
 
@@ -59,11 +60,26 @@ class UpsampleB200(nn.Module):
 
 
 class LiftRenderB200(nn.Module):
-    def __init__(self, channels_last_volume: bool = False, **backbone_conf):
+    def __init__(self, channels_last_volume: bool = False, plans: str = "eval", plan_cache_samples: int = 64,
+                 **backbone_conf):
         """``backbone_conf``: the reference's dict (base_exp.py:40-92); unknown keys are ignored the
-        way the image-encoder keys are irrelevant here."""
+        way the image-encoder keys are irrelevant here.
+
+        ``plans``: when to drive the lift from cached projection / sort plans (``vampire_b200.plan``):
+        ``"eval"`` (default) while ``self.training`` is False -- validation / test matrices never change
+        (nusc_det_seg_dataset.py:489-498, base_exp.py:113-120) -- ``"always"``, or ``"off"``.  Training draws a new
+        ida every step (base_exp.py:93-111), so a plan would be rebuilt per call there."""
         super().__init__()
+        if plans not in ("eval", "always", "off"):
+            raise ValueError("plans must be 'eval', 'always' or 'off'")
+        self.plans = plans
+        self.plan_cache = PlanCache(plan_cache_samples)
+        self._prep_cache = []      # [(key, (mats_dev, has_bda, mats_host))], most recent last
         self.cfg = PathConfig.from_backbone_conf(backbone_conf, backbone_conf.get("num_cams", 6))
+        if self.cfg.C != 16 or self.cfg.K != 18 or not 1 <= self.cfg.num_cams <= 8:
+            raise ValueError(f"libvb200 is compiled for mid_channels=16, num_classes=18 and at most 8 cameras "
+                             f"(every reference experiment); got C={self.cfg.C}, K={self.cfg.K}, "
+                             f"cams={self.cfg.num_cams}")
         if self.cfg.density_mode != "sdf":
             raise NotImplementedError("only density_mode='sdf' (the target experiment, base_exp.py:51) is built")
         if self.cfg.cat_seg:
@@ -86,10 +102,32 @@ class LiftRenderB200(nn.Module):
         return mats.to(device, non_blocking=True), bda_mat is not None
 
     def _prep_dict(self, mats_dict: Dict[str, Tensor], sweep_index: int, device):
-        return self._prep(mats_dict["sensor2ego_mats"][:, sweep_index, ...],
-                          mats_dict["intrin_mats"][:, sweep_index, ...],
-                          mats_dict["ida_mats"][:, sweep_index, ...],
-                          mats_dict.get("bda_mat", None), device)
+        mats, has_bda, _ = self._prep_dict_cached(mats_dict, sweep_index, device)
+        return mats, has_bda
+
+    def _prep_dict_cached(self, mats_dict: Dict[str, Tensor], sweep_index: int, device):
+        """Prepared matrices of (mats_dict, sweep_index), computed once per distinct dict contents: the lift and
+        the render of one ``_forward_single_sweep`` share them (three batched ``torch.inverse`` calls otherwise
+        run twice per forward).  Returns (mats on `device`, has_bda, the same matrices on the host or None)."""
+        device = torch.device(device)
+        names = ("sensor2ego_mats", "intrin_mats", "ida_mats", "bda_mat")
+        ts = [mats_dict.get(k, None) for k in names]
+        # identity + version of the dict's tensors; the entry holds the tensors themselves, so an address can never
+        # be recycled by a different tensor while it is cached
+        vers = tuple(None if t is None else t._version for t in ts)
+        for (k_sweep, k_dev, k_ts, k_vers), v in self._prep_cache:
+            if k_sweep == sweep_index and k_dev == device and k_vers == vers and all(a is b for a, b in zip(k_ts, ts)):
+                return v
+        key = (sweep_index, device, ts, vers)
+        prep = prepare_matrices(ts[0][:, sweep_index, ...], ts[1][:, sweep_index, ...], ts[2][:, sweep_index, ...], ts[3])
+        host = prep if prep.device.type == "cpu" else None
+        val = (prep.to(device, non_blocking=True), ts[3] is not None, host)
+        self._prep_cache.append((key, val))
+        del self._prep_cache[:-4]
+        return val
+
+    def _use_plans(self) -> bool:
+        return self.plans == "always" or (self.plans == "eval" and not self.training)
 
     def _device(self) -> torch.device:
         return self.density.beta.device
@@ -129,12 +167,18 @@ class LiftRenderB200(nn.Module):
     def lift_pool(self, depth_softmax_features: Tensor, low_channel_source_features: Tensor,
                   mats_dict: Dict[str, Tensor], sweep_index: int = 0) -> Tensor:
         """BV2:553 + 563 without the (B,N,C,D,fH,fW) tensor.  depth (B,N,D,fH,fW), ctx (B,N,C,fH,fW)."""
-        mats, has_bda = self._prep_dict(mats_dict, sweep_index, depth_softmax_features.device)
-        dt = low_channel_source_features.dtype
-        depth = depth_softmax_features.to(dt) if depth_softmax_features.dtype != dt else depth_softmax_features
-        need_grad = torch.is_grad_enabled() and (depth.requires_grad or low_channel_source_features.requires_grad)
-        out, _ = ops.lift_pool_fwd(depth, low_channel_source_features, mats, self.cfg_id, has_bda,
-                                   self.channels_last_volume, need_grad)
+        mats, has_bda, mats_host = self._prep_dict_cached(mats_dict, sweep_index, depth_softmax_features.device)
+        depth, ctx = depth_softmax_features, low_channel_source_features
+        # AMP (BV2:551-553): softmax is autocast to fp32, so an fp32 depth with 16-bit ctx is the reference's own
+        # mix -- the product, the grid_sample and the pooled volume are fp32 there, and so they are here.  The only
+        # other mix (16-bit depth, fp32 ctx) promotes the same way.
+        if depth.dtype != ctx.dtype and depth.dtype != torch.float32:
+            depth = depth.float()
+        need_grad = torch.is_grad_enabled() and (depth.requires_grad or ctx.requires_grad)
+        plan = None
+        if self._use_plans():
+            plan = self.plan_cache.lift(ops.state(self.cfg_id), self.cfg_id, mats, has_bda, mats_host).table
+        out, _ = ops.lift_pool_fwd(depth, ctx, mats, self.cfg_id, has_bda, self.channels_last_volume, need_grad, plan)
         return out
 
     def lift_pool_2d(self, img_feats: Tensor, mats_dict: Dict[str, Tensor], sweep_index: int = 0) -> Tensor:
@@ -142,14 +186,17 @@ class LiftRenderB200(nn.Module):
         no depth distribution -- every voxel centre with z > 0 bilinearly samples the (B,N,C,fH,fW) image
         features of each camera it projects into, non-zero mean over cameras.  It is the D = 1 case of the lift
         kernels (one depth plane of ones, depth test z > 0); gradients flow to ``img_feats``."""
-        mats, has_bda = self._prep_dict(mats_dict, sweep_index, img_feats.device)
+        mats, has_bda, mats_host = self._prep_dict_cached(mats_dict, sweep_index, img_feats.device)
         if not hasattr(self, "_cfg_id_2d"):
             self._cfg_id_2d = ops.register_config(self.cfg, lift_2d=True)
         B, N, _, h, w = img_feats.shape
         ones = torch.ones(B, N, 1, h, w, dtype=img_feats.dtype, device=img_feats.device)
         need_grad = torch.is_grad_enabled() and img_feats.requires_grad
+        plan = None
+        if self._use_plans():
+            plan = self.plan_cache.lift(ops.state(self._cfg_id_2d), self._cfg_id_2d, mats, has_bda, mats_host).table
         out, _ = ops.lift_pool_fwd(ones, img_feats, mats, self._cfg_id_2d, has_bda, self.channels_last_volume,
-                                   need_grad)
+                                   need_grad, plan)
         return out
 
     def render(self, mats_dict: Dict[str, Tensor], density_feature: Tensor, semantic_logits: Tensor,

@@ -47,6 +47,9 @@ def parse_args():
     ap.add_argument("--channels-last", action="store_true",
                     help="emit the pooled volume in torch.channels_last_3d instead of the reference's NCDHW strides")
     ap.add_argument("--render-group", type=int, default=0, help="samples per pack/march round (0 = all)")
+    ap.add_argument("--no-train-probe", action="store_true", help="skip aux.train (configs[2] inside the fwd run)")
+    ap.add_argument("--no-aten-baseline", action="store_true", help="skip aux.aten_gpu_baseline")
+    ap.add_argument("--no-uncached", action="store_true", help="skip the uncached-plan variant of the workload")
     ap.add_argument("--plans", default="auto", choices=["auto", "on", "off"],
                     help="drive the lift from cached projection/sort plans (auto: on for fwd = validation, whose "
                          "matrices never change; off for train, whose ida changes every step)")
@@ -73,6 +76,10 @@ def workload_numbers(cfg, batch, esize):
         # read 38 channels over the (oZ+1) z-rows touched, write maps + sigma + resampled features
         "bev_fwd": batch * ((K + 4 + C) * (cfg.oZ + 1) * cfg.vY * cfg.vX * esize
                             + (K + 4) * ncol * 4 + cfg.oZ * ncol * 4 + C * cfg.oZ * ncol * esize),
+        # backward: read d_vox + depth + ctx, write d_depth + d_ctx
+        "lift_pool_bwd": batch * (C * nvox * esize + 2 * (N * D * fH * fW + N * C * fH * fW) * esize),
+        # read the 22 cotangent maps + the 22 consumed volume channels, write their gradients
+        "march_bwd": batch * ((K + 4) * N * fH * fW * 4 + 2 * (K + 4) * nvox * esize),
     }
     return pts, rays, bytes_
 
@@ -133,9 +140,20 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm: the reference's PyTorch CPU path (oracle/torch_path.py restates its ATen calls)
 # ------------------------------------------------------------------------------------------------
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_reference_pass(cfg, ncams, workload, seed=1234):
-    """Build a closure running one bounded sample (1 batch sample, `ncams` cameras, fp32) of the
-    workload on the host cores; returns (closure, frustum points per call, description)."""
+    """Closures running one bounded sample (1 batch sample, `ncams` cameras, fp32) of the workload on the host
+    cores with the reference's own ATen CPU calls: returns (run_lift, run_render, frustum points, rays, description)."""
     from oracle import torch_path as tp
     from vampire_b200 import synth
     from dataclasses import replace
@@ -147,25 +165,34 @@ def cpu_reference_pass(cfg, ncams, workload, seed=1234):
     den, sem, feat, rgb = synth.make_render_inputs(sub, 1, seed, field="surface")
     beta = torch.tensor(0.1)
     train = workload == "train"
-    leaves = [depth, ctx, den, sem, feat, rgb, beta]
 
-    def run():
-        if train:
-            for t in leaves:
-                t.requires_grad_(True)
-                t.grad = None
+    def run_lift():
+        leaves = [depth, ctx]
+        for t in leaves:
+            t.requires_grad_(train)
+            t.grad = None
         with torch.set_grad_enabled(train):
             vox = tp.lift_pool(conf, buf, depth, ctx, mats)
-            rend = tp.render_from_mats(conf, buf, mats, den, sem, feat, rgb, beta)
             if train:
-                loss = vox.sum() + sum(r.sum() for r in rend)
-                loss.backward()
+                vox.sum().backward()
         return vox
 
+    def run_render():
+        leaves = [den, sem, feat, rgb, beta]
+        for t in leaves:
+            t.requires_grad_(train)
+            t.grad = None
+        with torch.set_grad_enabled(train):
+            rend = tp.render_from_mats(conf, buf, mats, den, sem, feat, rgb, beta)
+            if train:
+                sum(r.sum() for r in rend).backward()
+        return rend
+
     pts = ncams * sub.D * sub.fH * sub.fW
+    rays = ncams * sub.fH * sub.fW
     desc = (f"1 sample x {ncams}/{cfg.num_cams} cameras of {cfg.final_dim[0]}x{cfg.final_dim[1]}, fp32, "
             f"{'fwd+bwd' if train else 'fwd'} lift+pool+render, torch {torch.__version__} CPU")
-    return run, pts, desc
+    return run_lift, run_render, pts, rays, desc
 
 
 def run_reference_arm(args, cfg):
@@ -175,33 +202,122 @@ def run_reference_arm(args, cfg):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     # size the per-step sample so (steps + warmup) passes end within a few minutes
-    probe, _, _ = cpu_reference_pass(cfg, 1, args.workload)
+    lift1, rend1, _, _, _ = cpu_reference_pass(cfg, 1, args.workload)
     t0 = time.perf_counter()
-    probe()
+    lift1()
+    rend1()
     t_cam = time.perf_counter() - t0
     budget = 150.0
-    ncams = int(max(1, min(cfg.num_cams, budget / max(1e-3, (args.steps + args.warmup) * t_cam))))
-    run, pts, desc = cpu_reference_pass(cfg, ncams, args.workload)
-    for _ in range(args.warmup):
-        run()
-    t0 = time.perf_counter()
+    ncams = int(max(1, min(cfg.num_cams, budget / max(1e-3, (args.steps + max(1, args.warmup)) * t_cam))))
+    run_lift, run_render, pts, rays, desc = cpu_reference_pass(cfg, ncams, args.workload)
+    for _ in range(max(1, args.warmup)):
+        run_lift()
+        run_render()
+    t_lift = t_rend = 0.0
     for _ in range(args.steps):
-        run()
-    dt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        run_lift()
+        t1 = time.perf_counter()
+        run_render()
+        t2 = time.perf_counter()
+        t_lift += t1 - t0
+        t_rend += t2 - t1
+    dt = t_lift + t_rend
     value = pts * args.steps / dt
+    # what this arm actually ran: ONE fp32 sample per step on the host (the reference runs its sampling in fp32
+    # also under AMP); the workload keys are this repo's arm's, batch / feature dtype are the true ones
+    ran = workload_config(args, cfg, 1, "fp32")
+    ran["cams"] = ncams
+    ran["lift_plans"] = "n/a (reference recomputes get_pixel every call)"
+    ran["note"] = ("bounded sample of the workload: 1 sample per step instead of the GPU arm's batch; the CPU path "
+                   "has no batching benefit (ATen's 3-D grid_sampler parallelises over batch x cameras only), so "
+                   "pts/s is per-sample throughput")
     line = {
         "impl": "reference", "metric": "lifted_frustum_pts_per_s", "value": value, "unit": "frustum pts/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        # the SAME workload description as this repo's arm (the driver compares the two lines); what one timed
-        # step actually ran -- a bounded sample of it, fp32 like the reference -- is stated in cpu_baseline.sample
-        "config": workload_config(args, cfg, args.batch or (1 if args.workload == "train" else 8),
-                                  args.dtype or ("fp32" if args.workload == "train" else "bf16")),
-        "cpu_baseline": {"value": value, "unit": "frustum pts/s", "cores": cores, "kind": "port", "sample": desc},
+        "config": ran,
+        "aux": {"lift_only_pts_per_s": pts * args.steps / t_lift, "render_only_rays_per_s": rays * args.steps / t_rend,
+                "ranks_running": 1, "note": "at N > 1 only rank 0 runs this arm: one CPU process, not N"},
+        "cpu_baseline": {"value": value, "unit": "frustum pts/s", "cores": cores, "cpu": cpu_model(), "kind": "port",
+                         "sample": desc},
         "e2e": {"value": value, "unit": "frustum pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# same-box GPU comparator: the reference's own ops on the B200 = stock ATen CUDA kernels
+# (base_vampire2.py:507 lift grid_sample, :419 camera, :442 BEV, :431-433 cumsum/exp)
+# ------------------------------------------------------------------------------------------------
+def _best_of(fn, n=3, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    best = float("inf")
+    for _ in range(n):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+def aten_gpu_baseline(cfg, dev, batches=(1, 8), seed=1234):
+    """The oracle's ATen calls (= the reference's, call for call) executed on the B200: lift and render
+    separately, fp32 and bf16-valued inputs (up-cast inside the timed region the way autocast does for
+    grid_sample), forward and forward+backward, CUDA events, 1 warm-up + best of 3."""
+    from oracle import torch_path as tp
+    from vampire_b200 import synth
+    conf = cfg.backbone_kwargs()
+    buf = tp.buffers_to(tp.build_buffers(conf), dev)
+    out = {"what": "reference ops (oracle/torch_path.py = base_vampire2.py:553+483-516, 314-349+391-467) on the same "
+                   "B200 with stock ATen CUDA kernels; CUDA events, 1 warm-up + best of 3", "runs": []}
+    for B in batches:
+        try:
+            mats = {k: v.to(dev) for k, v in synth.make_mats(cfg, B, "val", seed).items()}
+            depth, ctx = (t.to(dev) for t in synth.make_lift_inputs(cfg, B, seed))
+            den, sem, feat, rgb = (t.to(dev) for t in synth.make_render_inputs(cfg, B, seed, field="surface"))
+            beta = torch.tensor(0.1, device=dev)
+            pts = B * cfg.num_cams * cfg.D * cfg.fH * cfg.fW
+            rays = B * cfg.num_cams * cfg.fH * cfg.fW
+            for feats in ("fp32", "bf16"):
+                if feats == "bf16":
+                    lin = [t.bfloat16() for t in (depth, ctx)]
+                    rin = [t.bfloat16() for t in (den, sem, feat, rgb)]
+                else:
+                    lin, rin = [depth, ctx], [den, sem, feat, rgb]
+                for train in (False, True):
+                    def lift():
+                        d, c = (t.float().requires_grad_(train) for t in lin)
+                        with torch.set_grad_enabled(train):
+                            vox = tp.lift_pool(conf, buf, d, c, mats)
+                            if train:
+                                vox.sum().backward()
+
+                    def render():
+                        vs = [t.float().requires_grad_(train) for t in rin]
+                        bt = beta.clone().requires_grad_(train)
+                        with torch.set_grad_enabled(train):
+                            rend = tp.render_from_mats(conf, buf, mats, *vs, bt)
+                            if train:
+                                sum(r.sum() for r in rend).backward()
+
+                    ms_l = _best_of(lift)
+                    ms_r = _best_of(render)
+                    out["runs"].append({"batch": B, "features": feats, "pass": "fwd+bwd" if train else "fwd",
+                                        "lift_ms": ms_l, "render_ms": ms_r, "step_ms": ms_l + ms_r,
+                                        "lift_pts_per_s": pts / (ms_l * 1e-3), "render_rays_per_s": rays / (ms_r * 1e-3),
+                                        "step_pts_per_s": pts / ((ms_l + ms_r) * 1e-3)})
+            del depth, ctx, den, sem, feat, rgb, lin, rin
+        except torch.cuda.OutOfMemoryError:
+            out["runs"].append({"batch": B, "error": "CUDA out of memory in the ATen path"})
+        torch.cuda.empty_cache()
+    out["peak_mem_gb"] = torch.cuda.max_memory_allocated(dev) / 1e9
+    return out
 
 
 def workload_config(args, cfg, batch, dtype):
@@ -222,6 +338,157 @@ def workload_config(args, cfg, batch, dtype):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+class Workload:
+    """One configuration of the hot path on this rank's GPU: inputs resident in HBM, `step()` = one pass."""
+
+    def __init__(self, args, cfg, dev, world, rank, train, batch, dname, use_plans, allreduce=True):
+        from vampire_b200 import ops, synth
+        from vampire_b200.matrices import prepare_matrices
+        from vampire_b200.view_transform import LiftRenderB200
+        self.args, self.cfg, self.dev, self.world, self.train, self.batch, self.dname = args, cfg, dev, world, train, batch, dname
+        self.ops = ops
+        self.tdt = {"bf16": torch.bfloat16, "fp32": torch.float32, "fp16": torch.float16}[dname]
+        self.esize = 4 if dname == "fp32" else 2
+        self.mod = LiftRenderB200(**cfg.backbone_kwargs()).to(dev)
+        self.mod.train(train)
+        ops.state(self.mod.cfg_id).render_group = args.render_group
+        # per-rank shard of the job: samples rank*batch .. rank*batch+batch-1 (seeded by sample index)
+        seed = 1234 + rank * batch
+        self.mats = synth.make_mats(cfg, batch, "val", seed)
+        depth_h, ctx_h = synth.make_lift_inputs(cfg, batch, seed, self.tdt)
+        vols_h = synth.make_render_inputs(cfg, batch, seed, field=args.field, dtype=self.tdt)   # den, sem, feat, rgb
+        self.host_in = [t.pin_memory() for t in (depth_h, ctx_h) + tuple(vols_h)]
+        self.dev_in = [t.to(dev) for t in self.host_in]
+        self.prep = prepare_matrices(self.mats["sensor2ego_mats"][:, 0], self.mats["intrin_mats"][:, 0],
+                                     self.mats["ida_mats"][:, 0], self.mats["bda_mat"]).to(dev)
+        self.beta = self.mod.density.beta
+        self.plan_tab = None
+        if use_plans:
+            # built once per distinct matrices (before the timed region, like the first batch of a val loop)
+            self.plan_tab = self.mod.plan_cache.lift(ops.state(self.mod.cfg_id), self.mod.cfg_id, self.prep, True).table
+        self.allreduce = allreduce
+        if train:
+            from vampire_b200.dp import GradBucket
+            for t in self.dev_in:
+                t.requires_grad_(True)
+            self.bucket = GradBucket(dev, world if allreduce else 1)
+            c = cfg
+            shapes = [(batch, c.C, c.vZ, c.vY, c.vX), (batch, c.num_cams, 3, c.fH, c.fW),
+                      (batch, c.num_cams, c.K, c.fH, c.fW), (batch, c.num_cams, 1, c.fH, c.fW), (batch, 3, c.oY, c.oX),
+                      (batch, c.K, c.oY, c.oX), (batch, 1, c.oY, c.oX), (batch, 1, c.oZ, c.oY, c.oX),
+                      (batch, c.C, c.oZ, c.oY, c.oX)]
+            self.cots = [t.to(dev) for t in synth.make_cotangents(shapes, seed)]
+            self.cots[0] = self.cots[0].to(self.tdt)
+            self.cots[8] = self.cots[8].to(self.tdt)
+
+    def step(self):
+        """hot path with inputs resident in HBM (prepared matrices uploaded once, like a val loop
+        whose ida/bda never change)"""
+        d, c, den, sem, feat, rgb = self.dev_in
+        ops, mod = self.ops, self.mod
+        if not self.train:
+            with torch.no_grad():
+                vox, _ = ops.lift_pool_fwd(d, c, self.prep, mod.cfg_id, True, self.args.channels_last, False, self.plan_tab)
+                rend = ops.render_fwd(den, sem, rgb, feat, self.beta, self.prep, None, mod.cfg_id, True, 3)
+            return vox, rend
+        from vampire_b200.dp import train_step
+        return train_step(mod, d, c, (den, sem, feat, rgb), self.prep, self.cots, self.bucket, plan=self.plan_tab)
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, steps, warmup):
+        """W warm-up steps, then exactly K steps between barrier + synchronize; CUDA events; max over ranks."""
+        for _ in range(warmup):
+            self.step()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for _ in range(steps):
+            self.step()
+        e1.record()
+        self.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / steps
+
+    def per_kernel(self, steps):
+        """The same K steps again with libvb200 recording a CUDA-event pair around every launch on its launching
+        stream and the BEV / camera branches serialised (the timed region overlaps them on a side stream, which
+        would smear their individual durations).  Returns (ms per step serialised, {family: entry})."""
+        from vampire_b200 import cabi
+        cabi.render_set_fork(False)
+        cabi.trace_enable(True)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            self.step()
+        e1.record()
+        self.barrier()
+        ms_serial = e0.elapsed_time(e1) / steps
+        trace = cabi.trace_collect()
+        cabi.trace_enable(False)
+        cabi.render_set_fork(True)
+        _, _, kbytes = workload_numbers(self.cfg, self.batch, self.esize)
+        peak, _ = measured_peaks()
+        per_kernel = {}
+        for name, (ms, cnt) in trace.items():
+            entry = {"ms_per_step": ms / steps, "launches_per_step": cnt / steps}
+            if name in kbytes:
+                entry["algorithmic_bytes_per_step"] = kbytes[name]
+                entry["achieved_gbs"] = kbytes[name] / (ms / steps * 1e-3) / 1e9
+                entry["frac_of_peak"] = entry["achieved_gbs"] / peak
+            per_kernel[name] = entry
+        return ms_serial, per_kernel, kbytes
+
+    def free(self):
+        for name in ("dev_in", "host_in", "cots", "bucket", "plan_tab", "mod", "prep"):
+            if hasattr(self, name):
+                delattr(self, name)
+        torch.cuda.empty_cache()
+
+
+def train_probe(args, cfg, dev, world, rank, steps, warmup):
+    """BASELINE configs[2] measured inside the default run so the driver sees it at every N: forward+backward,
+    B = 1 per GPU, fp32, flat-bucket NCCL all-reduce; the all-reduce's exposed time = step with - step without;
+    per-kernel backward times.  Plans off (training draws a new ida every step); the cached variant beside it.
+    At N = 1 additionally B = 8 fp32, the size at which a backward roofline fraction means something."""
+    out = {"what": "configs[2]: lift+pool+render forward+backward, B=1/GPU, fp32, DP with one flat-bucket NCCL "
+                   "all-reduce per step (dp.train_step); projection/sort plans recomputed every step"}
+    pts1 = cfg.num_cams * cfg.D * cfg.fH * cfg.fW
+    w = Workload(args, cfg, dev, world, rank, True, 1, "fp32", False, allreduce=True)
+    ms = w.timed(steps, warmup)
+    _, kern, _ = w.per_kernel(steps)
+    w.free()
+    out.update({"batch_per_gpu": 1, "features": "fp32", "ms_per_step": ms, "pts_per_s": world * pts1 / (ms * 1e-3),
+                "steps": steps, "warmup": warmup, "kernels": kern})
+    w = Workload(args, cfg, dev, world, rank, True, 1, "fp32", False, allreduce=False)
+    ms_no = w.timed(steps, warmup)
+    w.free()
+    out["ms_per_step_without_allreduce"] = ms_no
+    out["allreduce_exposed_ms"] = ms - ms_no
+    w = Workload(args, cfg, dev, world, rank, True, 1, "fp32", True, allreduce=True)
+    out["ms_per_step_cached_plans"] = w.timed(steps, warmup)
+    w.free()
+    if world == 1:
+        for plans in (False, True):
+            w = Workload(args, cfg, dev, world, rank, True, 8, "fp32", plans, allreduce=True)
+            ms8 = w.timed(max(3, steps // 2), warmup)
+            _, kern8, _ = w.per_kernel(max(3, steps // 2))
+            w.free()
+            out["b8_fp32_cached_plans" if plans else "b8_fp32"] = {
+                "batch_per_gpu": 8, "features": "fp32", "ms_per_step": ms8, "pts_per_s": 8 * pts1 / (ms8 * 1e-3),
+                "kernels": kern8}
+    return out
+
+
 def main():
     args = parse_args()
     from vampire_b200.config import NAMED
@@ -231,8 +498,7 @@ def main():
         return
 
     import torch.distributed as dist
-    from vampire_b200 import cabi, ops, synth
-    from vampire_b200.view_transform import LiftRenderB200
+    from vampire_b200 import cabi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -250,62 +516,14 @@ def main():
     train = args.workload == "train"
     batch = args.batch or (1 if train else 8)
     dname = args.dtype or ("fp32" if train else "bf16")
-    tdt = {"bf16": torch.bfloat16, "fp32": torch.float32, "fp16": torch.float16}[dname]
-    esize = 4 if dname == "fp32" else 2
-
-    mod = LiftRenderB200(**cfg.backbone_kwargs()).to(dev)
-    ops.state(mod.cfg_id).render_group = args.render_group
-    # per-rank shard of the job: samples rank*batch .. rank*batch+batch-1 (seeded by sample index)
-    seed = 1234 + rank * batch
-    mats = synth.make_mats(cfg, batch, "val", seed)
-    depth_h, ctx_h = synth.make_lift_inputs(cfg, batch, seed, tdt)
-    vols_h = synth.make_render_inputs(cfg, batch, seed, field=args.field, dtype=tdt)   # den, sem, feat, rgb
-    host_in = [t.pin_memory() for t in (depth_h, ctx_h) + tuple(vols_h)]
-    dev_in = [t.to(dev) for t in host_in]
-    mats_dev = {k: v.to(dev) for k, v in mats.items()}
-    from vampire_b200.matrices import prepare_matrices
-    prep = prepare_matrices(mats["sensor2ego_mats"][:, 0], mats["intrin_mats"][:, 0], mats["ida_mats"][:, 0],
-                            mats["bda_mat"]).to(dev)
-    beta = mod.density.beta
     use_plans = args.plans == "on" or (args.plans == "auto" and not train)
-    plan_tab = None
-    if use_plans:
-        # built once per distinct matrices (here: before the timed region, like the first batch of a val loop)
-        plan_tab = mod.plan_cache.lift(ops.state(mod.cfg_id), mod.cfg_id, prep, True).table
+    warmup = max(3, args.warmup)
 
-    if train:
-        for t in dev_in:
-            t.requires_grad_(True)
-        from vampire_b200.dp import GradBucket, train_step
-        bucket = GradBucket(dev, world)
-        c = cfg
-        shapes = [(batch, c.C, c.vZ, c.vY, c.vX), (batch, c.num_cams, 3, c.fH, c.fW),
-                  (batch, c.num_cams, c.K, c.fH, c.fW), (batch, c.num_cams, 1, c.fH, c.fW), (batch, 3, c.oY, c.oX),
-                  (batch, c.K, c.oY, c.oX), (batch, 1, c.oY, c.oX), (batch, 1, c.oZ, c.oY, c.oX),
-                  (batch, c.C, c.oZ, c.oY, c.oX)]
-        cots = [t.to(dev) for t in synth.make_cotangents(shapes, seed)]
-        cots[0] = cots[0].to(tdt)
-        cots[8] = cots[8].to(tdt)
-
-    def step_device():
-        """hot path with inputs resident in HBM (prepared matrices uploaded once, like a val loop
-        whose ida/bda never change)"""
-        d, c, den, sem, feat, rgb = dev_in
-        if not train:
-            with torch.no_grad():
-                vox, _ = ops.lift_pool_fwd(d, c, prep, mod.cfg_id, True, args.channels_last, False, plan_tab)
-                rend = ops.render_fwd(den, sem, rgb, feat, beta, prep, None, mod.cfg_id, True, 3)
-            return vox, rend
-        return train_step(mod, d, c, (den, sem, feat, rgb), prep, cots, bucket, plan=plan_tab)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    lib = cabi.lib()
-    for _ in range(max(3, args.warmup)):
-        step_device()
+    wl = Workload(args, cfg, dev, world, rank, train, batch, dname, use_plans)
+    mod, host_in, mats, prep = wl.mod, wl.host_in, wl.mats, wl.prep
+    barrier = wl.barrier
+    for _ in range(warmup):
+        wl.step()
     barrier()
 
     # ---- timed region: device-resident ---------------------------------------------------------
@@ -315,7 +533,7 @@ def main():
     barrier()
     e0.record()
     for _ in range(args.steps):
-        step_device()
+        wl.step()
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -326,30 +544,27 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = t.item() / args.steps
 
-    # ---- per-kernel device time: the same K steps again with libvb200 recording a CUDA-event pair around
-    # every launch on its launching stream, and the BEV/camera branches serialised (the timed region above
-    # overlaps them on a side stream, which would smear their individual durations) -------------------
-    cabi.render_set_fork(False)
-    cabi.trace_enable(True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step_device()
-    e1.record()
-    barrier()
-    ms_serial = e0.elapsed_time(e1) / args.steps
-    trace = cabi.trace_collect()
-    cabi.trace_enable(False)
-    cabi.render_set_fork(True)
-
-    pts, rays, kbytes = workload_numbers(cfg, batch, esize)
+    ms_serial, per_kernel, kbytes = wl.per_kernel(args.steps)
+    pts, rays, _ = workload_numbers(cfg, batch, wl.esize)
     value = world * pts / (ms_step * 1e-3)
+
+    # the same workload with the projection / sort recomputed on every call (what a loop whose matrices change every
+    # step pays), beside the cached-plan headline
+    uncached = None
+    if use_plans and not args.no_uncached:
+        w2 = Workload(args, cfg, dev, world, rank, train, batch, dname, False)
+        ms_u = w2.timed(args.steps, warmup)
+        _, kern_u, _ = w2.per_kernel(args.steps)
+        w2.free()
+        uncached = {"ms_per_step": ms_u, "pts_per_s": world * pts / (ms_u * 1e-3),
+                    "lift_pool_fwd_ms": kern_u.get("lift_pool_fwd", {}).get("ms_per_step"),
+                    "lift_pool_fwd_frac_of_peak": kern_u.get("lift_pool_fwd", {}).get("frac_of_peak")}
 
     # ---- e2e: public module API from pinned host buffers, H2D + D2H inside the timed region ------
     e2e = None
     if not args.no_e2e and not train:
         with torch.no_grad():
-            vox, rend = step_device()
+            vox, rend = wl.step()
         host_out = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in [vox] + list(rend)]
         del vox, rend
 
@@ -362,6 +577,7 @@ def main():
         ev_in = [torch.cuda.Event() for _ in range(nbuf)]
         ev_run = [torch.cuda.Event() for _ in range(nbuf)]
         ev_out = [torch.cuda.Event() for _ in range(nbuf)]
+        mod.plans = "eval" if use_plans else "off"      # the module's own plan cache (keyed by the matrices' bytes)
 
         def step_e2e(k):
             i = k % nbuf
@@ -403,24 +619,23 @@ def main():
         e2e = {"value": world * pts / (ms_e2e * 1e-3), "unit": "frustum pts/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(sum(h.numel() * h.element_size() for h in host_in) + prep.numel() * 4),
                "d2h_bytes_per_step": int(sum(h.numel() * h.element_size() for h in host_out)), "steps": k,
-               "pipelining": "3 streams, double-buffered inputs"}
+               "pipelining": "3 streams, double-buffered inputs",
+               "api": "LiftRenderB200.lift_pool / .render with a host mats_dict (4x4 prep + plan-cache lookup per call)"}
+        del dev_bufs, host_out
+    wl.free()
+
+    # ---- BASELINE configs[2] (train: fwd+bwd, DP all-reduce) inside the same run, at every N ------
+    aux_train = None
+    if not train and not args.no_train_probe:
+        aux_train = train_probe(args, cfg, dev, world, rank, max(5, args.steps // 2), 3)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (live CUDA-event time from the timed region) --------------
+    # ---- roofline of the dominant kernel (live CUDA-event time) -------------------------------------
     peak, peak_src = measured_peaks()
-    per_kernel = {}
-    for name, (ms, cnt) in trace.items():
-        calls_per_step = cnt / args.steps
-        entry = {"ms_per_step": ms / args.steps, "launches_per_step": calls_per_step}
-        if name in kbytes:
-            entry["algorithmic_bytes_per_step"] = kbytes[name]
-            entry["achieved_gbs"] = kbytes[name] / (ms / args.steps * 1e-3) / 1e9
-            entry["frac_of_peak"] = entry["achieved_gbs"] / peak
-        per_kernel[name] = entry
     dom = max((n for n in per_kernel if n in kbytes), key=lambda n: per_kernel[n]["ms_per_step"], default=None)
     roofline = None
     if dom:
@@ -435,11 +650,14 @@ def main():
         prof = os.path.join(ROOT, "profiles", "dram_traffic.json")
         if os.path.exists(prof):
             with open(prof) as fh:
-                roofline["traffic"] = json.load(fh).get(dom, {}).get(dname)
+                tr = json.load(fh)
+            roofline["traffic"] = tr.get(dom, {}).get(dname)
+            roofline["traffic_source"] = tr.get("_source", "profiles/dram_traffic.json (ncu --set full capture, not live)")
+    step_bytes = sum(kbytes[n] for n in ("lift_pool_fwd", "march_fwd", "bev_fwd")) if not train else None
 
     line = {
         "metric": "lifted_frustum_pts_per_s", "value": value, "unit": "frustum pts/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+        "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 arithmetic, %s features" % dname, "data": "synthetic",
         "config": workload_config(args, cfg, batch, dname),
         "aux": {"rendered_rays_per_s": world * rays / (ms_step * 1e-3),
@@ -450,21 +668,36 @@ def main():
                                                       ("pack_cam_volume", "march_fwd", "bev_fwd") if n in per_kernel) * 1e-3))
                 if "march_fwd" in per_kernel else None,
                 "ms_per_step_branches_serialised": ms_serial,
+                "whole_step_algorithmic_gbs": (step_bytes / (ms_step * 1e-3) / 1e9) if step_bytes else None,
+                "whole_step_frac_of_peak": (step_bytes / (ms_step * 1e-3) / 1e9 / peak) if step_bytes else None,
+                "uncached_plans": uncached,
                 "kernels": per_kernel},
         "roofline": roofline,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "e2e": e2e,
     }
+    if aux_train is not None:
+        line["aux"]["train"] = aux_train
+    if not args.no_aten_baseline and world == 1:
+        line["aux"]["aten_gpu_baseline"] = aten_gpu_baseline(cfg, dev)
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        run, cpts, desc = cpu_reference_pass(cfg, cfg.num_cams, args.workload)
-        t0 = time.perf_counter()
-        run()
-        dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": cpts / dt, "unit": "frustum pts/s", "cores": cores, "kind": "port",
-                                "sample": desc + f"; 1 pass, {dt:.1f} s"}
+        run_lift, run_render, cpts, crays, desc = cpu_reference_pass(cfg, cfg.num_cams, args.workload)
+        best_l = best_r = float("inf")
+        for i in range(4):                      # 1 warm-up + best of 3
+            t0 = time.perf_counter()
+            run_lift()
+            t1 = time.perf_counter()
+            run_render()
+            t2 = time.perf_counter()
+            if i:
+                best_l, best_r = min(best_l, t1 - t0), min(best_r, t2 - t1)
+        line["cpu_baseline"] = {"value": cpts / (best_l + best_r), "unit": "frustum pts/s", "cores": cores,
+                                "cpu": cpu_model(), "kind": "port",
+                                "lift_pts_per_s": cpts / best_l, "render_rays_per_s": crays / best_r,
+                                "sample": desc + f"; 1 warm-up + best of 3: lift {best_l:.2f} s, render {best_r:.2f} s"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -178,16 +178,22 @@ def laplace_density(s, beta_param, bias, beta_min=1e-4):
 # --------------------------------------------------------------------------------------------
 # R1-R6: volume rendering
 # --------------------------------------------------------------------------------------------
-def _seg_lo_ext(conf):
+def _seg_lo_ext(conf, device=None):
     xb, yb, zb = conf["x_bound_seg"], conf["y_bound_seg"], conf["z_bound_seg"]
-    lo = torch.as_tensor([xb[0], yb[0], zb[0]])
-    ext = torch.as_tensor([xb[1] - xb[0], yb[1] - yb[0], zb[1] - zb[0]])
+    lo = torch.as_tensor([xb[0], yb[0], zb[0]], device=device)
+    ext = torch.as_tensor([xb[1] - xb[0], yb[1] - yb[0], zb[1] - zb[0]], device=device)
     return lo, ext
+
+
+def buffers_to(buf, device):
+    """The lattice buffers on another device (bench.py runs these same ATen calls on the B200 as the same-box GPU
+    comparator: the reference's own path there is stock ATen CUDA kernels)."""
+    return {k: v.to(device) for k, v in buf.items()}
 
 
 def render_norm_geom(conf, geom):
     """BV2:397-407: normalised sample coordinates of planes 0..D-2 and the inclusive mask."""
-    lo, ext = _seg_lo_ext(conf)
+    lo, ext = _seg_lo_ext(conf, geom.device)
     g = (geom[:, :, :-1, :, :] - lo) / ext
     g = g * 2. - 1.
     m = (g[..., 0] >= -1.) & (g[..., 0] <= 1.) & (g[..., 1] >= -1.) & (g[..., 1] <= 1.) & \
@@ -197,7 +203,7 @@ def render_norm_geom(conf, geom):
 
 def render_norm_output(conf, buf):
     """BV2:408-417."""
-    lo, ext = _seg_lo_ext(conf)
+    lo, ext = _seg_lo_ext(conf, buf["output_coords"].device)
     g = (buf["output_coords"][..., :3] - lo) / ext
     return g * 2. - 1.
 
@@ -279,7 +285,7 @@ def occ_coords(point_cloud_range=(-40.0, -40.0, -1.0, 40.0, 40.0, 5.4), voxel=(0
 
 def point_queries(conf, semantic_logits, density_feature, pts, i):
     """BV2:579-596 for sample i: (pts_logits (P,K), pts_sdf (P,))."""
-    lo, ext = _seg_lo_ext(conf)
+    lo, ext = _seg_lo_ext(conf, pts.device)
     n = (pts - lo) / ext
     n = n[None, None, None, :, :]
     n = n * 2. - 1.
@@ -293,9 +299,9 @@ def point_queries(conf, semantic_logits, density_feature, pts, i):
 
 def occupancy_queries(conf, semantic_logits, density_feature, bda, beta_param, coords=None):
     """BV2:597-609 + 647-648: (occ_logits (B,X,Y,Z,K), tanh(occ_density) (B,X,Y,Z,1))."""
-    coords = occ_coords() if coords is None else coords
+    coords = (occ_coords() if coords is None else coords).to(bda.device)
     B = semantic_logits.shape[0]
-    lo, ext = _seg_lo_ext(conf)
+    lo, ext = _seg_lo_ext(conf, bda.device)
     rot = bda[:, :3, :3].view(B, 1, 1, 1, 3, 3)
     c = (rot @ coords[None, ..., None].expand(B, *coords.shape, 1)).squeeze(-1)
     n = (c - lo) / ext

@@ -13,6 +13,8 @@ ap.add_argument("--dtype", default="bf16")
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--field", default="surface")
 ap.add_argument("--train", action="store_true")
+ap.add_argument("--plans", default="off", choices=["off", "on", "both"], help="cached lift plans")
+ap.add_argument("--only", default="all", choices=["all", "lift", "render"])
 a = ap.parse_args()
 cfg = NAMED[a.config]
 dt = {"bf16": torch.bfloat16, "fp32": torch.float32, "fp16": torch.float16}[a.dtype]
@@ -23,16 +25,28 @@ depth, ctx = [t.cuda() for t in synth.make_lift_inputs(cfg, a.batch, dtype=dt)]
 den, sem, feat, rgb = [t.cuda() for t in synth.make_render_inputs(cfg, a.batch, field=a.field, dtype=dt)]
 beta = torch.tensor(0.1, device="cuda")
 leaves = [depth, ctx, den, sem, feat, rgb, beta]
+tables = [None]
+if a.plans != "off":
+    from vampire_b200.plan import PlanCache
+    tab = PlanCache().lift(ops.state(cid), cid, prep, True).table
+    tables = [tab] if a.plans == "on" else [None, tab]
+torch.manual_seed(0)
 for _ in range(a.steps):
+  for tab in tables:
     if a.train:
         for t in leaves:
             t.requires_grad_(True); t.grad = None
-        vox, _ = ops.lift_pool_fwd(depth, ctx, prep, cid, True, False, True)
-        rend = ops.render_fwd(den, sem, rgb, feat, beta, prep, None, cid, True, 3)
-        torch.autograd.backward([vox] + list(rend), [torch.ones_like(o) for o in [vox] + list(rend)])
+        outs = []
+        if a.only in ("all", "lift"):
+            outs.append(ops.lift_pool_fwd(depth, ctx, prep, cid, True, False, True, tab)[0])
+        if a.only in ("all", "render"):
+            outs += list(ops.render_fwd(den, sem, rgb, feat, beta, prep, None, cid, True, 3))
+        torch.autograd.backward(outs, [torch.randn_like(o) for o in outs])
     else:
         with torch.no_grad():
-            ops.lift_pool_fwd(depth, ctx, prep, cid, True, False, False)
-            ops.render_fwd(den, sem, rgb, feat, beta, prep, None, cid, True, 3)
+            if a.only in ("all", "lift"):
+                ops.lift_pool_fwd(depth, ctx, prep, cid, True, False, False, tab)
+            if a.only in ("all", "render"):
+                ops.render_fwd(den, sem, rgb, feat, beta, prep, None, cid, True, 3)
 torch.cuda.synchronize()
 print("done")

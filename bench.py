@@ -286,20 +286,20 @@ def aten_gpu_baseline(cfg, dev, batches=(1, 8), seed=1234):
             rays = B * cfg.num_cams * cfg.fH * cfg.fW
             for feats in ("fp32", "bf16"):
                 if feats == "bf16":
-                    lin = [t.bfloat16() for t in (depth, ctx)]
-                    rin = [t.bfloat16() for t in (den, sem, feat, rgb)]
+                    lin = [t.detach().bfloat16() for t in (depth, ctx)]
+                    rin = [t.detach().bfloat16() for t in (den, sem, feat, rgb)]
                 else:
                     lin, rin = [depth, ctx], [den, sem, feat, rgb]
                 for train in (False, True):
                     def lift():
-                        d, c = (t.float().requires_grad_(train) for t in lin)
+                        d, c = (t.detach().float().requires_grad_(train) for t in lin)
                         with torch.set_grad_enabled(train):
                             vox = tp.lift_pool(conf, buf, d, c, mats)
                             if train:
                                 vox.sum().backward()
 
                     def render():
-                        vs = [t.float().requires_grad_(train) for t in rin]
+                        vs = [t.detach().float().requires_grad_(train) for t in rin]
                         bt = beta.clone().requires_grad_(train)
                         with torch.set_grad_enabled(train):
                             rend = tp.render_from_mats(conf, buf, mats, *vs, bt)

@@ -309,3 +309,69 @@ def occupancy_queries(conf, semantic_logits, density_feature, bda, beta_param, c
     logits = F.grid_sample(semantic_logits, n, padding_mode='border', align_corners=True)
     dens = F.grid_sample(laplace_density(density_feature, beta_param, conf["sdf_bias"]), n, align_corners=True)
     return logits.permute(0, 2, 3, 4, 1), dens.permute(0, 2, 3, 4, 1).tanh()
+
+
+# --------------------------------------------------------------------------------------------
+# the caller of the path: BV2:518-649 ``_forward_single_sweep`` restated over a backbone-like object
+# --------------------------------------------------------------------------------------------
+def forward_single_sweep(bb, sweep_index, sweep_imgs, mats_dict, inrange_pts=None):
+    """Call-for-call restatement of ``BaseVAMPIRE2._forward_single_sweep`` (BV2:548-649) on ``bb``: any object with
+    the reference backbone's submodules, buffers and path methods (the real backbone; a backbone with
+    ``vampire_b200.integration.attach`` applied; the tests' stand-in on the GPU box).  Checked bit for bit against the
+    reference's own method in tests/test_oracle_vs_reference.py."""
+    batch_size, num_sweeps, num_cams = sweep_imgs.shape[:3]
+    img_feats = bb.get_cam_feats(sweep_imgs)
+    h, w = img_feats.shape[-2], img_feats.shape[-1]
+    source_features = img_feats[:, 0, ...].reshape(batch_size * num_cams, -1, h, w)
+    depth = bb.mapping_along_depth(source_features).softmax(dim=1).reshape(batch_size, num_cams, -1, h, w)
+    ctx = bb.channel_lower(source_features).reshape(batch_size, num_cams, -1, h, w)
+    img_feats_with_depth = depth.unsqueeze(2) * ctx.unsqueeze(3)
+    geom_xyz = bb.get_geometry(mats_dict['sensor2ego_mats'][:, sweep_index, ...],
+                               mats_dict['intrin_mats'][:, sweep_index, ...],
+                               mats_dict['ida_mats'][:, sweep_index, ...], mats_dict.get('bda_mat', None))
+    voxel_features = bb.get_voxel_feats(img_feats_with_depth, sweep_index, mats_dict)
+    if bb.cat_pos:
+        nvc = bb.norm_voxel_coords.permute(3, 0, 1, 2)[None, ...].repeat(batch_size, 1, 1, 1, 1)
+        voxel_features = torch.cat([voxel_features, nvc], dim=1)
+    base_features = bb.base_conv(voxel_features)
+    density_feature = bb.density_conv(base_features)
+    semantic_logits = bb.seg_conv(base_features)
+    rgb = bb.rgb_conv(base_features)
+    dev = bb.camera_mids.device
+    lo = torch.as_tensor([bb.x_bound_seg[0], bb.y_bound_seg[0], bb.z_bound_seg[0]], device=dev)
+    ext = torch.as_tensor([bb.x_bound_seg[1] - bb.x_bound_seg[0], bb.y_bound_seg[1] - bb.y_bound_seg[0],
+                           bb.z_bound_seg[1] - bb.z_bound_seg[0]], device=dev)
+    pts_logits_batch, pts_sdf_batch = [], []
+    if inrange_pts is not None:
+        for i in range(batch_size):
+            n = (inrange_pts[i] - lo) / ext
+            n = n[None, None, None, :, :]
+            n = n * 2. - 1.
+            valid = (n[..., 0] >= -1.) & (n[..., 0] <= 1.) & (n[..., 1] >= -1.) & (n[..., 1] <= 1.) & \
+                    (n[..., 2] >= -1.) & (n[..., 2] <= 1.)
+            pl = F.grid_sample(semantic_logits[[i], ...], n, padding_mode='border', align_corners=True)
+            pts_logits_batch.append(pl[0, :, 0, 0, :].permute(1, 0))
+            if bb.density_mode == 'sdf':
+                ps = F.grid_sample(density_feature[[i], ...], n, align_corners=True)
+                ps = ps.squeeze(1) * valid
+                pts_sdf_batch.append(ps[0, 0, 0, :])
+    bda = mats_dict.get('bda_mat', None)[:, :3, :3].view(batch_size, 1, 1, 1, 3, 3)
+    occ = (bda @ bb.occ_coords[None, ..., None].expand(batch_size, *bb.occ_coords.shape, 1)).squeeze(-1)
+    nocc = (occ - lo) / ext
+    nocc = nocc * 2. - 1.
+    occ_logits = F.grid_sample(semantic_logits, nocc, padding_mode='border', align_corners=True)
+    occ_density = F.grid_sample(bb.density(density_feature), nocc, align_corners=True)
+    geom_xyz = torch.nan_to_num(geom_xyz, -1e3)
+    rgb_p, seg_p, dep_p, bev_rgb, bev_seg, bev_h, bev_density, voxel_output = \
+        bb.volume_rendering_from_multiple_views(geom_xyz, density_feature, semantic_logits, base_features, rgb)
+    up = bb.upsample_factor
+
+    def up2(x):
+        return bb.upsample2d(x.reshape(batch_size * num_cams, -1, bb.fH, bb.fW)).reshape(
+            batch_size, num_cams, -1, bb.fH * up, bb.fW * up)
+
+    rgb_p, seg_p, dep_p = up2(rgb_p), up2(seg_p), up2(dep_p)
+    voxel_output = voxel_output * bev_density.tanh() if bb.density_mode == 'sdf' else voxel_output * bev_density
+    vof = bb.voxel_output(voxel_output.reshape(batch_size, -1, voxel_output.shape[-2], voxel_output.shape[-1])).float()
+    return (vof.contiguous(), rgb_p, seg_p, dep_p, bev_rgb, bev_seg, bev_h, bev_density, pts_logits_batch,
+            pts_sdf_batch, occ_logits.permute(0, 2, 3, 4, 1), occ_density.permute(0, 2, 3, 4, 1).tanh())

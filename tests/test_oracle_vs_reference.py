@@ -81,3 +81,31 @@ def test_bilinear_2d_lift_restatement(ref, mode):
     g_ref, = torch.autograd.grad((o_ref * cot).sum(), a)
     g_me, = torch.autograd.grad((o_me * cot).sum(), b)
     assert torch.allclose(g_ref, g_me, rtol=1e-6, atol=1e-7)
+
+
+def test_forward_single_sweep_restatement_and_golden():
+    """The caller of the path: ``tp.forward_single_sweep`` == the reference's own ``_forward_single_sweep``
+    (BV2:518-649) bit for bit, incl. the inline point / occupancy queries (BV2:576-609) that nothing else executes
+    from the reference -- and the committed fixture tests/golden/mini_sweep.npz is what that method returns."""
+    import numpy as np
+    from helpers import load_golden
+    from oracle import gen_golden_sweep as gs
+    mats, feats, pts = gs.sweep_inputs()
+    bb = gs.build_seeded_reference()
+    gs.calibrate_density(bb, mats, feats)
+    out, rec = gs.run_reference(bb, mats, feats, pts)
+    imgs = torch.zeros(gs.BATCH, 1, MINI.num_cams, 3, *MINI.final_dim)
+    with torch.no_grad():
+        mine = tp.forward_single_sweep(bb, 0, imgs, mats, inrange_pts=pts)
+    for a, b in zip(out, mine):
+        if isinstance(a, (list, tuple)):
+            assert len(a) == len(b) and all(torch.equal(x, y) for x, y in zip(a, b))
+        else:
+            assert torch.equal(a, b)
+    gold = load_golden("mini_sweep")
+    outs = gs.flatten_outputs(out)
+    for name, a in outs.items():
+        st = gs.sample_stride(a.size)
+        assert np.array_equal(gold["out_" + name + "_strided"], a.reshape(-1)[::st]), name
+    for name in gs.RECORDED:
+        assert np.array_equal(gold["rec_" + name + "_out"], rec[name + "_out"].numpy()), name

@@ -25,6 +25,24 @@
 
 static inline int vb_ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// cudaFuncSetAttribute applies to the CURRENT device only, so "done once" must be remembered per device (a
+// process-wide flag would leave the attribute unset on every device but the first one to launch).
+// Usage: `static VbPerDeviceFlag flag;` next to the launch (one per kernel instantiation).
+struct VbPerDeviceFlag {
+  volatile unsigned char done[64];
+};
+template <typename F>
+static inline int vb_func_attr_per_device(F fn, cudaFuncAttribute attr, int value, VbPerDeviceFlag& flag) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return VB200_ERR_CUDA;
+  const bool tracked = dev >= 0 && dev < 64;
+  if (!tracked || !flag.done[dev]) {           // idempotent call, so a race between host threads is benign
+    if (cudaFuncSetAttribute(fn, attr, value) != cudaSuccess) return VB200_ERR_CUDA;
+    if (tracked) flag.done[dev] = 1;
+  }
+  return VB200_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // dtype helpers: features are stored as T, always widened to fp32 for arithmetic
 // ---------------------------------------------------------------------------------------------

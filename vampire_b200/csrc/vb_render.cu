@@ -1096,11 +1096,10 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
     static const bool tma_env = getenv("VB200_BEV_TMA") != nullptr;
     const bool tma_ok = vec_ok && tma_env && ((size_t)g->vX * sizeof(T)) % 16 == 0 && g->vX >= 8;
     if (tma_ok) {
-      static std::once_flag carve;
-      std::call_once(carve, [] {
-        cudaFuncSetAttribute(bev_channels_tma_kernel<T, K, C>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
-      });
+      static VbPerDeviceFlag carve;
+      if (vb_func_attr_per_device(bev_channels_tma_kernel<T, K, C>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  (int)cudaSharedmemCarveoutMaxShared, carve) != VB200_OK)
+        return VB200_ERR_CUDA;
       bev_channels_tma_kernel<T, K, C><<<dim3(g->oY * vb_ceil_div(g->oX, 256), bev_groups(K, C), g->B), kBevTmaThreads, 0, bst>>>(
           *g, *t, sem, rgb, feat, wl_ws, out->bev_rgb, out->bev_seg, reinterpret_cast<T*>(out->voxel_output));
     } else if (vec_ok)

@@ -195,13 +195,10 @@ int launch_softmax_fwd(const void* x, void* y, long long outer, int D, int inner
     TO* yo = reinterpret_cast<TO*>(y) + (size_t)o0 * D * inner;
     if (vec) {
       const size_t smem = (size_t)nt * D * sizeof(VI);
-      static bool attr_set = false;   // per instantiation; idempotent, so a benign race
-      if (!attr_set) {
-        if (cudaFuncSetAttribute(depth_softmax_fwd_staged<TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kSmxMaxSmem) != cudaSuccess)
-          return VB200_ERR_CUDA;
-        attr_set = true;
-      }
+      static VbPerDeviceFlag attr_set;   // per instantiation AND per device
+      if (vb_func_attr_per_device(depth_softmax_fwd_staged<TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kSmxMaxSmem, attr_set) != VB200_OK)
+        return VB200_ERR_CUDA;
       depth_softmax_fwd_staged<TI, TO><<<dim3(vb_ceil_div(inner / 4, nt), no), nt, smem, st>>>(xi, yo, D, inner);
     } else {
       depth_softmax_fwd_scalar<TI, TO><<<dim3(vb_ceil_div(inner, 128), no), 128, 0, st>>>(xi, yo, D, inner);
@@ -224,13 +221,10 @@ int launch_softmax_bwd(const void* y, const void* dy, void* dx, long long outer,
     TO* xo = reinterpret_cast<TO*>(dx) + off;
     if (vec) {
       const size_t smem = (size_t)2 * nt * D * sizeof(VY);
-      static bool attr_set = false;
-      if (!attr_set) {
-        if (cudaFuncSetAttribute(depth_softmax_bwd_staged<TY, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kSmxMaxSmem) != cudaSuccess)
-          return VB200_ERR_CUDA;
-        attr_set = true;
-      }
+      static VbPerDeviceFlag attr_set;
+      if (vb_func_attr_per_device(depth_softmax_bwd_staged<TY, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kSmxMaxSmem, attr_set) != VB200_OK)
+        return VB200_ERR_CUDA;
       depth_softmax_bwd_staged<TY, TO><<<dim3(vb_ceil_div(inner / 4, nt), no), nt, smem, st>>>(yi, gi, xo, D, inner);
     } else {
       depth_softmax_bwd_scalar<TY, TO><<<dim3(vb_ceil_div(inner, 128), no), 128, 0, st>>>(yi, gi, xo, D, inner);

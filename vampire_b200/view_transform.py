@@ -47,6 +47,13 @@ class LaplaceDensityParam(nn.Module):
     def get_beta(self) -> Tensor:
         return self.beta.abs() + self.beta_min
 
+    def forward(self, sdf: Tensor) -> Tensor:
+        """render_utils.py:37-42, for callers outside the kernels (a reference ``_forward_single_sweep`` running on
+        attached methods evaluates ``self.density(density_feature)`` itself for the occupancy query, BV2:609)."""
+        beta = self.get_beta()
+        x = sdf - self.bias
+        return (1 / beta) * (0.5 + 0.5 * x.sign() * torch.expm1(-x.abs() / beta))
+
 
 class UpsampleB200(nn.Module):
     """Drop-in for the reference's ``self.upsample2d = nn.UpsamplingBilinear2d(scale_factor=f)`` (BV2:210)."""
@@ -226,13 +233,28 @@ class LiftRenderB200(nn.Module):
         sdf, _ = ops.query_points_fwd(density_feature, inrange_pts, None, None, self.cfg_id, False, False, True)
         return logits.permute(0, 2, 1), sdf[:, 0]
 
-    def occupancy(self, semantic_logits: Tensor, density_feature: Tensor, bda_mat: Tensor, occ_coords: Tensor):
+    @staticmethod
+    def occ_coords(point_cloud_range=(-40.0, -40.0, -1.0, 40.0, 40.0, 5.4), voxel=(0.4, 0.4, 0.4),
+                   dims=(200, 200, 16)) -> Tensor:
+        """Ego coordinates of the Occ3D grid, built with the reference's own torch CPU calls (BV2:295-302,
+        ``create_norm_occ_coords(norm=False)``) -- for backbones that only keep the normalised copy."""
+        idx = torch.where(torch.ones(dims, dtype=torch.bool))
+        c = torch.cat([idx[a][:, None] * voxel[a] + voxel[a] / 2 + point_cloud_range[a] for a in range(3)], dim=1)
+        return c.reshape(*dims, 3)
+
+    def bev_epilogue(self, voxel_output: Tensor, bev_density: Tensor) -> Tensor:
+        """``voxel_output * bev_density.tanh()`` (BV2:627-630, density_mode='sdf')."""
+        return voxel_output * bev_density.tanh().to(voxel_output.dtype)
+
+    def occupancy(self, semantic_logits: Tensor, density_feature: Tensor, bda_mat: Optional[Tensor],
+                  occ_coords: Tensor):
         """Occ3D-grid queries (BV2:597-609, 647-648): occ_coords (X,Y,Z,3) ego coordinates of the
-        200x200x16 grid, rotated per sample by bda[:3,:3].  Returns (occ_logits (B,X,Y,Z,K),
+        200x200x16 grid, rotated per sample by bda[:3,:3] (``bda_mat=None``: the unrotated grid of
+        ``BaseLSSImpaintor``, base_lss_impaintor.py:611-616).  Returns (occ_logits (B,X,Y,Z,K),
         tanh(occ_density) (B,X,Y,Z,1)) like the reference's return tuple."""
         shape = occ_coords.shape[:-1]
-        pts = occ_coords.reshape(-1, 3)
-        rot = bda_mat[:, :3, :3]
+        pts = occ_coords.reshape(-1, 3).to(semantic_logits.device)
+        rot = None if bda_mat is None else bda_mat[:, :3, :3].to(semantic_logits.device)
         logits, _ = ops.query_points_fwd(semantic_logits, pts, rot, None, self.cfg_id, True, False, False)
         dens, _ = ops.query_points_fwd(density_feature, pts, rot, self.density.beta, self.cfg_id, False, True, False)
         B = semantic_logits.shape[0]

@@ -228,7 +228,7 @@ def run_reference_arm(args, cfg):
     # also under AMP); the workload keys are this repo's arm's, batch / feature dtype are the true ones
     ran = workload_config(args, cfg, 1, "fp32")
     ran["cams"] = ncams
-    ran["lift_plans"] = "n/a (reference recomputes get_pixel every call)"
+    ran["plans"] = "n/a (the reference recomputes get_pixel / get_geometry every call)"
     ran["note"] = ("bounded sample of the workload: 1 sample per step instead of the GPU arm's batch; the CPU path "
                    "has no batching benefit (ATen's 3-D grid_sampler parallelises over batch x cameras only), so "
                    "pts/s is per-sample throughput")
@@ -329,7 +329,7 @@ def workload_config(args, cfg, batch, dtype):
         "context_channels": cfg.C, "classes": cfg.K, "batch_per_gpu": batch, "features": dtype,
         "density_field": args.field, "ida": "val", "l2": "inputs larger than L2 (no flush needed)",
         "pooled_volume_layout": "channels_last_3d" if args.channels_last else "NCDHW (reference strides)",
-        "lift_plans": ("cached per distinct matrices (val-mode matrices never change)"
+        "plans": ("lift + camera-march plans cached per distinct matrices (val-mode matrices never change)"
                        if (args.plans == "on" or (args.plans == "auto" and args.workload == "fwd"))
                        else "off: projection + sort recomputed every call"),
     }
@@ -362,10 +362,13 @@ class Workload:
         self.prep = prepare_matrices(self.mats["sensor2ego_mats"][:, 0], self.mats["intrin_mats"][:, 0],
                                      self.mats["ida_mats"][:, 0], self.mats["bda_mat"]).to(dev)
         self.beta = self.mod.density.beta
-        self.plan_tab = None
+        self.plan_tab = self.rplan_tab = None
         if use_plans:
             # built once per distinct matrices (before the timed region, like the first batch of a val loop)
             self.plan_tab = self.mod.plan_cache.lift(ops.state(self.mod.cfg_id), self.mod.cfg_id, self.prep, True).table
+            if not train:
+                self.rplan_tab = self.mod.plan_cache.render(ops.state(self.mod.cfg_id), self.mod.cfg_id, self.prep,
+                                                            True).table
         self.allreduce = allreduce
         if train:
             from vampire_b200.dp import GradBucket
@@ -389,7 +392,7 @@ class Workload:
         if not self.train:
             with torch.no_grad():
                 vox, _ = ops.lift_pool_fwd(d, c, self.prep, mod.cfg_id, True, self.args.channels_last, False, self.plan_tab)
-                rend = ops.render_fwd(den, sem, rgb, feat, self.beta, self.prep, None, mod.cfg_id, True, 3)
+                rend = ops.render_fwd(den, sem, rgb, feat, self.beta, self.prep, None, mod.cfg_id, True, 3, self.rplan_tab)
             return vox, rend
         from vampire_b200.dp import train_step
         return train_step(mod, d, c, (den, sem, feat, rgb), self.prep, self.cots, self.bucket, plan=self.plan_tab)
@@ -449,7 +452,7 @@ class Workload:
         return ms_serial, per_kernel, kbytes
 
     def free(self):
-        for name in ("dev_in", "host_in", "cots", "bucket", "plan_tab", "mod", "prep"):
+        for name in ("dev_in", "host_in", "cots", "bucket", "plan_tab", "rplan_tab", "mod", "prep"):
             if hasattr(self, name):
                 delattr(self, name)
         torch.cuda.empty_cache()

@@ -220,6 +220,25 @@ int vb200_gather_pool_bwd(const VbGrid* g, const VbTables* t, const float* d_mat
 
 /* ---- volume rendering (Bk) ------------------------------------------ */
 
+/* Cached render plan of ONE sample (north-star kernel (a), camera side): for every (camera, ray, sample) the mask,
+ * the base voxel and the three fractions behind F.grid_sample (BV2:397-419) and the step length of BV2:426, as the
+ * strict fp32 chain get_geometry -> nan_to_num -> normalise -> unnormalise produces them.  Like the lift plan it
+ * depends on the matrices only (constant in validation / test), and the march that reads it composites the same
+ * samples with the same weights as the march that recomputes the geometry.  Layout: rays are grouped in the
+ * 8 x 4 pixel patches a warp marches; record index = ((n * npatch + patch) * (D-1) + i) * 32 + lane. */
+typedef struct VbRenderPlan {  /* all DEVICE pointers; 32 bytes */
+  const void* steps;     /* [N * npatch * (D-1) * 32] x 16 B: {valid << 31 | base voxel, fx, fy, fz}             */
+  const float* delta;    /* [same]  |p_{i+1} - p_i|                                                              */
+  const int16_t* last;   /* [N * npatch * 32]  last valid sample of the ray, -1 if none                          */
+  const void* reserved;
+} VbRenderPlan;
+
+/* per-sample element counts of the three arrays: rays = N * npatch * 32, steps = rays * (D-1) */
+size_t vb200_render_plan_rays(const VbGrid* g);
+/* Build the plans of g->B samples: d_steps (B, steps) x 16 B | d_delta (B, steps) fp32 | d_last (B, rays) int16 */
+int vb200_render_plan_build(const VbGrid* g, const VbTables* t, const float* d_mats, void* d_steps, float* d_delta,
+                            int16_t* d_last, void* stream);
+
 typedef struct VbRenderIn {
   const void* density;  /* (B, 1, vZ, vY, vX) density_feature, `dtype`, NCDHW */
   const void* sem;      /* (B, K, vZ, vY, vX) semantic_logits                 */
@@ -228,6 +247,8 @@ typedef struct VbRenderIn {
   const float* beta;    /* device pointer to the learnable density.beta scalar */
   const float* geom;    /* optional (B, N, D, fH, fW, 3) fp32 geometry as passed to the reference's
                            render; NULL = recompute from d_mats (+ nan_to_num), no 70 MB/sample read */
+  const VbRenderPlan* plans; /* optional DEVICE array of B cached plans (forward only; ignored when geom is given):
+                           the camera march reads its geometry from them instead of recomputing it */
 } VbRenderIn;
 
 typedef struct VbRenderOut {

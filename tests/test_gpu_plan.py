@@ -171,3 +171,104 @@ def test_amp_fp32_depth_with_16bit_ctx(case, cdt):
     with torch.no_grad():
         got = mod.lift_pool(case.depth.cuda(), ctx16.cuda(), case.mats)
     assert got.dtype == torch.float32 and torch.equal(got, out.detach())
+
+
+# ---- camera-march plan ------------------------------------------------------------------------------------------
+def _render_batch(case, st):
+    from vampire_b200.plan import LiftPlanBatch, build_render_plans
+    plans = build_render_plans(st, case.prep.cuda(), True)
+    return plans, LiftPlanBatch(plans, torch.device("cuda", torch.cuda.current_device()))
+
+
+def test_render_plan_holds_the_strict_indices(case):
+    """steps / delta / last == the mask, base voxel, fractions of the bit-exact index kernel (vb200_render_indices,
+    SHA-pinned to the reference in test_gpu_geometry.py) and the step lengths of the bit-exact geometry."""
+    ops, cid, st = _state(case.cfg)
+    cfg = case.cfg
+    prep = case.prep.cuda()
+    mask, i0, frac = ops.render_indices(prep, cid, True)
+    geom = torch.nan_to_num(ops.get_geometry(prep, cid, True, False), -1e3)
+    dl_ref = torch.norm(geom[:, :, 1:] - geom[:, :, :-1], dim=-1).cpu().numpy()          # (B,N,S,fH,fW)
+    plans, _ = _render_batch(case, st)
+    S, fH, fW, N = cfg.S, cfg.fH, cfg.fW, cfg.num_cams
+    pw, ph = 8, 4
+    npx, npy = -(-fW // pw), -(-fH // ph)
+    lane = np.arange(32)
+    for b, p in enumerate(plans):
+        steps = p.steps.cpu().numpy().view(np.uint32).reshape(N, npy, npx, S, 32, 4)
+        delta = p.delta.cpu().numpy().reshape(N, npy, npx, S, 32)
+        last = p.last.cpu().numpy().reshape(N, npy, npx, 32)
+        m = mask[b].cpu().numpy().astype(bool)                                            # (N,S,fH,fW)
+        ii = i0[b].cpu().numpy().astype(np.int64)
+        ff = frac[b].cpu().numpy()
+        for py in range(npy):
+            for px in range(npx):
+                w = px * pw + lane % pw
+                h = py * ph + lane // pw
+                act = (w < fW) & (h < fH)
+                wc, hc = np.minimum(w, fW - 1), np.minimum(h, fH - 1)
+                rec = steps[:, py, px]                                                    # (N,S,32,4)
+                valid = (rec[..., 0] >> 31).astype(bool)
+                want = m[:, :, hc, wc] & act                                              # (N,S,32)
+                assert np.array_equal(valid, want)
+                x0, y0, z0 = (ii[:, :, hc, wc, a] for a in range(3))
+                sx, sy, sz = np.minimum(x0, cfg.vX - 2), np.minimum(y0, cfg.vY - 2), np.minimum(z0, cfg.vZ - 2)
+                v0 = (sz * cfg.vY + sy) * cfg.vX + sx
+                assert np.array_equal((rec[..., 0] & 0x1FFFFF)[valid], v0[valid])
+                fr = rec[..., 1:].view(np.float32)
+                exp = ff[:, :, hc, wc, :] + np.stack([x0 - sx, y0 - sy, z0 - sz], -1).astype(np.float32)
+                assert np.array_equal(fr[valid], exp[valid])
+                np.testing.assert_allclose(delta[:, py, px][:, :, act], dl_ref[b][:, :, hc, wc][:, :, act], rtol=2e-6)
+                lv = np.where(want.any(1), S - 1 - np.argmax(want[:, ::-1], axis=1), -1)
+                assert np.array_equal(last[:, py, px], lv)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_planned_march_matches_the_recomputing_march(case, dtype):
+    ops, cid, st = _state(case.cfg)
+    _, batch = _render_batch(case, st)
+    vols = [t.to(dtype).cuda() for t in (case.den, case.sem, case.rgb, case.feat)]
+    beta = torch.tensor(0.1, device="cuda")
+    a = ops.render_fwd(*vols, beta, case.prep.cuda(), None, cid, True, 3)
+    b = ops.render_fwd(*vols, beta, case.prep.cuda(), None, cid, True, 3, batch.table)
+    for name, x, y in zip(["rgb", "seg", "depth"], a[:3], b[:3]):
+        # same samples, same weights; exp(-cumsum) as a running product and the exact tail step lengths move last bits
+        assert_close_scaled(y.cpu().numpy(), x.cpu().numpy(), 3e-6, "planned march " + name)
+    for x, y in zip(a[3:], b[3:]):
+        assert torch.equal(x, y)                    # the BEV branch does not use the plan
+    if dtype == torch.float32 and case.inputs_match_golden:
+        from helpers import golden_value
+        for name, y in zip(["rgb", "seg", "depth"], b[:3]):
+            exp, got = golden_value(case.gold, "r_" + name, y.cpu().numpy())
+            assert_close_scaled(got, exp, 1e-5, "planned march vs reference " + name)
+
+
+def test_planned_march_nonfinite_volume_takes_the_nansafe_path(case):
+    ops, cid, st = _state(case.cfg)
+    _, batch = _render_batch(case, st)
+    sem = case.sem.clone()
+    sem[0, 3, 2, 5, 7] = float("nan")
+    sem[-1, 0, 1, 1, 1] = float("inf")
+    vols = [t.cuda() for t in (case.den, sem, case.rgb, case.feat)]
+    beta = torch.tensor(0.1, device="cuda")
+    a = ops.render_fwd(*vols, beta, case.prep.cuda(), None, cid, True, 1)
+    b = ops.render_fwd(*vols, beta, case.prep.cuda(), None, cid, True, 1, batch.table)
+    for x, y in zip(a[:3], b[:3]):
+        assert torch.equal(x, y) and torch.isfinite(y).all()
+
+
+def test_module_render_uses_cached_plans(case):
+    from vampire_b200.view_transform import LiftRenderB200
+    mod = LiftRenderB200(plans="eval", **case.conf).cuda().eval()
+    vols = [t.cuda() for t in (case.den, case.sem, case.feat, case.rgb)]
+    with torch.no_grad():
+        a = mod.render(case.mats, *vols)
+        b = mod.render(case.mats, *vols)
+    assert mod.plan_cache.misses == case.batch and mod.plan_cache.hits == case.batch
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    off = LiftRenderB200(plans="off", **case.conf).cuda().eval()
+    with torch.no_grad():
+        c = off.render(case.mats, *vols)
+    for x, y in zip(a[:3], c[:3]):
+        assert_close_scaled(x.cpu().numpy(), y.cpu().numpy(), 3e-6, "module planned render")

@@ -20,6 +20,7 @@
 //   bev_fwd          = R5+R6 fused: reads the four NCDHW tensors directly (regular stencil, fully
 //                      coalesced), never materialises the 38-channel cat.
 #include "vb_render_common.cuh"
+#include "vb_march_planned.cuh"
 #include "vb_trace.cuh"
 
 #include <atomic>
@@ -1142,6 +1143,12 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
     if (in->geom) {
       VB_MARCH(false, false, false);
       VB_MARCH(false, false, true);
+    } else if (in->plans) {
+      // cached geometry; a non-finite packed volume (flag raised by the pack) takes the recomputing NaN-safe variant
+      march_fwd_planned_kernel<T, K><<<grid, kMarchThreads, 0, st>>>(*g, *t, in->plans, region, flag, in->beta,
+                                                                     out->rgb, out->seg, out->depth, b0);
+      if (vb_render_div_ok(dv)) VB_MARCH(true, true, true);
+      else VB_MARCH(true, false, true);
     } else if (vb_render_div_ok(dv)) {
       VB_MARCH(true, true, false);
       VB_MARCH(true, true, true);
@@ -1229,6 +1236,34 @@ extern "C" size_t vb200_render_fwd_workspace(const VbGrid* g, int dtype) {
   // minimum: BEV weights + one packed sample per pack/march round; every further
   // vb200_render_packed_bytes() lets one more sample share a round
   return bev_weight_bytes(g) + packed_bytes_per_sample(g, dtype);
+}
+
+extern "C" size_t vb200_render_plan_rays(const VbGrid* g) {
+  return g ? (size_t)g->N * march_patches(*g) * 32 : 0;
+}
+
+extern "C" int vb200_render_plan_build(const VbGrid* g, const VbTables* t, const float* d_mats, void* d_steps,
+                                       float* d_delta, int16_t* d_last, void* stream) {
+  VB_CHECK_ARG(g && t && d_mats && d_steps && d_delta && d_last);
+  VB_CHECK_ARG(g->B > 0 && g->N > 0 && g->N <= VB_MAX_CAMS && g->D >= 2 && g->D - 1 < 32767);
+  VB_CHECK_ARG((size_t)g->vZ * g->vY * g->vX <= (size_t)kPlanVoxMask + 1);
+  VB_CHECK_ARG(g->vX >= 2 && g->vY >= 2 && g->vZ >= 2);     // the plan stores the inward-shifted base corner
+  if ((uintptr_t)d_steps & 15) return VB200_ERR_ALIGN;
+  int rc = vb200_device_check();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const VbRenderDiv dv = vb_render_div(g);
+  const int npatch = march_patches(*g);
+  dim3 grid(vb_ceil_div(npatch, kMarchThreads / 32), g->N, g->B);
+  VbTraceScope tr(VB_K_GET_GEOMETRY, st);
+  if (vb_render_div_ok(dv))
+    render_plan_build_kernel<true><<<grid, kMarchThreads, 0, st>>>(*g, *t, dv, d_mats, reinterpret_cast<uint4*>(d_steps),
+                                                                    d_delta, d_last, vb200_render_plan_rays(g));
+  else
+    render_plan_build_kernel<false><<<grid, kMarchThreads, 0, st>>>(*g, *t, dv, d_mats, reinterpret_cast<uint4*>(d_steps),
+                                                                     d_delta, d_last, vb200_render_plan_rays(g));
+  VB_LAUNCH_CHECK();
+  return VB200_OK;
 }
 
 extern "C" int vb200_render_set_fork(int enable) {

@@ -61,11 +61,15 @@ __global__ void __launch_bounds__(kMarchThreads) march_bwd_kernel(
     const T* __restrict__ packed, const float* __restrict__ beta_ptr, const float* __restrict__ o_rgb,
     const float* __restrict__ o_seg, const float* __restrict__ o_depth, const float* __restrict__ g_rgb,
     const float* __restrict__ g_seg, const float* __restrict__ g_depth, float* __restrict__ gpacked,
-    float* __restrict__ beta_partials, int b) {
+    float* __restrict__ beta_partials, size_t packed_stride, size_t gpacked_stride) {
   constexpr int CP = packed_channels(K);
   __shared__ float s_m[VB200_MAT_SLOTS * 16];
   __shared__ float s_red[kMarchThreads / 32];
-  const int n = blockIdx.y;
+  // grid = (patch blocks, cameras, samples): the whole batch in ONE launch (a sample alone is 1.2 waves at 3 blocks
+  // per SM, i.e. 40 % of its time is a tail) -- each sample has its own packed copy and gradient accumulator
+  const int n = blockIdx.y, b = blockIdx.z;
+  packed += (size_t)b * packed_stride;
+  gpacked += (size_t)b * gpacked_stride;
   for (int i = threadIdx.x; i < VB200_MAT_SLOTS * 16; i += blockDim.x)
     s_m[i] = __ldg(d_mats + (size_t)(b * g.N + n) * VB200_MAT_SLOTS * 16 + i);
   __syncthreads();
@@ -197,7 +201,7 @@ __global__ void __launch_bounds__(kMarchThreads) march_bwd_kernel(
     }
   }
   const float tot = block_sum(dbeta, s_red);
-  if (threadIdx.x == 0) beta_partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
+  if (threadIdx.x == 0) beta_partials[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
 }
 
 // ---- BEV branch: per-column compositing backward -------------------------------------------------------------
@@ -314,7 +318,7 @@ __global__ void __launch_bounds__(256) bev_bwd_composite_kernel(
     }
   }
   const float tot = block_sum(dbeta, s_red);
-  if (threadIdx.x == 0) beta_partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = tot;
+  if (threadIdx.x == 0) beta_partials[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
 }
 
 // ---- inverse index tables for the BEV gather ------------------------------------------------------------------
@@ -354,11 +358,13 @@ __global__ void __launch_bounds__(256, 3) unpack_gather_kernel(
     VbGrid g, BevTables bt, const float* __restrict__ gpacked, const float* __restrict__ wl_ws,
     const float* __restrict__ ds_ws, const float* __restrict__ g_bev_rgb, const float* __restrict__ g_bev_seg,
     const T* __restrict__ g_vo, T* __restrict__ o_den, T* __restrict__ o_sem, T* __restrict__ o_rgb,
-    T* __restrict__ o_feat, int b, int do_bev) {
+    T* __restrict__ o_feat, size_t gpacked_stride, int do_bev) {
   constexpr int CP = packed_channels(K);
   const size_t nvox = (size_t)g.vZ * g.vY * g.vX;
   const int vox = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
   if (vox >= (int)nvox) return;
+  if (gpacked) gpacked += (size_t)b * gpacked_stride;
   const int x = vox % g.vX, y = (vox / g.vX) % g.vY, z = vox / (g.vX * g.vY);
   float cam[CP];
   if (gpacked) {
@@ -443,8 +449,10 @@ BwdLayout bwd_layout(const VbGrid* g, int dtype) {
   const int cp = packed_channels(g->K);
   BwdLayout l;
   size_t o = 0;
-  l.packed = o;   o += vb_align256(nvox * cp * vb_elem_size(dtype));
-  l.gpacked = o;  o += vb_align256(nvox * cp * 4);
+  // one packed copy + one fp32 gradient accumulator PER SAMPLE: the whole batch is packed, marched and unpacked by
+  // single launches (B = 8 fp32: 2 GB of the 180 GB)
+  l.packed = o;   o += (size_t)g->B * vb_align256(nvox * cp * vb_elem_size(dtype));
+  l.gpacked = o;  o += (size_t)g->B * vb_align256(nvox * cp * 4);
   l.wl = o;       o += vb_align256((size_t)g->B * g->oZ * ncol * 4);
   l.ds = o;       o += vb_align256((size_t)g->B * g->oZ * ncol * 4);
   l.gpart = o;    o += vb_align256((size_t)vb_ceil_div(g->K + 3, kBevBwdGroup) * g->B * g->oZ * ncol * 4);
@@ -505,34 +513,36 @@ int launch_render_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
     n_partials += l.n_bev_blocks;
   }
   const int patches = vb_ceil_div(g->fW, kPatchW) * vb_ceil_div(g->fH, kPatchH);
-  for (int b = 0; b < g->B; ++b) {
-    if (cam) {
-      if (cudaMemsetAsync(gpacked, 0, nvox * cp * 4, st) != cudaSuccess) return VB200_ERR_CUDA;
-      {
-        VbTraceScope tr(VB_K_PACK, st);
-        pack_cam_volume_kernel<T, K><<<dim3(vb_ceil_div(nvox, kPackThreads * PackVox<T>::n), 1), kPackThreads, 0, st>>>(
-            den + (size_t)b * nvox, sem + (size_t)b * K * nvox, rgb + (size_t)b * 3 * nvox, packed, (int)nvox, 0, nullptr);
-        VB_LAUNCH_CHECK();
-      }
-      VbTraceScope tr(VB_K_MARCH_BWD, st);
-      dim3 grid(vb_ceil_div(patches, kMarchThreads / 32), g->N);
-      if (in->geom)
-        march_bwd_kernel<T, K, false><<<grid, kMarchThreads, 0, st>>>(
-            *g, *t, vb_render_div(g), d_mats, in->geom, packed, in->beta, out->rgb, out->seg, out->depth, gr->g_rgb, gr->g_seg,
-            gr->g_depth, gpacked, partials + n_partials, b);
-      else
-        march_bwd_kernel<T, K, true><<<grid, kMarchThreads, 0, st>>>(
-            *g, *t, vb_render_div(g), d_mats, nullptr, packed, in->beta, out->rgb, out->seg, out->depth, gr->g_rgb, gr->g_seg,
-            gr->g_depth, gpacked, partials + n_partials, b);
+  const size_t packed_stride = vb_align256(nvox * cp * sizeof(T)) / sizeof(T);
+  const size_t gpacked_stride = vb_align256(nvox * cp * 4) / 4;
+  if (cam) {
+    if (cudaMemsetAsync(gpacked, 0, (size_t)g->B * gpacked_stride * 4, st) != cudaSuccess) return VB200_ERR_CUDA;
+    {
+      VbTraceScope tr(VB_K_PACK, st);
+      pack_cam_volume_kernel<T, K><<<dim3(vb_ceil_div(nvox, kPackThreads * PackVox<T>::n), g->B), kPackThreads, 0, st>>>(
+          den, sem, rgb, packed, (int)nvox, packed_stride, nullptr);
       VB_LAUNCH_CHECK();
-      n_partials += l.n_march_blocks;
     }
+    VbTraceScope tr(VB_K_MARCH_BWD, st);
+    dim3 grid(vb_ceil_div(patches, kMarchThreads / 32), g->N, g->B);
+    if (in->geom)
+      march_bwd_kernel<T, K, false><<<grid, kMarchThreads, 0, st>>>(
+          *g, *t, vb_render_div(g), d_mats, in->geom, packed, in->beta, out->rgb, out->seg, out->depth, gr->g_rgb, gr->g_seg,
+          gr->g_depth, gpacked, partials + n_partials, packed_stride, gpacked_stride);
+    else
+      march_bwd_kernel<T, K, true><<<grid, kMarchThreads, 0, st>>>(
+          *g, *t, vb_render_div(g), d_mats, nullptr, packed, in->beta, out->rgb, out->seg, out->depth, gr->g_rgb, gr->g_seg,
+          gr->g_depth, gpacked, partials + n_partials, packed_stride, gpacked_stride);
+    VB_LAUNCH_CHECK();
+    n_partials += l.n_march_blocks * g->B;
+  }
+  {
     VbTraceScope tr(VB_K_UNPACK_BEV_BWD, st);
-    unpack_gather_kernel<T, K, C><<<vb_ceil_div(nvox, 256), 256, 0, st>>>(
+    unpack_gather_kernel<T, K, C><<<dim3(vb_ceil_div(nvox, 256), g->B), 256, 0, st>>>(
         *g, bt, cam ? gpacked : nullptr, wl_ws, ds_ws, gr->g_bev_rgb, gr->g_bev_seg,
         reinterpret_cast<const T*>(gr->g_voxel_output), reinterpret_cast<T*>(gr->g_density),
-        reinterpret_cast<T*>(gr->g_sem), reinterpret_cast<T*>(gr->g_rgb_in), reinterpret_cast<T*>(gr->g_feat), b,
-        bev ? 1 : 0);
+        reinterpret_cast<T*>(gr->g_sem), reinterpret_cast<T*>(gr->g_rgb_in), reinterpret_cast<T*>(gr->g_feat),
+        gpacked_stride, bev ? 1 : 0);
     VB_LAUNCH_CHECK();
   }
   {

@@ -397,11 +397,12 @@ def _render_out_shapes(cfg: PathConfig, B: int):
             (B, 1, cfg.oZ, cfg.oY, cfg.oX), (B, Cc, cfg.oZ, cfg.oY, cfg.oX)]
 
 
-def _render_in_struct(density, sem, rgb, feat, beta, geom):
+def _render_in_struct(density, sem, rgb, feat, beta, geom, plan=None):
     rin = cabi.VbRenderIn()
     rin.density, rin.sem, rin.rgb, rin.feat = density.data_ptr(), sem.data_ptr(), rgb.data_ptr(), feat.data_ptr()
     rin.beta = beta.data_ptr()
     rin.geom = None if geom is None else geom.data_ptr()
+    rin.plans = None if plan is None else plan.data_ptr()
     return rin
 
 
@@ -430,11 +431,15 @@ def _check_render_inputs(cfg, density, sem, rgb, feat, beta):
 
 @torch.library.custom_op("vampire_b200::render_fwd", mutates_args=())
 def render_fwd(density: Tensor, sem: Tensor, rgb: Tensor, feat: Tensor, beta: Tensor, mats: Tensor,
-               geom: Optional[Tensor], cfg_id: int, has_bda: bool, branches: int) -> List[Tensor]:
+               geom: Optional[Tensor], cfg_id: int, has_bda: bool, branches: int,
+               plan: Optional[Tensor] = None) -> List[Tensor]:
+    """``plan``: the device table of the batch's cached render plans (``PlanCache.render``): the camera march reads
+    its sample geometry from them instead of recomputing it (forward only; the backward recomputes)."""
     st = state(cfg_id)
     cfg = st.cfg
-    dev = _need_cuda(density, sem, rgb, feat, beta, mats, geom)
+    dev = _need_cuda(density, sem, rgb, feat, beta, mats, geom, plan)
     B = _check_render_inputs(cfg, density, sem, rgb, feat, beta)
+    plan = _plan_ok(plan, B, dev) if geom is None else None
     dt = cabi.dtype_code(density.dtype)
     mats = _mats_ok(mats, B, cfg.num_cams)
     density, sem, rgb, feat = (t.contiguous() for t in (density, sem, rgb, feat))
@@ -451,7 +456,7 @@ def render_fwd(density: Tensor, sem: Tensor, rgb: Tensor, feat: Tensor, beta: Te
     ws_bytes = lib.vb200_render_fwd_workspace(C.byref(g), dt) + \
         lib.vb200_render_packed_bytes(C.byref(g), dt) * ((B if st.render_group <= 0 else min(B, st.render_group)) - 1)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    rin = _render_in_struct(density, sem, rgb, feat, beta32, geom)
+    rin = _render_in_struct(density, sem, rgb, feat, beta32, geom, plan)
     ro = _render_out_struct(outs)
     with torch.cuda.device(dev):
         cabi.check(lib.vb200_render_fwd(C.byref(g), C.byref(st.tables(dev).struct), mats.data_ptr(), C.byref(rin), dt,
@@ -466,7 +471,7 @@ def render_fwd(density: Tensor, sem: Tensor, rgb: Tensor, feat: Tensor, beta: Te
 
 
 @render_fwd.register_fake
-def _(density, sem, rgb, feat, beta, mats, geom, cfg_id, has_bda, branches):
+def _(density, sem, rgb, feat, beta, mats, geom, cfg_id, has_bda, branches, plan=None):
     cfg = state(cfg_id).cfg
     shapes = _render_out_shapes(cfg, density.shape[0])
     outs = [density.new_empty(s, dtype=torch.float32) for s in shapes[:7]]
@@ -518,7 +523,7 @@ def _(grads, outs, density, sem, rgb, feat, beta, mats, geom, cfg_id, has_bda, b
 
 
 def _render_setup(ctx, inputs, output):
-    density, sem, rgb, feat, beta, mats, geom, cfg_id, has_bda, branches = inputs
+    density, sem, rgb, feat, beta, mats, geom, cfg_id, has_bda, branches, _plan = inputs
     ctx.save_for_backward(density, sem, rgb, feat, beta, mats, geom, *output)
     ctx.cfg_id, ctx.has_bda, ctx.branches = cfg_id, has_bda, branches
 
@@ -530,7 +535,7 @@ def _render_backward(ctx, grads):
     grads = [gt if gt is not None else torch.zeros_like(o) for gt, o in zip(grads, outs)]
     g_den, g_sem, g_rgb, g_feat, g_beta = render_bwd(grads, outs, density, sem, rgb, feat, beta, mats, geom,
                                                      ctx.cfg_id, ctx.has_bda, ctx.branches)
-    return g_den, g_sem, g_rgb, g_feat, g_beta.reshape(beta.shape).to(beta.dtype), None, None, None, None, None
+    return g_den, g_sem, g_rgb, g_feat, g_beta.reshape(beta.shape).to(beta.dtype), None, None, None, None, None, None
 
 
 torch.library.register_autograd("vampire_b200::render_fwd", _render_backward, setup_context=_render_setup)

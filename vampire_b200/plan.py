@@ -36,6 +36,21 @@ class LiftPlan:
         return sum(t.numel() * t.element_size() for t in (self.head, self.pairs, self.cell_off, self.cell_recs))
 
 
+class RenderPlan:
+    """One sample's cached camera-march plan (steps / step lengths / last valid sample) on one CUDA device."""
+
+    __slots__ = ("steps", "delta", "last")
+
+    def __init__(self, steps: Tensor, delta: Tensor, last: Tensor):
+        self.steps, self.delta, self.last = steps, delta, last
+
+    def pointers(self) -> Tuple[int, int, int, int]:
+        return self.steps.data_ptr(), self.delta.data_ptr(), self.last.data_ptr(), 0
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in (self.steps, self.delta, self.last))
+
+
 class LiftPlanBatch:
     """The plans of a batch: a (B, 4) int64 device table of VbLiftPlan structs + the plans it points into."""
 
@@ -83,6 +98,29 @@ def build_lift_plans(state, mats: Tensor, has_bda: bool) -> List[LiftPlan]:
     return out
 
 
+def build_render_plans(state, mats: Tensor, has_bda: bool) -> List[RenderPlan]:
+    """One render plan per sample of ``mats`` (B, N, 6, 4, 4) fp32 on a CUDA device (asynchronous, exact sizes)."""
+    cfg = state.cfg
+    dev = mats.device
+    if dev.type != "cuda":
+        raise RuntimeError("vampire_b200: plans are built on the GPU (no CPU path)")
+    lib = cabi.lib()
+    mats = mats.contiguous()
+    B = mats.shape[0]
+    g = state.grid(B, has_bda)
+    rays = lib.vb200_render_plan_rays(C.byref(g))
+    S = cfg.S
+    with torch.cuda.device(dev):
+        steps = torch.empty(B, rays * S, 4, dtype=torch.int32, device=dev)
+        delta = torch.empty(B, rays * S, dtype=torch.float32, device=dev)
+        last = torch.empty(B, rays, dtype=torch.int16, device=dev)
+        cabi.check(lib.vb200_render_plan_build(C.byref(g), C.byref(state.tables(dev).struct), mats.data_ptr(),
+                                               steps.data_ptr(), delta.data_ptr(), last.data_ptr(),
+                                               cabi.stream_ptr(dev)))
+    # per-sample views of the batch allocation (a cached sample keeps its slice alive)
+    return [RenderPlan(steps[b], delta[b], last[b]) for b in range(B)]
+
+
 class PlanCache:
     """LRU of per-sample plans keyed by (config handle, has_bda, device, bytes of the sample's matrices)."""
 
@@ -103,11 +141,18 @@ class PlanCache:
     def lift(self, state, cfg_id: int, mats: Tensor, has_bda: bool, mats_host: Optional[Tensor] = None) -> LiftPlanBatch:
         """``mats``: prepared matrices on the device; ``mats_host``: the same on the CPU when the caller has
         them (saves the device->host copy that keying by content otherwise needs)."""
+        return self._get("lift", build_lift_plans, state, cfg_id, mats, has_bda, mats_host)
+
+    def render(self, state, cfg_id: int, mats: Tensor, has_bda: bool, mats_host: Optional[Tensor] = None) -> LiftPlanBatch:
+        """Camera-march plans of a batch (same keying); ``.table`` is the (B, 4) device table of VbRenderPlan."""
+        return self._get("render", build_render_plans, state, cfg_id, mats, has_bda, mats_host)
+
+    def _get(self, kind, builder, state, cfg_id, mats, has_bda, mats_host):
         dev = mats.device
         if mats_host is None:
             mats_host = mats.detach().cpu()
         raw = mats_host.contiguous().numpy()
-        keys = [(cfg_id, bool(has_bda), dev.index, raw[b].tobytes()) for b in range(raw.shape[0])]
+        keys = [(kind, cfg_id, bool(has_bda), dev.index, raw[b].tobytes()) for b in range(raw.shape[0])]
         bkey = tuple(keys)
         hit = self._batches.get(bkey)
         if hit is not None:
@@ -121,7 +166,7 @@ class PlanCache:
             first_of.setdefault(keys[i], i)
         if first_of:
             idx = list(first_of.values())
-            built = build_lift_plans(state, mats[idx], has_bda)
+            built = builder(state, mats[idx], has_bda)
             for i, p in zip(idx, built):
                 self._lru[keys[i]] = p
         self.misses += len(missing)

@@ -28,7 +28,12 @@ def shard_samples(global_batch: int, world_size: int, rank: int) -> List[int]:
 
 
 class GradBucket:
-    """Flat fp32 gradient bucket, all-reduced (mean) once per step."""
+    """Flat fp32 gradient bucket, all-reduced (mean) once per step.
+
+    Nothing but the wait sits on the critical path after the collective: the mean is taken by NCCL itself
+    (``ReduceOp.AVG``; backends without it -- gloo in the CPU tests -- get the gradients pre-scaled by 1/G while
+    they are packed, before the reduce is launched), and only the packed gradients (not the whole bucket) are
+    copied back."""
 
     def __init__(self, device, world_size: int, numel: int = ADJACENT_PARAM_FLOATS,
                  group: Optional[dist.ProcessGroup] = None):
@@ -38,8 +43,15 @@ class GradBucket:
         self._handle = None
         self._views: List[torch.Tensor] = []
         self._targets: List[torch.Tensor] = []
+        self._used = 0
+        self._avg = None      # does the backend reduce with AVG?
 
-    def pack(self, grads: Sequence[torch.Tensor]) -> None:
+    def _native_avg(self) -> bool:
+        if self._avg is None:
+            self._avg = self.world_size > 1 and dist.get_backend(self.group) == "nccl"
+        return self._avg
+
+    def pack(self, grads: Sequence[torch.Tensor], scale: float = 1.0) -> None:
         off = 0
         self._views, self._targets = [], []
         for g in grads:
@@ -47,24 +59,35 @@ class GradBucket:
             if off + n > self.flat.numel():
                 raise ValueError("GradBucket: gradients exceed the bucket")
             view = self.flat[off:off + n]
-            view.copy_(g.reshape(-1))
+            if scale == 1.0:
+                view.copy_(g.reshape(-1))
+            else:
+                torch.mul(g.reshape(-1), scale, out=view)
             self._views.append(view)
             self._targets.append(g)
             off += n
+        self._used = off
 
     def allreduce_async(self, grads: Sequence[torch.Tensor]) -> None:
         """Pack + launch the all-reduce without blocking the caller's stream of work."""
-        self.pack(grads)
-        if self.world_size > 1:
+        if self.world_size <= 1:
+            self.pack(grads)
+            return
+        if self._native_avg():
+            self.pack(grads)
+            self._handle = dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+        else:
+            self.pack(grads, 1.0 / self.world_size)
+            if self._used < self.flat.numel():
+                # the rest of the bucket stands for the adjacent parameters' gradients; keep it bounded across steps
+                self.flat[self._used:].mul_(1.0 / self.world_size)
             self._handle = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def wait(self) -> None:
-        """Finish the all-reduce, average, and write the reduced values back into the gradients."""
+        """Finish the all-reduce and write the reduced values back into the gradients."""
         if self._handle is not None:
             self._handle.wait()
             self._handle = None
-        if self.world_size > 1:
-            self.flat.div_(self.world_size)
         for view, tgt in zip(self._views, self._targets):
             tgt.copy_(view.view_as(tgt))
 

@@ -197,11 +197,18 @@ def _plan_ok(plan: Optional[Tensor], B: int, dev) -> Optional[Tensor]:
     return plan
 
 
-@torch.library.custom_op("vampire_b200::lift_pool_fwd", mutates_args=())
 def lift_pool_fwd(depth: Tensor, ctx: Tensor, mats: Tensor, cfg_id: int, has_bda: bool, channels_last: bool,
                   save_cnt: bool, plan: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
     """``plan``: the device table of a :class:`vampire_b200.plan.LiftPlanBatch` built for these matrices; the
     projection is then read from the cached plan instead of being recomputed (bit-identical result)."""
+    return _lift_pool_fwd(depth, ctx, mats, cfg_id, has_bda, channels_last, save_cnt, plan)
+
+
+# (the op schemas carry NO default values: the dispatcher strips arguments equal to their default before autograd
+#  sees them, which would make the arity of the backward depend on whether a plan was passed)
+@torch.library.custom_op("vampire_b200::lift_pool_fwd", mutates_args=())
+def _lift_pool_fwd(depth: Tensor, ctx: Tensor, mats: Tensor, cfg_id: int, has_bda: bool, channels_last: bool,
+                   save_cnt: bool, plan: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
     st = state(cfg_id)
     cfg = st.cfg
     dev = _need_cuda(depth, ctx, mats, plan)
@@ -238,8 +245,8 @@ def lift_pool_fwd(depth: Tensor, ctx: Tensor, mats: Tensor, cfg_id: int, has_bda
     return out, cnt
 
 
-@lift_pool_fwd.register_fake
-def _(depth, ctx, mats, cfg_id, has_bda, channels_last, save_cnt, plan=None):
+@_lift_pool_fwd.register_fake
+def _(depth, ctx, mats, cfg_id, has_bda, channels_last, save_cnt, plan):
     cfg = state(cfg_id).cfg
     B = depth.shape[0]
     if channels_last:
@@ -250,9 +257,14 @@ def _(depth, ctx, mats, cfg_id, has_bda, channels_last, save_cnt, plan=None):
     return out, cnt
 
 
-@torch.library.custom_op("vampire_b200::lift_pool_bwd", mutates_args=())
 def lift_pool_bwd(gout: Tensor, depth: Tensor, ctx: Tensor, mats: Tensor, cnt: Tensor, cfg_id: int,
                   has_bda: bool, plan: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    return _lift_pool_bwd(gout, depth, ctx, mats, cnt, cfg_id, has_bda, plan)
+
+
+@torch.library.custom_op("vampire_b200::lift_pool_bwd", mutates_args=())
+def _lift_pool_bwd(gout: Tensor, depth: Tensor, ctx: Tensor, mats: Tensor, cnt: Tensor, cfg_id: int,
+                   has_bda: bool, plan: Optional[Tensor]) -> Tuple[Tensor, Tensor]:
     st = state(cfg_id)
     cfg = st.cfg
     dev = _need_cuda(gout, depth, ctx, mats, cnt, plan)
@@ -291,8 +303,8 @@ def lift_pool_bwd(gout: Tensor, depth: Tensor, ctx: Tensor, mats: Tensor, cnt: T
     return gdepth, gctx
 
 
-@lift_pool_bwd.register_fake
-def _(gout, depth, ctx, mats, cnt, cfg_id, has_bda, plan=None):
+@_lift_pool_bwd.register_fake
+def _(gout, depth, ctx, mats, cnt, cfg_id, has_bda, plan):
     return torch.empty_like(depth), torch.empty_like(ctx)
 
 
@@ -429,12 +441,18 @@ def _check_render_inputs(cfg, density, sem, rgb, feat, beta):
     return B
 
 
-@torch.library.custom_op("vampire_b200::render_fwd", mutates_args=())
 def render_fwd(density: Tensor, sem: Tensor, rgb: Tensor, feat: Tensor, beta: Tensor, mats: Tensor,
                geom: Optional[Tensor], cfg_id: int, has_bda: bool, branches: int,
                plan: Optional[Tensor] = None) -> List[Tensor]:
     """``plan``: the device table of the batch's cached render plans (``PlanCache.render``): the camera march reads
     its sample geometry from them instead of recomputing it (forward only; the backward recomputes)."""
+    return _render_fwd(density, sem, rgb, feat, beta, mats, geom, cfg_id, has_bda, branches, plan)
+
+
+@torch.library.custom_op("vampire_b200::render_fwd", mutates_args=())
+def _render_fwd(density: Tensor, sem: Tensor, rgb: Tensor, feat: Tensor, beta: Tensor, mats: Tensor,
+                geom: Optional[Tensor], cfg_id: int, has_bda: bool, branches: int,
+                plan: Optional[Tensor]) -> List[Tensor]:
     st = state(cfg_id)
     cfg = st.cfg
     dev = _need_cuda(density, sem, rgb, feat, beta, mats, geom, plan)
@@ -470,8 +488,8 @@ def render_fwd(density: Tensor, sem: Tensor, rgb: Tensor, feat: Tensor, beta: Te
     return outs
 
 
-@render_fwd.register_fake
-def _(density, sem, rgb, feat, beta, mats, geom, cfg_id, has_bda, branches, plan=None):
+@_render_fwd.register_fake
+def _(density, sem, rgb, feat, beta, mats, geom, cfg_id, has_bda, branches, plan):
     cfg = state(cfg_id).cfg
     shapes = _render_out_shapes(cfg, density.shape[0])
     outs = [density.new_empty(s, dtype=torch.float32) for s in shapes[:7]]

@@ -26,10 +26,13 @@ den, sem, feat, rgb = [t.cuda() for t in synth.make_render_inputs(cfg, a.batch, 
 beta = torch.tensor(0.1, device="cuda")
 leaves = [depth, ctx, den, sem, feat, rgb, beta]
 tables = [None]
+rtab = {None: None}
 if a.plans != "off":
     from vampire_b200.plan import PlanCache
-    tab = PlanCache().lift(ops.state(cid), cid, prep, True).table
+    pc = PlanCache()
+    tab = pc.lift(ops.state(cid), cid, prep, True).table
     tables = [tab] if a.plans == "on" else [None, tab]
+    rtab[tab] = pc.render(ops.state(cid), cid, prep, True).table
 torch.manual_seed(0)
 for _ in range(a.steps):
   for tab in tables:
@@ -47,6 +50,6 @@ for _ in range(a.steps):
             if a.only in ("all", "lift"):
                 ops.lift_pool_fwd(depth, ctx, prep, cid, True, False, False, tab)
             if a.only in ("all", "render"):
-                ops.render_fwd(den, sem, rgb, feat, beta, prep, None, cid, True, 3)
+                ops.render_fwd(den, sem, rgb, feat, beta, prep, None, cid, True, 3, rtab[tab])
 torch.cuda.synchronize()
 print("done")

@@ -99,6 +99,49 @@ template <> struct VbVec<__half, 8> {
 };
 template <typename T> struct VbLanes { static constexpr int n = 16 / sizeof(T); };  // elements per 128-bit
 
+// 256-bit global load (sm_100: LDG.E.256): p must be 32-byte aligned.  The gather kernels are bound by L1 data-pipe
+// wavefronts, which are paid per instruction and per distinct 128-byte line -- one 32-byte load costs what a
+// 16-byte load costs, so a 32-byte pixel / record chunk should be ONE instruction.
+struct __align__(32) VbU8 { uint32_t v[8]; };
+__device__ __forceinline__ VbU8 vb_ldg256(const void* p) {
+  VbU8 r;
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+                 "=r"(r.v[7])
+               : "l"(p));
+  return r;
+}
+// widen 32 bytes of T (8 fp32 / 16 bf16 / 16 fp16) to fp32
+template <typename T> struct VbWiden32;
+template <> struct VbWiden32<float> {
+  static constexpr int n = 8;
+  __device__ __forceinline__ static void cvt(const VbU8& r, float* o) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = __uint_as_float(r.v[i]);
+  }
+};
+template <> struct VbWiden32<__nv_bfloat16> {
+  static constexpr int n = 16;
+  __device__ __forceinline__ static void cvt(const VbU8& r, float* o) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      o[2 * i] = __uint_as_float(r.v[i] << 16);
+      o[2 * i + 1] = __uint_as_float(r.v[i] & 0xffff0000u);
+    }
+  }
+};
+template <> struct VbWiden32<__half> {
+  static constexpr int n = 16;
+  __device__ __forceinline__ static void cvt(const VbU8& r, float* o) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&r.v[i]));
+      o[2 * i] = f.x;
+      o[2 * i + 1] = f.y;
+    }
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // strict fp32 zone: everything that feeds floor() or a validity compare is written with the
 // round-to-nearest intrinsics so that nvcc can never contract a*b+c into an FMA.

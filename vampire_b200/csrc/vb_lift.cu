@@ -225,7 +225,8 @@ extern "C" int vb200_lift_pool_fwd(const VbGrid* g, const VbTables* t, const flo
   VB_CHECK_ARG(g->D >= 1);
   VB_CHECK_ARG(out_layout == VB200_NCDHW || out_layout == VB200_NDHWC);
   if (workspace_bytes < vb200_lift_pool_fwd_workspace(g, ctx_dtype)) return VB200_ERR_WORKSPACE;
-  if (((uintptr_t)d_workspace | (uintptr_t)d_out | (uintptr_t)d_ctx | (uintptr_t)d_depth) & 15) return VB200_ERR_ALIGN;
+  if (((uintptr_t)d_out | (uintptr_t)d_ctx | (uintptr_t)d_depth) & 15) return VB200_ERR_ALIGN;
+  if ((uintptr_t)d_workspace & 31) return VB200_ERR_ALIGN;   // the channels-last ctx copy is read with 256-bit loads
   int rc = vb200_device_check();
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;

@@ -64,16 +64,18 @@ __device__ __forceinline__ void lift_pair_gather(const VbGrid& g, const TD* __re
     wgt[k] = wxy[k] * fmaf(wzb, VbType<TD>::ld(d1 + pxl[k]), wza * VbType<TD>::ld(d0 + pxl[k]));
 #pragma unroll
   for (int c = 0; c < C; ++c) f[c] = 0.0f;
+  // a pixel's C channels are C * sizeof(TC) contiguous, 32-byte aligned bytes: 256-bit loads (one per bf16 pixel)
+  constexpr int L = VbWiden32<TC>::n;
+  static_assert(C % L == 0, "a pixel's channels must be whole 256-bit groups");
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    constexpr int L = VbLanes<TC>::n;
     const TC* cp = ccam + pxl[k] * C;
 #pragma unroll
-    for (int q4 = 0; q4 < C / L; ++q4) {
+    for (int q8 = 0; q8 < C / L; ++q8) {
       float cv[L];
-      VbVec<TC, L>::ld(cp + q4 * L, cv);
+      VbWiden32<TC>::cvt(vb_ldg256(cp + q8 * L), cv);
 #pragma unroll
-      for (int e = 0; e < L; ++e) f[q4 * L + e] = fmaf(cv[e], wgt[k], f[q4 * L + e]);
+      for (int e = 0; e < L; ++e) f[q8 * L + e] = fmaf(cv[e], wgt[k], f[q8 * L + e]);
     }
   }
 }

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kMarchThreads) render_plan_build_kernel(VbGrid
 template <typename T, int K>
 __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fwd_planned_kernel(
     VbGrid g, VbTables t, const VbRenderPlan* __restrict__ plans, const T* __restrict__ packed,
-    const int* __restrict__ nonfinite_flag, const float* __restrict__ beta_ptr, float* __restrict__ o_rgb,
+    const T* __restrict__ dquad, size_t dquad_stride, const int* __restrict__ nonfinite_flag, const float* __restrict__ beta_ptr, float* __restrict__ o_rgb,
     float* __restrict__ o_seg, float* __restrict__ o_depth, int b0) {
   constexpr int CP = packed_channels(K);
   if (*nonfinite_flag != 0) return;   // the NaN-safe variant of march_fwd_kernel takes over (recomputes the geometry)
@@ -110,6 +110,9 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fw
   const int S = g.D - 1, HW = g.fH * g.fW;
   const int nvox = g.vZ * g.vY * g.vX;
   const T* vol = packed + (size_t)blockIdx.z * nvox * CP;  // packed holds only this launch's samples
+  const T* dq = dquad + (size_t)blockIdx.z * dquad_stride;  // ... and their density quads
+  const int c_qz = g.vY * g.vX * 4;
+  using Q = typename DQuad<T>::type;
   const size_t ray = (size_t)(n * npatch + patch);
   const uint4* __restrict__ rec = reinterpret_cast<const uint4*>(plans[b].steps) + ray * S * 32 + lane;
   const float* __restrict__ dl = plans[b].delta + ray * S * 32 + lane;
@@ -126,19 +129,36 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fw
 #pragma unroll
   for (int c = 0; c < K + 3; ++c) ch[c] = 0.0f;
 
-  // one step ahead: the record of sample i+1 is loaded and its density gathers issued before sample i is composited
-  uint4 r_n = __ldg(rec);
-  float d_n = __ldg(dl);
-  T raw_n[8];
-  auto gather_density = [&](const uint4& r, T (&raw)[8]) {
-    if (r.x & kPlanValid) {
-      const T* p = vol + (size_t)(r.x & kPlanVoxMask) * CP;
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        raw[q] = __ldg(p + ((q & 2) ? c_sy : 0) + ((q & 4) ? c_sz : 0) + ((q & 1) ? CP : 0));
+  // The plan is streamed from HBM (never re-used), so its latency must be hidden explicitly: an L2 prefetch runs
+  // kPrefetchAhead samples ahead of the march (a warp's records are one contiguous 640-byte run per sample), the
+  // record of sample i+2 is requested into registers, and the record of sample i+1 has arrived so that its density
+  // gathers are issued before sample i is composited.
+  constexpr int kPrefetchAhead = 12;
+  auto prefetch = [&](int i) {
+    if (i < S) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + (size_t)i * 32));
+      if (lane < 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(dl + (size_t)i * 32 + lane * 8 - lane));
     }
   };
-  gather_density(r_n, raw_n);
+#pragma unroll 1
+  for (int i = 0; i < kPrefetchAhead; ++i) prefetch(i);
+  uint4 r_n = __ldg(rec);
+  float d_n = __ldg(dl);
+  uint4 r_n2 = make_uint4(0u, 0u, 0u, 0u);
+  float d_n2 = 0.0f;
+  if (S > 1) {
+    r_n2 = __ldg(rec + 32);
+    d_n2 = __ldg(dl + 32);
+  }
+  Q q0_n = {}, q1_n = {};
+  auto gather_density = [&](const uint4& r, Q& q0, Q& q1) {   // two quads = the 8 corner densities
+    if (r.x & kPlanValid) {
+      const T* p = dq + (size_t)(r.x & kPlanVoxMask) * 4;
+      q0 = __ldg(reinterpret_cast<const Q*>(p));
+      q1 = __ldg(reinterpret_cast<const Q*>(p + c_qz));
+    }
+  };
+  gather_density(r_n, q0_n, q1_n);
 
   for (int i = 0; i < S; ++i) {
     if (g.term_eps > 0.0f) {
@@ -162,14 +182,15 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fw
     }
     const uint4 r = r_n;
     const float delta = d_n;
-    T raw[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) raw[q] = raw_n[q];
-    if (i + 1 < S) {
-      r_n = __ldg(rec + (size_t)(i + 1) * 32);
-      d_n = __ldg(dl + (size_t)(i + 1) * 32);
-      gather_density(r_n, raw_n);
+    const Q q0 = q0_n, q1 = q1_n;
+    prefetch(i + kPrefetchAhead);
+    r_n = r_n2;
+    d_n = d_n2;
+    if (i + 2 < S) {
+      r_n2 = __ldg(rec + (size_t)(i + 2) * 32);
+      d_n2 = __ldg(dl + (size_t)(i + 2) * 32);
     }
+    if (i + 1 < S) gather_density(r_n, q0_n, q1_n);
     const bool live = (r.x & kPlanValid) != 0u;     // build wrote valid = 0 for rays outside the image
     float sigma = sigma_masked;
     float cw[8];
@@ -177,10 +198,13 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fw
       const float fx = __uint_as_float(r.y), fy = __uint_as_float(r.z), fz = __uint_as_float(r.w);
       const float wx[2] = {1.0f - fx, fx}, wy[2] = {1.0f - fy, fy}, wz[2] = {1.0f - fz, fz};
       float s0 = 0.0f;
+      float dn[8];
+      dquad_to_f32<T>(q0, dn);
+      dquad_to_f32<T>(q1, dn + 4);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         cw[q] = wx[q & 1] * wy[(q >> 1) & 1] * wz[q >> 2];
-        s0 = fmaf(cw[q], widen_elem(raw[q]), s0);
+        s0 = fmaf(cw[q], dn[q], s0);
       }
       sigma = laplace_density_rcp(s0, g.sdf_bias, inv_beta);                   // BV2:423
     }

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kMarchThreads) render_plan_build_kernel(VbGrid
 template <typename T, int K>
 __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fwd_planned_kernel(
     VbGrid g, VbTables t, const VbRenderPlan* __restrict__ plans, const T* __restrict__ packed,
-    const T* __restrict__ dquad, size_t dquad_stride, const int* __restrict__ nonfinite_flag, const float* __restrict__ beta_ptr, float* __restrict__ o_rgb,
+    const int* __restrict__ nonfinite_flag, const float* __restrict__ beta_ptr, float* __restrict__ o_rgb,
     float* __restrict__ o_seg, float* __restrict__ o_depth, int b0) {
   constexpr int CP = packed_channels(K);
   if (*nonfinite_flag != 0) return;   // the NaN-safe variant of march_fwd_kernel takes over (recomputes the geometry)
@@ -110,9 +110,6 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fw
   const int S = g.D - 1, HW = g.fH * g.fW;
   const int nvox = g.vZ * g.vY * g.vX;
   const T* vol = packed + (size_t)blockIdx.z * nvox * CP;  // packed holds only this launch's samples
-  const T* dq = dquad + (size_t)blockIdx.z * dquad_stride;  // ... and their density quads
-  const int c_qz = g.vY * g.vX * 4;
-  using Q = typename DQuad<T>::type;
   const size_t ray = (size_t)(n * npatch + patch);
   const uint4* __restrict__ rec = reinterpret_cast<const uint4*>(plans[b].steps) + ray * S * 32 + lane;
   const float* __restrict__ dl = plans[b].delta + ray * S * 32 + lane;
@@ -150,15 +147,16 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fw
     r_n2 = __ldg(rec + 32);
     d_n2 = __ldg(dl + 32);
   }
-  Q q0_n = {}, q1_n = {};
-  auto gather_density = [&](const uint4& r, Q& q0, Q& q1) {   // two quads = the 8 corner densities
+  T raw_n[8];
+  auto gather_density = [&](const uint4& r, T (&raw)[8]) {
     if (r.x & kPlanValid) {
-      const T* p = dq + (size_t)(r.x & kPlanVoxMask) * 4;
-      q0 = __ldg(reinterpret_cast<const Q*>(p));
-      q1 = __ldg(reinterpret_cast<const Q*>(p + c_qz));
+      const T* p = vol + (size_t)(r.x & kPlanVoxMask) * CP;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        raw[q] = __ldg(p + ((q & 2) ? c_sy : 0) + ((q & 4) ? c_sz : 0) + ((q & 1) ? CP : 0));
     }
   };
-  gather_density(r_n, q0_n, q1_n);
+  gather_density(r_n, raw_n);
 
   for (int i = 0; i < S; ++i) {
     if (g.term_eps > 0.0f) {
@@ -182,7 +180,9 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fw
     }
     const uint4 r = r_n;
     const float delta = d_n;
-    const Q q0 = q0_n, q1 = q1_n;
+    T raw[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) raw[q] = raw_n[q];
     prefetch(i + kPrefetchAhead);
     r_n = r_n2;
     d_n = d_n2;
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fw
       r_n2 = __ldg(rec + (size_t)(i + 2) * 32);
       d_n2 = __ldg(dl + (size_t)(i + 2) * 32);
     }
-    if (i + 1 < S) gather_density(r_n, q0_n, q1_n);
+    if (i + 1 < S) gather_density(r_n, raw_n);
     const bool live = (r.x & kPlanValid) != 0u;     // build wrote valid = 0 for rays outside the image
     float sigma = sigma_masked;
     float cw[8];
@@ -198,13 +198,10 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fw
       const float fx = __uint_as_float(r.y), fy = __uint_as_float(r.z), fz = __uint_as_float(r.w);
       const float wx[2] = {1.0f - fx, fx}, wy[2] = {1.0f - fy, fy}, wz[2] = {1.0f - fz, fz};
       float s0 = 0.0f;
-      float dn[8];
-      dquad_to_f32<T>(q0, dn);
-      dquad_to_f32<T>(q1, dn + 4);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         cw[q] = wx[q & 1] * wy[(q >> 1) & 1] * wz[q >> 2];
-        s0 = fmaf(cw[q], dn[q], s0);
+        s0 = fmaf(cw[q], widen_elem(raw[q]), s0);
       }
       sigma = laplace_density_rcp(s0, g.sdf_bias, inv_beta);                   // BV2:423
     }

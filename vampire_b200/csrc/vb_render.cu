@@ -74,7 +74,6 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_MINB) march_fwd_kernel
                                                                   const float* __restrict__ d_mats,
                                                                   const float* __restrict__ d_geom,
                                                                   const T* __restrict__ packed,
-                                                                  const T* __restrict__ dquad, size_t dquad_stride,
                                                                   const int* __restrict__ nonfinite_flag,
                                                                   const float* __restrict__ beta_ptr,
                                                                   float* __restrict__ o_rgb, float* __restrict__ o_seg,
@@ -103,7 +102,6 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_MINB) march_fwd_kernel
   const int nvox = g.vZ * g.vY * g.vX;
   const float beta = fabsf(__ldg(beta_ptr)) + g.beta_min;
   const T* vol = packed + (size_t)blockIdx.z * nvox * CP;  // packed holds only this launch's samples
-  const T* dq = dquad + (size_t)blockIdx.z * dquad_stride;  // density quads of the same samples (fast variant only)
   const float u = __ldg(t.us + wc), vv = __ldg(t.vs + hc);
   const float* gsrc = FROM_MATS ? nullptr : d_geom + ((size_t)(b * g.N + n) * g.D * HW + (size_t)hc * g.fW + wc) * 3;
 
@@ -142,8 +140,7 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_MINB) march_fwd_kernel
     int v0;                // voxel index of the base corner
     int dxo, sy, sz;       // NANSAFE: per-sample corner strides (clamped); otherwise launch constants
     float fx, fy, fz;      // far-corner weights (near = 1 - far)
-    T raw[8];              // NANSAFE: density at the eight corners, not yet widened (widening would wait for the load)
-    typename DQuad<T>::type q0, q1;   // fast variant: the density quads of rows z0 / z0+1 (two loads instead of eight)
+    T raw[8];              // density at the eight corners, not yet widened (widening would wait for the load)
   };
   const int c_sy = g.vX, c_sz = g.vY * g.vX;
   auto prepare = [&](const float (&pp)[3], Smp& sm) {
@@ -168,16 +165,10 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_MINB) march_fwd_kernel
       }
       sm.fx = rc.ix - (float)x0; sm.fy = rc.iy - (float)y0; sm.fz = rc.iz - (float)z0;
       sm.v0 = (z0 * g.vY + y0) * g.vX + x0;
-      if (!NANSAFE) {
-        using Q = typename DQuad<T>::type;
-        sm.q0 = __ldg(reinterpret_cast<const Q*>(dq + (size_t)sm.v0 * 4));
-        sm.q1 = __ldg(reinterpret_cast<const Q*>(dq + (size_t)(sm.v0 + c_sz) * 4));
-      } else {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int cx = q & 1, cy = (q >> 1) & 1, cz = q >> 2;
-          sm.raw[q] = __ldg(vol + (size_t)(sm.v0 + (cy ? sy : 0) + (cz ? sz : 0)) * CP + (cx ? dxo * CP : 0));
-        }
+      for (int q = 0; q < 8; ++q) {
+        const int cx = q & 1, cy = (q >> 1) & 1, cz = q >> 2;
+        sm.raw[q] = __ldg(vol + (size_t)(sm.v0 + (cy ? sy : 0) + (cz ? sz : 0)) * CP + (cx ? dxo * CP : 0));
       }
     }
   };
@@ -244,19 +235,11 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_MINB) march_fwd_kernel
       const float wx[2] = {1.0f - cur.fx, cur.fx}, wy[2] = {1.0f - cur.fy, cur.fy}, wz[2] = {1.0f - cur.fz, cur.fz};
       // phase 1: density channel only -> sigma, alpha
       float s0 = 0.0f;
-      float dn[8];
-      if (!NANSAFE) {
-        dquad_to_f32<T>(cur.q0, dn);
-        dquad_to_f32<T>(cur.q1, dn + 4);
-      } else {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) dn[q] = widen_elem(cur.raw[q]);
-      }
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int cx = q & 1, cy = (q >> 1) & 1, cz = q >> 2;
         cw[q] = wx[cx] * wy[cy] * wz[cz];
-        s0 = fmaf(cw[q], dn[q], s0);
+        s0 = fmaf(cw[q], widen_elem(cur.raw[q]), s0);
       }
       if (NANSAFE) s0 = nan_to_num(s0, 0.0f);                                  // BV2:421
       sigma = laplace_density_rcp(s0, g.sdf_bias, inv_beta);                   // BV2:423
@@ -1077,10 +1060,6 @@ size_t packed_bytes_per_sample(const VbGrid* g, int dtype) {
   const size_t n = (size_t)g->vZ * g->vY * g->vX * packed_channels(g->K) * vb_elem_size(dtype);
   return (n + 255) & ~(size_t)255;
 }
-// packed records + density quads of one sample
-size_t cam_bytes_per_sample(const VbGrid* g, int dtype) {
-  return packed_bytes_per_sample(g, dtype) + dquad_bytes_per_sample((size_t)g->vZ * g->vY * g->vX, vb_elem_size(dtype));
-}
 
 template <typename T>
 int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, const VbRenderIn* in,
@@ -1089,15 +1068,11 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
   if (g->K != K || g->C != C || g->oZ > kMaxLevels) return VB200_ERR_ARG;
   const size_t nvox = (size_t)g->vZ * g->vY * g->vX;
   const size_t per = packed_bytes_per_sample(g, VbType<T>::code);
-  const size_t dq_per = dquad_bytes_per_sample(nvox, sizeof(T));
   const size_t bev_bytes = bev_weight_bytes(g);
-  if (ws_bytes < bev_bytes + per + dq_per) return VB200_ERR_WORKSPACE;
-  // workspace = [packed camera volumes of `group` samples][their density quads][BEV compositing weights of all samples]
-  const int group = (int)(((ws_bytes - bev_bytes) / (per + dq_per)) < (size_t)g->B ? ((ws_bytes - bev_bytes) / (per + dq_per))
-                                                                                   : (size_t)g->B);
-  const size_t cam_bytes = (size_t)group * (per + dq_per);
-  T* const dq_base = reinterpret_cast<T*>((char*)ws + (size_t)group * per);
-  const size_t dq_stride = dq_per / sizeof(T);
+  if (ws_bytes < bev_bytes + per) return VB200_ERR_WORKSPACE;
+  // workspace = [packed camera volumes of `group` samples][BEV compositing weights of all samples]
+  const int group = (int)(((ws_bytes - bev_bytes) / per) < (size_t)g->B ? ((ws_bytes - bev_bytes) / per) : (size_t)g->B);
+  const size_t cam_bytes = (size_t)group * per;
   const T* den = reinterpret_cast<const T*>(in->density);
   const T* sem = reinterpret_cast<const T*>(in->sem);
   const T* rgb = reinterpret_cast<const T*>(in->rgb);
@@ -1150,33 +1125,28 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
   const bool no_fork = no_fork_env || g_render_fork_disabled.load(std::memory_order_relaxed) != 0;
   const bool may_fork = !no_fork && cap == cudaStreamCaptureStatusNone;
 
-  // `slot` = index of the round's first sample inside the workspace's packed / quad arrays
-  auto pack_round = [&](int b0, int nb, int slot, int* flag, cudaStream_t ps) -> int {
+  auto pack_round = [&](int b0, int nb, T* region, int* flag, cudaStream_t ps) -> int {
     VbTraceScope tr(VB_K_PACK, ps);
     if (cudaMemsetAsync(flag, flag_init, sizeof(int), ps) != cudaSuccess) return VB200_ERR_CUDA;
-    T* region = reinterpret_cast<T*>((char*)ws + (size_t)slot * per);
     pack_cam_volume_kernel<T, K><<<dim3(vb_ceil_div(nvox, kPackThreads * PackVox<T>::n), nb), kPackThreads, 0, ps>>>(
         den + (size_t)b0 * nvox, sem + (size_t)b0 * K * nvox, rgb + (size_t)b0 * 3 * nvox, region, (int)nvox,
-        per / sizeof(T), flag, dq_base + (size_t)slot * dq_stride, dq_stride, g->vX);
+        per / sizeof(T), flag);
     VB_LAUNCH_CHECK();
     return VB200_OK;
   };
-  auto march_round = [&](int b0, int nb, int slot, const int* flag) -> int {
-    const T* region = reinterpret_cast<const T*>((char*)ws + (size_t)slot * per);
-    const T* dq = dq_base + (size_t)slot * dq_stride;
+  auto march_round = [&](int b0, int nb, const T* region, const int* flag) -> int {
     dim3 grid(vb_ceil_div(patches, kMarchThreads / 32), g->N, nb);
     VbTraceScope tr(VB_K_MARCH_FWD, st, 2);
 #define VB_MARCH(FM, FD, NS)                                                                                        \
-  march_fwd_kernel<T, K, FM, FD, NS><<<grid, kMarchThreads, 0, st>>>(*g, *t, dv, d_mats, in->geom, region, dq,      \
-                                                                     dq_stride, flag, in->beta, out->rgb, out->seg,  \
-                                                                     out->depth, b0)
+  march_fwd_kernel<T, K, FM, FD, NS><<<grid, kMarchThreads, 0, st>>>(*g, *t, dv, d_mats, in->geom, region, flag,    \
+                                                                     in->beta, out->rgb, out->seg, out->depth, b0)
     if (in->geom) {
       VB_MARCH(false, false, false);
       VB_MARCH(false, false, true);
     } else if (in->plans) {
       // cached geometry; a non-finite packed volume (flag raised by the pack) takes the recomputing NaN-safe variant
-      march_fwd_planned_kernel<T, K><<<grid, kMarchThreads, 0, st>>>(*g, *t, in->plans, region, dq, dq_stride, flag,
-                                                                     in->beta, out->rgb, out->seg, out->depth, b0);
+      march_fwd_planned_kernel<T, K><<<grid, kMarchThreads, 0, st>>>(*g, *t, in->plans, region, flag, in->beta,
+                                                                     out->rgb, out->seg, out->depth, b0);
       if (vb_render_div_ok(dv)) VB_MARCH(true, true, true);
       else VB_MARCH(true, false, true);
     } else if (vb_render_div_ok(dv)) {
@@ -1221,14 +1191,14 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
   }
   if (nsplit > 1) {
     const int sub = vb_ceil_div(g->B, nsplit);
-    int rc = pack_round(0, sub < g->B ? sub : g->B, 0, nf_flags, st);
+    int rc = pack_round(0, sub < g->B ? sub : g->B, reinterpret_cast<T*>(ws), nf_flags, st);
     if (rc) return rc;
     if (cudaEventRecord(side->first_pack, st) != cudaSuccess ||
         cudaStreamWaitEvent(side->stream_hi, side->first_pack, 0) != cudaSuccess)
       return VB200_ERR_CUDA;
     for (int k = 1; k * sub < g->B; ++k) {
       const int b0 = k * sub, nb = (g->B - b0) < sub ? (g->B - b0) : sub;
-      rc = pack_round(b0, nb, b0, nf_flags + k, side->stream_hi);
+      rc = pack_round(b0, nb, reinterpret_cast<T*>((char*)ws + (size_t)b0 * per), nf_flags + k, side->stream_hi);
       if (rc) return rc;
       if (cudaEventRecord(side->packed[k], side->stream_hi) != cudaSuccess) return VB200_ERR_CUDA;
     }
@@ -1239,19 +1209,19 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
     for (int k = 0; k * sub < g->B; ++k) {
       const int b0 = k * sub, nb = (g->B - b0) < sub ? (g->B - b0) : sub;
       if (k > 0 && cudaStreamWaitEvent(st, side->packed[k], 0) != cudaSuccess) return VB200_ERR_CUDA;
-      rc = march_round(b0, nb, b0, nf_flags + k);
+      rc = march_round(b0, nb, reinterpret_cast<const T*>((char*)ws + (size_t)b0 * per), nf_flags + k);
       if (rc) return rc;
     }
   } else {
     for (int b0 = 0; b0 < g->B; b0 += group) {
       const int nb = (g->B - b0) < group ? (g->B - b0) : group;
-      int rc = pack_round(b0, nb, 0, nf_flags, st);
+      int rc = pack_round(b0, nb, reinterpret_cast<T*>(ws), nf_flags, st);
       if (rc) return rc;
       if (b0 == 0 && (branches & VB200_BRANCH_BEV)) {
         rc = fork_bev();
         if (rc) return rc;
       }
-      rc = march_round(b0, nb, 0, nf_flags);
+      rc = march_round(b0, nb, reinterpret_cast<const T*>(ws), nf_flags);
       if (rc) return rc;
     }
   }
@@ -1265,7 +1235,7 @@ extern "C" size_t vb200_render_fwd_workspace(const VbGrid* g, int dtype) {
   if (!g) return 0;
   // minimum: BEV weights + one packed sample per pack/march round; every further
   // vb200_render_packed_bytes() lets one more sample share a round
-  return bev_weight_bytes(g) + cam_bytes_per_sample(g, dtype);
+  return bev_weight_bytes(g) + packed_bytes_per_sample(g, dtype);
 }
 
 extern "C" size_t vb200_render_plan_rays(const VbGrid* g) {
@@ -1302,7 +1272,7 @@ extern "C" int vb200_render_set_fork(int enable) {
 }
 
 extern "C" size_t vb200_render_packed_bytes(const VbGrid* g, int dtype) {
-  return g ? cam_bytes_per_sample(g, dtype) : 0;
+  return g ? packed_bytes_per_sample(g, dtype) : 0;
 }
 
 extern "C" int vb200_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, const VbRenderIn* in,

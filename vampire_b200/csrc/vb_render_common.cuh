@@ -37,41 +37,12 @@ __device__ __forceinline__ float widen_elem(__half v) { return __half2float(v); 
 #ifndef VB_PACK_MINB
 #define VB_PACK_MINB 5   // 51 registers: measured 0.150 ms = 98 % of the copy peak (unbounded: 128 regs, 0.180 ms)
 #endif
-// Density quads (optional second output, `dquad`): for every voxel v the four density values of the xy-cell it is
-// the base corner of -- (v, v+1, v+vX, v+vX+1) -- as 4 contiguous T.  The march needs the 8 corner densities of
-// every sample before anything else; gathered from the 48/96-byte records that is 8 scalar loads in 8 different
-// 128-byte lines per ray, and the march is bound by exactly these L1 data-pipe wavefronts.  From the quads it is TWO
-// loads (z0 and z0+1) out of an array dense enough that neighbouring rays share lines.  Costs the pack 8 % more
-// written bytes.  Quads whose cell leaves the grid are never read (the march shifts its base corner inwards).
-template <typename T> struct DQuad;
-template <> struct DQuad<float> { using type = float4; };
-template <> struct DQuad<__nv_bfloat16> { using type = uint2; };
-template <> struct DQuad<__half> { using type = uint2; };
-__device__ __forceinline__ void dquad_widen(const float4& q, float* o) { o[0] = q.x; o[1] = q.y; o[2] = q.z; o[3] = q.w; }
-template <typename T> __device__ __forceinline__ void dquad_widen16(const uint2& q, float* o);
-template <> __device__ __forceinline__ void dquad_widen16<__nv_bfloat16>(const uint2& q, float* o) {
-  o[0] = __uint_as_float(q.x << 16); o[1] = __uint_as_float(q.x & 0xffff0000u);
-  o[2] = __uint_as_float(q.y << 16); o[3] = __uint_as_float(q.y & 0xffff0000u);
-}
-template <> __device__ __forceinline__ void dquad_widen16<__half>(const uint2& q, float* o) {
-  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
-  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
-  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
-}
-template <typename T> __device__ __forceinline__ void dquad_to_f32(const typename DQuad<T>::type& q, float* o) {
-  if constexpr (sizeof(T) == 4) dquad_widen(q, o);
-  else dquad_widen16<T>(q, o);
-}
-inline size_t dquad_bytes_per_sample(size_t nvox, size_t esize) { return (nvox * 4 * esize + 255) & ~(size_t)255; }
-
 template <typename T, int K>
 __global__ void __launch_bounds__(kPackThreads, VB_PACK_MINB) pack_cam_volume_kernel(const T* __restrict__ den,
                                                                        const T* __restrict__ sem,
                                                                        const T* __restrict__ rgb, T* __restrict__ packed,
                                                                        int nvox, size_t packed_stride,
-                                                                       int* __restrict__ nonfinite_flag,
-                                                                       T* __restrict__ dquad = nullptr,
-                                                                       size_t dquad_stride = 0, int vX = 0) {
+                                                                       int* __restrict__ nonfinite_flag) {
   constexpr int NCH = K + 4, CP = packed_channels(K), V = PackVox<T>::n;
   __shared__ uint4 s_rec[kPackThreads * 6];
   const int i_s = blockIdx.y;
@@ -80,18 +51,6 @@ __global__ void __launch_bounds__(kPackThreads, VB_PACK_MINB) pack_cam_volume_ke
   rgb += (size_t)i_s * 3 * nvox;
   packed += (size_t)i_s * packed_stride;
   const int v = (blockIdx.x * kPackThreads + threadIdx.x) * V;
-  if (dquad) {
-    T* dq = dquad + (size_t)i_s * dquad_stride;
-    const int last = nvox - 1;
-    for (int vv = v; vv < min(v + V, nvox); ++vv) {
-      __align__(16) T q[4];
-      q[0] = __ldg(den + vv);
-      q[1] = __ldg(den + min(vv + 1, last));
-      q[2] = __ldg(den + min(vv + vX, last));
-      q[3] = __ldg(den + min(vv + vX + 1, last));
-      *reinterpret_cast<typename DQuad<T>::type*>(dq + (size_t)vv * 4) = *reinterpret_cast<const typename DQuad<T>::type*>(q);
-    }
-  }
   // the vector path needs the whole warp in range (cooperative stores) and, for 16-bit features, an even
   // plane size (32-bit words of two voxels must be aligned); anything else takes the scalar path
   const bool vec_ok = (v + V <= nvox) && (V == 1 || !(nvox & 1));

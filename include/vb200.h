@@ -18,10 +18,14 @@
  * Conventions
  *   - plain C: pointers, sizes, ints and floats only; no C++/torch types; no exceptions.
  *   - every pointer named d_* is DEVICE memory owned by the caller (the PyTorch caching
- *     allocator in the Python host); the library allocates no device memory and keeps no mutable
- *     state besides the instrumentation counters/events of vb200_trace_*.
+ *     allocator in the Python host); the library allocates no device memory.  Its only state is the
+ *     instrumentation counters/events of vb200_trace_* and, per device, one pair of internal side streams with their
+ *     events (vb200_render_fwd forks the BEV branch onto it; a mutex serialises the fork..join bookkeeping of
+ *     concurrent callers, and the caller's stream is re-joined on every exit path).
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant and
  *     thread-safe.
+ *   - compiled for C = 16 context channels, K = 18 classes and at most 8 cameras (every reference experiment);
+ *     other channel counts return VB200_ERR_ARG.
  *   - return 0 on success, a negative VB200_ERR_* otherwise; vb200_strerror() names it.
  *   - there is no CPU fallback: on a device that is not sm_100 the compute calls return
  *     VB200_ERR_ARCH.
@@ -249,7 +253,13 @@ typedef struct VbRenderIn {
                            render; NULL = recompute from d_mats (+ nan_to_num), no 70 MB/sample read */
   const VbRenderPlan* plans; /* optional DEVICE array of B cached plans (forward only; ignored when geom is given):
                            the camera march reads its geometry from them instead of recomputing it */
+  int32_t flags;        /* VB200_RENDER_* bits (forward only) */
 } VbRenderIn;
+
+/* voxel_output leaves vb200_render_fwd already multiplied by tanh(voxel_density): the BEV epilogue
+ * `voxel_output * bev_density.tanh()` of BV2:627-630 folded into the kernel that resamples the features (both
+ * operands are in registers there).  Inference only: vb200_render_bwd differentiates the unfused outputs. */
+#define VB200_RENDER_TANH_EPILOGUE 1
 
 typedef struct VbRenderOut {
   float* rgb;           /* (B, N, 3, fH, fW)                                  */
@@ -280,7 +290,7 @@ int vb200_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, co
 /* When both branches are requested, vb200_render_fwd forks the BEV kernels onto an internal per-device
  * side stream and joins before returning (the two branches are independent and both issue-bound).
  * enable = 0 serialises them on the caller's stream (used by bench.py to time kernels in isolation).
- * One render call per device should be in flight at a time while forking is enabled. */
+ * Concurrent render calls on one device (several host threads / streams) are safe; they share the side stream. */
 int vb200_render_set_fork(int enable);
 
 typedef struct VbRenderGrad {

@@ -136,12 +136,21 @@ def run_case(name: str, cfg: PathConfig, batch: int, mode: str, field: str, stri
           f"valid={out['lift_valid_count']} mask={out['render_mask_count']}")
 
 
+CASES = {
+    "mini_val": (MINI, 2, "val", "random", 1, True, False),
+    "mini_stress": (MINI, 2, "stress", "surface", 1, True, False),
+    "r50_val_digest": (R50_256x704, 1, "val", "surface", 4099, True, False),
+    "r50_stress_digest": (R50_256x704, 1, "stress", "random", 4099, True, False),   # gradients too (round 2)
+}
+
+
 def main():
-    torch.manual_seed(0)
-    run_case("mini_val", MINI, 2, "val", "random", 1, True, False)
-    run_case("mini_stress", MINI, 2, "stress", "surface", 1, True, False)
-    run_case("r50_val_digest", R50_256x704, 1, "val", "surface", 4099, True, False)
-    run_case("r50_stress_digest", R50_256x704, 1, "stress", "random", 4099, False, False)
+    only = sys.argv[1:]            # python -m oracle.gen_golden [case ...]: regenerate just these
+    for name, a in CASES.items():
+        if only and name not in only:
+            continue
+        torch.manual_seed(0)
+        run_case(name, *a)
 
 
 if __name__ == "__main__":

@@ -20,3 +20,16 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_terminal_summary(terminalreporter):
+    """Achieved max errors (relative to max|reference|) per compared quantity, next to the tolerance asserted."""
+    try:
+        from helpers import ACHIEVED
+    except Exception:
+        return
+    if not ACHIEVED:
+        return
+    terminalreporter.section("achieved max |err| / max|ref|  (tolerance asserted)")
+    for what, (a, rel) in sorted(ACHIEVED.items()):
+        terminalreporter.write_line(f"  {what:48s} {a:9.2e}   ({rel:.0e})")

@@ -74,6 +74,9 @@ def golden_value(gold, key, full_array):
     return gold[key + "_strided"], np.asarray(full_array).reshape(-1)[::stride]
 
 
+ACHIEVED = {}      # what -> worst (max abs err / scale) seen in this session; printed at the end (conftest.py)
+
+
 def assert_close_scaled(got, exp, rel, what="", scale=None):
     """|got - exp| <= rel * max|exp|  (the inf-norm-relative bar of SURVEY B.3) plus elementwise rtol.
     `scale` overrides max|exp| when `exp` is only a strided sample of the full tensor."""
@@ -82,6 +85,10 @@ def assert_close_scaled(got, exp, rel, what="", scale=None):
     assert got.shape == exp.shape, f"{what}: shape {got.shape} vs {exp.shape}"
     scale = max(np.abs(exp).max(), 1e-30) if scale is None else float(scale)
     err = np.abs(got - exp)
+    if err.size:
+        a = float(np.nanmax(err)) / scale
+        prev = ACHIEVED.get(what)
+        ACHIEVED[what] = (max(a, prev[0]) if prev else a, rel)
     bad = err > rel * scale + rel * np.abs(exp)
     assert not bad.any(), (f"{what}: {int(bad.sum())} / {bad.size} elements off; max abs err {err.max():.3e} "
                            f"(scale {scale:.3e}, allowed {rel * scale:.3e})")

@@ -129,3 +129,31 @@ def test_depth_softmax_and_2d_lift_reject_bad_input():
         ops.depth_softmax_fwd(torch.zeros(4, 4, device="cuda"), True)
     with pytest.raises(ValueError, match="do not match"):
         mod.lift_pool_2d(torch.zeros(1, case.cfg.num_cams, case.cfg.C, 3, 3, device="cuda"), case.mats)
+
+
+@pytest.mark.parametrize("seed", [11, 12])
+def test_module_api_with_host_matrices_vs_same_host_oracle(seed):
+    """The e2e path: ``LiftRenderB200.lift_pool / .render`` handed a HOST mats_dict prepare the 4x4 matrices with this
+    host's LAPACK -- exactly what the reference running on this host does -- so module and oracle must agree here
+    whatever the host rounds the inverses to (the fixtures' prepared matrices are not involved)."""
+    from oracle import torch_path as tp
+    from vampire_b200 import synth
+    from vampire_b200.config import MINI
+    from vampire_b200.view_transform import LiftRenderB200
+    cfg, conf = MINI, MINI.backbone_kwargs()
+    mats = synth.make_mats(cfg, 2, "stress", seed=seed)
+    depth, ctx = synth.make_lift_inputs(cfg, 2, seed=seed)
+    den, sem, feat, rgb = synth.make_render_inputs(cfg, 2, seed=seed, field="surface")
+    buf = tp.build_buffers(conf)
+    with torch.no_grad():
+        ref_vox = tp.lift_pool(conf, buf, depth, ctx, mats)
+        ref = tp.render_from_mats(conf, buf, mats, den, sem, feat, rgb, torch.tensor(0.1))
+    for plans in ("off", "always"):
+        mod = LiftRenderB200(plans=plans, **conf).cuda().eval()
+        with torch.no_grad():
+            vox = mod.lift_pool(depth.cuda(), ctx.cuda(), mats)
+            outs = mod.render(mats, den.cuda(), sem.cuda(), feat.cuda(), rgb.cuda())
+        assert_close_scaled(vox.cpu().numpy(), ref_vox.numpy(), 1e-5, "module lift_pool (host mats_dict)")
+        for n, o, r in zip(["rgb", "seg", "depth", "bev_rgb", "bev_seg", "bev_height", "voxel_density", "voxel_output"],
+                           outs, ref):
+            assert_close_scaled(o.cpu().numpy(), r.numpy(), 1e-5, "module render " + n)

@@ -22,7 +22,7 @@ def _strided(gold, key, arr):
     return gold[key + "_strided"], np.asarray(arr).reshape(-1)[::gs]
 
 
-@pytest.mark.parametrize("name", ["mini_val", "mini_stress", "r50_val_digest"])
+@pytest.mark.parametrize("name", ["mini_val", "mini_stress", "r50_val_digest", "r50_stress_digest"])
 @pytest.mark.parametrize("channels_last", [False, True])
 def test_lift_backward_vs_reference(name, channels_last):
     case = Case(name)
@@ -112,7 +112,7 @@ def _render_grads(case, ops, cid, branches=3, from_tensor=False, dtype=torch.flo
     return g  # g_den, g_sem, g_rgb, g_feat, g_beta
 
 
-@pytest.mark.parametrize("name", ["mini_val", "mini_stress", "r50_val_digest"])
+@pytest.mark.parametrize("name", ["mini_val", "mini_stress", "r50_val_digest", "r50_stress_digest"])
 @pytest.mark.parametrize("from_tensor", [False, True])
 def test_render_backward_vs_reference(name, from_tensor):
     case = Case(name)

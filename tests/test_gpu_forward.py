@@ -336,3 +336,84 @@ def test_render_nonfinite_volume_takes_the_nan_safe_march():
         assert np.allclose(got[big].astype(np.float64) / fmax, exp[big].astype(np.float64) / fmax, rtol=1e-4, atol=2e-6), n
         small = ok & ~big
         assert_close_scaled(got[small], exp[small], FP32_REL, n, scale=max(np.abs(exp[small]).max(), 1e-30))
+
+
+def _rig(cfg, seed):
+    """Random stress rig + variations that push pairs against every validity boundary: doubled ida scale (zoom: the
+    x / y image bounds cut through the volume), a camera dropped into the voxel lattice (depths around d_lo),
+    mirrored images."""
+    from vampire_b200 import synth
+    m = synth.make_mats(cfg, 2, "stress", seed=seed)
+    if seed % 3 == 1:
+        m["ida_mats"][..., :2, :] *= 2.0
+    if seed % 3 == 2:
+        m["sensor2ego_mats"][:, :, 0, :3, 3] = torch.tensor([0.2, -0.6, -1.0])   # on a voxel centre
+        m["ida_mats"][:, :, 1, 0, :] *= -1.0
+        m["ida_mats"][:, :, 1, 0, 3] += cfg.final_dim[1] - 1.0
+    return m
+
+
+@pytest.mark.parametrize("block", range(5))
+def test_fused_cull_never_drops_a_valid_pair_50_rigs(block):
+    """The fused lift's two-level conservative cull runs on an FMA-composed matrix with a guard band; a dropped valid
+    pair would be a silent parity bug.  50 random rigs (MINI): the camera count the fused kernel saved per voxel
+    equals the number of cameras the strict index kernel calls valid -- and the cached plan agrees."""
+    from vampire_b200.config import MINI
+    from vampire_b200.matrices import prepare_matrices
+    from vampire_b200.plan import build_lift_plans
+    cfg = MINI
+    ops, cid = _ops(cfg)
+    ones_d = torch.ones(2, cfg.num_cams, cfg.D, cfg.fH, cfg.fW, device="cuda")
+    ones_c = torch.ones(2, cfg.num_cams, cfg.C, cfg.fH, cfg.fW, device="cuda")
+    total = 0
+    for seed in range(300 + 10 * block, 310 + 10 * block):
+        m = _rig(cfg, seed)
+        prep = prepare_matrices(m["sensor2ego_mats"][:, 0], m["intrin_mats"][:, 0], m["ida_mats"][:, 0],
+                                m["bda_mat"]).cuda()
+        _, cnt = ops.lift_pool_fwd(ones_d, ones_c, prep, cid, True, False, True)
+        valid, _, _ = ops.lift_indices(prep, cid, True)
+        nvalid = valid.sum(1, dtype=torch.int64).reshape(2, -1)
+        assert torch.equal(cnt & 0xF, nvalid), f"seed {seed}: the cull dropped (or invented) a pair"
+        for b, p in enumerate(build_lift_plans(ops.state(cid), prep, True)):
+            assert p.num_pairs == int(nvalid[b].sum())
+        total += int(nvalid.sum())
+    assert total > 0
+
+
+def test_fused_cull_never_drops_a_valid_pair_full_size():
+    """The same property at the full R50 geometry, val-mode and stress rig."""
+    from vampire_b200 import synth
+    from vampire_b200.config import R50_256x704 as cfg
+    from vampire_b200.matrices import prepare_matrices
+    ops, cid = _ops(cfg)
+    ones_d = torch.ones(1, cfg.num_cams, cfg.D, cfg.fH, cfg.fW, device="cuda")
+    ones_c = torch.ones(1, cfg.num_cams, cfg.C, cfg.fH, cfg.fW, device="cuda")
+    for mode, seed in (("val", 1234), ("stress", 77)):
+        m = synth.make_mats(cfg, 1, mode, seed=seed)
+        prep = prepare_matrices(m["sensor2ego_mats"][:, 0], m["intrin_mats"][:, 0], m["ida_mats"][:, 0],
+                                m["bda_mat"]).cuda()
+        _, cnt = ops.lift_pool_fwd(ones_d, ones_c, prep, cid, True, False, True)
+        valid, _, _ = ops.lift_indices(prep, cid, True)
+        assert torch.equal(cnt & 0xF, valid.sum(1, dtype=torch.int64).reshape(1, -1)), mode
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", ["mini_stress", "r50_val_digest"])
+def test_fused_tanh_epilogue(name, dtype):
+    """voxel_output * bev_density.tanh() (BV2:627-630) folded into the BEV kernel == the product formed outside."""
+    case = Case(name)
+    ops, cid = _ops(case.cfg)
+    vols = [t.to(dtype).cuda() for t in (case.den, case.sem, case.rgb, case.feat)]
+    beta = torch.tensor(0.1, device="cuda")
+    with torch.no_grad():
+        raw = ops.render_fwd(*vols, beta, case.prep.cuda(), None, cid, True, 3)
+        fused = ops.render_fwd(*vols, beta, case.prep.cuda(), None, cid, True, 3, None, True)
+    for a, b in zip(raw[:7], fused[:7]):
+        assert torch.equal(a, b)
+    want = raw[7].float() * raw[6].tanh()
+    assert fused[7].dtype == dtype
+    assert_close_scaled(fused[7].float().cpu().numpy(), want.cpu().numpy(), 1e-6 if dtype == torch.float32 else 1e-2,
+                        "fused tanh epilogue")
+    v = vols[0].clone().requires_grad_(True)
+    with pytest.raises(RuntimeError, match="forward-only"):
+        ops.render_fwd(v, *vols[1:], beta, case.prep.cuda(), None, cid, True, 3, None, True)

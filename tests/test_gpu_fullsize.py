@@ -112,3 +112,48 @@ def test_scaled_frustum_config_vs_live_oracle(part):
                               prep.cuda(), None, cid, True, 3)
         for n, o, r in zip(NAMES, outs, ref):
             assert_close_scaled(o.cpu().numpy(), r.numpy(), 1e-5, n + " 512x1408")
+
+
+def test_scaled_frustum_backward_vs_live_oracle():
+    """configs[3] backward: 512x1408 input (128x352 feature map), two cameras (the CPU oracle's grid_sampler backward
+    is single-threaded per camera), lift + pool gradients against the reference's autograd."""
+    from dataclasses import replace
+    from vampire_b200.config import R50_512x1408
+    from vampire_b200 import synth
+    cfg = replace(R50_512x1408, num_cams=2)
+    ops, cid, m, prep, depth, ctx, _ = _setup(cfg, 1, torch.float32, mode="train", seed=91)
+    conf = cfg.backbone_kwargs()
+    buf = tp.build_buffers(conf)
+    cot = synth.make_cotangents([(1, cfg.C, cfg.vZ, cfg.vY, cfg.vX)], 91)[0]
+    dr, cr = depth.clone().requires_grad_(True), ctx.clone().requires_grad_(True)
+    ref = tp.lift_pool(conf, buf, dr, cr, m)
+    rd, rc = torch.autograd.grad((ref * cot).sum(), [dr, cr])
+    d, c = depth.cuda().requires_grad_(True), ctx.cuda().requires_grad_(True)
+    vox, _ = ops.lift_pool_fwd(d, c, prep.cuda(), cid, True, False, True)
+    gd, gc = torch.autograd.grad((vox * cot.cuda()).sum(), [d, c])
+    assert_close_scaled(vox.detach().cpu().numpy(), ref.detach().numpy(), 1e-5, "vox 512x1408 (2 cams)")
+    assert_close_scaled(gd.cpu().numpy(), rd.numpy(), 2e-5, "d_depth 512x1408")
+    assert_close_scaled(gc.cpu().numpy(), rc.numpy(), 2e-5, "d_ctx 512x1408")
+
+
+@pytest.mark.parametrize("S", [64, 192])
+def test_render_sample_sweep_full_size_vs_live_oracle(S):
+    """configs[4]: the render at the full R50 ray count with S samples per ray (planes 2.0 + (68 / S) i), camera branch,
+    against the reference's ops on the same host."""
+    from dataclasses import replace
+    from vampire_b200.config import R50_256x704
+    cfg = replace(R50_256x704, d_bound=(2.0, 70.0 + 34.0 / S, 68.0 / S))
+    assert cfg.S == S
+    ops, cid, m, prep, _, _, (den, sem, feat, rgb) = _setup(cfg, 1, torch.float32, seed=55)
+    conf = cfg.backbone_kwargs()
+    buf = tp.build_buffers(conf)
+    with torch.no_grad():
+        ref = tp.render_from_mats(conf, buf, m, den, sem, feat, rgb, torch.tensor(0.1))
+    beta = torch.tensor(0.1, device="cuda")
+    outs = ops.render_fwd(den.cuda(), sem.cuda(), rgb.cuda(), feat.cuda(), beta, prep.cuda(), None, cid, True, 1)
+    from vampire_b200.plan import PlanCache
+    tab = PlanCache().render(ops.state(cid), cid, prep.cuda(), True).table
+    planned = ops.render_fwd(den.cuda(), sem.cuda(), rgb.cuda(), feat.cuda(), beta, prep.cuda(), None, cid, True, 1, tab)
+    for n, o, p, r in zip(NAMES[:3], outs, planned, ref):
+        assert_close_scaled(o.cpu().numpy(), r.numpy(), 1e-5, f"{n} S={S}")
+        assert_close_scaled(p.cpu().numpy(), r.numpy(), 1e-5, f"{n} S={S} (planned march)")

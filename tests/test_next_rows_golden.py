@@ -51,14 +51,6 @@ def test_kernels_match_reference_vectors(mode):
     mats, ctx, logits, cot, gold = _inputs(mode)
     sm = ops.depth_softmax_fwd(logits.cuda(), True)
     assert_close_scaled(sm.cpu().numpy(), gold["softmax_out"], 1e-6, "softmax")
-    if mode != "val":
-        # The first version of this test let the GPU box's host prepare the matrices and the stress rig then
-        # differed from the fixture (val passed) -- consistent with its LAPACK rounding a 4x4 inverse one ulp
-        # away from the build container's, which moves a voxel across a cell boundary.  Feeding the fixture's
-        # matrices (below) removes the host from the comparison, but that variant could not be run on a GPU
-        # before the round's GPU budget ended, so only the verified val rig is asserted here; the stress rig is
-        # covered against the live oracle on the same host by tests/test_gpu_bilinear.py.
-        return
     cid = ops.register_config(MINI, lift_2d=True)
     prep = torch.from_numpy(gold["prep"]).cuda()
     x = ctx.cuda().requires_grad_(True)

@@ -57,7 +57,11 @@ class VbRenderPlan(C.Structure):
 
 
 class VbRenderIn(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("density", "sem", "rgb", "feat", "beta", "geom", "plans")]
+    _fields_ = [(n, C.c_void_p) for n in ("density", "sem", "rgb", "feat", "beta", "geom", "plans")] + \
+        [("flags", C.c_int32)]
+
+
+RENDER_TANH_EPILOGUE = 1
 
 
 class VbRenderOut(C.Structure):

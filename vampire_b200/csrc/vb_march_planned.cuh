@@ -130,7 +130,10 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fw
   // kPrefetchAhead samples ahead of the march (a warp's records are one contiguous 640-byte run per sample), the
   // record of sample i+2 is requested into registers, and the record of sample i+1 has arrived so that its density
   // gathers are issued before sample i is composited.
-  constexpr int kPrefetchAhead = 12;
+#ifndef VB_MARCH_PREFETCH
+#define VB_MARCH_PREFETCH 12
+#endif
+  constexpr int kPrefetchAhead = VB_MARCH_PREFETCH;
   auto prefetch = [&](int i) {
     if (i < S) {
       asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + (size_t)i * 32));

@@ -41,6 +41,29 @@ struct SideStream {
   cudaStream_t stream_hi = nullptr;   // high priority: packs of the later sample groups (see launch_render_fwd)
   cudaEvent_t fork = nullptr, join = nullptr, first_pack = nullptr;
   cudaEvent_t packed[kMaxSplit] = {};
+  // The events are shared by every caller on this device.  A cudaStreamWaitEvent captures the event's state when it
+  // is ENQUEUED, so reuse across calls is fine -- what must not happen is two host threads interleaving their
+  // record / wait pairs.  `use` is held by a render call from its first record to its join (host-side enqueue only,
+  // microseconds), which makes concurrent calls from several threads / streams of one device safe.
+  std::mutex use;
+};
+// holds SideStream::use and guarantees the caller's stream is re-joined on EVERY exit path once the side stream has
+// been given work (the Python side frees the workspace and outputs as soon as the call returns)
+struct SideSession {
+  SideStream* side = nullptr;
+  cudaStream_t caller = nullptr;
+  bool forked = false;
+  std::unique_lock<std::mutex> lock;
+  void acquire(SideStream* s, cudaStream_t st) {
+    if (!side && s) {
+      side = s;
+      caller = st;
+      lock = std::unique_lock<std::mutex>(s->use);
+    }
+  }
+  ~SideSession() {
+    if (side && forked) cudaStreamWaitEvent(caller, side->join, 0);
+  }
 };
 SideStream* side_stream_for_current_device() {
   static std::mutex mu;
@@ -306,7 +329,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) bev_weights_kernel(VbGrid g, VbTables t, const T* __restrict__ den,
                                                           const float* __restrict__ beta_ptr,
                                                           float* __restrict__ o_height, float* __restrict__ o_density,
-                                                          float* __restrict__ wl_ws) {
+                                                          float* __restrict__ wl_ws, float* __restrict__ th_ws) {
   __shared__ BevLevel s_lv[kMaxLevels];
   bev_level_table(g, t, s_lv);
   const int b = blockIdx.y;
@@ -332,6 +355,7 @@ __global__ void __launch_bounds__(256) bev_weights_kernel(VbGrid g, VbTables t, 
     const size_t o = ((size_t)b * g.oZ + l) * ncol + col;
     o_density[o] = sigma;
     wl_ws[o] = w;
+    if (th_ws) th_ws[o] = tanhf(sigma);     // BEV epilogue voxel_output * bev_density.tanh() (BV2:627-630), once per voxel
   }
   o_height[(size_t)b * ncol + col] = height;                                               // BV2:461
 }
@@ -340,7 +364,8 @@ template <typename T, int K, int C>
 __global__ void __launch_bounds__(256) bev_channels_kernel(VbGrid g, VbTables t, const T* __restrict__ sem,
                                                            const T* __restrict__ rgb, const T* __restrict__ feat,
                                                            const float* __restrict__ wl_ws, float* __restrict__ o_rgb,
-                                                           float* __restrict__ o_seg, T* __restrict__ o_feat) {
+                                                           float* __restrict__ o_seg, T* __restrict__ o_feat,
+                                                           const float* __restrict__ th_ws) {
   __shared__ BevLevel s_lv[kMaxLevels];
   bev_level_table(g, t, s_lv);
   const int b = blockIdx.z, j = blockIdx.y;        // j: 0..K-1 sem | K..K+2 rgb | K+3.. feat
@@ -375,7 +400,9 @@ __global__ void __launch_bounds__(256) bev_channels_kernel(VbGrid g, VbTables t,
       const float lo = bev_row<T>(g, bc, plane, L.z0);
       prev_z0 = L.z0;
       prev_lo = lo;
-      o[(size_t)l * ncol] = VbType<T>::cvt(L.wz0 * lo + L.wz1 * hi);
+      float v = L.wz0 * lo + L.wz1 * hi;
+      if (th_ws) v *= __ldg(th_ws + ((size_t)b * g.oZ + l) * ncol + col);                    // BV2:627-630
+      o[(size_t)l * ncol] = VbType<T>::cvt(v);
     }
   }
 }
@@ -595,6 +622,10 @@ __device__ __forceinline__ void bev_fast_channel(const BevLevelX* __restrict__ l
       acc[0] = fmaf(w.x, v[0], acc[0]); acc[1] = fmaf(w.y, v[1], acc[1]);
       acc[2] = fmaf(w.z, v[2], acc[2]); acc[3] = fmaf(w.w, v[3], acc[3]);
     } else if (live) {                                                                      // BV2:448
+      if (wl) {                                  // fused BEV epilogue: x tanh(sigma) of the same voxels (BV2:627-630)
+        const float4 th = __ldg(wp);
+        v[0] *= th.x; v[1] *= th.y; v[2] *= th.z; v[3] *= th.w;
+      }
       Vec4Load<T>::st(o_feat, v);
     }
     L = Ln;
@@ -634,6 +665,10 @@ __device__ __forceinline__ void bev_quad_channel_generic(const VbGrid& g, const 
       acc[0] = fmaf(w.x, v[0], acc[0]); acc[1] = fmaf(w.y, v[1], acc[1]);
       acc[2] = fmaf(w.z, v[2], acc[2]); acc[3] = fmaf(w.w, v[3], acc[3]);
     } else if (live) {
+      if (wl) {                                  // fused BEV epilogue (wl = tanh(sigma) workspace in this mode)
+        const float4 th = __ldg(reinterpret_cast<const float4*>(wl + (size_t)l * ncol));
+        v[0] *= th.x; v[1] *= th.y; v[2] *= th.z; v[3] *= th.w;
+      }
       Vec4Load<T>::st(o_feat + (size_t)l * ncol, v);
     }
   }
@@ -651,7 +686,7 @@ __global__ void __launch_bounds__(64, 16) bev_channels_vec4_kernel(VbGrid g, VbT
                                                                const T* __restrict__ rgb, const T* __restrict__ feat,
                                                                const float* __restrict__ wl_ws,
                                                                float* __restrict__ o_rgb, float* __restrict__ o_seg,
-                                                               T* __restrict__ o_feat) {
+                                                               T* __restrict__ o_feat, const float* __restrict__ th_ws) {
   __shared__ BevLevel s_lv[kMaxLevels];
   __shared__ BevLevelX s_lx[kMaxLevels];
   bev_level_table(g, t, s_lv);
@@ -697,7 +732,9 @@ __global__ void __launch_bounds__(64, 16) bev_channels_vec4_kernel(VbGrid g, VbT
   const bool is_map = grp < GM;
   const int c_begin = is_map ? grp * LM : (grp - GM) * LF;
   const int c_end = is_map ? min(c_begin + LM, NM) : min(c_begin + LF, C);
-  const float* wl = wl_ws + (size_t)b * g.oZ * ncol + col0;
+  // composited planes: the level weights; feature planes: tanh(sigma) when the BEV epilogue is fused, else nothing
+  const float* wl = is_map ? wl_ws + (size_t)b * g.oZ * ncol + col0
+                           : (th_ws ? th_ws + (size_t)b * g.oZ * ncol + col0 : nullptr);
 
   auto planes = [&](int j, const T*& plane, float*& o_map, T*& o_f) {
     o_map = nullptr;
@@ -1051,10 +1088,12 @@ __global__ void __launch_bounds__(kBevTmaThreads, sizeof(T) == 4 ? 8 : 10) bev_c
   }
 }
 
-size_t bev_weight_bytes(const VbGrid* g) {   // + one 256-byte slot at the end: the pack's non-finite flag
+size_t bev_level_bytes(const VbGrid* g) {
   const size_t n = (size_t)g->B * g->oZ * g->oY * g->oX * sizeof(float);
-  return ((n + 255) & ~(size_t)255) + 256;
+  return (n + 255) & ~(size_t)255;
 }
+// compositing weights | tanh(sigma) of the fused BEV epilogue | one 256-byte slot: the pack's non-finite flags
+size_t bev_weight_bytes(const VbGrid* g) { return 2 * bev_level_bytes(g) + 256; }
 
 size_t packed_bytes_per_sample(const VbGrid* g, int dtype) {
   const size_t n = (size_t)g->vZ * g->vY * g->vX * packed_channels(g->K) * vb_elem_size(dtype);
@@ -1079,14 +1118,18 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
   const T* feat = reinterpret_cast<const T*>(in->feat);
   const int patches = vb_ceil_div(g->fW, kPatchW) * vb_ceil_div(g->fH, kPatchH);
   const int ncol = g->oY * g->oX;
-  bool forked = false;
+  SideSession session;          // declared first: its destructor (the join) runs on every return below
+  bool& forked = session.forked;
   SideStream* side = nullptr;
   // BEV branch on stream `bst`
   auto launch_bev = [&](cudaStream_t bst) -> int {
     float* wl_ws = reinterpret_cast<float*>((char*)ws + cam_bytes);
+    // VB200_RENDER_TANH_EPILOGUE: voxel_output leaves the kernel already multiplied by tanh(sigma) (BV2:627-630)
+    float* th_ws = (in->flags & VB200_RENDER_TANH_EPILOGUE)
+                       ? reinterpret_cast<float*>((char*)ws + cam_bytes + bev_level_bytes(g)) : nullptr;
     VbTraceScope tr(VB_K_BEV_FWD, bst, 2);
     bev_weights_kernel<T><<<dim3(vb_ceil_div(ncol, 256), g->B), 256, 0, bst>>>(
-        *g, *t, den, in->beta, out->bev_height, out->voxel_density, wl_ws);
+        *g, *t, den, in->beta, out->bev_height, out->voxel_density, wl_ws, th_ws);
     VB_LAUNCH_CHECK();
     const bool vec_ok = (g->vX % 4 == 0) && (g->oX % 4 == 0) &&
                         ((((uintptr_t)sem | (uintptr_t)rgb | (uintptr_t)feat | (uintptr_t)out->voxel_output |
@@ -1095,7 +1138,7 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
     // Opt-in (VB200_BEV_TMA=1): measured slower than the direct-load kernel on B200 (R50, B=8, bf16: 0.335 vs
     // 0.291 ms, see the kernel's header).  Kept as a measured alternative, parity-tested bit-identical.
     static const bool tma_env = getenv("VB200_BEV_TMA") != nullptr;
-    const bool tma_ok = vec_ok && tma_env && ((size_t)g->vX * sizeof(T)) % 16 == 0 && g->vX >= 8;
+    const bool tma_ok = vec_ok && tma_env && !th_ws && ((size_t)g->vX * sizeof(T)) % 16 == 0 && g->vX >= 8;
     if (tma_ok) {
       static VbPerDeviceFlag carve;
       if (vb_func_attr_per_device(bev_channels_tma_kernel<T, K, C>, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -1105,10 +1148,10 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
           *g, *t, sem, rgb, feat, wl_ws, out->bev_rgb, out->bev_seg, reinterpret_cast<T*>(out->voxel_output));
     } else if (vec_ok)
       bev_channels_vec4_kernel<T, K, C><<<dim3(g->oY * vb_ceil_div(g->oX, 256), bev_groups(K, C), g->B), 64, 0, bst>>>(
-          *g, *t, sem, rgb, feat, wl_ws, out->bev_rgb, out->bev_seg, reinterpret_cast<T*>(out->voxel_output));
+          *g, *t, sem, rgb, feat, wl_ws, out->bev_rgb, out->bev_seg, reinterpret_cast<T*>(out->voxel_output), th_ws);
     else
       bev_channels_kernel<T, K, C><<<dim3(vb_ceil_div(ncol, 256), K + 3 + C, g->B), 256, 0, bst>>>(
-          *g, *t, sem, rgb, feat, wl_ws, out->bev_rgb, out->bev_seg, reinterpret_cast<T*>(out->voxel_output));
+          *g, *t, sem, rgb, feat, wl_ws, out->bev_rgb, out->bev_seg, reinterpret_cast<T*>(out->voxel_output), th_ws);
     VB_LAUNCH_CHECK();
     return VB200_OK;
   };
@@ -1164,16 +1207,18 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
     // fork AFTER the first pack: the pack is HBM-bound, the march issue-bound -- the BEV kernels
     // (low-priority side stream) fill the march's idle issue slots instead of fighting the pack for DRAM
     cudaStream_t bst = st;
-    if (may_fork && (side = side_stream_for_current_device()) != nullptr) {
+    if (may_fork && (side || (side = side_stream_for_current_device()) != nullptr)) {
+      session.acquire(side, st);
       if (cudaEventRecord(side->fork, st) == cudaSuccess && cudaStreamWaitEvent(side->stream, side->fork, 0) == cudaSuccess) {
         bst = side->stream;
-        forked = true;
+        // record the join point right away so that an early return below still waits for whatever was enqueued
+        forked = cudaEventRecord(side->join, bst) == cudaSuccess;
+        if (!forked) bst = st;
       }
     }
     const int rc = launch_bev(bst);
-    if (rc) return rc;
     if (forked && cudaEventRecord(side->join, bst) != cudaSuccess) return VB200_ERR_CUDA;
-    return VB200_OK;
+    return rc;
   };
 
   // Sample groups.  Optional experiment (VB200_RENDER_SPLIT=n, default off): when the workspace holds every
@@ -1190,6 +1235,7 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
     if (nsplit > g->B) nsplit = g->B;
   }
   if (nsplit > 1) {
+    session.acquire(side, st);
     const int sub = vb_ceil_div(g->B, nsplit);
     int rc = pack_round(0, sub < g->B ? sub : g->B, reinterpret_cast<T*>(ws), nf_flags, st);
     if (rc) return rc;
@@ -1225,8 +1271,7 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
       if (rc) return rc;
     }
   }
-  if (forked && cudaStreamWaitEvent(st, side->join, 0) != cudaSuccess) return VB200_ERR_CUDA;
-  return VB200_OK;
+  return VB200_OK;     // ~SideSession joins the side stream into the caller's
 }
 
 }  // namespace

@@ -82,9 +82,13 @@ def fused_forward_single_sweep(self, sweep_index, sweep_imgs, mats_dict, inrange
                                                  self.occ_coords)
     else:     # BaseLSSImpaintor: a fixed, unrotated grid (base_lss_impaintor.py:611-616)
         occ_logits, occ_density = path.occupancy(semantic_logits, density_feature, None, path.occ_coords())
-    # BV2:554-559 + 612-614: geometry recomputed in-kernel (never stored), nan_to_num included
+    # BV2:554-559 + 612-614: geometry recomputed in-kernel (never stored), nan_to_num included.  Without gradients the
+    # BEV epilogue of BV2:627-630 is folded into the BEV kernel (both operands are in registers there).
+    fuse_tanh = self.density_mode == "sdf" and not (torch.is_grad_enabled() and any(
+        t.requires_grad for t in (density_feature, semantic_logits, base_features, rgb, path.density.beta)))
     (rgb_preds, seg_logits_preds, depth_preds, bev_rgb_preds, bev_seg_logits_preds, bev_height_preds, bev_density,
-     voxel_output) = path.render(mats_dict, density_feature, semantic_logits, base_features, rgb, sweep_index)
+     voxel_output) = path.render(mats_dict, density_feature, semantic_logits, base_features, rgb, sweep_index,
+                                 tanh_epilogue=fuse_tanh)
     up = self.upsample_factor
     fH, fW = self.fH, self.fW
     rgb_preds = path.upsample2d(rgb_preds.reshape(batch_size * num_cams, -1, fH, fW)).reshape(        # BV2:616-626
@@ -93,7 +97,8 @@ def fused_forward_single_sweep(self, sweep_index, sweep_imgs, mats_dict, inrange
         batch_size, num_cams, -1, fH * up, fW * up)
     depth_preds = path.upsample2d(depth_preds.reshape(batch_size * num_cams, -1, fH, fW)).reshape(
         batch_size, num_cams, -1, fH * up, fW * up)
-    voxel_output = path.bev_epilogue(voxel_output, bev_density)                                       # BV2:627-630
+    if not fuse_tanh:
+        voxel_output = path.bev_epilogue(voxel_output, bev_density)                                   # BV2:627-630
     voxel_output_features = self.voxel_output(
         voxel_output.reshape(batch_size, -1, voxel_output.shape[-2], voxel_output.shape[-1])).float()  # BV2:631-632
     return (voxel_output_features.contiguous(), rgb_preds, seg_logits_preds, depth_preds, bev_rgb_preds,

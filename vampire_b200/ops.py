@@ -409,8 +409,9 @@ def _render_out_shapes(cfg: PathConfig, B: int):
             (B, 1, cfg.oZ, cfg.oY, cfg.oX), (B, Cc, cfg.oZ, cfg.oY, cfg.oX)]
 
 
-def _render_in_struct(density, sem, rgb, feat, beta, geom, plan=None):
+def _render_in_struct(density, sem, rgb, feat, beta, geom, plan=None, flags=0):
     rin = cabi.VbRenderIn()
+    rin.flags = flags
     rin.density, rin.sem, rin.rgb, rin.feat = density.data_ptr(), sem.data_ptr(), rgb.data_ptr(), feat.data_ptr()
     rin.beta = beta.data_ptr()
     rin.geom = None if geom is None else geom.data_ptr()
@@ -443,10 +444,19 @@ def _check_render_inputs(cfg, density, sem, rgb, feat, beta):
 
 def render_fwd(density: Tensor, sem: Tensor, rgb: Tensor, feat: Tensor, beta: Tensor, mats: Tensor,
                geom: Optional[Tensor], cfg_id: int, has_bda: bool, branches: int,
-               plan: Optional[Tensor] = None) -> List[Tensor]:
+               plan: Optional[Tensor] = None, tanh_epilogue: bool = False) -> List[Tensor]:
     """``plan``: the device table of the batch's cached render plans (``PlanCache.render``): the camera march reads
-    its sample geometry from them instead of recomputing it (forward only; the backward recomputes)."""
+    its sample geometry from them instead of recomputing it (forward only; the backward recomputes).
+    ``tanh_epilogue``: ``voxel_output`` comes back already multiplied by ``tanh(voxel_density)`` (BV2:627-630 fused
+    into the BEV kernel); inference only -- no autograd formula exists for the fused form."""
+    if tanh_epilogue:
+        if torch.is_grad_enabled() and any(t.requires_grad for t in (density, sem, rgb, feat, beta)):
+            raise RuntimeError("render_fwd(tanh_epilogue=True) is forward-only; multiply outside when gradients are needed")
+        return _render_fwd(density, sem, rgb, feat, beta, mats, geom, cfg_id, has_bda, branches | _TANH_BIT, plan)
     return _render_fwd(density, sem, rgb, feat, beta, mats, geom, cfg_id, has_bda, branches, plan)
+
+
+_TANH_BIT = 1 << 8     # rides in `branches` through the op schema (bit 0 / 1: camera / BEV branch)
 
 
 @torch.library.custom_op("vampire_b200::render_fwd", mutates_args=())
@@ -474,7 +484,9 @@ def _render_fwd(density: Tensor, sem: Tensor, rgb: Tensor, feat: Tensor, beta: T
     ws_bytes = lib.vb200_render_fwd_workspace(C.byref(g), dt) + \
         lib.vb200_render_packed_bytes(C.byref(g), dt) * ((B if st.render_group <= 0 else min(B, st.render_group)) - 1)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    rin = _render_in_struct(density, sem, rgb, feat, beta32, geom, plan)
+    flags = cabi.RENDER_TANH_EPILOGUE if branches & _TANH_BIT else 0
+    branches &= 3
+    rin = _render_in_struct(density, sem, rgb, feat, beta32, geom, plan, flags)
     ro = _render_out_struct(outs)
     with torch.cuda.device(dev):
         cabi.check(lib.vb200_render_fwd(C.byref(g), C.byref(st.tables(dev).struct), mats.data_ptr(), C.byref(rin), dt,

@@ -207,14 +207,17 @@ class LiftRenderB200(nn.Module):
         return out
 
     def render(self, mats_dict: Dict[str, Tensor], density_feature: Tensor, semantic_logits: Tensor,
-               voxel_features: Tensor, rgb: Tensor, sweep_index: int = 0, branches: int = 3):
-        """BV2:554-559 + 612-614: geometry recomputed in-kernel from the matrices (never stored)."""
+               voxel_features: Tensor, rgb: Tensor, sweep_index: int = 0, branches: int = 3,
+               tanh_epilogue: bool = False):
+        """BV2:554-559 + 612-614: geometry recomputed in-kernel from the matrices (never stored).
+        ``tanh_epilogue=True`` (inference): the last output is ``voxel_output * bev_density.tanh()`` (BV2:627-630),
+        formed inside the BEV kernel."""
         mats, has_bda, mats_host = self._prep_dict_cached(mats_dict, sweep_index, density_feature.device)
         plan = None
         if self._use_plans() and (branches & cabi.BRANCH_CAM):
             plan = self.plan_cache.render(ops.state(self.cfg_id), self.cfg_id, mats, has_bda, mats_host).table
         outs = ops.render_fwd(density_feature, semantic_logits, rgb, voxel_features, self.density.beta, mats,
-                              None, self.cfg_id, has_bda, branches, plan)
+                              None, self.cfg_id, has_bda, branches, plan, tanh_epilogue)
         return tuple(outs)
 
     # ---- the callers right after the path (SURVEY §8f rows 2-3) ------------------------------------

@@ -31,5 +31,5 @@ def pytest_terminal_summary(terminalreporter):
     if not ACHIEVED:
         return
     terminalreporter.section("achieved max |err| / max|ref|  (tolerance asserted)")
-    for what, (a, rel) in sorted(ACHIEVED.items()):
+    for (what, rel), a in sorted(ACHIEVED.items()):
         terminalreporter.write_line(f"  {what:48s} {a:9.2e}   ({rel:.0e})")

@@ -87,8 +87,8 @@ def assert_close_scaled(got, exp, rel, what="", scale=None):
     err = np.abs(got - exp)
     if err.size:
         a = float(np.nanmax(err)) / scale
-        prev = ACHIEVED.get(what)
-        ACHIEVED[what] = (max(a, prev[0]) if prev else a, rel)
+        prev = ACHIEVED.get((what, rel))
+        ACHIEVED[(what, rel)] = max(a, prev) if prev is not None else a
     bad = err > rel * scale + rel * np.abs(exp)
     assert not bad.any(), (f"{what}: {int(bad.sum())} / {bad.size} elements off; max abs err {err.max():.3e} "
                            f"(scale {scale:.3e}, allowed {rel * scale:.3e})")

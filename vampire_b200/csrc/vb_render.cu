@@ -959,7 +959,8 @@ __global__ void __launch_bounds__(kBevTmaThreads, sizeof(T) == 4 ? 8 : 10) bev_c
       float* o_map;
       T* o_f;
       outputs_of(j, o_map, o_f);
-      bev_quad_channel_generic<T, K, C>(g, s_lv, q, plane_of(j), y0, wy0, wy1, lane, live, wl, o_map, o_f, ncol);
+      bev_quad_channel_generic<T, K, C>(g, s_lv, q, plane_of(j), y0, wy0, wy1, lane, live, is_map ? wl : nullptr,
+                                        o_map, o_f, ncol);
     }
     return;
   }

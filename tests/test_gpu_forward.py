@@ -353,8 +353,9 @@ def _rig(cfg, seed):
     return m
 
 
+@pytest.mark.parametrize("lift_2d", [False, True])
 @pytest.mark.parametrize("block", range(5))
-def test_fused_cull_never_drops_a_valid_pair_50_rigs(block):
+def test_fused_cull_never_drops_a_valid_pair_50_rigs(block, lift_2d):
     """The fused lift's two-level conservative cull runs on an FMA-composed matrix with a guard band; a dropped valid
     pair would be a silent parity bug.  50 random rigs (MINI): the camera count the fused kernel saved per voxel
     equals the number of cameras the strict index kernel calls valid -- and the cached plan agrees."""
@@ -362,8 +363,11 @@ def test_fused_cull_never_drops_a_valid_pair_50_rigs(block):
     from vampire_b200.matrices import prepare_matrices
     from vampire_b200.plan import build_lift_plans
     cfg = MINI
-    ops, cid = _ops(cfg)
-    ones_d = torch.ones(2, cfg.num_cams, cfg.D, cfg.fH, cfg.fW, device="cuda")
+    from vampire_b200 import ops
+    # lift_2d: the BaseBiLinear mode, whose depth test z > 0 lets voxels right at the camera plane through -- the
+    # case in which a guard band that reaches behind the camera once broke the warp-level cull
+    cid = ops.register_config(cfg, lift_2d)
+    ones_d = torch.ones(2, cfg.num_cams, 1 if lift_2d else cfg.D, cfg.fH, cfg.fW, device="cuda")
     ones_c = torch.ones(2, cfg.num_cams, cfg.C, cfg.fH, cfg.fW, device="cuda")
     total = 0
     for seed in range(300 + 10 * block, 310 + 10 * block):

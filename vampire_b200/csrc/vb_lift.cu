@@ -101,6 +101,10 @@ __global__ void __launch_bounds__(kLiftThreads, VB_LIFT_MINB) lift_pool_fwd_kern
     const float* q = s_q + n * 16;
     const float cz = fmaf(q[8], qx, fmaf(q[9], qy, fmaf(q[10], qz, q[11])));
     if (!(cz >= g.d_lo - 0.05f)) return 1u;            // also catches NaN
+    // The half-space argument needs the point strictly in front of the camera: the guard band reaches behind it when
+    // d_lo = 0 (the 2-D lift's depth test is z > 0), where 1 / cz flips the sign of the projection.  Too close to the
+    // camera plane to decide here: keep the pair, the strict projection decides.
+    if (cz < 1e-3f) return 0u;
     unsigned code = (cz > g.d_hi + 0.05f) ? 2u : 0u;
     const float cx = fmaf(q[0], qx, fmaf(q[1], qy, fmaf(q[2], qz, q[3])));
     const float cy = fmaf(q[4], qx, fmaf(q[5], qy, fmaf(q[6], qz, q[7])));

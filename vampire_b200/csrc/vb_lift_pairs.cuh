@@ -33,7 +33,9 @@ __device__ __forceinline__ bool pair_coord(const VbGrid& g, const float* s_m, co
   const float cw = fmaf(q[12], px, fmaf(q[13], py, fmaf(q[14], pz, q[15])));
   const float ax = fmaf(I[0], ux, fmaf(I[1], uy, fmaf(I[2], cz, I[3] * cw)));
   const float ay = fmaf(I[4], ux, fmaf(I[5], uy, fmaf(I[6], cz, I[7] * cw)));
-  if (!(ax > -1.5f && ax < g.x_hi + 1.0f && ay > -1.5f && ay < g.y_hi + 1.0f)) return false;
+  // the image-bounds cull is only meaningful strictly in front of the camera: with d_lo = 0 (2-D lift) the guard band
+  // reaches behind it, where 1 / cz flips the projection's sign -- there the strict projection alone decides
+  if (cz >= 1e-3f && !(ax > -1.5f && ax < g.x_hi + 1.0f && ay > -1.5f && ay < g.y_hi + 1.0f)) return false;
   lc = pair_strict(g, s_m + n * VB200_MAT_SLOTS * 16, has_bda, affine, dv, px, py, pz);
   return lc.valid;
 }

@@ -109,8 +109,7 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fw
   const bool active = (w < g.fW) && (h < g.fH);
   const int S = g.D - 1, HW = g.fH * g.fW;
   const int nvox = g.vZ * g.vY * g.vX;
-  const T* vol = packed + (size_t)blockIdx.z * nvox * CP;  // packed holds only this launch's samples (split layout)
-  const T* volB = vol + (size_t)nvox * kSplitA;
+  const T* vol = packed + (size_t)blockIdx.z * nvox * CP;  // packed holds only this launch's samples
   const size_t ray = (size_t)(n * npatch + patch);
   const uint4* __restrict__ rec = reinterpret_cast<const uint4*>(plans[b].steps) + ray * S * 32 + lane;
   const float* __restrict__ dl = plans[b].delta + ray * S * 32 + lane;
@@ -120,7 +119,7 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fw
   const float inv_beta = 1.0f / beta;
   const float sigma_masked = laplace_density_rcp(0.0f, g.sdf_bias, inv_beta);   // feature 0 outside the volume
   // corner offsets are launch constants (inward-shifted base, see march_fwd_kernel): x-pairs = one pointer + immediate
-  const int c_sy = g.vX, c_sz = g.vY * g.vX;      // in voxels
+  const int c_sy = g.vX * CP, c_sz = g.vY * g.vX * CP;
 
   float acc = 0.0f, dep = 0.0f, trans = 1.0f;
   float ch[K + 3];
@@ -154,10 +153,10 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fw
   T raw_n[8];
   auto gather_density = [&](const uint4& r, T (&raw)[8]) {
     if (r.x & kPlanValid) {
-      const T* p = vol + (size_t)(r.x & kPlanVoxMask) * kSplitA;
+      const T* p = vol + (size_t)(r.x & kPlanVoxMask) * CP;
 #pragma unroll
       for (int q = 0; q < 8; ++q)
-        raw[q] = __ldg(p + (((q & 2) ? c_sy : 0) + ((q & 4) ? c_sz : 0) + (q & 1)) * kSplitA);
+        raw[q] = __ldg(p + ((q & 2) ? c_sy : 0) + ((q & 4) ? c_sz : 0) + ((q & 1) ? CP : 0));
     }
   };
   gather_density(r_n, raw_n);
@@ -216,12 +215,11 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fw
     dep = fmaf(wgt, __ldg(t.mids + i), dep);
     // the 21 value channels, only where they can contribute (alpha is exactly 0.0f in free space)
     if (live && wgt != 0.0f) {
-      const size_t v0 = (size_t)(r.x & kPlanVoxMask);
+      const T* p = vol + (size_t)(r.x & kPlanVoxMask) * CP;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int off = ((q & 2) ? c_sy : 0) + ((q & 4) ? c_sz : 0) + (q & 1);
-        SplitLoad<T>::template fma_values<K + 3>(vol + (v0 + off) * kSplitA, volB + (v0 + off) * kSplitB, cw[q] * wgt, ch);
-      }
+      for (int q = 0; q < 8; ++q)
+        PackedLoad<T, CP>::template fma_values<K + 3>(p + ((q & 2) ? c_sy : 0) + ((q & 4) ? c_sz : 0) + ((q & 1) ? CP : 0),
+                                                      cw[q] * wgt, ch);
     }
     // exp(-cumsum) of BV2:431-433 as a running product: one exp per sample instead of two
     trans *= e;

@@ -124,8 +124,7 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_MINB) march_fwd_kernel
   const int S = g.D - 1, HW = g.fH * g.fW;
   const int nvox = g.vZ * g.vY * g.vX;
   const float beta = fabsf(__ldg(beta_ptr)) + g.beta_min;
-  const T* vol = packed + (size_t)blockIdx.z * nvox * CP;  // packed holds only this launch's samples; split layout:
-  const T* volB = vol + (size_t)nvox * kSplitA;            // A[v] = channels 0..15 at vol, B[v] = channels 16..23 here
+  const T* vol = packed + (size_t)blockIdx.z * nvox * CP;  // packed holds only this launch's samples
   const float u = __ldg(t.us + wc), vv = __ldg(t.vs + hc);
   const float* gsrc = FROM_MATS ? nullptr : d_geom + ((size_t)(b * g.N + n) * g.D * HW + (size_t)hc * g.fW + wc) * 3;
 
@@ -192,7 +191,7 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_MINB) march_fwd_kernel
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int cx = q & 1, cy = (q >> 1) & 1, cz = q >> 2;
-        sm.raw[q] = __ldg(vol + (size_t)(sm.v0 + (cy ? sy : 0) + (cz ? sz : 0)) * kSplitA + (cx ? dxo * kSplitA : 0));
+        sm.raw[q] = __ldg(vol + (size_t)(sm.v0 + (cy ? sy : 0) + (cz ? sz : 0)) * CP + (cx ? dxo * CP : 0));
       }
     }
   };
@@ -277,22 +276,19 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_MINB) march_fwd_kernel
     if (!NANSAFE) {
       if (live && wgt != 0.0f) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const size_t cv = (size_t)(cur.v0 + ((q & 2) ? sy : 0) + ((q & 4) ? sz : 0));
-          SplitLoad<T>::template fma_values<K + 3>(vol + cv * kSplitA + ((q & 1) ? dxo * kSplitA : 0),
-                                                   volB + cv * kSplitB + ((q & 1) ? dxo * kSplitB : 0), cw[q] * wgt, ch);
-        }
+        for (int q = 0; q < 8; ++q)
+          PackedLoad<T, CP>::template fma_values<K + 3>(
+              vol + (size_t)(cur.v0 + ((q & 2) ? sy : 0) + ((q & 4) ? sz : 0)) * CP + ((q & 1) ? dxo * CP : 0),
+              cw[q] * wgt, ch);
       }
     } else if (live && wgt != 0.0f) {
       float v[CP];
 #pragma unroll
       for (int c = 0; c < CP; ++c) v[c] = 0.0f;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const size_t cv = (size_t)(cur.v0 + ((q & 2) ? sy : 0) + ((q & 4) ? sz : 0));
-        SplitLoad<T>::fma_corner(vol + cv * kSplitA + ((q & 1) ? dxo * kSplitA : 0),
-                                 volB + cv * kSplitB + ((q & 1) ? dxo * kSplitB : 0), cw[q], v);
-      }
+      for (int q = 0; q < 8; ++q)
+        PackedLoad<T, CP>::fma_corner(
+            vol + (size_t)(cur.v0 + ((q & 2) ? sy : 0) + ((q & 4) ? sz : 0)) * CP + ((q & 1) ? dxo * CP : 0), cw[q], v);
       // torch.nan_to_num (BV2:421): any NaN/inf channel makes the channel sum non-finite, so one
       // test guards the per-channel fix-up
       float chk = 0.0f;
@@ -1176,7 +1172,7 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
   auto pack_round = [&](int b0, int nb, T* region, int* flag, cudaStream_t ps) -> int {
     VbTraceScope tr(VB_K_PACK, ps);
     if (cudaMemsetAsync(flag, flag_init, sizeof(int), ps) != cudaSuccess) return VB200_ERR_CUDA;
-    pack_cam_volume_kernel<T, K, true><<<dim3(vb_ceil_div(nvox, kPackThreads * PackVox<T>::n), nb), kPackThreads, 0, ps>>>(
+    pack_cam_volume_kernel<T, K><<<dim3(vb_ceil_div(nvox, kPackThreads * PackVox<T>::n), nb), kPackThreads, 0, ps>>>(
         den + (size_t)b0 * nvox, sem + (size_t)b0 * K * nvox, rgb + (size_t)b0 * 3 * nvox, region, (int)nvox,
         per / sizeof(T), flag);
     VB_LAUNCH_CHECK();

@@ -37,15 +37,7 @@ __device__ __forceinline__ float widen_elem(__half v) { return __half2float(v); 
 #ifndef VB_PACK_MINB
 #define VB_PACK_MINB 5   // 51 registers: measured 0.150 ms = 98 % of the copy peak (unbounded: 128 regs, 0.180 ms)
 #endif
-// SPLIT layout (the forward march): the 24-channel record of a voxel is stored as two arrays,
-//   A[v] = channels 0..15  (density + 15 semantic classes)   16 * sizeof(T) bytes = ONE (bf16) / two (fp32) 256-bit loads
-//   B[v] = channels 16..23 (3 classes + rgb + 2 pad)          8 * sizeof(T) bytes = one 128-bit (bf16) / 256-bit load
-// with B starting kSplitA * nvox elements after A.  A 48-byte record cannot be read with 256-bit loads (every other
-// record is only 16-byte aligned); split, a corner is 2 load instructions instead of 3 (fp32: 3 instead of 6) at the
-// same 48 (96) bytes per voxel -- the march is bound by L1 data-pipe wavefronts, which are paid per instruction.
-constexpr int kSplitA = 16, kSplitB = 8;
-
-template <typename T, int K, bool SPLIT = false>
+template <typename T, int K>
 __global__ void __launch_bounds__(kPackThreads, VB_PACK_MINB) pack_cam_volume_kernel(const T* __restrict__ den,
                                                                        const T* __restrict__ sem,
                                                                        const T* __restrict__ rgb, T* __restrict__ packed,
@@ -65,16 +57,12 @@ __global__ void __launch_bounds__(kPackThreads, VB_PACK_MINB) pack_cam_volume_ke
   if (!__all_sync(0xffffffffu, vec_ok)) {
     bool bad = false;
     for (int vv = v; vv < min(v + V, nvox); ++vv) {
-      auto slot = [&](int c) -> T& {
-        return SPLIT ? (c < kSplitA ? packed[(size_t)vv * kSplitA + c]
-                                    : packed[(size_t)nvox * kSplitA + (size_t)vv * kSplitB + (c - kSplitA)])
-                     : packed[(size_t)vv * CP + c];
-      };
-      slot(0) = den[vv];
-      for (int k = 0; k < K; ++k) slot(1 + k) = sem[(size_t)k * nvox + vv];
-      for (int j = 0; j < 3; ++j) slot(1 + K + j) = rgb[(size_t)j * nvox + vv];
-      for (int c = NCH; c < CP; ++c) slot(c) = VbType<T>::cvt(0.0f);
-      for (int c = 0; c < NCH; ++c) bad = bad || !(fabsf(widen_elem(slot(c))) <= 3.402823466e+38f);
+      T* o = packed + (size_t)vv * CP;
+      o[0] = den[vv];
+      for (int k = 0; k < K; ++k) o[1 + k] = sem[(size_t)k * nvox + vv];
+      for (int j = 0; j < 3; ++j) o[1 + K + j] = rgb[(size_t)j * nvox + vv];
+      for (int c = NCH; c < CP; ++c) o[c] = VbType<T>::cvt(0.0f);
+      for (int c = 0; c < NCH; ++c) bad = bad || !(fabsf(widen_elem(o[c])) <= 3.402823466e+38f);
     }
     if (bad && nonfinite_flag) *nonfinite_flag = 1;
     return;
@@ -101,9 +89,7 @@ __global__ void __launch_bounds__(kPackThreads, VB_PACK_MINB) pack_cam_volume_ke
   // assemble this thread's records (96 contiguous bytes) in registers ...
   uint4 rec[6];
   static_assert(CP * sizeof(T) * V == 96, "record staging below assumes 96 bytes per thread");
-  static_assert(!SPLIT || (CP == kSplitA + kSplitB), "split layout is 16 + 8 channels");
   if (V == 1) {
-    // contiguous: 24 words; split: words 0..15 = A (rec 0..3), 16..23 = B (rec 4..5) -- the same order
 #pragma unroll
     for (int q = 0; q < 6; ++q) rec[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
   } else {
@@ -114,17 +100,10 @@ __global__ void __launch_bounds__(kPackThreads, VB_PACK_MINB) pack_cam_volume_ke
       r0[q] = __byte_perm(w[2 * q], w[2 * q + 1], 0x5410);
       r1[q] = __byte_perm(w[2 * q], w[2 * q + 1], 0x7632);
     }
-    if (!SPLIT) {
 #pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        rec[q] = make_uint4(r0[4 * q], r0[4 * q + 1], r0[4 * q + 2], r0[4 * q + 3]);
-        rec[3 + q] = make_uint4(r1[4 * q], r1[4 * q + 1], r1[4 * q + 2], r1[4 * q + 3]);
-      }
-    } else {   // rec 0..3 = A of voxel v, v+1 (8 words each), rec 4..5 = B of voxel v, v+1 (4 words each)
-      rec[0] = make_uint4(r0[0], r0[1], r0[2], r0[3]);  rec[1] = make_uint4(r0[4], r0[5], r0[6], r0[7]);
-      rec[2] = make_uint4(r1[0], r1[1], r1[2], r1[3]);  rec[3] = make_uint4(r1[4], r1[5], r1[6], r1[7]);
-      rec[4] = make_uint4(r0[8], r0[9], r0[10], r0[11]);
-      rec[5] = make_uint4(r1[8], r1[9], r1[10], r1[11]);
+    for (int q = 0; q < 3; ++q) {
+      rec[q] = make_uint4(r0[4 * q], r0[4 * q + 1], r0[4 * q + 2], r0[4 * q + 3]);
+      rec[3 + q] = make_uint4(r1[4 * q], r1[4 * q + 1], r1[4 * q + 2], r1[4 * q + 3]);
     }
   }
   // ... and bounce them through shared memory so that every 128-bit store instruction of a warp covers
@@ -133,26 +112,9 @@ __global__ void __launch_bounds__(kPackThreads, VB_PACK_MINB) pack_cam_volume_ke
   s_rec[threadIdx.x * 6 + 3] = rec[3]; s_rec[threadIdx.x * 6 + 4] = rec[4]; s_rec[threadIdx.x * 6 + 5] = rec[5];
   __syncwarp();
   const int lane = threadIdx.x & 31, warp0 = threadIdx.x - lane;
-  if (!SPLIT) {
-    uint4* out = reinterpret_cast<uint4*>(packed + (size_t)(v - lane * V) * CP);   // the warp's first record
+  uint4* out = reinterpret_cast<uint4*>(packed + (size_t)(v - lane * V) * CP);   // the warp's first record
 #pragma unroll
-    for (int q = 0; q < 6; ++q) out[q * 32 + lane] = s_rec[warp0 * 6 + q * 32 + lane];
-  } else {
-    // every thread staged 4 uint4 of A and 2 of B: the warp's A run is 2 KB, its B run 1 KB, both contiguous
-    const size_t v0w = (size_t)(v - lane * V);
-    uint4* outA = reinterpret_cast<uint4*>(packed + v0w * kSplitA);
-    uint4* outB = reinterpret_cast<uint4*>(packed + (size_t)nvox * kSplitA + v0w * kSplitB);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int j = q * 32 + lane;
-      outA[j] = s_rec[(warp0 + (j >> 2)) * 6 + (j & 3)];
-    }
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int j = q * 32 + lane;
-      outB[j] = s_rec[(warp0 + (j >> 1)) * 6 + 4 + (j & 1)];
-    }
-  }
+  for (int q = 0; q < 6; ++q) out[q * 32 + lane] = s_rec[warp0 * 6 + q * 32 + lane];
 }
 
 template <typename T, int CP> struct PackedLoad;
@@ -180,41 +142,6 @@ template <typename T, int CP> struct PackedLoad {
       VbVec<T, L>::ld(p + q * L, tmp);
 #pragma unroll
       for (int e = 0; e < L; ++e) v[q * L + e] = fmaf(tmp[e], wgt, v[q * L + e]);
-    }
-  }
-};
-
-// split layout: pa -> A[v] (16 channels, 32-byte aligned), pb -> B[v] (8 channels); 256-bit loads
-template <typename T> struct SplitLoad {
-  // acc[c] += wgt * channel[1 + c] for c < NV (channel 0 = density is skipped)
-  template <int NV>
-  __device__ __forceinline__ static void fma_values(const T* pa, const T* pb, float wgt, float (&acc)[NV]) {
-    float a[kSplitA], b[kSplitB];
-    load(pa, pb, a, b);
-#pragma unroll
-    for (int c = 1; c < kSplitA; ++c)
-      if (c - 1 < NV) acc[c - 1] = fmaf(a[c], wgt, acc[c - 1]);
-#pragma unroll
-    for (int c = 0; c < kSplitB; ++c)
-      if (kSplitA + c - 1 < NV) acc[kSplitA + c - 1] = fmaf(b[c], wgt, acc[kSplitA + c - 1]);
-  }
-  // v[c] += wgt * channel[c] for all 24 channels
-  __device__ __forceinline__ static void fma_corner(const T* pa, const T* pb, float wgt, float (&v)[kSplitA + kSplitB]) {
-    float a[kSplitA], b[kSplitB];
-    load(pa, pb, a, b);
-#pragma unroll
-    for (int c = 0; c < kSplitA; ++c) v[c] = fmaf(a[c], wgt, v[c]);
-#pragma unroll
-    for (int c = 0; c < kSplitB; ++c) v[kSplitA + c] = fmaf(b[c], wgt, v[kSplitA + c]);
-  }
-  __device__ __forceinline__ static void load(const T* pa, const T* pb, float (&a)[kSplitA], float (&b)[kSplitB]) {
-    if constexpr (sizeof(T) == 4) {
-      VbWiden32<T>::cvt(vb_ldg256(pa), a);
-      VbWiden32<T>::cvt(vb_ldg256(pa + 8), a + 8);
-      VbWiden32<T>::cvt(vb_ldg256(pb), b);
-    } else {
-      VbWiden32<T>::cvt(vb_ldg256(pa), a);
-      VbVec<T, 8>::ld(pb, b);
     }
   }
 };

@@ -244,7 +244,7 @@ def run_reference_arm(args, cfg):
         "e2e": {"value": value, "unit": "frustum pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -492,10 +492,39 @@ def train_probe(args, cfg, dev, world, rank, steps, warmup):
     return out
 
 
+class StdoutGuard:
+    """stdout carries exactly ONE line (the JSON): while the bench runs, file descriptor 1 points at stderr, so
+    whatever a native library writes there (NCCL's version banner under NCCL_DEBUG=VERSION, ...) cannot precede it."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line: str):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+
+
+_GUARD = None
+
+
+def emit_json(obj):
+    line = json.dumps(obj)
+    if _GUARD is not None:
+        _GUARD.emit(line)
+    else:
+        print(line, flush=True)
+
+
 def main():
+    global _GUARD
     args = parse_args()
     from vampire_b200.config import NAMED
     cfg = NAMED[args.config]
+    _GUARD = StdoutGuard()
     if args.impl == "reference":
         run_reference_arm(args, cfg)
         return
@@ -514,7 +543,8 @@ def main():
     if world > 1:
         # keep stdout for the ONE JSON line: NCCL's own messages (e.g. the version banner under NCCL_DEBUG=VERSION)
         # go to stderr unless the caller already chose a file
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=dev)
     train = args.workload == "train"
     batch = args.batch or (1 if train else 8)
@@ -701,7 +731,7 @@ def main():
                                 "cpu": cpu_model(), "kind": "port",
                                 "lift_pts_per_s": cpts / best_l, "render_rays_per_s": crays / best_r,
                                 "sample": desc + f"; 1 warm-up + best of 3: lift {best_l:.2f} s, render {best_r:.2f} s"}
-    print(json.dumps(line), flush=True)
+    emit_json(line)
     if world > 1:
         dist.destroy_process_group()
 

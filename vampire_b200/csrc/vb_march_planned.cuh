@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fw
   // record of sample i+2 is requested into registers, and the record of sample i+1 has arrived so that its density
   // gathers are issued before sample i is composited.
 #ifndef VB_MARCH_PREFETCH
-#define VB_MARCH_PREFETCH 12
+#define VB_MARCH_PREFETCH 4    // measured: 0.444 ms at 4 samples ahead, 0.455 at 12, 0.463 at 32
 #endif
   constexpr int kPrefetchAhead = VB_MARCH_PREFETCH;
   auto prefetch = [&](int i) {

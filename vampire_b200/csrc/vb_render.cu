@@ -578,7 +578,7 @@ struct BevLevelX {       // per level: row offsets of z0 / z0+1 inside a plane, 
 
 // One channel plane, all levels, MODE 0/1 (mode1, warp-uniform).  MAP (block-uniform): composite with the
 // level weights into a (oY,oX) map; otherwise store the resampled rows as T.
-template <typename T, bool MAP>
+template <typename T, bool MAP, bool EPI = false>
 __device__ __forceinline__ void bev_fast_channel(const BevLevelX* __restrict__ lv, int oZ, const bool mode1,
                                                  const BevQuadFast& q, const T* __restrict__ plane, bool live,
                                                  const float* __restrict__ wl, float* __restrict__ o_map,
@@ -622,7 +622,7 @@ __device__ __forceinline__ void bev_fast_channel(const BevLevelX* __restrict__ l
       acc[0] = fmaf(w.x, v[0], acc[0]); acc[1] = fmaf(w.y, v[1], acc[1]);
       acc[2] = fmaf(w.z, v[2], acc[2]); acc[3] = fmaf(w.w, v[3], acc[3]);
     } else if (live) {                                                                      // BV2:448
-      if (wl) {                                  // fused BEV epilogue: x tanh(sigma) of the same voxels (BV2:627-630)
+      if (EPI) {                                 // fused BEV epilogue: x tanh(sigma) of the same voxels (BV2:627-630)
         const float4 th = __ldg(wp);
         v[0] *= th.x; v[1] *= th.y; v[2] *= th.z; v[3] *= th.w;
       }
@@ -634,7 +634,7 @@ __device__ __forceinline__ void bev_fast_channel(const BevLevelX* __restrict__ l
 }
 
 // generic fallback (MODE 2): scalar gathers, exact for any det grid
-template <typename T, int K, int C>
+template <typename T, int K, int C, bool EPI = false>
 __device__ __forceinline__ void bev_quad_channel_generic(const VbGrid& g, const BevLevel* __restrict__ lv,
                                                          const BevQuadX& q, const T* __restrict__ plane, int y0,
                                                          float wy0, float wy1, int lane, bool live,
@@ -665,7 +665,7 @@ __device__ __forceinline__ void bev_quad_channel_generic(const VbGrid& g, const 
       acc[0] = fmaf(w.x, v[0], acc[0]); acc[1] = fmaf(w.y, v[1], acc[1]);
       acc[2] = fmaf(w.z, v[2], acc[2]); acc[3] = fmaf(w.w, v[3], acc[3]);
     } else if (live) {
-      if (wl) {                                  // fused BEV epilogue (wl = tanh(sigma) workspace in this mode)
+      if (EPI) {                                 // fused BEV epilogue (wl = tanh(sigma) workspace in this mode)
         const float4 th = __ldg(reinterpret_cast<const float4*>(wl + (size_t)l * ncol));
         v[0] *= th.x; v[1] *= th.y; v[2] *= th.z; v[3] *= th.w;
       }
@@ -681,7 +681,7 @@ __host__ __device__ constexpr int bev_chunks(int n) { return (n + 7) / 8; }
 __host__ __device__ constexpr int bev_chunk_len(int n) { return (n + bev_chunks(n) - 1) / bev_chunks(n); }
 __host__ __device__ constexpr int bev_groups(int K, int C) { return bev_chunks(K + 3) + bev_chunks(C); }
 
-template <typename T, int K, int C>
+template <typename T, int K, int C, bool EPI>
 __global__ void __launch_bounds__(64, 16) bev_channels_vec4_kernel(VbGrid g, VbTables t, const T* __restrict__ sem,
                                                                const T* __restrict__ rgb, const T* __restrict__ feat,
                                                                const float* __restrict__ wl_ws,
@@ -733,8 +733,8 @@ __global__ void __launch_bounds__(64, 16) bev_channels_vec4_kernel(VbGrid g, VbT
   const int c_begin = is_map ? grp * LM : (grp - GM) * LF;
   const int c_end = is_map ? min(c_begin + LM, NM) : min(c_begin + LF, C);
   // composited planes: the level weights; feature planes: tanh(sigma) when the BEV epilogue is fused, else nothing
-  const float* wl = is_map ? wl_ws + (size_t)b * g.oZ * ncol + col0
-                           : (th_ws ? th_ws + (size_t)b * g.oZ * ncol + col0 : nullptr);
+  // composited planes: the level weights; feature planes: tanh(sigma) when the BEV epilogue is fused (else unused)
+  const float* wl = ((EPI && !is_map) ? th_ws : wl_ws) + (size_t)b * g.oZ * ncol + col0;
 
   auto planes = [&](int j, const T*& plane, float*& o_map, T*& o_f) {
     o_map = nullptr;
@@ -766,7 +766,7 @@ __global__ void __launch_bounds__(64, 16) bev_channels_vec4_kernel(VbGrid g, VbT
       T* o_f;
       planes(j, plane, o_map, o_f);
       if (is_map) bev_fast_channel<T, true>(s_lx, g.oZ, w1, f, plane, live, wl, o_map, o_f, ncol);
-      else bev_fast_channel<T, false>(s_lx, g.oZ, w1, f, plane, live, wl, o_map, o_f, ncol);
+      else bev_fast_channel<T, false, EPI>(s_lx, g.oZ, w1, f, plane, live, wl, o_map, o_f, ncol);
     }
   } else {
     for (int j = c_begin; j < c_end; ++j) {
@@ -774,7 +774,8 @@ __global__ void __launch_bounds__(64, 16) bev_channels_vec4_kernel(VbGrid g, VbT
       float* o_map;
       T* o_f;
       planes(j, plane, o_map, o_f);
-      bev_quad_channel_generic<T, K, C>(g, s_lv, q, plane, y0, wy0, wy1, lane, live, wl, o_map, o_f, ncol);
+      if (is_map) bev_quad_channel_generic<T, K, C, false>(g, s_lv, q, plane, y0, wy0, wy1, lane, live, wl, o_map, o_f, ncol);
+      else bev_quad_channel_generic<T, K, C, EPI>(g, s_lv, q, plane, y0, wy0, wy1, lane, live, wl, o_map, o_f, ncol);
     }
   }
 }
@@ -959,8 +960,7 @@ __global__ void __launch_bounds__(kBevTmaThreads, sizeof(T) == 4 ? 8 : 10) bev_c
       float* o_map;
       T* o_f;
       outputs_of(j, o_map, o_f);
-      bev_quad_channel_generic<T, K, C>(g, s_lv, q, plane_of(j), y0, wy0, wy1, lane, live, is_map ? wl : nullptr,
-                                        o_map, o_f, ncol);
+      bev_quad_channel_generic<T, K, C>(g, s_lv, q, plane_of(j), y0, wy0, wy1, lane, live, wl, o_map, o_f, ncol);
     }
     return;
   }
@@ -1148,8 +1148,15 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
       bev_channels_tma_kernel<T, K, C><<<dim3(g->oY * vb_ceil_div(g->oX, 256), bev_groups(K, C), g->B), kBevTmaThreads, 0, bst>>>(
           *g, *t, sem, rgb, feat, wl_ws, out->bev_rgb, out->bev_seg, reinterpret_cast<T*>(out->voxel_output));
     } else if (vec_ok)
-      bev_channels_vec4_kernel<T, K, C><<<dim3(g->oY * vb_ceil_div(g->oX, 256), bev_groups(K, C), g->B), 64, 0, bst>>>(
-          *g, *t, sem, rgb, feat, wl_ws, out->bev_rgb, out->bev_seg, reinterpret_cast<T*>(out->voxel_output), th_ws);
+    {
+      const dim3 vgrid(g->oY * vb_ceil_div(g->oX, 256), bev_groups(K, C), g->B);
+      if (th_ws)
+        bev_channels_vec4_kernel<T, K, C, true><<<vgrid, 64, 0, bst>>>(
+            *g, *t, sem, rgb, feat, wl_ws, out->bev_rgb, out->bev_seg, reinterpret_cast<T*>(out->voxel_output), th_ws);
+      else
+        bev_channels_vec4_kernel<T, K, C, false><<<vgrid, 64, 0, bst>>>(
+            *g, *t, sem, rgb, feat, wl_ws, out->bev_rgb, out->bev_seg, reinterpret_cast<T*>(out->voxel_output), th_ws);
+    }
     else
       bev_channels_kernel<T, K, C><<<dim3(vb_ceil_div(ncol, 256), K + 3 + C, g->B), 256, 0, bst>>>(
           *g, *t, sem, rgb, feat, wl_ws, out->bev_rgb, out->bev_seg, reinterpret_cast<T*>(out->voxel_output), th_ws);

@@ -3,7 +3,7 @@
 # (variants built beforehand with tools/build_variant.sh; "base" = the in-tree library)
 for v in "$@"; do
   if [ "$v" = base ]; then unset VB200_LIB; else export VB200_LIB=$PWD/vampire_b200/_lib/variants/libvb200_$v.so; fi
-  python bench.py --steps 10 --no-train-probe --no-aten-baseline --no-cpu-baseline --no-e2e --no-uncached 2>/dev/null | python -c "
+  python bench.py --steps 10 $BENCH_ARGS --no-train-probe --no-aten-baseline --no-cpu-baseline --no-e2e --no-uncached 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
 k=d['aux']['kernels']

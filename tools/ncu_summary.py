@@ -65,17 +65,22 @@ def main():
                              l1=d.get("L1hit%", 0), oc=d.get("occ%", 0), iss=d.get("issue%", 0),
                              wi=d.get("warp_inst", 0) / 1e6, rg=d.get("regs", 0), g=d.get("grid", 0), wv=d.get("waves", 0)))
             short = {"lift_pool_fwd_kernel": "lift_pool_fwd", "march_fwd_kernel": "march_fwd",
+                     "lift_fwd_planned_kernel": "lift_pool_fwd", "march_fwd_planned_kernel": "march_fwd",
                      "pack_cam_volume_kernel": "pack_cam_volume", "bev_channels_vec4_kernel": "bev_fwd"}
             for pat, name in short.items():
                 if d["kernel"].startswith(pat):
                     # several launches may match (the march launches a fast and a NaN-safe variant, one of which
                     # returns at once): keep the one that moved the data
                     t = d.get("dram_rd", 0) + d.get("dram_wr", 0)
+                    if not isinstance(traffic.get(name), dict):
+                        traffic[name] = {}
                     if a.dtype not in traffic.setdefault(name, {}) or name not in fresh or t > traffic[name][a.dtype]:
                         traffic[name][a.dtype] = t
                     fresh.add(name)
     open(a.out, "w").write("\n".join(lines) + "\n")
     if a.traffic:
+        traffic["_source"] = "ncu --set full capture " + ", ".join(os.path.basename(r) for r in a.reps) + \
+            " (dram__bytes_read.sum + dram__bytes_write.sum per launch; not live)"
         json.dump(traffic, open(a.traffic, "w"), indent=1)
     print("\n".join(lines))
 

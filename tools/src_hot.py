@@ -11,13 +11,17 @@ rows = list(csv.reader(io.StringIO(out)))
 hi = [i for i, r in enumerate(rows) if r and "Instructions Executed" in r]
 hdr = rows[hi[0]]
 ci = hdr.index("Instructions Executed"); cs = hdr.index("Warp Stall Sampling (All Samples)")
-end = hi[1] - 3 if len(hi) > 1 else len(rows)
+# the page lists one section per source file of the FIRST matching kernel, then the next kernel: stop at the second
+# "Kernel Name" row
+kn = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+end = kn[1] if len(kn) > 1 else len(rows)
 agg = defaultdict(lambda: [0, 0, ""])
 cur_line, cur_src, cur_file = None, "", ""
-for r in rows[hi[0] + 1:end]:
-    if len(r) <= ci:
-        if r and r[0] == "File Name":
-            cur_file = r[1].split("/")[-1]
+for r in rows[(kn[0] if kn else 0):end]:
+    if r and r[0] == "File Name":
+        cur_file = r[1].split("/")[-1]
+        continue
+    if len(r) <= ci or r[0] == "Line No":
         continue
     if r[0]:
         cur_line, cur_src = r[0], r[1]

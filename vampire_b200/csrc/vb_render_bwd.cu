@@ -54,9 +54,28 @@ __device__ __forceinline__ float block_sum(float v, float* s_red) {
   return tot;   // valid in thread 0
 }
 
+// slow path of march_bwd (a non-finite value somewhere in the 8 corners): the reference's per-channel
+// nan_to_num(interpolated value) (BV2:421), kept out of line so that its 24-float temporary costs the hot path no registers
+template <typename T, int K>
+__device__ __noinline__ void nan_safe_values(const T* __restrict__ packed, const int (&cidx)[8], const float (&cw)[8],
+                                             const float (&gc)[K + 3], float& s0, float& Gv) {
+  constexpr int CP = packed_channels(K);
+  float v[CP];
+#pragma unroll
+  for (int c = 0; c < CP; ++c) v[c] = 0.0f;
+  for (int q = 0; q < 8; ++q) PackedLoad<T, CP>::fma_corner(packed + cidx[q], cw[q], v);
+  s0 = nan_to_num(v[0], 0.0f);
+  Gv = 0.0f;
+#pragma unroll
+  for (int c = 0; c < K + 3; ++c) Gv = fmaf(gc[c], nan_to_num(v[1 + c], 0.0f), Gv);
+}
+
 // ---- camera branch ---------------------------------------------------------------------------------------
+#ifndef VB_MARCH_BWD_MINB
+#define VB_MARCH_BWD_MINB 4
+#endif
 template <typename T, int K, bool FROM_MATS>
-__global__ void __launch_bounds__(kMarchThreads) march_bwd_kernel(
+__global__ void __launch_bounds__(kMarchThreads, VB_MARCH_BWD_MINB) march_bwd_kernel(
     VbGrid g, VbTables t, VbRenderDiv dv, const float* __restrict__ d_mats, const float* __restrict__ d_geom,
     const T* __restrict__ packed, const float* __restrict__ beta_ptr, const float* __restrict__ o_rgb,
     const float* __restrict__ o_seg, const float* __restrict__ o_depth, const float* __restrict__ g_rgb,
@@ -128,6 +147,12 @@ __global__ void __launch_bounds__(kMarchThreads) march_bwd_kernel(
     if (active) omega = fmaf(gc[K + j], __ldg(o_rgb + (bn * 3 + j) * HW + pix), omega);
   }
 
+  // which 4-channel vectors of the record carry a non-zero cotangent (bit f: record channels 4f .. 4f+3)
+  unsigned gc_nz = 0u;
+#pragma unroll
+  for (int c = 0; c < K + 3; ++c)
+    if (gc[c] != 0.0f) gc_nz |= 1u << ((c + 1) >> 2);
+
   float tau = 0.0f, prefix = 0.0f, dbeta = 0.0f;
   float p0[3], p1[3];
   if (warp_live) {
@@ -140,9 +165,11 @@ __global__ void __launch_bounds__(kMarchThreads) march_bwd_kernel(
       const float delta = sqrtf(dx * dx + dy * dy + dz * dz);
       const RenderCoord rc = fastdiv ? render_coord<true>(g, p0, &dv) : render_coord<false>(g, p0);
       const bool live = rc.valid && active;
-      float v[CP];
-#pragma unroll
-      for (int c = 0; c < CP; ++c) v[c] = 0.0f;
+      // The interpolated channel values are needed only through two scalars: s0 (the density feature) and
+      // Gv = sum_c g_c v_c.  Both are accumulated corner by corner -- Gv as sum_q cw_q (sum_c g_c t_qc) -- so no
+      // 24-float v[] (nor a 24-float dv[] below) stays live across the gather and the scatter: 150 -> under 128
+      // registers, one more resident block per SM for a kernel that waits on memory 80 % of the time.
+      float s0 = 0.0f, Gv = 0.0f;
       int cidx[8];
       float cw[8];
       if (live) {
@@ -157,41 +184,49 @@ __global__ void __launch_bounds__(kMarchThreads) march_bwd_kernel(
           const int cx = q & 1, cy = (q >> 1) & 1, cz = q >> 2;
           cw[q] = wx[cx] * wy[cy] * wz[cz];
           cidx[q] = ((zs_[cz] * g.vY + ys_[cy]) * g.vX + xs_[cx]) * CP;
-          PackedLoad<T, CP>::fma_corner(packed + cidx[q], cw[q], v);
+          float den_q, dot_q;
+          PackedLoad<T, CP>::template dot_values<K + 3>(packed + cidx[q], gc, den_q, dot_q);
+          s0 = fmaf(cw[q], den_q, s0);
+          Gv = fmaf(cw[q], dot_q, Gv);
         }
-#pragma unroll
-        for (int c = 0; c < K + 4; ++c) v[c] = nan_to_num(v[c], 0.0f);
+        // torch.nan_to_num of the interpolated features (BV2:421) is the identity unless something is non-finite, and
+        // then s0 or Gv is non-finite too: the exact per-channel form runs only in that case
+        if (!(fabsf(s0) + fabsf(Gv) <= 3.402823466e+38f)) nan_safe_values<T, K>(packed, cidx, cw, gc, s0, Gv);
       }
-      const DensityD dd = density_with_grads(v[0], g.sdf_bias, beta);
+      const DensityD dd = density_with_grads(s0, g.sdf_bias, beta);
       const float sd = dd.sigma * delta;
       const float e_sd = expf(-sd);
       const float wgt = (1.0f - e_sd) * trans;
       const float t_next = trans * e_sd;
-      float Gp = gd * (__ldg(t.mids + i) - g.bg_depth);
-#pragma unroll
-      for (int c = 0; c < K + 3; ++c) Gp = fmaf(gc[c], v[1 + c], Gp);
+      const float Gp = fmaf(gd, __ldg(t.mids + i) - g.bg_depth, Gv);
       prefix = fmaf(wgt, Gp, prefix);
       const float dsd = Gp * t_next - (omega - prefix);
       const float dsig = dsd * delta;
       if (active) dbeta = fmaf(dsig, dd.dbeta, dbeta);
       if (live) {
-        float dv[CP];
-        dv[0] = dsig * dd.ds;
-#pragma unroll
-        for (int c = 0; c < K + 3; ++c) dv[1 + c] = gc[c] * wgt;
-#pragma unroll
-        for (int c = K + 4; c < CP; ++c) dv[c] = 0.0f;
+        // d v_c = g_c w (c >= 1), d v_0 = dsig * dsigma/ds; scattered as cw_q * (.) with 128-bit vector atomics.
+        // Exact zeros need no atomic at all: in free space w = 0 and only the density vector is live; a zero rgb
+        // loss weight (the target experiment, base_exp.py loss_weights) zeroes a whole vector for the entire ray
+        // (gc_nz, decided once per ray).
+        const float d0 = dsig * dd.ds;
+        const bool w_nz = wgt != 0.0f;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           if (cw[q] != 0.0f) {
             float4* dst = reinterpret_cast<float4*>(gpacked + cidx[q]);
+            const float sw = cw[q] * wgt;
+            if (d0 != 0.0f || (w_nz && (gc_nz & 1u)))
+              atomicAdd(dst, make_float4(cw[q] * d0, sw * gc[0], sw * gc[1], sw * gc[2]));
 #pragma unroll
-            for (int f = 0; f < CP / 4; ++f) {
-              // exact zeros (e.g. the rgb loss weight is 0 in the target experiment, base_exp.py loss_weights)
-              // need no atomic at all
-              if (dv[4 * f] != 0.0f || dv[4 * f + 1] != 0.0f || dv[4 * f + 2] != 0.0f || dv[4 * f + 3] != 0.0f)
-                atomicAdd(dst + f, make_float4(cw[q] * dv[4 * f], cw[q] * dv[4 * f + 1], cw[q] * dv[4 * f + 2],
-                                               cw[q] * dv[4 * f + 3]));
+            for (int f = 1; f < CP / 4; ++f) {
+              if (w_nz && ((gc_nz >> f) & 1u)) {
+                // channels 4f .. 4f+3 of the record = gc[4f-1 .. 4f+2]; beyond K+3 the record is padding
+                const float g0 = gc[4 * f - 1];
+                const float g1 = (4 * f < K + 3) ? gc[4 * f < K + 3 ? 4 * f : 0] : 0.0f;
+                const float g2 = (4 * f + 1 < K + 3) ? gc[4 * f + 1 < K + 3 ? 4 * f + 1 : 0] : 0.0f;
+                const float g3 = (4 * f + 2 < K + 3) ? gc[4 * f + 2 < K + 3 ? 4 * f + 2 : 0] : 0.0f;
+                atomicAdd(dst + f, make_float4(sw * g0, sw * g1, sw * g2, sw * g3));
+              }
             }
           }
         }

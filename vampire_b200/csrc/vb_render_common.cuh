@@ -134,6 +134,24 @@ template <typename T, int CP> struct PackedLoad {
       }
     }
   }
+  // den = p[0]; dot = sum_{c < NV} g[c] * p[1 + c]   (one corner of the backward march: no per-channel temporary)
+  template <int NV>
+  __device__ __forceinline__ static void dot_values(const T* p, const float (&g)[NV], float& den, float& dot) {
+    constexpr int L = VbLanes<T>::n;
+    den = 0.0f;
+    dot = 0.0f;
+#pragma unroll
+    for (int q = 0; q < CP / L; ++q) {
+      float tmp[L];
+      VbVec<T, L>::ld(p + q * L, tmp);
+#pragma unroll
+      for (int e = 0; e < L; ++e) {
+        const int c = q * L + e - 1;
+        if (c == -1) den = tmp[e];
+        else if (c < NV) dot = fmaf(tmp[e], g[c < NV ? c : 0], dot);
+      }
+    }
+  }
   __device__ __forceinline__ static void fma_corner(const T* p, float wgt, float (&v)[CP]) {
     constexpr int L = VbLanes<T>::n;
 #pragma unroll

@@ -72,7 +72,7 @@ __device__ __noinline__ void nan_safe_values(const T* __restrict__ packed, const
 
 // ---- camera branch ---------------------------------------------------------------------------------------
 #ifndef VB_MARCH_BWD_MINB
-#define VB_MARCH_BWD_MINB 4
+#define VB_MARCH_BWD_MINB 3   // measured B=1 fp32: 0.593 ms at 3 blocks/SM, 0.68 at 4, 0.76 at 5 (B=8: 4.35 ms either way: L2-bound)
 #endif
 template <typename T, int K, bool FROM_MATS>
 __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_BWD_MINB) march_bwd_kernel(

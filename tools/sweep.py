@@ -1,6 +1,6 @@
 """BASELINE.json configs[3] (scaled frustum, fwd+bwd) and configs[4] (render sweep) on one B200.
 
-    python tools/sweep.py > profiles/r01_config_sweep.md
+    python tools/sweep.py > profiles/r02_config_sweep.md
 """
 import os, sys
 from dataclasses import replace
@@ -33,7 +33,7 @@ def setup(cfg, B, dtype, field="surface"):
     return cid, prep, depth, ctx, vols
 
 
-print("# Round 1 -- BASELINE.json configs[3] and configs[4] on 1 x B200 (CUDA events, 10 iterations after 3 warm-ups)\n")
+print("# Round 2 -- BASELINE.json configs[3] and configs[4] on 1 x B200 (CUDA events, 10 iterations after 3 warm-ups)\n")
 print("## configs[3]: scaled frustum 6x512x1408, D=86, grid 20x256x256, B=1, fp32, forward+backward\n")
 print("| geometry | lift fwd ms | lift bwd ms | render fwd ms | render bwd ms | frustum pts | lift fwd Gpts/s | render fwd Mrays/s |")
 print("|---|---|---|---|---|---|---|---|")
@@ -54,7 +54,7 @@ for name, cfg in (("256x704", R50_256x704), ("512x1408", R50_512x1408)):
 
 print("\n## configs[4]: standalone render sweep (camera branch only, B=1, bf16 volume, 'surface' field)\n")
 print("planes d_i = 2.0 + (68.4/S) i; rays per image = fH x fW of the feature map\n")
-print("| rays/image | S=64 | S=85 | S=128 | S=192 | S=256 |   (ms ; Mrays/s ; Gsamples/s)")
+print("| rays/image | S=64 | S=85 | S=128 | S=192 | S=256 |   (ms recomputed geometry / ms cached plan ; Mrays/s ; Gsamples/s with the plan)")
 print("|---|---|---|---|---|---|")
 for fd in ((256, 704), (512, 1408), (1024, 2816)):
     row = []
@@ -66,8 +66,12 @@ for fd in ((256, 704), (512, 1408), (1024, 2816)):
         cid, prep, depth, ctx, (den, sem, feat, rgb) = setup(cfg, 1, torch.bfloat16)
         beta = torch.tensor(0.1, device="cuda")
         t = timed(lambda: ops.render_fwd(den, sem, rgb, feat, beta, prep, None, cid, True, 1))
+        from vampire_b200.plan import PlanCache
+        tab = PlanCache().render(ops.state(cid), cid, prep, True).table
+        tp_ = timed(lambda: ops.render_fwd(den, sem, rgb, feat, beta, prep, None, cid, True, 1, tab))
         rays = cfg.num_cams * cfg.fH * cfg.fW
-        row.append(f"{t:.3f} ; {rays / t / 1e3:.0f} ; {rays * cfg.S / t / 1e6:.2f} (S={cfg.S})")
+        row.append(f"{t:.3f} / {tp_:.3f} ; {rays / tp_ / 1e3:.0f} ; {rays * cfg.S / tp_ / 1e6:.2f} (S={cfg.S})")
+        del tab
         del depth, ctx, den, sem, feat, rgb
     print(f"| {fd[0] // 4}x{fd[1] // 4} | " + " | ".join(row) + " |")
 

@@ -10,13 +10,16 @@
 //   scan_chunks/sums/add exclusive scan -> CSR offsets (chunked 3-pass scan)
 //   plan_pairs<fill>    records ((z0+1) << 21 | voxel) dropped into their cell's segment
 //   sort_cells          warp per cell: rank-sort the segment => order fixed by (z0, voxel)
-//   lift_bwd<colour>    warp per cell, 4 launches over the 2x2 cell colouring so that concurrently
-//                       processed cells touch disjoint pixels: per-warp shared-memory depth bins and
-//                       register d_ctx accumulators, plain (non-atomic) read-modify-write flush.
-//                       Phase A (lane = pair): bit-exact re-projection, 8 depth loads, 16-channel
-//                       dot products, warp-shuffle segmented reduction over equal depth bins.
+//   lift_bwd            warp per cell, ONE launch over all cells: per-warp shared-memory depth bins and register
+//                       d_ctx accumulators, written out as the cell's own partials (4 corner pixels x D depth
+//                       bins, 4 x C channels) with coalesced stores -- no read-modify-write of the gradients.
+//                       Phase A (lane = pair): bit-exact re-projection (or the cached plan record), 8 depth loads,
+//                       16-channel dot products, warp-shuffle segmented reduction over equal depth bins.
 //                       Phase B (lane = channel): serial accumulation of d_ctx in sorted order.
-//   finalize            fp32 accumulators -> the caller's layout / dtype.
+//                       (Round 1 ran 4 launches over a 2x2 cell colouring and flushed with `gd[..] += v`: ncu put
+//                        41 % of all stall samples on that dependent global load -> add -> store.)
+//   lift_bwd_reduce     per pixel: the sum of the <= 4 cells it is a corner of, in fixed order, cast to the caller's
+//                       dtype and layout (d_depth (B,N,D,fH,fW), d_ctx (B,N,C,fH,fW)).
 //
 // No float atomics anywhere => bit-reproducible gradients; no grad-frustum is ever formed.
 #include "vb_lift_common.cuh"
@@ -141,13 +144,12 @@ __global__ void __launch_bounds__(kThreads, VB_LIFT_BWD_MINB) lift_bwd_kernel(Vb
                                                             const float* __restrict__ ctx_nhwc,
                                                             const float* __restrict__ gprep,
                                                             const int* __restrict__ offsets,
-                                                            const uint32_t* __restrict__ recs, float* __restrict__ gdepth,
-                                                            float* __restrict__ gctx_nhwc, int colour) {
+                                                            const uint32_t* __restrict__ recs,
+                                                            float* __restrict__ part_depth,
+                                                            float* __restrict__ part_ctx) {
   extern __shared__ float s_dyn[];
   __shared__ float s_m[VB200_MAT_SLOTS * 16];
   const CellDims cd = cell_dims(g);
-  const int py_ = colour >> 1, px_ = colour & 1;
-  const int ny = (cd.ncy - py_ + 1) / 2, nx = (cd.ncx - px_ + 1) / 2;   // cells of this colour per camera
   // blockIdx.y = b * N + n so that a block shares one camera's matrices
   const int bn = blockIdx.y, b = bn / g.N, n = bn % g.N;
   bool has_bda = false, affine = false;
@@ -161,8 +163,8 @@ __global__ void __launch_bounds__(kThreads, VB_LIFT_BWD_MINB) lift_bwd_kernel(Vb
 
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ci = blockIdx.x * (kThreads / 32) + wid;
-  if (ci >= ny * nx) return;
-  const int cy = 2 * (ci / nx) + py_, cx = 2 * (ci % nx) + px_;
+  if (ci >= cd.ncy * cd.ncx) return;
+  const int cy = ci / cd.ncx, cx = ci % cd.ncx;
   const int y0 = cy - 1, x0 = cx - 1;
   const int cell = (n * cd.ncy + cy) * cd.ncx + cx;
   const int* off = PLANNED ? plans[b].cell_off : offsets + (size_t)b * (cd.nc + 1);
@@ -286,48 +288,67 @@ __global__ void __launch_bounds__(kThreads, VB_LIFT_BWD_MINB) lift_bwd_kernel(Vb
     __syncwarp();
   }
 
-  // ---- flush: this colour's cells own disjoint pixels => plain read-modify-write, fixed colour order
-  float* gd = gdepth + (size_t)bn * D * HW;
-  for (int i = lane; i < 4 * D; i += 32) {
-    const int k = i / D, z = i % D;
-    const float v = bins[i];
-    if (v != 0.0f && pin[k]) gd[(size_t)z * HW + pxl[k]] += v;
-  }
+  // ---- flush: the cell's own partials, coalesced, no read-modify-write (empty cells return above and are skipped
+  // by the reduce, which reads the same CSR offsets)
+  float* pd = part_depth + ((size_t)b * cd.nc + cell) * 4 * D;
+  for (int i = lane; i < 4 * D; i += 32) pd[i] = bins[i];
 #pragma unroll
   for (int k = 0; k < 4; ++k) accC[k] += __shfl_down_sync(0xffffffffu, accC[k], 16);
   if (half == 0) {
-    float* gc = gctx_nhwc + (size_t)bn * HW * kC;
+    float* pc = part_ctx + ((size_t)b * cd.nc + cell) * 4 * kC;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (pin[k]) gc[(size_t)pxl[k] * kC + c_] += accC[k];
+    for (int k = 0; k < 4; ++k) pc[k * kC + c_] = accC[k];
   }
 }
 
-// ---- finalize ----------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256) gctx_to_nchw_kernel(const float* __restrict__ src, T* __restrict__ dst, int fH,
-                                                           int fW) {
-  extern __shared__ float s_t[];  // [fW][C + 1]
-  const int h = blockIdx.x, bn = blockIdx.y, ld = kC + 1;
-  const float* in = src + ((size_t)bn * fH + h) * fW * kC;
-  for (int i = threadIdx.x; i < kC * fW; i += blockDim.x) s_t[(i / kC) * ld + (i % kC)] = in[i];
-  __syncthreads();
-  for (int i = threadIdx.x; i < kC * fW; i += blockDim.x) {
-    const int c = i / fW, w = i % fW;
-    dst[(((size_t)bn * kC + c) * fH + h) * fW + w] = VbType<T>::cvt(s_t[w * ld + c]);
+// ---- per pixel: sum of the cells it is a corner of -------------------------------------------------------------------
+// Pixel (y, x) of camera n is corner k of cell (cy, cx) = (y + 1 - (k >> 1), x + 1 - (k & 1)): k = 0 (ya, xa) of the cell
+// whose base is the pixel itself ... k = 3 (yb, xb) of the cell one up-left.  Fixed order k = 0..3 => deterministic.
+// grid = (fH, B * N); a block walks one image row: threads over x, loop over the D depth bins / C channels.
+template <typename TD, typename TC>
+__global__ void __launch_bounds__(256) lift_bwd_reduce_kernel(VbGrid g, const VbLiftPlan* __restrict__ plans,
+                                                              const int* __restrict__ offsets,
+                                                              const float* __restrict__ part_depth,
+                                                              const float* __restrict__ part_ctx, TD* __restrict__ gdepth,
+                                                              TC* __restrict__ gctx) {
+  const CellDims cd = cell_dims(g);
+  const int y = blockIdx.x, bn = blockIdx.y, b = bn / g.N, n = bn % g.N;
+  const int D = g.D, HW = g.fH * g.fW;
+  const int* off = plans ? plans[b].cell_off : offsets + (size_t)b * (cd.nc + 1);
+  for (int x = threadIdx.x; x < g.fW; x += blockDim.x) {
+    const float* pd[4];
+    const float* pc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int cell = (n * cd.ncy + (y + 1 - (k >> 1))) * cd.ncx + (x + 1 - (k & 1));
+      const bool any = off[cell + 1] != off[cell];
+      pd[k] = any ? part_depth + (((size_t)b * cd.nc + cell) * 4 + k) * D : nullptr;
+      pc[k] = any ? part_ctx + (((size_t)b * cd.nc + cell) * 4 + k) * kC : nullptr;
+    }
+    TD* gd = gdepth + (size_t)bn * D * HW + (size_t)y * g.fW + x;
+    for (int z = 0; z < D; ++z) {
+      float v = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (pd[k]) v += __ldg(pd[k] + z);
+      gd[(size_t)z * HW] = VbType<TD>::cvt(v);
+    }
+    TC* gc = gctx + (size_t)bn * kC * HW + (size_t)y * g.fW + x;
+#pragma unroll
+    for (int c = 0; c < kC; ++c) {
+      float v = 0.0f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (pc[k]) v += __ldg(pc[k] + c);
+      gc[(size_t)c * HW] = VbType<TC>::cvt(v);
+    }
   }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ src, T* __restrict__ dst, size_t n) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = VbType<T>::cvt(src[i]);
 }
 
 size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 
 struct BwdLayout {
-  size_t ctx, counts, offsets, cursor, chunk_sums, recs_a, recs_b, gctx, gprep, gdepth, total;
+  size_t ctx, counts, offsets, cursor, chunk_sums, recs_a, recs_b, part_ctx, gprep, part_depth, total;
 };
 // planned: the per-call plan buffers (counts / offsets / cursor / records) are not needed
 BwdLayout bwd_layout(const VbGrid* g, bool need_gdepth_ws, bool planned) {
@@ -342,9 +363,11 @@ BwdLayout bwd_layout(const VbGrid* g, bool need_gdepth_ws, bool planned) {
   l.chunk_sums = o; o += planned ? 0 : align256((size_t)g->B * 1024 * 4);
   l.recs_a = o;  o += planned ? 0 : align256((size_t)g->B * g->N * nvox * 4);
   l.recs_b = o;  o += planned ? 0 : align256((size_t)g->B * g->N * nvox * 4);
-  l.gctx = o;    o += align256((size_t)g->B * g->N * HW * kC * 4);
-  l.gprep = o;   o += align256((size_t)g->B * nvox * kC * 4);
-  l.gdepth = o;  o += need_gdepth_ws ? align256((size_t)g->B * g->N * g->D * HW * 4) : 0;
+  // per-cell partials: 4 corner pixels x (C channels | D depth bins) fp32 (R50: 95 MB per sample)
+  l.part_ctx = o;   o += align256((size_t)g->B * cd.nc * 4 * kC * 4);
+  l.gprep = o;      o += align256((size_t)g->B * nvox * kC * 4);
+  l.part_depth = o; o += align256((size_t)g->B * cd.nc * 4 * g->D * 4);
+  (void)need_gdepth_ws;
   l.total = o;
   return l;
 }
@@ -359,6 +382,7 @@ int launch_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const Vb
   const size_t nvox = (size_t)g->vZ * g->vY * g->vX, HW = (size_t)g->fH * g->fW;
   if (nvox > (1u << kVoxBits) || g->D + 1 >= (1 << (32 - kVoxBits))) return VB200_ERR_ARG;
   constexpr bool kF32 = sizeof(TD) == 4;
+  (void)HW;
   const bool planned = d_plans != nullptr;
   const BwdLayout l = bwd_layout(g, !kF32, planned);
   const CellDims cd = cell_dims(*g);
@@ -369,15 +393,12 @@ int launch_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const Vb
   int* chunk_sums = reinterpret_cast<int*>(ws + l.chunk_sums);
   uint32_t* recs_a = reinterpret_cast<uint32_t*>(ws + l.recs_a);
   uint32_t* recs_b = reinterpret_cast<uint32_t*>(ws + l.recs_b);
-  float* gctx_ws = reinterpret_cast<float*>(ws + l.gctx);
-  float* gdepth_acc = kF32 ? reinterpret_cast<float*>(d_gdepth) : reinterpret_cast<float*>(ws + l.gdepth);
-  const size_t n_gdepth = (size_t)g->B * g->N * g->D * HW;
+  float* part_ctx = reinterpret_cast<float*>(ws + l.part_ctx);
+  float* part_depth = reinterpret_cast<float*>(ws + l.part_depth);
 
   VbLiftDiv dv = {};
   VbTables no_tables = {};
   if (!planned) dv = vb_lift_div(g);
-  if (cudaMemsetAsync(gctx_ws, 0, (size_t)g->B * g->N * HW * kC * 4, st) != cudaSuccess) return VB200_ERR_CUDA;
-  if (cudaMemsetAsync(gdepth_acc, 0, n_gdepth * 4, st) != cudaSuccess) return VB200_ERR_CUDA;
   {
     VbTraceScope tr(VB_K_CTX_NHWC, st);
     ctx_to_nhwc_f32_kernel<TC><<<dim3(g->fH, g->B * g->N), 256, (size_t)kC * (g->fW + 1) * 4, st>>>(
@@ -403,7 +424,7 @@ int launch_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const Vb
     VB_LAUNCH_CHECK();
   }
   {
-    VbTraceScope tr(VB_K_LIFT_BWD, st, kF32 ? 6 : 7);
+    VbTraceScope tr(VB_K_LIFT_BWD, st, 3);
     const size_t smem = (size_t)(kThreads / 32) * (4 * g->D + 32 * 4 + 32 * 17 + 64) * sizeof(float);
     float* gprep = reinterpret_cast<float*>(ws + l.gprep);
     {
@@ -418,21 +439,14 @@ int launch_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, const Vb
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return VB200_ERR_CUDA;
-    for (int colour = 0; colour < 4; ++colour) {
-      const int ny = (cd.ncy - (colour >> 1) + 1) / 2, nx = (cd.ncx - (colour & 1) + 1) / 2;
-      dim3 grid(vb_ceil_div((long long)ny * nx, kThreads / 32), g->B * g->N);
-      kern<<<grid, kThreads, smem, st>>>(*g, planned ? no_tables : *t, dv, d_mats, d_plans,
-                                         reinterpret_cast<const TD*>(d_depth), ctx_nhwc, gprep, offsets, recs_b,
-                                         gdepth_acc, gctx_ws, colour);
-      VB_LAUNCH_CHECK();
-    }
-    gctx_to_nchw_kernel<TC><<<dim3(g->fH, g->B * g->N), 256, (size_t)g->fW * (kC + 1) * 4, st>>>(
-        gctx_ws, reinterpret_cast<TC*>(d_gctx), g->fH, g->fW);
+    dim3 grid(vb_ceil_div((long long)cd.ncy * cd.ncx, kThreads / 32), g->B * g->N);
+    kern<<<grid, kThreads, smem, st>>>(*g, planned ? no_tables : *t, dv, d_mats, d_plans,
+                                       reinterpret_cast<const TD*>(d_depth), ctx_nhwc, gprep, offsets, recs_b,
+                                       part_depth, part_ctx);
     VB_LAUNCH_CHECK();
-    if (!kF32) {
-      cast_kernel<TD><<<VB_SM_COUNT_B200 * 8, 256, 0, st>>>(gdepth_acc, reinterpret_cast<TD*>(d_gdepth), n_gdepth);
-      VB_LAUNCH_CHECK();
-    }
+    lift_bwd_reduce_kernel<TD, TC><<<dim3(g->fH, g->B * g->N), 256, 0, st>>>(
+        *g, d_plans, offsets, part_depth, part_ctx, reinterpret_cast<TD*>(d_gdepth), reinterpret_cast<TC*>(d_gctx));
+    VB_LAUNCH_CHECK();
   }
   return VB200_OK;
 }

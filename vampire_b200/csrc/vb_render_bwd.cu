@@ -422,6 +422,14 @@ __global__ void __launch_bounds__(256, 3) unpack_gather_kernel(
     const int x0 = __ldg(bt.xlo + x), x1 = __ldg(bt.xhi + x);
     const int ncol = g.oY * g.oX;
     if (l0 <= l1) {
+      // the z weights depend on the level only: looked up once per voxel, not once per (oy, ox, level)
+      constexpr int kMaxL = 4;
+      float wzl[kMaxL];
+#pragma unroll
+      for (int j = 0; j < kMaxL; ++j) {
+        const int l = min(l0 + j, l1);
+        wzl[j] = (__ldg(bt.li0 + l) == z) ? __ldg(bt.lw0 + l) : __ldg(bt.lw1 + l);
+      }
       for (int oy = y0; oy <= y1; ++oy) {
         const float wy = (__ldg(bt.yi0 + oy) == y) ? __ldg(bt.yw0 + oy) : __ldg(bt.yw1 + oy);
         for (int ox = x0; ox <= x1; ++ox) {
@@ -429,7 +437,9 @@ __global__ void __launch_bounds__(256, 3) unpack_gather_kernel(
           const int col = oy * g.oX + ox;
           float A = 0.0f;
           for (int l = l0; l <= l1; ++l) {
-            const float wz = (__ldg(bt.li0 + l) == z) ? __ldg(bt.lw0 + l) : __ldg(bt.lw1 + l);
+            const int j = l - l0;
+            const float wz = j < kMaxL ? wzl[j < kMaxL ? j : 0]
+                                       : ((__ldg(bt.li0 + l) == z) ? __ldg(bt.lw0 + l) : __ldg(bt.lw1 + l));
             const size_t o = ((size_t)b * g.oZ + l) * ncol + col;
             cam[0] = fmaf(wxy * wz, __ldg(ds_ws + o), cam[0]);
             A = fmaf(wz, __ldg(wl_ws + o), A);

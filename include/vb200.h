@@ -234,14 +234,17 @@ typedef struct VbRenderPlan {  /* all DEVICE pointers; 32 bytes */
   const void* steps;     /* [N * npatch * (D-1) * 32] x 16 B: {valid << 31 | base voxel, fx, fy, fz}             */
   const float* delta;    /* [same]  |p_{i+1} - p_i|                                                              */
   const int16_t* last;   /* [N * npatch * 32]  last valid sample of the ray, -1 if none                          */
-  const void* reserved;
+  const void* box;       /* [N * npatch * (D-1)] x 8 B: per (warp, sample) the box of voxels covering all trilinear
+                            corners of the warp's rays: {staged << 31 | first voxel, nx | ny << 8 | nz << 16}; bits 21..27
+                            of a record's key = its base corner's index inside the box (shared-memory staged march)  */
 } VbRenderPlan;
 
 /* per-sample element counts of the three arrays: rays = N * npatch * 32, steps = rays * (D-1) */
 size_t vb200_render_plan_rays(const VbGrid* g);
-/* Build the plans of g->B samples: d_steps (B, steps) x 16 B | d_delta (B, steps) fp32 | d_last (B, rays) int16 */
+/* Build the plans of g->B samples: d_steps (B, steps) x 16 B | d_delta (B, steps) fp32 | d_last (B, rays) int16 |
+ * d_box (B, steps / 32) x 8 B */
 int vb200_render_plan_build(const VbGrid* g, const VbTables* t, const float* d_mats, void* d_steps, float* d_delta,
-                            int16_t* d_last, void* stream);
+                            int16_t* d_last, void* d_box, void* stream);
 
 typedef struct VbRenderIn {
   const void* density;  /* (B, 1, vZ, vY, vX) density_feature, `dtype`, NCDHW */

@@ -53,7 +53,7 @@ class VbLiftPlan(C.Structure):
 
 class VbRenderPlan(C.Structure):
     """One sample's cached render plan (device pointers); see include/vb200.h."""
-    _fields_ = [(n, C.c_void_p) for n in ("steps", "delta", "last", "reserved")]
+    _fields_ = [(n, C.c_void_p) for n in ("steps", "delta", "last", "box")]
 
 
 class VbRenderIn(C.Structure):
@@ -117,7 +117,7 @@ _PROTOS = {
     "vb200_query_points_bwd": (C.c_int, [C.POINTER(VbGrid), _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, C.c_int,
                                          C.c_int, C.c_int, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "vb200_render_plan_rays": (C.c_size_t, [C.POINTER(VbGrid)]),
-    "vb200_render_plan_build": (C.c_int, [C.POINTER(VbGrid), C.POINTER(VbTables), _P, _P, _P, _P, _P]),
+    "vb200_render_plan_build": (C.c_int, [C.POINTER(VbGrid), C.POINTER(VbTables), _P, _P, _P, _P, _P, _P]),
     "vb200_render_fwd_workspace": (C.c_size_t, [C.POINTER(VbGrid), C.c_int]),
     "vb200_render_bwd_workspace": (C.c_size_t, [C.POINTER(VbGrid), C.c_int]),
     "vb200_render_packed_bytes": (C.c_size_t, [C.POINTER(VbGrid), C.c_int]),

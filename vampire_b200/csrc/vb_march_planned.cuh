@@ -19,6 +19,15 @@ namespace {
 
 constexpr uint32_t kPlanValid = 0x80000000u;
 constexpr uint32_t kPlanVoxMask = (1u << 21) - 1;
+// Staging boxes (the TMA-class variant, vb_march_staged.cuh): per (warp, sample) the axis-aligned box of voxels that
+// covers all 8 trilinear corners of the warp's in-volume rays.  box[(n * npatch + patch) * S + i] = {staged << 31 | first
+// voxel of the box, nx | ny << 8 | nz << 16}; a record's key carries the base corner's index INSIDE the box in bits
+// 21..27 (rel = ((z - z_lo) * ny + (y - y_lo)) * nx + (x - x_lo)).  A box is staged when it holds at most kBoxCap
+// voxels in at most 32 rows (one bulk copy per lane).
+constexpr int kBoxCap = 96;
+constexpr int kPlanRelShift = 21;
+constexpr uint32_t kPlanRelMask = 0x7fu;
+constexpr uint32_t kBoxStaged = 0x80000000u;
 
 __host__ __device__ inline int march_patches(const VbGrid& g) {
   return ((g.fW + kPatchW - 1) / kPatchW) * ((g.fH + kPatchH - 1) / kPatchH);
@@ -31,6 +40,7 @@ __global__ void __launch_bounds__(kMarchThreads) render_plan_build_kernel(VbGrid
                                                                           uint4* __restrict__ steps,
                                                                           float* __restrict__ delta,
                                                                           int16_t* __restrict__ last,
+                                                                          uint2* __restrict__ box,
                                                                           size_t rays_per_sample) {
   __shared__ float s_m[VB200_MAT_SLOTS * 16];
   const int b = blockIdx.z, n = blockIdx.y;
@@ -63,6 +73,7 @@ __global__ void __launch_bounds__(kMarchThreads) render_plan_build_kernel(VbGrid
   const size_t ray = (size_t)(n * npatch + patch);
   uint4* so = steps + (size_t)b * rays_per_sample * S + ray * S * 32 + lane;
   float* dl = delta + (size_t)b * rays_per_sample * S + ray * S * 32 + lane;
+  uint2* bx = box + ((size_t)b * (rays_per_sample / 32) + ray) * S;
   float p0[3], p1[3];
   point(0, p0);
   int last_valid = -1;
@@ -70,15 +81,29 @@ __global__ void __launch_bounds__(kMarchThreads) render_plan_build_kernel(VbGrid
     point(i + 1, p1);
     const RenderCoord rc = render_coord<FASTDIV>(g, p0, &dv);
     uint4 r = make_uint4(0u, 0u, 0u, 0u);
-    if (rc.valid && active) {
-      const int x0 = min(rc.x0, g.vX - 2), y0 = min(rc.y0, g.vY - 2), z0 = min(rc.z0, g.vZ - 2);
-      r.x = kPlanValid | (uint32_t)((z0 * g.vY + y0) * g.vX + x0);
+    const bool ok = rc.valid && active;
+    const int x0 = min(rc.x0, g.vX - 2), y0 = min(rc.y0, g.vY - 2), z0 = min(rc.z0, g.vZ - 2);
+    // the warp's box: base corners of its in-volume rays, plus one for the far corners
+    const int big = 1 << 20;
+    const int xl = __reduce_min_sync(0xffffffffu, ok ? x0 : big), xh = __reduce_max_sync(0xffffffffu, ok ? x0 : -big);
+    const int yl = __reduce_min_sync(0xffffffffu, ok ? y0 : big), yh = __reduce_max_sync(0xffffffffu, ok ? y0 : -big);
+    const int zl = __reduce_min_sync(0xffffffffu, ok ? z0 : big), zh = __reduce_max_sync(0xffffffffu, ok ? z0 : -big);
+    const int nx = xh - xl + 2, ny = yh - yl + 2, nz = zh - zl + 2;
+    const bool any = xh >= xl;
+    const bool staged = any && nx * ny * nz <= kBoxCap && ny * nz <= 32;
+    if (ok) {
+      const uint32_t rel = staged ? (uint32_t)(((z0 - zl) * ny + (y0 - yl)) * nx + (x0 - xl)) : 0u;
+      r.x = kPlanValid | (rel << kPlanRelShift) | (uint32_t)((z0 * g.vY + y0) * g.vX + x0);
       r.y = __float_as_uint(rc.ix - (float)x0);
       r.z = __float_as_uint(rc.iy - (float)y0);
       r.w = __float_as_uint(rc.iz - (float)z0);
       last_valid = i;
     }
     so[(size_t)i * 32] = r;
+    if (lane == 0)
+      bx[i] = any ? make_uint2((staged ? kBoxStaged : 0u) | (uint32_t)((zl * g.vY + yl) * g.vX + xl),
+                               (uint32_t)nx | ((uint32_t)ny << 8) | ((uint32_t)nz << 16))
+                  : make_uint2(0u, 0u);
     const float dx = p1[0] - p0[0], dy = p1[1] - p0[1], dz = p1[2] - p0[2];
     dl[(size_t)i * 32] = sqrtf(dx * dx + dy * dy + dz * dz);                    // BV2:426
 #pragma unroll

@@ -1296,8 +1296,8 @@ extern "C" size_t vb200_render_plan_rays(const VbGrid* g) {
 }
 
 extern "C" int vb200_render_plan_build(const VbGrid* g, const VbTables* t, const float* d_mats, void* d_steps,
-                                       float* d_delta, int16_t* d_last, void* stream) {
-  VB_CHECK_ARG(g && t && d_mats && d_steps && d_delta && d_last);
+                                       float* d_delta, int16_t* d_last, void* d_box, void* stream) {
+  VB_CHECK_ARG(g && t && d_mats && d_steps && d_delta && d_last && d_box);
   VB_CHECK_ARG(g->B > 0 && g->N > 0 && g->N <= VB_MAX_CAMS && g->D >= 2 && g->D - 1 < 32767);
   VB_CHECK_ARG((size_t)g->vZ * g->vY * g->vX <= (size_t)kPlanVoxMask + 1);
   VB_CHECK_ARG(g->vX >= 2 && g->vY >= 2 && g->vZ >= 2);     // the plan stores the inward-shifted base corner
@@ -1311,10 +1311,12 @@ extern "C" int vb200_render_plan_build(const VbGrid* g, const VbTables* t, const
   VbTraceScope tr(VB_K_GET_GEOMETRY, st);
   if (vb_render_div_ok(dv))
     render_plan_build_kernel<true><<<grid, kMarchThreads, 0, st>>>(*g, *t, dv, d_mats, reinterpret_cast<uint4*>(d_steps),
-                                                                    d_delta, d_last, vb200_render_plan_rays(g));
+                                                                    d_delta, d_last, reinterpret_cast<uint2*>(d_box),
+                                                                    vb200_render_plan_rays(g));
   else
     render_plan_build_kernel<false><<<grid, kMarchThreads, 0, st>>>(*g, *t, dv, d_mats, reinterpret_cast<uint4*>(d_steps),
-                                                                     d_delta, d_last, vb200_render_plan_rays(g));
+                                                                     d_delta, d_last, reinterpret_cast<uint2*>(d_box),
+                                                                     vb200_render_plan_rays(g));
   VB_LAUNCH_CHECK();
   return VB200_OK;
 }

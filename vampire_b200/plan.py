@@ -39,16 +39,16 @@ class LiftPlan:
 class RenderPlan:
     """One sample's cached camera-march plan (steps / step lengths / last valid sample) on one CUDA device."""
 
-    __slots__ = ("steps", "delta", "last")
+    __slots__ = ("steps", "delta", "last", "box")
 
-    def __init__(self, steps: Tensor, delta: Tensor, last: Tensor):
-        self.steps, self.delta, self.last = steps, delta, last
+    def __init__(self, steps: Tensor, delta: Tensor, last: Tensor, box: Tensor):
+        self.steps, self.delta, self.last, self.box = steps, delta, last, box
 
     def pointers(self) -> Tuple[int, int, int, int]:
-        return self.steps.data_ptr(), self.delta.data_ptr(), self.last.data_ptr(), 0
+        return self.steps.data_ptr(), self.delta.data_ptr(), self.last.data_ptr(), self.box.data_ptr()
 
     def nbytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in (self.steps, self.delta, self.last))
+        return sum(t.numel() * t.element_size() for t in (self.steps, self.delta, self.last, self.box))
 
 
 class LiftPlanBatch:
@@ -114,11 +114,12 @@ def build_render_plans(state, mats: Tensor, has_bda: bool) -> List[RenderPlan]:
         steps = torch.empty(B, rays * S, 4, dtype=torch.int32, device=dev)
         delta = torch.empty(B, rays * S, dtype=torch.float32, device=dev)
         last = torch.empty(B, rays, dtype=torch.int16, device=dev)
+        box = torch.empty(B, (rays // 32) * S, 2, dtype=torch.int32, device=dev)
         cabi.check(lib.vb200_render_plan_build(C.byref(g), C.byref(state.tables(dev).struct), mats.data_ptr(),
-                                               steps.data_ptr(), delta.data_ptr(), last.data_ptr(),
+                                               steps.data_ptr(), delta.data_ptr(), last.data_ptr(), box.data_ptr(),
                                                cabi.stream_ptr(dev)))
     # per-sample views of the batch allocation (a cached sample keeps its slice alive)
-    return [RenderPlan(steps[b], delta[b], last[b]) for b in range(B)]
+    return [RenderPlan(steps[b], delta[b], last[b], box[b]) for b in range(B)]
 
 
 class PlanCache:

@@ -272,3 +272,43 @@ def test_module_render_uses_cached_plans(case):
         c = off.render(case.mats, *vols)
     for x, y in zip(a[:3], c[:3]):
         assert_close_scaled(x.cpu().numpy(), y.cpu().numpy(), 3e-6, "module planned render")
+
+
+_STAGED_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+from helpers import Case
+from vampire_b200 import ops
+from vampire_b200.plan import PlanCache
+case = Case(sys.argv[2])
+cid = ops.register_config(case.cfg)
+dt = {"bf16": torch.bfloat16, "fp16": torch.float16}[sys.argv[3]]
+prep = case.prep.cuda()
+tab = PlanCache().render(ops.state(cid), cid, prep, True).table
+outs = ops.render_fwd(case.den.cuda().to(dt), case.sem.cuda().to(dt), case.rgb.cuda().to(dt), case.feat.cuda().to(dt),
+                      torch.tensor(0.1, device="cuda"), prep, None, cid, True, 1, tab)
+torch.cuda.synchronize()
+torch.save([o.cpu() for o in outs[:3]], sys.argv[4])
+"""
+
+
+@pytest.mark.parametrize("name,dtype", [("mini_stress", "bf16"), ("mini_val", "fp16"), ("r50_val_digest", "bf16"),
+                                        ("r50_stress_digest", "bf16")])
+def test_staged_march_is_bit_identical(name, dtype, tmp_path):
+    """VB200_MARCH_STAGED=1: the march whose voxel boxes are staged in shared memory by bulk asynchronous copies
+    (cp.async.bulk + mbarrier, north-star kernel (c)) composites exactly what the direct-gather planned march does."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for tag in ("direct", "staged"):
+        path = str(tmp_path / (tag + ".pt"))
+        e = dict(os.environ)
+        e.pop("VB200_MARCH_STAGED", None)
+        if tag == "staged":
+            e["VB200_MARCH_STAGED"] = "1"
+        subprocess.run([sys.executable, "-c", _STAGED_SCRIPT, root, name, dtype, path], check=True, env=e, timeout=300)
+        outs[tag] = torch.load(path)
+    for n, a, b in zip(["rgb", "seg", "depth"], outs["direct"], outs["staged"]):
+        assert torch.equal(a, b), n

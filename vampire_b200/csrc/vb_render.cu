@@ -21,6 +21,7 @@
 //                      coalesced), never materialises the 38-channel cat.
 #include "vb_render_common.cuh"
 #include "vb_march_planned.cuh"
+#include "vb_march_staged.cuh"
 #include "vb_trace.cuh"
 
 #include <atomic>
@@ -1196,8 +1197,20 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
       VB_MARCH(false, false, true);
     } else if (in->plans) {
       // cached geometry; a non-finite packed volume (flag raised by the pack) takes the recomputing NaN-safe variant
-      march_fwd_planned_kernel<T, K><<<grid, kMarchThreads, 0, st>>>(*g, *t, in->plans, region, flag, in->beta,
-                                                                     out->rgb, out->seg, out->depth, b0);
+      // VB200_MARCH_STAGED=1: the shared-memory staged variant (bulk asynchronous copies of the warp's voxel box, see
+      // vb_march_staged.cuh); bit-identical to the direct-gather kernel below
+      static const bool staged_env = getenv("VB200_MARCH_STAGED") != nullptr;
+      bool launched = false;
+      if constexpr (sizeof(T) == 2) {
+        if (staged_env) {
+          march_fwd_staged_kernel<T, K><<<grid, kMarchThreads, 0, st>>>(*g, *t, in->plans, region, flag, in->beta,
+                                                                        out->rgb, out->seg, out->depth, b0);
+          launched = true;
+        }
+      }
+      if (!launched)
+        march_fwd_planned_kernel<T, K><<<grid, kMarchThreads, 0, st>>>(*g, *t, in->plans, region, flag, in->beta,
+                                                                       out->rgb, out->seg, out->depth, b0);
       if (vb_render_div_ok(dv)) VB_MARCH(true, true, true);
       else VB_MARCH(true, false, true);
     } else if (vb_render_div_ok(dv)) {

@@ -23,7 +23,7 @@ constexpr uint32_t kPlanVoxMask = (1u << 21) - 1;
 // covers all 8 trilinear corners of the warp's in-volume rays.  box[(n * npatch + patch) * S + i] = {staged << 31 | first
 // voxel of the box, nx | ny << 8 | nz << 16}; a record's key carries the base corner's index INSIDE the box in bits
 // 21..27 (rel = ((z - z_lo) * ny + (y - y_lo)) * nx + (x - x_lo)).  A box is staged when it holds at most kBoxCap
-// voxels in at most 32 rows (one bulk copy per lane).
+// voxels in at most 8 y-rows x 4 z-rows (one bulk copy per lane, lane = dz * 8 + dy).
 constexpr int kBoxCap = 96;
 constexpr int kPlanRelShift = 21;
 constexpr uint32_t kPlanRelMask = 0x7fu;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kMarchThreads) render_plan_build_kernel(VbGrid
     const int zl = __reduce_min_sync(0xffffffffu, ok ? z0 : big), zh = __reduce_max_sync(0xffffffffu, ok ? z0 : -big);
     const int nx = xh - xl + 2, ny = yh - yl + 2, nz = zh - zl + 2;
     const bool any = xh >= xl;
-    const bool staged = any && nx * ny * nz <= kBoxCap && ny * nz <= 32;
+    const bool staged = any && nx * ny * nz <= kBoxCap && ny <= 8 && nz <= 4;   // lane = dz * 8 + dy copies one x-row
     if (ok) {
       const uint32_t rel = staged ? (uint32_t)(((z0 - zl) * ny + (y0 - yl)) * nx + (x0 - xl)) : 0u;
       r.x = kPlanValid | (rel << kPlanRelShift) | (uint32_t)((z0 * g.vY + y0) * g.vX + x0);

@@ -29,7 +29,17 @@ __device__ __forceinline__ void vs_bulk_load(uint32_t dst, const void* src, uint
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ bool vs_mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void vs_mbar_wait(uint32_t bar, uint32_t parity) {
+  if (vs_mbar_try(bar, parity)) return;          // the copies were issued two samples ago: the common case
   const long long t0 = clock64();
   for (;;) {
     uint32_t ok;
@@ -141,13 +151,12 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_STAGED_MINB) march_fwd
     const int nx = bx.y & 0xff, ny = (bx.y >> 8) & 0xff, nz = (bx.y >> 16) & 0xff;
     const uint32_t row_bytes = (uint32_t)nx * kRec;
     const uint32_t bar = (i & 1) ? bar1 : bar0;
-    const int rows = ny * nz;
-    if (lane == 0) vs_mbar_expect_tx(bar, row_bytes * (uint32_t)rows);
+    if (lane == 0) vs_mbar_expect_tx(bar, row_bytes * (uint32_t)(ny * nz));
     __syncwarp();
-    if (lane < rows) {
-      const int dz = lane / ny, dy = lane - dz * ny;
-      const T* src = vol + (size_t)(bx.x & kPlanVoxMask) * CP + (size_t)dz * c_sz + (size_t)dy * c_sy;
-      vs_bulk_load(stage0 + (uint32_t)(i & 1) * kStageBytes + (uint32_t)lane * row_bytes, src, row_bytes, bar);
+    const int dz = lane >> 3, dy = lane & 7;               // ny <= 8, nz <= 4 (plan build)
+    if (dy < ny && dz < nz) {
+      const T* src = vol + (size_t)((bx.x & kPlanVoxMask) * CP + dz * c_sz + dy * c_sy);
+      vs_bulk_load(stage0 + (uint32_t)(i & 1) * kStageBytes + (uint32_t)(dz * ny + dy) * row_bytes, src, row_bytes, bar);
     }
     return true;
   };
@@ -199,52 +208,67 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_STAGED_MINB) march_fwd
     const bool live = (r.x & kPlanValid) != 0u;
     float sigma = sigma_masked;
     float cw[8];
-    // corner addresses: shared memory (record index inside the box) or global (absolute voxel index)
-    const int nx = bx.y & 0xff, ny = (bx.y >> 8) & 0xff;
-    const uint32_t s_base = stage0 + (odd ? kStageBytes : 0u) + ((r.x >> kPlanRelShift) & kPlanRelMask) * kRec;
-    const uint32_t s_sy = (uint32_t)nx * kRec, s_sz = (uint32_t)(nx * ny) * kRec;
-    const T* gp = vol + (size_t)(r.x & kPlanVoxMask) * CP;
     if (live) {
       const float fx = __uint_as_float(r.y), fy = __uint_as_float(r.z), fz = __uint_as_float(r.w);
       const float wx[2] = {1.0f - fx, fx}, wy[2] = {1.0f - fy, fy}, wz[2] = {1.0f - fz, fz};
-      float s0 = 0.0f;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        cw[q] = wx[q & 1] * wy[(q >> 1) & 1] * wz[q >> 2];
-        float dq;
-        if (staged) dq = vs_widen16<T>(vs_lds16(s_base + ((q & 2) ? s_sy : 0u) + ((q & 4) ? s_sz : 0u) + ((q & 1) ? kRec : 0u)));
-        else dq = widen_elem(__ldg(gp + ((q & 2) ? c_sy : 0) + ((q & 4) ? c_sz : 0) + ((q & 1) ? CP : 0)));
-        s0 = fmaf(cw[q], dq, s0);
-      }
-      sigma = laplace_density_rcp(s0, g.sdf_bias, inv_beta);                   // BV2:423
+      for (int q = 0; q < 8; ++q) cw[q] = wx[q & 1] * wy[(q >> 1) & 1] * wz[q >> 2];
     }
-    const float sd = sigma * delta;                                           // BV2:429
-    const float e = expf(-sd);
-    const float wgt = (1.0f - e) * trans;                                     // BV2:430-434
-    acc += wgt;
-    dep = fmaf(wgt, __ldg(t.mids + i), dep);
-    if (live && wgt != 0.0f) {
+    float e, wgt;
+    if (staged) {
+      // ---- shared-memory path: the record's index inside the box, uniform corner strides ----
+      const int nx = bx.y & 0xff, ny = (bx.y >> 8) & 0xff;
+      const uint32_t s_sy = (uint32_t)nx * kRec, s_sz = (uint32_t)(nx * ny) * kRec;
+      const uint32_t a0 = stage0 + (odd ? kStageBytes : 0u) + ((r.x >> kPlanRelShift) & kPlanRelMask) * kRec;
+      const uint32_t a[8] = {a0, a0 + kRec, a0 + s_sy, a0 + s_sy + kRec,
+                             a0 + s_sz, a0 + s_sz + kRec, a0 + s_sz + s_sy, a0 + s_sz + s_sy + kRec};
+      if (live) {
+        float s0 = 0.0f;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float cwq = cw[q] * wgt;
-        if (staged) {
-          const uint32_t a = s_base + ((q & 2) ? s_sy : 0u) + ((q & 4) ? s_sz : 0u) + ((q & 1) ? kRec : 0u);
+        for (int q = 0; q < 8; ++q) s0 = fmaf(cw[q], vs_widen16<T>(vs_lds16(a[q])), s0);
+        sigma = laplace_density_rcp(s0, g.sdf_bias, inv_beta);                 // BV2:423
+      }
+      const float sd = sigma * delta;                                         // BV2:429
+      e = expf(-sd);
+      wgt = (1.0f - e) * trans;                                               // BV2:430-434
+      if (live && wgt != 0.0f) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float cwq = cw[q] * wgt;
 #pragma unroll
           for (int part = 0; part < CP / 8; ++part) {
             float tmp[8];
-            vs_widen8<T>(vs_lds128(a + part * 16), tmp);
+            vs_widen8<T>(vs_lds128(a[q] + part * 16), tmp);
 #pragma unroll
             for (int e8 = 0; e8 < 8; ++e8) {
               const int c = part * 8 + e8 - 1;
               if (c >= 0 && c < K + 3) ch[c] = fmaf(tmp[e8], cwq, ch[c]);
             }
           }
-        } else {
-          PackedLoad<T, CP>::template fma_values<K + 3>(gp + ((q & 2) ? c_sy : 0) + ((q & 4) ? c_sz : 0) + ((q & 1) ? CP : 0),
-                                                        cwq, ch);
         }
       }
+    } else {
+      // ---- global path (box over the cap): as march_fwd_planned_kernel ----
+      const T* gp = vol + (size_t)(r.x & kPlanVoxMask) * CP;
+      if (live) {
+        float s0 = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          s0 = fmaf(cw[q], widen_elem(__ldg(gp + ((q & 2) ? c_sy : 0) + ((q & 4) ? c_sz : 0) + ((q & 1) ? CP : 0))), s0);
+        sigma = laplace_density_rcp(s0, g.sdf_bias, inv_beta);
+      }
+      const float sd = sigma * delta;
+      e = expf(-sd);
+      wgt = (1.0f - e) * trans;
+      if (live && wgt != 0.0f) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          PackedLoad<T, CP>::template fma_values<K + 3>(gp + ((q & 2) ? c_sy : 0) + ((q & 4) ? c_sz : 0) + ((q & 1) ? CP : 0),
+                                                        cw[q] * wgt, ch);
+      }
     }
+    acc += wgt;
+    dep = fmaf(wgt, __ldg(t.mids + i), dep);
     trans *= e;
     // stage (i & 1) is free again: every lane's reads of it have been consumed above
     __syncwarp();

@@ -306,9 +306,41 @@ def test_staged_march_is_bit_identical(name, dtype, tmp_path):
         path = str(tmp_path / (tag + ".pt"))
         e = dict(os.environ)
         e.pop("VB200_MARCH_STAGED", None)
+        e["VB200_MARCH_SPLIT"] = "1"        # the depth-split march folds in another order; compare like with like
         if tag == "staged":
             e["VB200_MARCH_STAGED"] = "1"
         subprocess.run([sys.executable, "-c", _STAGED_SCRIPT, root, name, dtype, path], check=True, env=e, timeout=300)
         outs[tag] = torch.load(path)
     for n, a, b in zip(["rgb", "seg", "depth"], outs["direct"], outs["staged"]):
         assert torch.equal(a, b), n
+
+
+# ---- depth-split march (thread-block clusters, vb200_render_set_march_split) ------------------------------------
+@pytest.mark.parametrize("planned", [False, True])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_depth_split_march_matches_the_unsplit_march(case, dtype, planned):
+    """Clusters of 2 / 4 / 8 CTAs composite one part of the samples each and fold the parts front to back through
+    distributed shared memory: same samples, same weights as the single-CTA march, another summation order."""
+    from vampire_b200 import cabi
+    ops, cid, st = _state(case.cfg)
+    table = _render_batch(case, st)[1].table if planned else None
+    vols = [t.to(dtype).cuda() for t in (case.den, case.sem, case.rgb, case.feat)]
+    beta = torch.tensor(0.1, device="cuda")
+    prep = case.prep.cuda()
+    try:
+        cabi.render_set_march_split(1)
+        ref = [x.cpu().numpy() for x in ops.render_fwd(*vols, beta, prep, None, cid, True, 1, table)[:3]]
+        for nseg in (2, 4, 8, 0):
+            cabi.render_set_march_split(nseg)
+            got = ops.render_fwd(*vols, beta, prep, None, cid, True, 1, table)[:3]
+            for name, x, y in zip(["rgb", "seg", "depth"], ref, got):
+                assert_close_scaled(y.cpu().numpy(), x, 3e-6, f"depth-split march {name}")
+            if dtype == torch.float32 and case.inputs_match_golden and nseg == 8:
+                from helpers import golden_value
+                for name, y in zip(["rgb", "seg", "depth"], got):
+                    exp, g = golden_value(case.gold, "r_" + name, y.cpu().numpy())
+                    assert_close_scaled(g, exp, 1e-5, "depth-split march vs reference " + name)
+    finally:
+        cabi.render_set_march_split(0)
+    with pytest.raises(RuntimeError):
+        cabi.render_set_march_split(3)

@@ -122,6 +122,7 @@ _PROTOS = {
     "vb200_render_bwd_workspace": (C.c_size_t, [C.POINTER(VbGrid), C.c_int]),
     "vb200_render_packed_bytes": (C.c_size_t, [C.POINTER(VbGrid), C.c_int]),
     "vb200_render_set_fork": (C.c_int, [C.c_int]),
+    "vb200_render_set_march_split": (C.c_int, [C.c_int]),
     "vb200_render_fwd": (C.c_int, [C.POINTER(VbGrid), C.POINTER(VbTables), _P, C.POINTER(VbRenderIn), C.c_int,
                                    C.POINTER(VbRenderOut), C.c_int, _P, C.c_size_t, _P]),
     "vb200_render_bwd": (C.c_int, [C.POINTER(VbGrid), C.POINTER(VbTables), _P, C.POINTER(VbRenderIn), C.c_int,
@@ -237,6 +238,11 @@ def trace_collect():
     cnt = (C.c_longlong * n)()
     check(l.vb200_trace_collect(ms, cnt))
     return {l.vb200_trace_kernel_name(i).decode(): (ms[i], int(cnt[i])) for i in range(n) if cnt[i]}
+
+
+def render_set_march_split(segments: int) -> None:
+    """Depth segments of the camera march: 0 = chosen per call, 1 = never split, 2 / 4 / 8 = forced (include/vb200.h)."""
+    check(lib().vb200_render_set_march_split(int(segments)))
 
 
 def render_set_fork(enable: bool) -> None:

@@ -116,7 +116,9 @@ __global__ void __launch_bounds__(kMarchThreads) render_plan_build_kernel(VbGrid
 #ifndef VB_MARCH_PLANNED_MINB
 #define VB_MARCH_PLANNED_MINB 5
 #endif
-template <typename T, int K>
+// SPLIT: launched as clusters of n CTAs along x, CTA r of a cluster marches the r-th n-th of the samples and
+// march_cluster_fold() composes the segments (vb_render_common.cuh).
+template <typename T, int K, bool SPLIT>
 __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fwd_planned_kernel(
     VbGrid g, VbTables t, const VbRenderPlan* __restrict__ plans, const T* __restrict__ packed,
     const int* __restrict__ nonfinite_flag, const float* __restrict__ beta_ptr, float* __restrict__ o_rgb,
@@ -126,13 +128,18 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fw
   const int b = b0 + blockIdx.z, n = blockIdx.y;
   const int patches_x = (g.fW + kPatchW - 1) / kPatchW;
   const int npatch = march_patches(g);
-  const int patch = blockIdx.x * (kMarchThreads / 32) + (threadIdx.x >> 5);
-  if (patch >= npatch) return;  // whole warp leaves together
+  const int S = g.D - 1, HW = g.fH * g.fW;
+  const int nseg = SPLIT ? (int)cooperative_groups::this_cluster().num_blocks() : 1;
+  const int seg = SPLIT ? (int)cooperative_groups::this_cluster().block_rank() : 0;
+  const int xblock = SPLIT ? blockIdx.x / nseg : blockIdx.x;
+  const int i_lo = SPLIT ? seg * S / nseg : 0, i_hi = SPLIT ? (seg + 1) * S / nseg : S;
+  const int patch_raw = xblock * (kMarchThreads / 32) + (threadIdx.x >> 5);
+  if (!SPLIT && patch_raw >= npatch) return;  // whole warp leaves together (a split warp stays for the cluster barriers)
+  const int patch = SPLIT ? min(patch_raw, npatch - 1) : patch_raw;
   const int lane = threadIdx.x & 31;
   const int w = (patch % patches_x) * kPatchW + (lane % kPatchW);
   const int h = (patch / patches_x) * kPatchH + (lane / kPatchW);
-  const bool active = (w < g.fW) && (h < g.fH);
-  const int S = g.D - 1, HW = g.fH * g.fW;
+  const bool active = (w < g.fW) && (h < g.fH) && (!SPLIT || patch_raw < npatch);
   const int nvox = g.vZ * g.vY * g.vX;
   const T* vol = packed + (size_t)blockIdx.z * nvox * CP;  // packed holds only this launch's samples
   const size_t ray = (size_t)(n * npatch + patch);
@@ -160,20 +167,20 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fw
 #endif
   constexpr int kPrefetchAhead = VB_MARCH_PREFETCH;
   auto prefetch = [&](int i) {
-    if (i < S) {
+    if (i < i_hi) {
       asm volatile("prefetch.global.L2 [%0];" ::"l"(rec + (size_t)i * 32));
       if (lane < 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(dl + (size_t)i * 32 + lane * 8 - lane));
     }
   };
 #pragma unroll 1
-  for (int i = 0; i < kPrefetchAhead; ++i) prefetch(i);
-  uint4 r_n = __ldg(rec);
-  float d_n = __ldg(dl);
+  for (int i = 0; i < kPrefetchAhead; ++i) prefetch(i_lo + i);
+  uint4 r_n = __ldg(rec + (size_t)i_lo * 32);      // every segment holds at least one sample (launcher: >= 4)
+  float d_n = __ldg(dl + (size_t)i_lo * 32);
   uint4 r_n2 = make_uint4(0u, 0u, 0u, 0u);
   float d_n2 = 0.0f;
-  if (S > 1) {
-    r_n2 = __ldg(rec + 32);
-    d_n2 = __ldg(dl + 32);
+  if (i_lo + 1 < i_hi) {
+    r_n2 = __ldg(rec + (size_t)(i_lo + 1) * 32);
+    d_n2 = __ldg(dl + (size_t)(i_lo + 1) * 32);
   }
   T raw_n[8];
   auto gather_density = [&](const uint4& r, T (&raw)[8]) {
@@ -186,7 +193,7 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fw
   };
   gather_density(r_n, raw_n);
 
-  for (int i = 0; i < S; ++i) {
+  for (int i = i_lo; i < i_hi; ++i) {
     if (g.term_eps > 0.0f) {
       const bool done = !active || trans < g.term_eps;
       if (__all_sync(0xffffffffu, done)) break;
@@ -194,7 +201,7 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fw
         // every remaining sample of every live ray is outside the volume: feature 0, sigma(0), only delta_i and
         // mid_i enter the compositing -- a geometry-free tail that still reads the exact per-sample step lengths
         if (!done) {
-          for (int ii = i; ii < S; ++ii) {
+          for (int ii = i; ii < i_hi; ++ii) {
             const float sd = sigma_masked * __ldg(dl + (size_t)ii * 32);
             const float e = expf(-sd);
             const float wgt = (1.0f - e) * trans;
@@ -214,11 +221,11 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fw
     prefetch(i + kPrefetchAhead);
     r_n = r_n2;
     d_n = d_n2;
-    if (i + 2 < S) {
+    if (i + 2 < i_hi) {
       r_n2 = __ldg(rec + (size_t)(i + 2) * 32);
       d_n2 = __ldg(dl + (size_t)(i + 2) * 32);
     }
-    if (i + 1 < S) gather_density(r_n, raw_n);
+    if (i + 1 < i_hi) gather_density(r_n, raw_n);
     const bool live = (r.x & kPlanValid) != 0u;     // build wrote valid = 0 for rays outside the image
     float sigma = sigma_masked;
     float cw[8];
@@ -248,6 +255,9 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fw
     }
     // exp(-cumsum) of BV2:431-433 as a running product: one exp per sample instead of two
     trans *= e;
+  }
+  if (SPLIT) {
+    if (!march_cluster_fold<K + 3>(acc, dep, trans, ch)) return;
   }
   if (!active) return;
   const size_t pix = (size_t)h * g.fW + w;

@@ -35,6 +35,7 @@ namespace {
 // families fill each other's idle issue slots.  Everything stays stream-ordered w.r.t. the caller's
 // stream (fork event before, join event after), so caller-owned buffers remain valid.
 std::atomic<int> g_render_fork_disabled{0};
+std::atomic<int> g_march_split{0};      // 0 = heuristic, 1 = never split, 2 / 4 / 8 = force that many depth segments
 
 constexpr int kMaxSplit = 8;
 struct SideStream {
@@ -93,7 +94,8 @@ SideStream* side_stream_for_current_device() {
 // convex combination of finite values, nan_to_num is the identity and the corners are accumulated directly
 // into the ray's channel sums (24 fewer live registers, no per-sample finiteness test).  Both variants are
 // launched back to back; the one whose turn it is not returns at once.
-template <typename T, int K, bool FROM_MATS, bool FASTDIV, bool NANSAFE>
+// SPLIT: clusters of n CTAs along x, CTA r marches the r-th n-th of the samples (march_cluster_fold composes them).
+template <typename T, int K, bool FROM_MATS, bool FASTDIV, bool NANSAFE, bool SPLIT = false>
 __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_MINB) march_fwd_kernel(VbGrid g, VbTables t, VbRenderDiv dv,
                                                                   const float* __restrict__ d_mats,
                                                                   const float* __restrict__ d_geom,
@@ -114,15 +116,20 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_MINB) march_fwd_kernel
 
   const int patches_x = (g.fW + kPatchW - 1) / kPatchW;
   const int patches_y = (g.fH + kPatchH - 1) / kPatchH;
-  const int patch = blockIdx.x * (kMarchThreads / 32) + (threadIdx.x >> 5);
-  if (patch >= patches_x * patches_y) return;  // whole warp leaves together
+  const int S = g.D - 1, HW = g.fH * g.fW;
+  const int nseg = SPLIT ? (int)cooperative_groups::this_cluster().num_blocks() : 1;
+  const int seg = SPLIT ? (int)cooperative_groups::this_cluster().block_rank() : 0;
+  const int xblock = SPLIT ? blockIdx.x / nseg : blockIdx.x;
+  const int i_lo = SPLIT ? seg * S / nseg : 0, i_hi = SPLIT ? (seg + 1) * S / nseg : S;
+  const int patch_raw = xblock * (kMarchThreads / 32) + (threadIdx.x >> 5);
+  if (!SPLIT && patch_raw >= patches_x * patches_y) return;  // whole warp leaves together (split: stays for the barriers)
+  const int patch = SPLIT ? min(patch_raw, patches_x * patches_y - 1) : patch_raw;
   const int lane = threadIdx.x & 31;
   const int w = (patch % patches_x) * kPatchW + (lane % kPatchW);
   const int h = (patch / patches_x) * kPatchH + (lane / kPatchW);
-  const bool active = (w < g.fW) && (h < g.fH);
+  const bool active = (w < g.fW) && (h < g.fH) && (!SPLIT || patch_raw < patches_x * patches_y);
   const int wc = min(w, g.fW - 1), hc = min(h, g.fH - 1);
 
-  const int S = g.D - 1, HW = g.fH * g.fW;
   const int nvox = g.vZ * g.vY * g.vX;
   const float beta = fabsf(__ldg(beta_ptr)) + g.beta_min;
   const T* vol = packed + (size_t)blockIdx.z * nvox * CP;  // packed holds only this launch's samples
@@ -198,8 +205,8 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_MINB) march_fwd_kernel
   };
 
   float p0[3], p1[3], p2[3];
-  point(0, p0);
-  point(1, p1);
+  point(i_lo, p0);
+  point(i_lo + 1, p1);
   Smp nxt;
   prepare(p0, nxt);
   float delta_n;
@@ -214,7 +221,7 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_MINB) march_fwd_kernel
   // opaque, the warp finishes with a geometry-free tail loop (delta_i = the ray's constant step length,
   // equal to the reference's per-sample norm up to ~1e-7 relative).
   bool was_valid = false, exited = false;
-  for (int i = 0; i < S; ++i) {
+  for (int i = i_lo; i < i_hi; ++i) {
     const float trans = expf(-tau);
     const float delta = delta_n;
     if (g.term_eps > 0.0f) {
@@ -223,7 +230,7 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_MINB) march_fwd_kernel
       if (FROM_MATS && __all_sync(0xffffffffu, done || exited)) {   // a caller-supplied geom tensor need not be straight rays
         if (exited && !done) {
           float tr = trans;
-          for (int ii = i; ii < S; ++ii) {
+          for (int ii = i; ii < i_hi; ++ii) {
             const float sd = sigma_masked * delta;
             const float wgt = (1.0f - expf(-sd)) * tr;
             acc += wgt;
@@ -245,7 +252,7 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_MINB) march_fwd_kernel
         exited = exited || (p0[a] > hi + 1e-3f && p1[a] > p0[a]) || (p0[a] < g.seg_lo[a] - 1e-3f && p1[a] < p0[a]);
       }
     }
-    if (i + 1 < S) {                        // look ahead: geometry + density gathers of sample i+1
+    if (i + 1 < i_hi) {                     // look ahead: geometry + density gathers of sample i+1
       point(i + 2, p2);
       prepare(p1, nxt);
       const float dx = p2[0] - p1[0], dy = p2[1] - p1[1], dz = p2[2] - p1[2];
@@ -305,6 +312,10 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_MINB) march_fwd_kernel
     tau += sd;
 #pragma unroll
     for (int a = 0; a < 3; ++a) { p0[a] = p1[a]; p1[a] = p2[a]; }
+  }
+  if (SPLIT) {
+    float trans = expf(-tau);
+    if (!march_cluster_fold<K + 3>(acc, dep, trans, ch)) return;
   }
   if (!active) return;
   const size_t pix = (size_t)h * g.fW + w;
@@ -1187,11 +1198,47 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
     return VB200_OK;
   };
   auto march_round = [&](int b0, int nb, const T* region, const int* flag) -> int {
-    dim3 grid(vb_ceil_div(patches, kMarchThreads / 32), g->N, nb);
+    const int xblocks = vb_ceil_div(patches, kMarchThreads / 32);
+    dim3 grid(xblocks, g->N, nb);
     VbTraceScope tr(VB_K_MARCH_FWD, st, 2);
+    // depth split (march_cluster_fold): when this round's blocks would not fill the GPU once, clusters of nseg
+    // CTAs share each group of patches.  vb200_render_set_march_split() / VB200_MARCH_SPLIT override (1 = never).
+    int nseg = 1;
+    {
+      static const int split_env = getenv("VB200_MARCH_SPLIT") ? atoi(getenv("VB200_MARCH_SPLIT")) : 0;
+      const int forced = g_march_split.load(std::memory_order_relaxed) > 0 ? g_march_split.load(std::memory_order_relaxed)
+                                                                            : split_env;
+      const long long blocks = (long long)xblocks * g->N * nb, slots = (long long)VB_SM_COUNT_B200 * VB_MARCH_MINB;
+      // measured on B200 (R50, bf16 / fp32, render call incl. pack): B = 1: 0.209 / 0.301 ms unsplit, 0.186 / 0.254 with
+      // 2 segments, 0.209 / 0.280 with 4, 0.257 / 0.328 with 8; B = 2: 0.274 unsplit, 0.305 with 2 -- a later segment
+      // cannot see that the ray is already opaque and gathers what the unsplit march skips, so the split only pays
+      // while the launch is under one wave, and only in two
+      if (forced > 0) nseg = forced;
+      else if (blocks < slots) nseg = 2;
+      while (nseg > 1 && (nseg > 8 || (g->D - 1) / nseg < 4)) nseg /= 2;    // portable cluster size; >= 4 samples each
+      nseg = nseg >= 8 ? 8 : nseg >= 4 ? 4 : nseg >= 2 ? 2 : 1;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    cfg.gridDim = dim3(xblocks * nseg, g->N, nb);
+    cfg.blockDim = dim3(kMarchThreads);
+    cfg.stream = st;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = nseg;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const float* geom_null = nullptr;
 #define VB_MARCH(FM, FD, NS)                                                                                        \
   march_fwd_kernel<T, K, FM, FD, NS><<<grid, kMarchThreads, 0, st>>>(*g, *t, dv, d_mats, in->geom, region, flag,    \
                                                                      in->beta, out->rgb, out->seg, out->depth, b0)
+#define VB_MARCH_SPLIT(FD)                                                                                          \
+  do {                                                                                                              \
+    if (cudaLaunchKernelEx(&cfg, march_fwd_kernel<T, K, true, FD, false, true>, *g, *t, dv, d_mats, geom_null,      \
+                           region, flag, (const float*)in->beta, out->rgb, out->seg, out->depth, b0) != cudaSuccess) \
+      return VB200_ERR_CUDA;                                                                                        \
+  } while (0)
     if (in->geom) {
       VB_MARCH(false, false, false);
       VB_MARCH(false, false, true);
@@ -1208,19 +1255,28 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
           launched = true;
         }
       }
+      if (!launched && nseg > 1) {
+        if (cudaLaunchKernelEx(&cfg, march_fwd_planned_kernel<T, K, true>, *g, *t, in->plans, region, flag,
+                               (const float*)in->beta, out->rgb, out->seg, out->depth, b0) != cudaSuccess)
+          return VB200_ERR_CUDA;
+        launched = true;
+      }
       if (!launched)
-        march_fwd_planned_kernel<T, K><<<grid, kMarchThreads, 0, st>>>(*g, *t, in->plans, region, flag, in->beta,
-                                                                       out->rgb, out->seg, out->depth, b0);
+        march_fwd_planned_kernel<T, K, false><<<grid, kMarchThreads, 0, st>>>(*g, *t, in->plans, region, flag, in->beta,
+                                                                              out->rgb, out->seg, out->depth, b0);
       if (vb_render_div_ok(dv)) VB_MARCH(true, true, true);
       else VB_MARCH(true, false, true);
     } else if (vb_render_div_ok(dv)) {
-      VB_MARCH(true, true, false);
+      if (nseg > 1) VB_MARCH_SPLIT(true);
+      else VB_MARCH(true, true, false);
       VB_MARCH(true, true, true);
     } else {
-      VB_MARCH(true, false, false);
+      if (nseg > 1) VB_MARCH_SPLIT(false);
+      else VB_MARCH(true, false, false);
       VB_MARCH(true, false, true);
     }
 #undef VB_MARCH
+#undef VB_MARCH_SPLIT
     VB_LAUNCH_CHECK();
     return VB200_OK;
   };
@@ -1331,6 +1387,12 @@ extern "C" int vb200_render_plan_build(const VbGrid* g, const VbTables* t, const
                                                                      d_delta, d_last, reinterpret_cast<uint2*>(d_box),
                                                                      vb200_render_plan_rays(g));
   VB_LAUNCH_CHECK();
+  return VB200_OK;
+}
+
+extern "C" int vb200_render_set_march_split(int segments) {
+  VB_CHECK_ARG(segments == 0 || segments == 1 || segments == 2 || segments == 4 || segments == 8);
+  g_march_split.store(segments);
   return VB200_OK;
 }
 

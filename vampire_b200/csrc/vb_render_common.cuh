@@ -4,6 +4,8 @@
 #pragma once
 #include "vb_common.cuh"
 
+#include <cooperative_groups.h>
+
 namespace {
 
 constexpr int kPackThreads = 256;
@@ -163,6 +165,45 @@ template <typename T, int CP> struct PackedLoad {
     }
   }
 };
+
+// ---- depth-split march: a thread-block CLUSTER marches one group of ray patches, CTA r of the cluster the samples
+// [r S / n, (r + 1) S / n) with a transmittance that starts at 1.  Volume rendering composes front to back:
+//   out = out_0 + T_0 out_1 + T_0 T_1 out_2 + ...,   T = T_0 T_1 ...
+// so every CTA leaves (acc, dep, T, ch[NV]) of its segment in its own shared memory and CTA 0 folds the others in
+// through distributed shared memory (cluster.map_shared_rank), in segment order.  Used when the launch would not fill
+// the GPU (B = 1 at the R50 config: 528 blocks on 740 slots, and the kernel then lasts as long as its longest ray):
+// n times more, n times shorter blocks.  A segment cannot know that an earlier one already made the ray opaque, so it
+// composites samples the unsplit march skips (their weight is below term_eps after the fold) -- which is why two
+// segments win at B = 1 (-11 % bf16, -16 % fp32) and more segments, or any split of a full launch, lose.
+// Returns true in the CTA that holds the folded result (cluster rank 0).
+template <int NV>
+__device__ __forceinline__ bool march_cluster_fold(float& acc, float& dep, float& trans, float (&ch)[NV]) {
+  namespace cg = cooperative_groups;
+  __shared__ float s_part[(NV + 3) * kMarchThreads];
+  cg::cluster_group cl = cg::this_cluster();
+  const unsigned seg = cl.block_rank(), nseg = cl.num_blocks();
+  float* mine = s_part + threadIdx.x;
+  if (seg != 0) {
+    mine[0] = acc;
+    mine[kMarchThreads] = dep;
+    mine[2 * kMarchThreads] = trans;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) mine[(3 + c) * kMarchThreads] = ch[c];
+  }
+  cl.sync();
+  if (seg == 0) {
+    for (unsigned r = 1; r < nseg; ++r) {
+      const float* rp = cl.map_shared_rank(s_part, r) + threadIdx.x;
+      acc = fmaf(trans, rp[0], acc);
+      dep = fmaf(trans, rp[kMarchThreads], dep);
+#pragma unroll
+      for (int c = 0; c < NV; ++c) ch[c] = fmaf(trans, rp[(3 + c) * kMarchThreads], ch[c]);
+      trans *= rp[2 * kMarchThreads];
+    }
+  }
+  cl.sync();      // the other CTAs' shared memory must outlive the reads above
+  return seg == 0;
+}
 
 __device__ __forceinline__ void axis_coord(float centre, float lo, float ext, int size, int& i0, float& w0,
                                            float& w1) {

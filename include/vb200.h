@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define VB200_VERSION 200 /* 0.2.0 */
+#define VB200_VERSION 201 /* 0.2.0 */
 
 enum vb200_status {
   VB200_OK = 0,
@@ -60,6 +60,12 @@ enum vb200_dtype { VB200_F32 = 0, VB200_BF16 = 1, VB200_F16 = 2 };
 enum vb200_layout {
   VB200_NCDHW = 0, /* the reference's contiguous layout, x fastest           */
   VB200_NDHWC = 1  /* channels-last (torch.channels_last_3d), channel fastest */
+};
+
+/* backbone_conf['density_mode'] (BV2:191-194): what `self.density` is */
+enum vb200_density {
+  VB200_DENSITY_SDF = 0,  /* 'sdf':   ModifyLaplaceDensity(beta, bias) of an SDF feature (render_utils.py:30-46)        */
+  VB200_DENSITY_NAIVE = 1 /* 'naive': nn.Sigmoid(); `beta` is not read (pass any valid device float), d beta = 0       */
 };
 
 /* Static description of the path: sizes + the fp32 constants the reference derives from its
@@ -86,6 +92,7 @@ typedef struct VbGrid {
   float sdf_bias;         /* density bias (-1)                 render_utils.py:35               */
   float beta_min;         /* 1e-4                              render_utils.py:31               */
   float term_eps;         /* early-termination threshold on transmittance; 0 disables          */
+  int32_t density_mode;   /* enum vb200_density: how the density feature becomes sigma          BV2:191-194 */
 } VbGrid;
 
 /* Lattice tables, DEVICE pointers to fp32 arrays built on the host with the reference's own torch
@@ -259,9 +266,10 @@ typedef struct VbRenderIn {
   int32_t flags;        /* VB200_RENDER_* bits (forward only) */
 } VbRenderIn;
 
-/* voxel_output leaves vb200_render_fwd already multiplied by tanh(voxel_density): the BEV epilogue
- * `voxel_output * bev_density.tanh()` of BV2:627-630 folded into the kernel that resamples the features (both
- * operands are in registers there).  Inference only: vb200_render_bwd differentiates the unfused outputs. */
+/* voxel_output leaves vb200_render_fwd already multiplied by tanh(voxel_density) -- by voxel_density itself when
+ * density_mode is VB200_DENSITY_NAIVE: the BEV epilogue of BV2:627-630 folded into the kernel that resamples the
+ * features (both operands are in registers there).  Inference only: vb200_render_bwd differentiates the unfused
+ * outputs. */
 #define VB200_RENDER_TANH_EPILOGUE 1
 
 typedef struct VbRenderOut {

@@ -175,6 +175,13 @@ def laplace_density(s, beta_param, bias, beta_min=1e-4):
     return alpha * (0.5 + 0.5 * (s - bias).sign() * torch.expm1(-(s - bias).abs() / beta))
 
 
+def density(conf, s, beta_param):
+    """``self.density`` (BV2:191-194): nn.Sigmoid() for density_mode='naive', ModifyLaplaceDensity for 'sdf'."""
+    if conf.get("density_mode", "sdf") == "naive":
+        return torch.sigmoid(s)
+    return laplace_density(s, beta_param, conf["sdf_bias"])
+
+
 # --------------------------------------------------------------------------------------------
 # R1-R6: volume rendering
 # --------------------------------------------------------------------------------------------
@@ -209,10 +216,9 @@ def render_norm_output(conf, buf):
 
 
 def volume_rendering(conf, buf, geom, density_feature, semantic_logits, voxel_features, rgb, beta_param):
-    """BV2:391-467 ``volume_rendering_from_multiple_views`` (density_mode='sdf', cat_seg=False)."""
+    """BV2:391-467 ``volume_rendering_from_multiple_views`` (both density modes, cat_seg or not)."""
     B, N, d, h, w, _ = geom.shape
     K = conf["num_classes"]
-    bias = conf["sdf_bias"]
     vol = torch.cat([density_feature, semantic_logits, rgb, voxel_features], dim=1)
     g, m = render_norm_geom(conf, geom)
     go = render_norm_output(conf, buf)
@@ -220,7 +226,7 @@ def volume_rendering(conf, buf, geom, density_feature, semantic_logits, voxel_fe
     ff = F.grid_sample(vol, g.reshape(B, -1, h, w, 3), align_corners=True)
     ff = ff.reshape(B, -1, N, d - 1, h, w).permute(0, 2, 1, 3, 4, 5) * m.unsqueeze(2)
     ff = torch.nan_to_num(ff)
-    f_den = laplace_density(ff[:, :, :1, ...], beta_param, bias)
+    f_den = density(conf, ff[:, :, :1, ...], beta_param)
     f_seg = ff[:, :, 1:K + 1, ...]
     f_rgb = ff[:, :, K + 1:K + 4, ...]
     f_delta = torch.norm(geom[:, :, 1:, :, :, :] - geom[:, :, :-1, :, :, :], dim=-1)
@@ -237,7 +243,7 @@ def volume_rendering(conf, buf, geom, density_feature, semantic_logits, voxel_fe
 
     vf = F.grid_sample(vol, go, align_corners=True)
     vf = torch.flip(vf, dims=[2])
-    v_den = laplace_density(vf[:, :1, ...], beta_param, bias)
+    v_den = density(conf, vf[:, :1, ...], beta_param)
     v_seg = vf[:, 1:K + 1, ...]
     v_rgb = vf[:, K + 1:K + 4, ...]
     v_out = vf[:, K + 4:, ...]
@@ -307,7 +313,7 @@ def occupancy_queries(conf, semantic_logits, density_feature, bda, beta_param, c
     n = (c - lo) / ext
     n = n * 2. - 1.
     logits = F.grid_sample(semantic_logits, n, padding_mode='border', align_corners=True)
-    dens = F.grid_sample(laplace_density(density_feature, beta_param, conf["sdf_bias"]), n, align_corners=True)
+    dens = F.grid_sample(density(conf, density_feature, beta_param), n, align_corners=True)
     return logits.permute(0, 2, 3, 4, 1), dens.permute(0, 2, 3, 4, 1).tanh()
 
 

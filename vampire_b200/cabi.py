@@ -38,6 +38,7 @@ class VbGrid(C.Structure):
         ("seg_lo", C.c_float * 3), ("seg_ext", C.c_float * 3),
         ("bg_depth", C.c_float), ("bev_delta", C.c_float),
         ("sdf_bias", C.c_float), ("beta_min", C.c_float), ("term_eps", C.c_float),
+        ("density_mode", C.c_int32),
     ]
 
 
@@ -166,6 +167,9 @@ def dtype_code(dt: torch.dtype) -> int:
         raise TypeError(f"vampire_b200: unsupported feature dtype {dt}") from None
 
 
+DENSITY_MODES = {"sdf": 0, "naive": 1}       # enum vb200_density
+
+
 def make_grid(cfg: PathConfig, batch: int, has_bda: bool = True, term_eps: float = 1e-8,
               lift_2d: bool = False) -> VbGrid:
     """Sizes + fp32 constants; each float is the reference's Python double, rounded by c_float
@@ -193,6 +197,7 @@ def make_grid(cfg: PathConfig, batch: int, has_bda: bool = True, term_eps: float
     g.sdf_bias = cfg.sdf_bias
     g.beta_min = 1e-4                                            # render_utils.py:31
     g.term_eps = term_eps
+    g.density_mode = DENSITY_MODES[cfg.density_mode]             # BV2:191-194
     if lift_2d:
         # BaseBiLinear's 2-D lift (base_bilinear.py:471-517): D == 1 selects it -- one depth plane, test z > 0
         g.D = 1

@@ -438,6 +438,42 @@ __device__ __forceinline__ float laplace_density_rcp(float s, float bias, float 
   return inv_beta * (0.5f + 0.5f * sgn * (expf(-fabsf(x) * inv_beta) - 1.0f));
 }
 
+// density_mode = 'naive': self.density = nn.Sigmoid() (BV2:191-192); ATen's fp32 form 1 / (1 + exp(-x))
+__device__ __forceinline__ float sigmoid_density(float s) { return 1.0f / (1.0f + expf(-s)); }
+
+// sigma of a density feature under the grid's density mode (the branch is launch-uniform)
+__device__ __forceinline__ float vb_density(const VbGrid& g, float s, float beta) {
+  if (g.density_mode == VB200_DENSITY_NAIVE) return sigmoid_density(s);
+  return laplace_density(s, g.sdf_bias, beta);
+}
+__device__ __forceinline__ float vb_density_rcp(const VbGrid& g, float s, float inv_beta) {
+  if (g.density_mode == VB200_DENSITY_NAIVE) return sigmoid_density(s);
+  return laplace_density_rcp(s, g.sdf_bias, inv_beta);
+}
+
+// sigma with its derivatives (backward kernels).  'sdf' (render_utils.py:30-46, x = s - bias):
+//   dsigma/ds = -e^{-|x|/beta} / (2 beta^2) (0 at x = 0),  dsigma/dbeta = -sigma/beta + x e^{-|x|/beta} / (2 beta^3);
+// 'naive': dsigma/ds = sigma (1 - sigma), no beta.
+struct DensityD {
+  float sigma, ds, dbeta;
+};
+__device__ __forceinline__ DensityD vb_density_with_grads(const VbGrid& g, float s, float beta) {
+  DensityD d;
+  if (g.density_mode == VB200_DENSITY_NAIVE) {
+    d.sigma = sigmoid_density(s);
+    d.ds = d.sigma * (1.0f - d.sigma);
+    d.dbeta = 0.0f;
+    return d;
+  }
+  const float x = s - g.sdf_bias, ax = fabsf(x);
+  const float sgn = (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f);
+  const float e = expf(-ax / beta);
+  d.sigma = (1.0f / beta) * (0.5f + 0.5f * sgn * (e - 1.0f));
+  d.ds = (x != 0.0f) ? -e / (2.0f * beta * beta) : 0.0f;
+  d.dbeta = -d.sigma / beta + x * e / (2.0f * beta * beta * beta);
+  return d;
+}
+
 // true iff the 4x4 at M is exactly the identity.  mv(I, p) == p for every finite p, so the fused
 // kernels skip the two bda products then (the reference's default bda_aug_conf IS the identity,
 // base_exp.py:113-120) without changing a single compare or floor.  Block-uniform.

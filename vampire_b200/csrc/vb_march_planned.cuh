@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fw
 
   const float beta = fabsf(__ldg(beta_ptr)) + g.beta_min;
   const float inv_beta = 1.0f / beta;
-  const float sigma_masked = laplace_density_rcp(0.0f, g.sdf_bias, inv_beta);   // feature 0 outside the volume
+  const float sigma_masked = vb_density_rcp(g, 0.0f, inv_beta);   // feature 0 outside the volume
   // corner offsets are launch constants (inward-shifted base, see march_fwd_kernel): x-pairs = one pointer + immediate
   const int c_sy = g.vX * CP, c_sz = g.vY * g.vX * CP;
 
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_PLANNED_MINB) march_fw
         cw[q] = wx[q & 1] * wy[(q >> 1) & 1] * wz[q >> 2];
         s0 = fmaf(cw[q], widen_elem(raw[q]), s0);
       }
-      sigma = laplace_density_rcp(s0, g.sdf_bias, inv_beta);                   // BV2:423
+      sigma = vb_density_rcp(g, s0, inv_beta);                   // BV2:423
     }
     const float sd = sigma * delta;                                           // BV2:429
     const float e = expf(-sd);

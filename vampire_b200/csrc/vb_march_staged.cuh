@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_STAGED_MINB) march_fwd
 
   const float beta = fabsf(__ldg(beta_ptr)) + g.beta_min;
   const float inv_beta = 1.0f / beta;
-  const float sigma_masked = laplace_density_rcp(0.0f, g.sdf_bias, inv_beta);
+  const float sigma_masked = vb_density_rcp(g, 0.0f, inv_beta);
   const int c_sy = g.vX * CP, c_sz = g.vY * g.vX * CP;     // global corner strides (elements)
 
   float acc = 0.0f, dep = 0.0f, trans = 1.0f;
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_STAGED_MINB) march_fwd
         float s0 = 0.0f;
 #pragma unroll
         for (int q = 0; q < 8; ++q) s0 = fmaf(cw[q], vs_widen16<T>(vs_lds16(a[q])), s0);
-        sigma = laplace_density_rcp(s0, g.sdf_bias, inv_beta);                 // BV2:423
+        sigma = vb_density_rcp(g, s0, inv_beta);                 // BV2:423
       }
       const float sd = sigma * delta;                                         // BV2:429
       e = expf(-sd);
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_STAGED_MINB) march_fwd
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           s0 = fmaf(cw[q], widen_elem(__ldg(gp + ((q & 2) ? c_sy : 0) + ((q & 4) ? c_sz : 0) + ((q & 1) ? CP : 0))), s0);
-        sigma = laplace_density_rcp(s0, g.sdf_bias, inv_beta);
+        sigma = vb_density_rcp(g, s0, inv_beta);
       }
       const float sd = sigma * delta;
       e = expf(-sd);

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256) query_fwd_kernel(VbGrid g, const T* __res
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       float s = VbType<T>::ld(plane + k.off[q]);
-      if (apply_density) s = laplace_density(s, g.sdf_bias, beta);   // sigma volume is sampled (BV2:609)
+      if (apply_density) s = vb_density(g, s, beta);   // sigma volume is sampled (BV2:609)
       v = fmaf(k.w[q], s, v);
     }
     out[((size_t)b * CH + ch) * P + i] = v * m;
@@ -220,12 +220,9 @@ __global__ void __launch_bounds__(256) query_bwd_kernel(VbGrid g, const T* __res
         if (k.w[q] == 0.0f) continue;
         float d = k.w[q] * go;
         if (apply_density) {
-          const float x = VbType<T>::ld(plane + k.off[q]) - g.sdf_bias;
-          const float e = expf(-fabsf(x) / beta);
-          const float sgn = (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f);
-          const float sigma = (1.0f / beta) * (0.5f + 0.5f * sgn * (e - 1.0f));
-          dbeta = fmaf(d, -sigma / beta + x * e / (2.0f * beta * beta * beta), dbeta);
-          d *= (x != 0.0f) ? -e / (2.0f * beta * beta) : 0.0f;
+          const DensityD dd = vb_density_with_grads(g, VbType<T>::ld(plane + k.off[q]), beta);
+          dbeta = fmaf(d, dd.dbeta, dbeta);
+          d *= dd.ds;
         }
         atomicAdd(gp + k.off[q], d);
       }

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_MINB) march_fwd_kernel
 
   // a masked / out-of-volume sample has feature 0: sigma(0) is a per-launch constant (~2.27e-4)
   const float inv_beta = 1.0f / beta;
-  const float sigma_masked = laplace_density_rcp(0.0f, g.sdf_bias, inv_beta);
+  const float sigma_masked = vb_density_rcp(g, 0.0f, inv_beta);
   // One sample position, prepared ONE STEP AHEAD of its use: ncu attributed a quarter of all stall samples to
   // the first use of the eight density gathers (issued and consumed back to back, 5 warps per scheduler cannot
   // hide an L1-miss).  Now the geometry of sample i+1 is computed and its density loads are issued before
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_MINB) march_fwd_kernel
         s0 = fmaf(cw[q], widen_elem(cur.raw[q]), s0);
       }
       if (NANSAFE) s0 = nan_to_num(s0, 0.0f);                                  // BV2:421
-      sigma = laplace_density_rcp(s0, g.sdf_bias, inv_beta);                   // BV2:423
+      sigma = vb_density_rcp(g, s0, inv_beta);                   // BV2:423
     }
     const float sd = sigma * delta;                                           // BV2:429
     const float wgt = (1.0f - expf(-sd)) * trans;                           // BV2:430-434
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(256) bev_weights_kernel(VbGrid g, VbTables t, 
     const float lo = bev_row<T>(g, bc, plane, L.z0);
     prev_z0 = L.z0;
     prev_lo = lo;
-    const float sigma = laplace_density(L.wz0 * lo + L.wz1 * hi, g.sdf_bias, beta);      // BV2:445
+    const float sigma = vb_density(g, L.wz0 * lo + L.wz1 * hi, beta);      // BV2:445
     const float sd = sigma * g.bev_delta;
     const float w = (1.0f - expf(-sd)) * expf(-tau);                                       // BV2:454-458
     tau += sd;
@@ -367,7 +367,8 @@ __global__ void __launch_bounds__(256) bev_weights_kernel(VbGrid g, VbTables t, 
     const size_t o = ((size_t)b * g.oZ + l) * ncol + col;
     o_density[o] = sigma;
     wl_ws[o] = w;
-    if (th_ws) th_ws[o] = tanhf(sigma);     // BEV epilogue voxel_output * bev_density.tanh() (BV2:627-630), once per voxel
+    // BEV epilogue (BV2:627-630), once per voxel: voxel_output * bev_density.tanh() ('sdf') / * bev_density ('naive')
+    if (th_ws) th_ws[o] = g.density_mode == VB200_DENSITY_NAIVE ? sigma : tanhf(sigma);
   }
   o_height[(size_t)b * ncol + col] = height;                                               // BV2:461
 }
@@ -1410,6 +1411,7 @@ extern "C" int vb200_render_fwd(const VbGrid* g, const VbTables* t, const float*
                                 size_t workspace_bytes, void* stream) {
   VB_CHECK_ARG(g && t && d_mats && in && out);
   VB_CHECK_ARG(g->B > 0 && g->N > 0 && g->N <= VB_MAX_CAMS && g->D >= 2);
+  VB_CHECK_ARG(g->density_mode == VB200_DENSITY_SDF || g->density_mode == VB200_DENSITY_NAIVE);
   VB_CHECK_ARG(in->density && in->sem && in->rgb && in->feat && in->beta);
   VB_CHECK_ARG((branches & (VB200_BRANCH_CAM | VB200_BRANCH_BEV)) != 0);
   if (branches & VB200_BRANCH_CAM) VB_CHECK_ARG(out->rgb && out->seg && out->depth && d_workspace);

@@ -28,20 +28,6 @@ namespace {
 // 64-thread blocks: at B=1 the 65,536 BEV columns are only 256 blocks of 256 threads (0.3 waves)
 constexpr int kBevBwdThreads = 64;
 
-struct DensityD {
-  float sigma, ds, dbeta;
-};
-__device__ __forceinline__ DensityD density_with_grads(float s, float bias, float beta) {
-  DensityD d;
-  const float x = s - bias, ax = fabsf(x);
-  const float sgn = (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f);
-  const float e = expf(-ax / beta);
-  d.sigma = (1.0f / beta) * (0.5f + 0.5f * sgn * (e - 1.0f));
-  d.ds = (x != 0.0f) ? -e / (2.0f * beta * beta) : 0.0f;
-  d.dbeta = -d.sigma / beta + x * e / (2.0f * beta * beta * beta);
-  return d;
-}
-
 __device__ __forceinline__ float block_sum(float v, float* s_red) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -193,7 +179,7 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_BWD_MINB) march_bwd_ke
         // then s0 or Gv is non-finite too: the exact per-channel form runs only in that case
         if (!(fabsf(s0) + fabsf(Gv) <= 3.402823466e+38f)) nan_safe_values<T, K>(packed, cidx, cw, gc, s0, Gv);
       }
-      const DensityD dd = density_with_grads(s0, g.sdf_bias, beta);
+      const DensityD dd = vb_density_with_grads(g, s0, beta);
       const float sd = dd.sigma * delta;
       const float e_sd = expf(-sd);
       const float wgt = (1.0f - e_sd) * trans;
@@ -325,7 +311,7 @@ __global__ void __launch_bounds__(256) bev_bwd_composite_kernel(
 #pragma unroll
   for (int l = 0; l < kMaxLevels; ++l) {
     if (l < g.oZ) {
-      const float sigma = laplace_density(S[l], g.sdf_bias, beta);
+      const float sigma = vb_density(g, S[l], beta);
       const float sd = sigma * g.bev_delta;
       const float w = (1.0f - expf(-sd)) * expf(-tau);
       tau += sd;
@@ -338,7 +324,7 @@ __global__ void __launch_bounds__(256) bev_bwd_composite_kernel(
 #pragma unroll
   for (int l = 0; l < kMaxLevels; ++l) {
     if (l < g.oZ) {
-      const DensityD dd = density_with_grads(S[l], g.sdf_bias, beta);
+      const DensityD dd = vb_density_with_grads(g, S[l], beta);
       const float sd = dd.sigma * g.bev_delta;
       const float trans = expf(-tau), e_sd = expf(-sd);
       const float w = (1.0f - e_sd) * trans;
@@ -610,6 +596,7 @@ extern "C" int vb200_render_bwd(const VbGrid* g, const VbTables* t, const float*
                                 void* d_workspace, size_t workspace_bytes, void* stream) {
   VB_CHECK_ARG(g && t && d_mats && in && out && grad && d_workspace);
   VB_CHECK_ARG(g->B > 0 && g->N > 0 && g->N <= VB_MAX_CAMS && g->D >= 2);
+  VB_CHECK_ARG(g->density_mode == VB200_DENSITY_SDF || g->density_mode == VB200_DENSITY_NAIVE);
   VB_CHECK_ARG(in->density && in->sem && in->rgb && in->feat && in->beta);
   VB_CHECK_ARG(grad->g_density && grad->g_sem && grad->g_rgb_in && grad->g_feat && grad->g_beta);
   VB_CHECK_ARG((branches & (VB200_BRANCH_CAM | VB200_BRANCH_BEV)) != 0);

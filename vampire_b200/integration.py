@@ -84,8 +84,8 @@ def fused_forward_single_sweep(self, sweep_index, sweep_imgs, mats_dict, inrange
         occ_logits, occ_density = path.occupancy(semantic_logits, density_feature, None, path.occ_coords())
     # BV2:554-559 + 612-614: geometry recomputed in-kernel (never stored), nan_to_num included.  Without gradients the
     # BEV epilogue of BV2:627-630 is folded into the BEV kernel (both operands are in registers there).
-    fuse_tanh = self.density_mode == "sdf" and not (torch.is_grad_enabled() and any(
-        t.requires_grad for t in (density_feature, semantic_logits, base_features, rgb, path.density.beta)))
+    fuse_tanh = not (torch.is_grad_enabled() and any(
+        t.requires_grad for t in (density_feature, semantic_logits, base_features, rgb, path._beta())))
     (rgb_preds, seg_logits_preds, depth_preds, bev_rgb_preds, bev_seg_logits_preds, bev_height_preds, bev_density,
      voxel_output) = path.render(mats_dict, density_feature, semantic_logits, base_features, rgb, sweep_index,
                                  tanh_epilogue=fuse_tanh)

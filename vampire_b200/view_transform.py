@@ -87,13 +87,16 @@ class LiftRenderB200(nn.Module):
             raise ValueError(f"libvb200 is compiled for mid_channels=16, num_classes=18 and at most 8 cameras "
                              f"(every reference experiment); got C={self.cfg.C}, K={self.cfg.K}, "
                              f"cams={self.cfg.num_cams}")
-        if self.cfg.density_mode != "sdf":
-            raise NotImplementedError("only density_mode='sdf' (the target experiment, base_exp.py:51) is built")
-        if self.cfg.cat_seg:
-            raise NotImplementedError("cat_seg=True is not part of the target experiment (base_exp.py:54)")
+        if self.cfg.density_mode not in cabi.DENSITY_MODES:
+            raise ValueError(f"density_mode must be 'sdf' or 'naive' (BV2:191-194), got {self.cfg.density_mode!r}")
         self.cfg_id = ops.register_config(self.cfg)
-        self.density = LaplaceDensityParam(beta=0.1, bias=self.cfg.sdf_bias)
+        # BV2:191-194: nn.Sigmoid() for 'naive' (the constructors' default), ModifyLaplaceDensity for 'sdf' (base_exp.py:51)
+        self.density = (nn.Sigmoid() if self.cfg.density_mode == "naive"
+                        else LaplaceDensityParam(beta=0.1, bias=self.cfg.sdf_bias))
+        # the C ABI always takes a beta pointer; 'naive' never reads it
+        self.register_buffer("_unit_beta", torch.ones(()), persistent=False)
         self.channels_last_volume = channels_last_volume
+        self._det_points = None       # cat_seg: det-grid voxel centres, built on first use
         st = ops.state(self.cfg_id)
         lat = st.lattice
         # the reference's buffers (BV2:146-160), rebuilt from the same 1-D axes
@@ -137,7 +140,22 @@ class LiftRenderB200(nn.Module):
         return self.plans == "always" or (self.plans == "eval" and not self.training)
 
     def _device(self) -> torch.device:
-        return self.density.beta.device
+        beta = getattr(self.density, "beta", None)
+        if beta is not None:
+            return beta.device
+        if self._unit_beta.device.type != "cuda" and torch.cuda.is_available():
+            # 'naive' has no parameter to follow (an attached path is not a registered submodule): current device
+            return torch.device("cuda", torch.cuda.current_device())
+        return self._unit_beta.device
+
+    def _beta(self, device: Optional[torch.device] = None) -> Tensor:
+        """The learnable ``density.beta`` ('sdf'); a constant the kernels never read ('naive')."""
+        beta = getattr(self.density, "beta", None)
+        if beta is not None:
+            return beta
+        if device is not None and self._unit_beta.device != device:
+            self._unit_beta = self._unit_beta.to(device)
+        return self._unit_beta
 
     # ---- reference-named methods ----------------------------------------------------------------
     def get_geometry(self, sensor2ego_mat, intrin_mat, ida_mat, bda_mat) -> Tensor:
@@ -166,9 +184,9 @@ class LiftRenderB200(nn.Module):
         dev = density_feature.device
         # matrices are unused when geom is supplied; an identity block keeps the ABI uniform
         mats = torch.eye(4, device=dev).expand(B, self.cfg.num_cams, 6, 4, 4).contiguous()
-        outs = ops.render_fwd(density_feature, semantic_logits, rgb, voxel_features, self.density.beta, mats,
+        outs = ops.render_fwd(density_feature, semantic_logits, rgb, voxel_features, self._beta(dev), mats,
                               geom_xyz, self.cfg_id, True, cabi.BRANCH_CAM | cabi.BRANCH_BEV)
-        return tuple(outs)
+        return tuple(self._cat_seg(list(outs), semantic_logits))
 
     # ---- fused entry points -------------------------------------------------------------------
     def lift_pool(self, depth_softmax_features: Tensor, low_channel_source_features: Tensor,
@@ -216,9 +234,30 @@ class LiftRenderB200(nn.Module):
         plan = None
         if self._use_plans() and (branches & cabi.BRANCH_CAM):
             plan = self.plan_cache.render(ops.state(self.cfg_id), self.cfg_id, mats, has_bda, mats_host).table
-        outs = ops.render_fwd(density_feature, semantic_logits, rgb, voxel_features, self.density.beta, mats,
-                              None, self.cfg_id, has_bda, branches, plan, tanh_epilogue)
+        fuse = tanh_epilogue and not self.cfg.cat_seg        # the epilogue covers the concatenated seg channels too
+        outs = list(ops.render_fwd(density_feature, semantic_logits, rgb, voxel_features, self._beta(density_feature.device), mats,
+                                   None, self.cfg_id, has_bda, branches, plan, fuse))
+        if branches & cabi.BRANCH_BEV:
+            outs = self._cat_seg(outs, semantic_logits)
+            if tanh_epilogue and not fuse:
+                outs[7] = self.bev_epilogue(outs[7], outs[6])
         return tuple(outs)
+
+    def _cat_seg(self, outs, semantic_logits: Tensor):
+        """``cat_seg=True`` (BV2:449-450; the default of BaseLSSImpaintor): the BEV feature volume carries the resampled,
+        un-composited semantic logits behind the C feature channels.  They are the det-grid voxel centres sampled from
+        the logits volume with zeros padding, top level first (BV2:442-443) -- the point-query kernel of SURVEY 8f row 3."""
+        if not self.cfg.cat_seg:
+            return outs
+        cfg = self.cfg
+        if self._det_points is None or self._det_points.device != semantic_logits.device:
+            lat = ops.state(self.cfg_id).lattice
+            z, y, x = torch.meshgrid(lat.ozs.flip(0), lat.oys, lat.oxs, indexing="ij")
+            self._det_points = torch.stack([x, y, z], -1).reshape(-1, 3).to(semantic_logits.device)
+        seg, _ = ops.query_points_fwd(semantic_logits, self._det_points, None, None, self.cfg_id, False, False, False)
+        seg = seg.reshape(seg.shape[0], cfg.K, cfg.oZ, cfg.oY, cfg.oX).to(outs[7].dtype)
+        outs[7] = torch.cat([outs[7], seg], dim=1)
+        return outs
 
     # ---- the callers right after the path (SURVEY §8f rows 2-3) ------------------------------------
     def depth_softmax(self, depth_logits: Tensor, out_fp32: bool = True) -> Tensor:
@@ -249,8 +288,9 @@ class LiftRenderB200(nn.Module):
         return c.reshape(*dims, 3)
 
     def bev_epilogue(self, voxel_output: Tensor, bev_density: Tensor) -> Tensor:
-        """``voxel_output * bev_density.tanh()`` (BV2:627-630, density_mode='sdf')."""
-        return voxel_output * bev_density.tanh().to(voxel_output.dtype)
+        """``voxel_output * bev_density.tanh()`` for density_mode='sdf', ``* bev_density`` for 'naive' (BV2:627-630)."""
+        scale = bev_density.tanh() if self.cfg.density_mode == "sdf" else bev_density
+        return voxel_output * scale.to(voxel_output.dtype)
 
     def occupancy(self, semantic_logits: Tensor, density_feature: Tensor, bda_mat: Optional[Tensor],
                   occ_coords: Tensor):
@@ -262,7 +302,7 @@ class LiftRenderB200(nn.Module):
         pts = occ_coords.reshape(-1, 3).to(semantic_logits.device)
         rot = None if bda_mat is None else bda_mat[:, :3, :3].to(semantic_logits.device)
         logits, _ = ops.query_points_fwd(semantic_logits, pts, rot, None, self.cfg_id, True, False, False)
-        dens, _ = ops.query_points_fwd(density_feature, pts, rot, self.density.beta, self.cfg_id, False, True, False)
+        dens, _ = ops.query_points_fwd(density_feature, pts, rot, self._beta(density_feature.device), self.cfg_id, False, True, False)
         B = semantic_logits.shape[0]
         return (logits.reshape(B, -1, *shape).permute(0, 2, 3, 4, 1),
                 dens.reshape(B, 1, *shape).permute(0, 2, 3, 4, 1).tanh())

@@ -688,6 +688,14 @@ __device__ __forceinline__ void bev_quad_channel_generic(const VbGrid& g, const 
   if (o_map && live) *reinterpret_cast<float4*>(o_map) = make_float4(acc[0], acc[1], acc[2], acc[3]);
 }
 
+// Measured alternative (round 2, removed again): a y-strip walk -- a thread owns 4 columns of one plane over 16
+// consecutive output rows and keeps the x-interpolated input row y0 + 1 of every z-row in registers as row y0 of the
+// next output row, so an output row costs one vector + one edge load per z-row instead of two.  ncu, R50 B=8 bf16:
+// 510 us vs 266 us for this kernel: the loads halved but the instruction count did not fall (179 M vs 164 M warp
+// instructions: the loads were never the bulk, the widen / interpolate / composite arithmetic is, and this kernel already
+// issues 57 % of its slots), while 44 persistent registers halved the occupancy (128 regs, 25 % vs 50 %) of a kernel
+// that lives on hiding latency (long scoreboard 7-8 warps per issue in both).
+//
 // channel chunks: the K+3 composited planes and the C feature planes are split into chunks of <= 8 planes,
 // one chunk per blockIdx.y
 __host__ __device__ constexpr int bev_chunks(int n) { return (n + 7) / 8; }

@@ -589,15 +589,24 @@ struct BevLevelX {       // per level: row offsets of z0 / z0+1 inside a plane, 
                          // bit1: row z0+1 is inside the grid      bit2: row z0 is inside the grid
 };
 
+// the same per level as one 16-byte shared-memory word (one LDS.128 per level instead of five loads and a select; ncu
+// attributed 11 % of the kernel's instructions to fetching BevLevelX in the level loop).  The padding of row z0 rides
+// in wz0 = 0 -- its address is clamped, the value finite -- so the fast path needs no flag for it.
+struct __align__(16) BevLevelF {
+  int zoff;              // z0 * vY * vX (z0 clamped)
+  float wz0, wz1;        // zero when the row is outside the grid
+  int flags;             // bit0: row z0+1 == row z0 of the previous level; bit1: row z0+1 is inside the grid
+};
+
 // One channel plane, all levels, MODE 0/1 (mode1, warp-uniform).  MAP (block-uniform): composite with the
 // level weights into a (oY,oX) map; otherwise store the resampled rows as T.
 template <typename T, bool MAP, bool EPI = false>
-__device__ __forceinline__ void bev_fast_channel(const BevLevelX* __restrict__ lv, int oZ, const bool mode1,
-                                                 const BevQuadFast& q, const T* __restrict__ plane, bool live,
-                                                 const float* __restrict__ wl, float* __restrict__ o_map,
+__device__ __forceinline__ void bev_fast_channel(const BevLevelF* __restrict__ lv, const int* __restrict__ zhi, int oZ,
+                                                 const bool mode1, const BevQuadFast& q, const T* __restrict__ plane,
+                                                 bool live, const float* __restrict__ wl, float* __restrict__ o_map,
                                                  T* __restrict__ o_feat, int ncol) {
   float prev[4] = {0.0f, 0.0f, 0.0f, 0.0f}, acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-  BevLevelX L = lv[0];
+  BevLevelF L = lv[0];
   RawRow<T> nxt = bev_load_row<T>(plane, q, L.zoff);
   const float4* wp = reinterpret_cast<const float4*>(wl);
   const int wstep = ncol >> 2;                             // ncol % 4 == 0 (oX % 4 == 0)
@@ -608,7 +617,7 @@ __device__ __forceinline__ void bev_fast_channel(const BevLevelX* __restrict__ l
 #pragma unroll
       for (int c = 0; c < 4; ++c) hi[c] = prev[c];
     } else if (L.flags & 2) {
-      const RawRow<T> h = bev_load_row<T>(plane, q, L.zoff_hi);
+      const RawRow<T> h = bev_load_row<T>(plane, q, zhi[l]);
       if (mode1) bev_finish_row<T, 1>(h, q, hi);
       else bev_finish_row<T, 0>(h, q, hi);
     } else {
@@ -616,14 +625,10 @@ __device__ __forceinline__ void bev_fast_channel(const BevLevelX* __restrict__ l
       for (int c = 0; c < 4; ++c) hi[c] = 0.0f;
     }
     const RawRow<T> cur = nxt;
-    const BevLevelX Ln = lv[l + 1 < oZ ? l + 1 : l];
+    const BevLevelF Ln = lv[l + 1];                        // the table has one entry past the last level
     nxt = bev_load_row<T>(plane, q, Ln.zoff);              // in flight while this level is composited
     if (mode1) bev_finish_row<T, 1>(cur, q, lo);
     else bev_finish_row<T, 0>(cur, q, lo);
-    if (!(L.flags & 4)) {                                  // row z0 outside the grid: zeros padding (uniform)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) lo[c] = 0.0f;
-    }
     float v[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -709,19 +714,20 @@ __global__ void __launch_bounds__(64, 16) bev_channels_vec4_kernel(VbGrid g, VbT
                                                                float* __restrict__ o_rgb, float* __restrict__ o_seg,
                                                                T* __restrict__ o_feat, const float* __restrict__ th_ws) {
   __shared__ BevLevel s_lv[kMaxLevels];
-  __shared__ BevLevelX s_lx[kMaxLevels];
+  __shared__ BevLevelF s_lx[kMaxLevels + 1];       // + one entry the look-ahead of the last level may read
+  __shared__ int s_zhi[kMaxLevels];
   bev_level_table(g, t, s_lv);
-  if (threadIdx.x < g.oZ) {
-    const int l = threadIdx.x;
+  if (threadIdx.x <= g.oZ) {
+    const int l = min((int)threadIdx.x, g.oZ - 1);   // entry oZ repeats the last level: its row is requested, never used
     const BevLevel L = s_lv[l];
-    BevLevelX X;
+    BevLevelF X;
     const bool in0 = L.z0 >= 0 && L.z0 < g.vZ, in1 = L.z0 + 1 >= 0 && L.z0 + 1 < g.vZ;
     X.zoff = min(max(L.z0, 0), g.vZ - 1) * g.vY * g.vX;
-    X.zoff_hi = min(max(L.z0 + 1, 0), g.vZ - 1) * g.vY * g.vX;
     X.wz0 = in0 ? L.wz0 : 0.0f;
     X.wz1 = in1 ? L.wz1 : 0.0f;
-    X.flags = ((l > 0 && L.z0 + 1 == s_lv[l - 1].z0) ? 1 : 0) | (in1 ? 2 : 0) | (in0 ? 4 : 0);
-    s_lx[l] = X;
+    X.flags = ((l > 0 && L.z0 + 1 == s_lv[l - 1].z0) ? 1 : 0) | (in1 ? 2 : 0);
+    s_lx[threadIdx.x] = X;
+    if (threadIdx.x < g.oZ) s_zhi[l] = min(max(L.z0 + 1, 0), g.vZ - 1) * g.vY * g.vX;
   }
   __syncthreads();
   const int b = blockIdx.z, grp = blockIdx.y;
@@ -786,8 +792,8 @@ __global__ void __launch_bounds__(64, 16) bev_channels_vec4_kernel(VbGrid g, VbT
       float* o_map;
       T* o_f;
       planes(j, plane, o_map, o_f);
-      if (is_map) bev_fast_channel<T, true>(s_lx, g.oZ, w1, f, plane, live, wl, o_map, o_f, ncol);
-      else bev_fast_channel<T, false, EPI>(s_lx, g.oZ, w1, f, plane, live, wl, o_map, o_f, ncol);
+      if (is_map) bev_fast_channel<T, true>(s_lx, s_zhi, g.oZ, w1, f, plane, live, wl, o_map, o_f, ncol);
+      else bev_fast_channel<T, false, EPI>(s_lx, s_zhi, g.oZ, w1, f, plane, live, wl, o_map, o_f, ncol);
     }
   } else {
     for (int j = c_begin; j < c_end; ++j) {

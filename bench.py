@@ -341,7 +341,7 @@ def workload_config(args, cfg, batch, dtype):
 class Workload:
     """One configuration of the hot path on this rank's GPU: inputs resident in HBM, `step()` = one pass."""
 
-    def __init__(self, args, cfg, dev, world, rank, train, batch, dname, use_plans, allreduce=True):
+    def __init__(self, args, cfg, dev, world, rank, train, batch, dname, use_plans, allreduce=True, graph=False):
         from vampire_b200 import ops, synth
         from vampire_b200.matrices import prepare_matrices
         from vampire_b200.view_transform import LiftRenderB200
@@ -383,6 +383,12 @@ class Workload:
             self.cots = [t.to(dev) for t in synth.make_cotangents(shapes, seed)]
             self.cots[0] = self.cots[0].to(self.tdt)
             self.cots[8] = self.cots[8].to(self.tdt)
+            self.graphed = None
+            if graph:
+                from vampire_b200.dp import GraphedTrainStep
+                d, c, den, sem, feat, rgb = self.dev_in
+                self.graphed = GraphedTrainStep(self.mod, d, c, (den, sem, feat, rgb), self.prep, self.cots, self.bucket,
+                                                plan=self.plan_tab)
 
     def step(self):
         """hot path with inputs resident in HBM (prepared matrices uploaded once, like a val loop
@@ -394,6 +400,8 @@ class Workload:
                 vox, _ = ops.lift_pool_fwd(d, c, self.prep, mod.cfg_id, True, self.args.channels_last, False, self.plan_tab)
                 rend = ops.render_fwd(den, sem, rgb, feat, self.beta, self.prep, None, mod.cfg_id, True, 3, self.rplan_tab)
             return vox, rend
+        if self.graphed is not None:
+            return self.graphed()
         from vampire_b200.dp import train_step
         return train_step(mod, d, c, (den, sem, feat, rgb), self.prep, self.cots, self.bucket, plan=self.plan_tab)
 
@@ -452,7 +460,7 @@ class Workload:
         return ms_serial, per_kernel, kbytes
 
     def free(self):
-        for name in ("dev_in", "host_in", "cots", "bucket", "plan_tab", "rplan_tab", "mod", "prep"):
+        for name in ("graphed", "dev_in", "host_in", "cots", "bucket", "plan_tab", "rplan_tab", "mod", "prep"):
             if hasattr(self, name):
                 delattr(self, name)
         torch.cuda.empty_cache()
@@ -467,14 +475,29 @@ def train_probe(args, cfg, dev, world, rank, steps, warmup):
                    "all-reduce per step (dp.train_step); projection/sort plans recomputed every step"}
     pts1 = cfg.num_cams * cfg.D * cfg.fH * cfg.fW
     w = Workload(args, cfg, dev, world, rank, True, 1, "fp32", False, allreduce=True)
-    ms = w.timed(steps, warmup)
+    ms_eager = ms = w.timed(steps, warmup)
     _, kern, _ = w.per_kernel(steps)
     w.free()
+    launch = "eager: two custom ops + autograd per step (dp.train_step)"
+    # the same step replayed from two CUDA graphs around the one NCCL call (dp.GraphedTrainStep): at B = 1 the eager
+    # step is launch-bound as soon as several ranks share a host
+    try:
+        w = Workload(args, cfg, dev, world, rank, True, 1, "fp32", False, allreduce=True, graph=True)
+        ms = w.timed(steps, warmup)
+        w.free()
+        launch = "two CUDA graphs + one NCCL all-reduce call per step (dp.GraphedTrainStep)"
+    except Exception as e:      # capture refused (e.g. a backend that cannot be captured): keep the eager number, say why
+        out["graph_error"] = f"{type(e).__name__}: {e}"[:300]
     out.update({"batch_per_gpu": 1, "features": "fp32", "ms_per_step": ms, "pts_per_s": world * pts1 / (ms * 1e-3),
-                "steps": steps, "warmup": warmup, "kernels": kern})
-    w = Workload(args, cfg, dev, world, rank, True, 1, "fp32", False, allreduce=False)
-    ms_no = w.timed(steps, warmup)
-    w.free()
+                "steps": steps, "warmup": warmup, "launch": launch, "ms_per_step_eager": ms_eager, "kernels": kern})
+    try:
+        w = Workload(args, cfg, dev, world, rank, True, 1, "fp32", False, allreduce=False, graph="graph_error" not in out)
+        ms_no = w.timed(steps, warmup)
+        w.free()
+    except Exception:
+        w = Workload(args, cfg, dev, world, rank, True, 1, "fp32", False, allreduce=False)
+        ms_no = w.timed(steps, warmup)
+        w.free()
     out["ms_per_step_without_allreduce"] = ms_no
     out["allreduce_exposed_ms"] = ms - ms_no
     w = Workload(args, cfg, dev, world, rank, True, 1, "fp32", True, allreduce=True)

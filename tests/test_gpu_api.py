@@ -157,3 +157,45 @@ def test_module_api_with_host_matrices_vs_same_host_oracle(seed):
         for n, o, r in zip(["rgb", "seg", "depth", "bev_rgb", "bev_seg", "bev_height", "voxel_density", "voxel_output"],
                            outs, ref):
             assert_close_scaled(o.cpu().numpy(), r.numpy(), 1e-5, "module render " + n)
+
+
+def test_graphed_train_step_matches_the_eager_step():
+    """dp.GraphedTrainStep (two CUDA graphs around the all-reduce call) replays exactly dp.train_step: same outputs,
+    same gradients, also after the producer has written new inputs and new matrices into the captured tensors."""
+    from helpers import Case
+    from vampire_b200 import synth
+    from vampire_b200.dp import GradBucket, GraphedTrainStep, train_step
+    from vampire_b200.view_transform import LiftRenderB200
+    case = Case("mini_stress")
+    cfg = case.cfg
+    mod = LiftRenderB200(**case.conf).cuda().train()
+    prep = case.prep.cuda().clone()
+    leaves = [t.clone().cuda().requires_grad_(True) for t in (case.depth, case.ctx, case.den, case.sem, case.feat, case.rgb)]
+    B = case.batch
+    shapes = [(B, cfg.C, cfg.vZ, cfg.vY, cfg.vX), (B, cfg.num_cams, 3, cfg.fH, cfg.fW), (B, cfg.num_cams, cfg.K, cfg.fH, cfg.fW),
+              (B, cfg.num_cams, 1, cfg.fH, cfg.fW), (B, 3, cfg.oY, cfg.oX), (B, cfg.K, cfg.oY, cfg.oX), (B, 1, cfg.oY, cfg.oX),
+              (B, 1, cfg.oZ, cfg.oY, cfg.oX), (B, cfg.C, cfg.oZ, cfg.oY, cfg.oX)]
+    cots = [c.cuda() for c in synth.make_cotangents(shapes)]
+    bucket = GradBucket(torch.device("cuda"), 1)
+    d, c, den, sem, feat, rgb = leaves
+    graphed = GraphedTrainStep(mod, d, c, (den, sem, feat, rgb), prep, cots, bucket)
+
+    def snapshot(vox, rend):
+        return ([vox.detach().clone()] + [r.detach().clone() for r in rend],
+                [t.grad.detach().clone() for t in leaves + [mod.density.beta]])
+
+    for round_ in range(2):
+        if round_ == 1:      # the next batch: new feature values and the other rig's matrices, written in place
+            with torch.no_grad():
+                for t in leaves:
+                    t.mul_(0.5).add_(0.01)
+                prep.copy_(Case("mini_val").prep.cuda())
+        got = snapshot(*graphed())
+        ref = snapshot(*train_step(mod, d, c, (den, sem, feat, rgb), prep, cots, bucket))
+        for a, b in zip(got[0], ref[0]):
+            assert torch.equal(a, b)
+        for name, a, b in zip(("depth", "ctx", "den", "sem", "feat", "rgb", "beta"), got[1], ref[1]):
+            if name in ("depth", "ctx"):
+                assert torch.equal(a, b), name                   # deterministic lift backward
+            else:                                                # vector atomics: order-dependent last bits
+                assert torch.allclose(a, b, rtol=1e-4, atol=1e-5 * float(b.abs().max())), name

@@ -113,3 +113,65 @@ def train_step(mod, depth, ctx, vols, mats_prep, cotangents, bucket: GradBucket,
     torch.autograd.backward([vox], [cotangents[0]])
     bucket.wait()
     return vox, rend
+
+
+class GraphedTrainStep:
+    """``train_step`` replayed from two CUDA graphs.
+
+    At B = 1 per GPU the step is ~45 short launches plus the Python of two custom ops and their autograd nodes in
+    1.7 ms of GPU time: one process keeps up, eight processes on one host do not (measured on 8 x B200: 2.17 ms per
+    step against 1.72 ms on one GPU, with the all-reduce itself exposing 0.02 ms).  Captured once, the step is two graph
+    launches around the one NCCL call:
+
+        graph A: render forward + backward   ->   all-reduce launched (beta's gradient is final)
+        graph B: lift + pool forward + backward (runs under the all-reduce)   ->   wait
+
+    The inputs are the tensors given at construction: a producer writes the next batch (features, volumes, prepared
+    matrices) INTO them before each call, exactly like any graph-captured training loop; every kernel re-reads them on
+    replay, so per-step matrices (training draws a new ida every step, base_exp.py:93-111) cost nothing extra.  The
+    gradients live in ``.grad`` of the same tensors and are rewritten (not accumulated) by each replay."""
+
+    def __init__(self, mod, depth, ctx, vols, mats_prep, cotangents, bucket: GradBucket, has_bda: bool = True,
+                 plan=None, warmup: int = 3):
+        from . import ops
+        self.bucket = bucket
+        den, sem, feat, rgb = vols
+        self.beta = beta = mod.density.beta
+        self.leaves = (depth, ctx, den, sem, feat, rgb, beta)
+        cots = list(cotangents)
+
+        def render_part():
+            rend = ops.render_fwd(den, sem, rgb, feat, beta, mats_prep, None, mod.cfg_id, has_bda, 3)
+            torch.autograd.backward(list(rend), cots[1:])
+            return rend
+
+        def lift_part():
+            vox, _ = ops.lift_pool_fwd(depth, ctx, mats_prep, mod.cfg_id, has_bda, False, True, plan)
+            torch.autograd.backward([vox], [cots[0]])
+            return vox
+
+        def clear():
+            for t in self.leaves:
+                t.grad = None
+
+        side = torch.cuda.Stream(device=depth.device)
+        side.wait_stream(torch.cuda.current_stream(depth.device))
+        with torch.cuda.stream(side):                    # warm-up outside capture: lazy initialisation, allocator
+            for _ in range(warmup):
+                clear()
+                render_part()
+                lift_part()
+        torch.cuda.current_stream(depth.device).wait_stream(side)
+        clear()
+        self.graph_render, self.graph_lift = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_render):
+            self.rend = render_part()
+        with torch.cuda.graph(self.graph_lift, pool=self.graph_render.pool()):
+            self.vox = lift_part()
+
+    def __call__(self):
+        self.graph_render.replay()
+        self.bucket.allreduce_async([self.beta.grad])
+        self.graph_lift.replay()
+        self.bucket.wait()
+        return self.vox, self.rend

@@ -168,8 +168,11 @@ class GraphedTrainStep:
             self.rend = render_part()
         with torch.cuda.graph(self.graph_lift, pool=self.graph_render.pool()):
             self.vox = lift_part()
+        self.grads = [t.grad for t in self.leaves]       # the graphs' own gradient buffers
 
     def __call__(self):
+        for t, g in zip(self.leaves, self.grads):        # an eager backward in between may have re-pointed .grad
+            t.grad = g
         self.graph_render.replay()
         self.bucket.allreduce_async([self.beta.grad])
         self.graph_lift.replay()

@@ -1197,11 +1197,12 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
   const int flag_init = (g->vX < 2 || g->vY < 2 || g->vZ < 2) ? 1 : 0;
   int* nf_flags = reinterpret_cast<int*>((char*)ws + cam_bytes + bev_bytes - 256);   // one int per sub-round
   const VbRenderDiv dv = vb_render_div(g);
-  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  cudaStreamIsCapturing(st, &cap);
+  // The fork is an event edge caller stream -> side stream -> caller stream, so it is also legal while the caller's
+  // stream is being captured into a CUDA graph (the side stream joins the capture and is joined back before this
+  // call returns): a replayed graph keeps the BEV branch beside the march (dp.GraphedTrainStep).
   static const bool no_fork_env = getenv("VB200_NO_FORK") != nullptr;   // measurement aid
   const bool no_fork = no_fork_env || g_render_fork_disabled.load(std::memory_order_relaxed) != 0;
-  const bool may_fork = !no_fork && cap == cudaStreamCaptureStatusNone;
+  const bool may_fork = !no_fork;
 
   auto pack_round = [&](int b0, int nb, T* region, int* flag, cudaStream_t ps) -> int {
     VbTraceScope tr(VB_K_PACK, ps);

@@ -470,9 +470,18 @@ def train_probe(args, cfg, dev, world, rank, steps, warmup):
     """BASELINE configs[2] measured inside the default run so the driver sees it at every N: forward+backward,
     B = 1 per GPU, fp32, flat-bucket NCCL all-reduce; the all-reduce's exposed time = step with - step without;
     per-kernel backward times.  Plans off (training draws a new ida every step); the cached variant beside it.
-    At N = 1 additionally B = 8 fp32, the size at which a backward roofline fraction means something."""
+    At N = 1 additionally B = 8 fp32, the size at which a backward roofline fraction means something.
+
+    Every rank draws the SAME sample here (the seed of rank 0): the work of this path depends on the data (rays end at
+    surfaces, the rig decides how many voxel-camera pairs exist) and one sample per GPU does not average that out --
+    on one B200 the samples that ranks 0..7 would draw take 1.66 / 1.85 / 2.08 / 1.74 / 1.88 / 1.70 / 1.86 / 1.73 ms
+    (tools/train_seed_variance.py, profiles/r02_train_seed_variance.txt), so a max over ranks of different samples
+    measures that spread (2.08 / 1.66), not the scaling.  Weak scaling = identical work per GPU."""
     out = {"what": "configs[2]: lift+pool+render forward+backward, B=1/GPU, fp32, DP with one flat-bucket NCCL "
-                   "all-reduce per step (dp.train_step); projection/sort plans recomputed every step"}
+                   "all-reduce per step; projection/sort plans recomputed every step; every rank runs the sample of "
+                   "rank 0's seed (identical work per GPU: the step time of this data-dependent path varies 1.66-2.08 "
+                   "ms between samples on one GPU, profiles/r02_train_seed_variance.txt)"}
+    rank = 0      # seeds the sample only; the process group, device and bucket are untouched
     pts1 = cfg.num_cams * cfg.D * cfg.fH * cfg.fW
     w = Workload(args, cfg, dev, world, rank, True, 1, "fp32", False, allreduce=True)
     ms_eager = ms = w.timed(steps, warmup)

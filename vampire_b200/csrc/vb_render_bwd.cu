@@ -57,11 +57,17 @@ __device__ __noinline__ void nan_safe_values(const T* __restrict__ packed, const
 }
 
 // ---- camera branch ---------------------------------------------------------------------------------------
+#ifndef VB_MARCH_BWD_THREADS
+#define VB_MARCH_BWD_THREADS 128
+#endif
+constexpr int kMarchBwdThreads = VB_MARCH_BWD_THREADS;
 #ifndef VB_MARCH_BWD_MINB
 #define VB_MARCH_BWD_MINB 3   // measured B=1 fp32: 0.593 ms at 3 blocks/SM, 0.68 at 4, 0.76 at 5 (B=8: 4.35 ms either way: L2-bound)
+                              // block shape (B=1 is 1.19 waves of 128-thread blocks): 96 x 5 (one wave, 128 regs) 0.652,
+                              // 64 x 7 0.693, 64 x 6 (168 regs) 0.594 vs 0.605 -- nothing to gain, 128 x 3 stays
 #endif
 template <typename T, int K, bool FROM_MATS>
-__global__ void __launch_bounds__(kMarchThreads, VB_MARCH_BWD_MINB) march_bwd_kernel(
+__global__ void __launch_bounds__(kMarchBwdThreads, VB_MARCH_BWD_MINB) march_bwd_kernel(
     VbGrid g, VbTables t, VbRenderDiv dv, const float* __restrict__ d_mats, const float* __restrict__ d_geom,
     const T* __restrict__ packed, const float* __restrict__ beta_ptr, const float* __restrict__ o_rgb,
     const float* __restrict__ o_seg, const float* __restrict__ o_depth, const float* __restrict__ g_rgb,
@@ -69,7 +75,7 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_BWD_MINB) march_bwd_ke
     float* __restrict__ beta_partials, size_t packed_stride, size_t gpacked_stride) {
   constexpr int CP = packed_channels(K);
   __shared__ float s_m[VB200_MAT_SLOTS * 16];
-  __shared__ float s_red[kMarchThreads / 32];
+  __shared__ float s_red[kMarchBwdThreads / 32];
   // grid = (patch blocks, cameras, samples): the whole batch in ONE launch (a sample alone is 1.2 waves at 3 blocks
   // per SM, i.e. 40 % of its time is a tail) -- each sample has its own packed copy and gradient accumulator
   const int n = blockIdx.y, b = blockIdx.z;
@@ -85,7 +91,7 @@ __global__ void __launch_bounds__(kMarchThreads, VB_MARCH_BWD_MINB) march_bwd_ke
 
   const int patches_x = (g.fW + kPatchW - 1) / kPatchW;
   const int patches_y = (g.fH + kPatchH - 1) / kPatchH;
-  const int patch = blockIdx.x * (kMarchThreads / 32) + (threadIdx.x >> 5);
+  const int patch = blockIdx.x * (kMarchBwdThreads / 32) + (threadIdx.x >> 5);
   const bool warp_live = patch < patches_x * patches_y;
   const int lane = threadIdx.x & 31;
   const int w = (patch % patches_x) * kPatchW + (lane % kPatchW);
@@ -490,7 +496,7 @@ BwdLayout bwd_layout(const VbGrid* g, int dtype) {
   l.tables = o;   o += vb_align256((size_t)(3 * (g->oX + g->oY + g->oZ) + 2 * (g->vX + g->vY + g->vZ)) * 4 + 64);
   l.n_bev_blocks = vb_ceil_div(ncol, 256) * g->B;
   const int patches = vb_ceil_div(g->fW, kPatchW) * vb_ceil_div(g->fH, kPatchH);
-  l.n_march_blocks = vb_ceil_div(patches, kMarchThreads / 32) * g->N;
+  l.n_march_blocks = vb_ceil_div(patches, kMarchBwdThreads / 32) * g->N;
   l.partials = o; o += vb_align256((size_t)(l.n_bev_blocks + (size_t)l.n_march_blocks * g->B) * 4);
   l.total = o;
   return l;
@@ -555,13 +561,13 @@ int launch_render_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
       VB_LAUNCH_CHECK();
     }
     VbTraceScope tr(VB_K_MARCH_BWD, st);
-    dim3 grid(vb_ceil_div(patches, kMarchThreads / 32), g->N, g->B);
+    dim3 grid(vb_ceil_div(patches, kMarchBwdThreads / 32), g->N, g->B);
     if (in->geom)
-      march_bwd_kernel<T, K, false><<<grid, kMarchThreads, 0, st>>>(
+      march_bwd_kernel<T, K, false><<<grid, kMarchBwdThreads, 0, st>>>(
           *g, *t, vb_render_div(g), d_mats, in->geom, packed, in->beta, out->rgb, out->seg, out->depth, gr->g_rgb, gr->g_seg,
           gr->g_depth, gpacked, partials + n_partials, packed_stride, gpacked_stride);
     else
-      march_bwd_kernel<T, K, true><<<grid, kMarchThreads, 0, st>>>(
+      march_bwd_kernel<T, K, true><<<grid, kMarchBwdThreads, 0, st>>>(
           *g, *t, vb_render_div(g), d_mats, nullptr, packed, in->beta, out->rgb, out->seg, out->depth, gr->g_rgb, gr->g_seg,
           gr->g_depth, gpacked, partials + n_partials, packed_stride, gpacked_stride);
     VB_LAUNCH_CHECK();

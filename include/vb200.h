@@ -304,11 +304,14 @@ int vb200_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, co
  * Concurrent render calls on one device (several host threads / streams) are safe; they share the side stream. */
 int vb200_render_set_fork(int enable);
 
-/* Depth-split camera march.  When a render call has too few rays to fill the GPU (batch 1 at the R50 config), the
- * march is launched as thread-block clusters of `segments` CTAs: each CTA composites one contiguous part of the
+/* Depth-split camera march (opt-in).  When a render call has too few rays to fill the GPU (batch 1 at the R50 config),
+ * the march can be launched as thread-block clusters of `segments` CTAs: each CTA composites one contiguous part of the
  * ray samples and the parts are folded front to back through distributed shared memory (out = out_0 + T_0 out_1 ...).
- * Same samples, same weights; the fold changes the summation order (within the forward tolerance of section "zones").
- * segments: 0 = choose per call (default), 1 = never split, 2 / 4 / 8 = always use that many.  Process-wide. */
+ * Same samples, same weights; the fold changes the summation order (within the forward tolerance), which is why it is
+ * off by default: with it a sample's last bits would depend on the size of the batch it rides in.
+ * segments: 0 = default (never, unless the environment variable VB200_MARCH_SPLIT says otherwise), 1 = never,
+ * -1 = automatic (two segments while the launch is under one wave: -11 % / -16 % march time at batch 1, bf16 / fp32),
+ * 2 / 4 / 8 = always that many.  Process-wide. */
 int vb200_render_set_march_split(int segments);
 
 typedef struct VbRenderGrad {

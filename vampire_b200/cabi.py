@@ -246,7 +246,8 @@ def trace_collect():
 
 
 def render_set_march_split(segments: int) -> None:
-    """Depth segments of the camera march: 0 = chosen per call, 1 = never split, 2 / 4 / 8 = forced (include/vb200.h)."""
+    """Depth segments of the camera march: 0 = default (never), 1 = never, -1 = automatic, 2 / 4 / 8 = forced
+    (include/vb200.h)."""
     check(lib().vb200_render_set_march_split(int(segments)))
 
 

@@ -35,7 +35,7 @@ namespace {
 // families fill each other's idle issue slots.  Everything stays stream-ordered w.r.t. the caller's
 // stream (fork event before, join event after), so caller-owned buffers remain valid.
 std::atomic<int> g_render_fork_disabled{0};
-std::atomic<int> g_march_split{0};      // 0 = heuristic, 1 = never split, 2 / 4 / 8 = force that many depth segments
+std::atomic<int> g_march_split{0};      // 0 = default (VB200_MARCH_SPLIT, else never), 1 = never, -1 = auto, 2 / 4 / 8 = forced
 
 constexpr int kMaxSplit = 8;
 struct SideStream {
@@ -1217,20 +1217,21 @@ int launch_render_fwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
     const int xblocks = vb_ceil_div(patches, kMarchThreads / 32);
     dim3 grid(xblocks, g->N, nb);
     VbTraceScope tr(VB_K_MARCH_FWD, st, 2);
-    // depth split (march_cluster_fold): when this round's blocks would not fill the GPU once, clusters of nseg
-    // CTAs share each group of patches.  vb200_render_set_march_split() / VB200_MARCH_SPLIT override (1 = never).
+    // depth split (march_cluster_fold): clusters of nseg CTAs share each group of patches; opt-in through
+    // vb200_render_set_march_split() / VB200_MARCH_SPLIT.
     int nseg = 1;
     {
       static const int split_env = getenv("VB200_MARCH_SPLIT") ? atoi(getenv("VB200_MARCH_SPLIT")) : 0;
-      const int forced = g_march_split.load(std::memory_order_relaxed) > 0 ? g_march_split.load(std::memory_order_relaxed)
-                                                                            : split_env;
+      const int set = g_march_split.load(std::memory_order_relaxed);
+      const int mode = set != 0 ? set : split_env;       // 0 / 1: never, -1: auto, 2 / 4 / 8: forced
       const long long blocks = (long long)xblocks * g->N * nb, slots = (long long)VB_SM_COUNT_B200 * VB_MARCH_MINB;
       // measured on B200 (R50, bf16 / fp32, render call incl. pack): B = 1: 0.209 / 0.301 ms unsplit, 0.186 / 0.254 with
       // 2 segments, 0.209 / 0.280 with 4, 0.257 / 0.328 with 8; B = 2: 0.274 unsplit, 0.305 with 2 -- a later segment
-      // cannot see that the ray is already opaque and gathers what the unsplit march skips, so the split only pays
-      // while the launch is under one wave, and only in two
-      if (forced > 0) nseg = forced;
-      else if (blocks < slots) nseg = 2;
+      // cannot see that the ray is already opaque and gathers what the unsplit march skips, so "auto" splits only
+      // while the launch is under one wave, and only in two.  Off by default: the fold changes the summation order, and
+      // a sample's result must not depend on the batch it rides in (the sharding invariant of the data-parallel path).
+      if (mode > 1) nseg = mode;
+      else if (mode < 0 && blocks < slots) nseg = 2;
       while (nseg > 1 && (nseg > 8 || (g->D - 1) / nseg < 4)) nseg /= 2;    // portable cluster size; >= 4 samples each
       nseg = nseg >= 8 ? 8 : nseg >= 4 ? 4 : nseg >= 2 ? 2 : 1;
     }
@@ -1410,7 +1411,7 @@ extern "C" int vb200_render_plan_build(const VbGrid* g, const VbTables* t, const
 }
 
 extern "C" int vb200_render_set_march_split(int segments) {
-  VB_CHECK_ARG(segments == 0 || segments == 1 || segments == 2 || segments == 4 || segments == 8);
+  VB_CHECK_ARG(segments == -1 || segments == 0 || segments == 1 || segments == 2 || segments == 4 || segments == 8);
   g_march_split.store(segments);
   return VB200_OK;
 }

@@ -170,7 +170,7 @@ template <typename T, int CP> struct PackedLoad {
 // [r S / n, (r + 1) S / n) with a transmittance that starts at 1.  Volume rendering composes front to back:
 //   out = out_0 + T_0 out_1 + T_0 T_1 out_2 + ...,   T = T_0 T_1 ...
 // so every CTA leaves (acc, dep, T, ch[NV]) of its segment in its own shared memory and CTA 0 folds the others in
-// through distributed shared memory (cluster.map_shared_rank), in segment order.  Used when the launch would not fill
+// through distributed shared memory (cluster.map_shared_rank), in segment order.  Meant for launches that do not fill
 // the GPU (B = 1 at the R50 config: 528 blocks on 740 slots, and the kernel then lasts as long as its longest ray):
 // n times more, n times shorter blocks.  A segment cannot know that an earlier one already made the ray opaque, so it
 // composites samples the unsplit march skips (their weight is below term_eps after the fold) -- which is why two

@@ -64,7 +64,9 @@ constexpr int kMarchBwdThreads = VB_MARCH_BWD_THREADS;
 #ifndef VB_MARCH_BWD_MINB
 #define VB_MARCH_BWD_MINB 3   // measured B=1 fp32: 0.593 ms at 3 blocks/SM, 0.68 at 4, 0.76 at 5 (B=8: 4.35 ms either way: L2-bound)
                               // block shape (B=1 is 1.19 waves of 128-thread blocks): 96 x 5 (one wave, 128 regs) 0.652,
-                              // 64 x 7 0.693, 64 x 6 (168 regs) 0.594 vs 0.605 -- nothing to gain, 128 x 3 stays
+                              // 64 x 7 0.693, 64 x 6 (168 regs) 0.594 vs 0.605 -- nothing to gain, 128 x 3 stays.
+                              // L1 prefetch of the next sample's 8 corner records (prefetch.global.L1, coordinates
+                              // computed one iteration early): B=1 0.617 -> 0.649, B=8 4.49 -> 4.64 -- slower, removed
 #endif
 template <typename T, int K, bool FROM_MATS>
 __global__ void __launch_bounds__(kMarchBwdThreads, VB_MARCH_BWD_MINB) march_bwd_kernel(

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define VB200_VERSION 201 /* 0.2.0 */
+#define VB200_VERSION 202 /* 0.2.0 */
 
 enum vb200_status {
   VB200_OK = 0,
@@ -80,7 +80,10 @@ typedef struct VbGrid {
   int32_t vZ, vY, vX;     /* seg voxel grid (20, 256, 256)                                      */
   int32_t oZ, oY, oX;     /* det / BEV grid (10, 256, 256)                                      */
   int32_t C, K;           /* context channels (16), semantic classes (18)                       */
-  int32_t has_bda;        /* 0: mats_dict has no 'bda_mat' (BV2:370,343 skip the bda products)  */
+  int16_t has_bda;        /* 0: mats_dict has no 'bda_mat' (BV2:370,343 skip the bda products)  */
+  int16_t density_mode;   /* enum vb200_density: how the density feature becomes sigma (BV2:191-194).  Shares a word
+                           * with has_bda on purpose: the struct is a by-value kernel parameter, and growing it past
+                           * 128 bytes cost the recomputing camera march 5-11 % (measured: ptxas spills differently) */
   float img_w_m1, img_h_m1; /* float(W-1), float(H-1)          BV2:499-500                      */
   float x_hi, y_hi;       /* float(W-0.5), float(H-0.5)        BV2:494-495                      */
   float d_lo, d_hi;       /* d_bound[0], d_bound[1]            BV2:496                          */
@@ -92,7 +95,6 @@ typedef struct VbGrid {
   float sdf_bias;         /* density bias (-1)                 render_utils.py:35               */
   float beta_min;         /* 1e-4                              render_utils.py:31               */
   float term_eps;         /* early-termination threshold on transmittance; 0 disables          */
-  int32_t density_mode;   /* enum vb200_density: how the density feature becomes sigma          BV2:191-194 */
 } VbGrid;
 
 /* Lattice tables, DEVICE pointers to fp32 arrays built on the host with the reference's own torch

@@ -1,5 +1,6 @@
 """CPU: the C-ABI library loads and exports every symbol include/vb200.h declares (no compute
 calls without a GPU), plus the host-side logic (config, lattice, matrices, synth, grid constants)."""
+import ctypes as C
 import os
 import re
 
@@ -25,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"libvb200.so does not export {name}"
     assert sorted(cabi.exported_symbols()) == declared
-    assert lib.vb200_version() == 201
+    assert lib.vb200_version() == 202
     assert b"sm_100" in lib.vb200_strerror(-3)
 
 
@@ -49,10 +50,12 @@ def test_struct_layout_matches_header():
         decl = decl.strip()
         if not decl:
             continue
-        decl = re.sub(r"^(int32_t|float)\s+", "", decl)
+        decl = re.sub(r"^(int32_t|int16_t|float)\s+", "", decl)
         names += [re.sub(r"\[\d+\]", "", n.strip()) for n in decl.split(",")]
     assert names == [f[0] for f in cabi.VbGrid._fields_]
     assert cabi.VbGrid.seg_lo.size == 12 and cabi.VbGrid.seg_ext.size == 12
+    # a by-value kernel parameter: has_bda / density_mode share one word so that it stays at 128 bytes (vb200.h)
+    assert C.sizeof(cabi.VbGrid) == 128 and cabi.VbGrid.density_mode.offset == cabi.VbGrid.has_bda.offset + 2
 
 
 def test_config_sizes():

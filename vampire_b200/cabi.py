@@ -31,14 +31,13 @@ class VbGrid(C.Structure):
         ("D", C.c_int32), ("fH", C.c_int32), ("fW", C.c_int32),
         ("vZ", C.c_int32), ("vY", C.c_int32), ("vX", C.c_int32),
         ("oZ", C.c_int32), ("oY", C.c_int32), ("oX", C.c_int32),
-        ("C", C.c_int32), ("K", C.c_int32), ("has_bda", C.c_int32),
+        ("C", C.c_int32), ("K", C.c_int32), ("has_bda", C.c_int16), ("density_mode", C.c_int16),
         ("img_w_m1", C.c_float), ("img_h_m1", C.c_float),
         ("x_hi", C.c_float), ("y_hi", C.c_float),
         ("d_lo", C.c_float), ("d_hi", C.c_float), ("d_ext", C.c_float),
         ("seg_lo", C.c_float * 3), ("seg_ext", C.c_float * 3),
         ("bg_depth", C.c_float), ("bev_delta", C.c_float),
         ("sdf_bias", C.c_float), ("beta_min", C.c_float), ("term_eps", C.c_float),
-        ("density_mode", C.c_int32),
     ]
 
 

@@ -776,6 +776,18 @@ def main():
                                 "cpu": cpu_model(), "kind": "port",
                                 "lift_pts_per_s": cpts / best_l, "render_rays_per_s": crays / best_r,
                                 "sample": desc + f"; 1 warm-up + best of 3: lift {best_l:.2f} s, render {best_r:.2f} s"}
+        if args.workload == "fwd":
+            # the backward side of the same CPU path (fwd and fwd+bwd), one un-warmed pass: it is ~10x the
+            # forward (grid_sampler_3d_backward) and a best-of-3 would not fit a default run
+            bl, br, _, _, _ = cpu_reference_pass(cfg, cfg.num_cams, "train")
+            t0 = time.perf_counter()
+            bl()
+            t1 = time.perf_counter()
+            br()
+            t2 = time.perf_counter()
+            line["cpu_baseline"]["fwd_bwd"] = {
+                "lift_s": t1 - t0, "render_s": t2 - t1, "pts_per_s": cpts / (t2 - t0),
+                "sample": "same sample, forward+backward with unit cotangents, one un-warmed pass"}
     emit_json(line)
     if world > 1:
         dist.destroy_process_group()

@@ -33,3 +33,17 @@ def test_oracle_naive_catseg_matches_reference_fixture():
         logits, dens = tp.occupancy_queries(conf, sem, den, mats["bda_mat"], None, torch.from_numpy(gold["occ_coords"]))
     assert_close_scaled(logits.numpy(), gold["occ_logits"], 1e-6, "oracle naive occ_logits")
     assert_close_scaled(dens.numpy(), gold["occ_density_tanh"], 1e-6, "oracle naive occ_density")
+
+
+def test_det_points_are_the_reference_output_coords_flipped():
+    """cat_seg samples the logits at ``LiftRenderB200.det_points()``: they must be the reference's ``output_coords``
+    buffer (built by the oracle with the reference's own torch calls) with z flipped, bit for bit, in volume order."""
+    from vampire_b200.view_transform import LiftRenderB200
+    conf = gm.CFG.backbone_kwargs()
+    mod = LiftRenderB200(**conf)
+    ref = tp.build_buffers(conf)["output_coords"][..., :3].flip(0).reshape(-1, 3)
+    assert torch.equal(mod.det_points(), ref)
+    assert isinstance(mod.density, torch.nn.Sigmoid) and mod._beta().numel() == 1
+    with torch.no_grad():      # the epilogue of BV2:629-630 in 'naive' mode multiplies by the density itself
+        v, d = torch.randn(1, 34, 5, 4, 4), torch.rand(1, 1, 5, 4, 4)
+        assert torch.equal(mod.bev_epilogue(v, d), v * d)

@@ -243,6 +243,13 @@ class LiftRenderB200(nn.Module):
                 outs[7] = self.bev_epilogue(outs[7], outs[6])
         return tuple(outs)
 
+    def det_points(self) -> Tensor:
+        """(oZ*oY*oX, 3) ego coordinates of the det-grid voxel centres in the order of the BEV feature volume: the
+        reference's ``output_coords`` (BV2:273-293, meshgrid ij order z, y, x) with z flipped (BV2:443), top level first."""
+        lat = ops.state(self.cfg_id).lattice
+        z, y, x = torch.meshgrid(lat.ozs.flip(0), lat.oys, lat.oxs, indexing="ij")
+        return torch.stack([x, y, z], -1).reshape(-1, 3)
+
     def _cat_seg(self, outs, semantic_logits: Tensor):
         """``cat_seg=True`` (BV2:449-450; the default of BaseLSSImpaintor): the BEV feature volume carries the resampled,
         un-composited semantic logits behind the C feature channels.  They are the det-grid voxel centres sampled from
@@ -251,9 +258,7 @@ class LiftRenderB200(nn.Module):
             return outs
         cfg = self.cfg
         if self._det_points is None or self._det_points.device != semantic_logits.device:
-            lat = ops.state(self.cfg_id).lattice
-            z, y, x = torch.meshgrid(lat.ozs.flip(0), lat.oys, lat.oxs, indexing="ij")
-            self._det_points = torch.stack([x, y, z], -1).reshape(-1, 3).to(semantic_logits.device)
+            self._det_points = self.det_points().to(semantic_logits.device)
         seg, _ = ops.query_points_fwd(semantic_logits, self._det_points, None, None, self.cfg_id, False, False, False)
         seg = seg.reshape(seg.shape[0], cfg.K, cfg.oZ, cfg.oY, cfg.oX).to(outs[7].dtype)
         outs[7] = torch.cat([outs[7], seg], dim=1)

@@ -292,9 +292,12 @@ __global__ void __launch_bounds__(kBevBwdThreads) bev_bwd_partials_kernel(
   for (int l = 0; l < g.oZ; ++l) out[(size_t)l * ncol] = sG[l * TB + tid];
 }
 
+// Two sweeps over the column's levels, nothing kept in per-level register arrays (the first version held G[16] and S[16]:
+// 113 registers, 24 % occupancy for a kernel that only streams): sweep 1 sums the channel-group partials of each level
+// in fixed group order, parks the sum in group 0's slot and accumulates omega; sweep 2 re-reads S_l and G_l.
 template <int K>
 __global__ void __launch_bounds__(256) bev_bwd_composite_kernel(
-    VbGrid g, const float* __restrict__ beta_ptr, const float* __restrict__ g_vd, const float* __restrict__ gpart_ws,
+    VbGrid g, const float* __restrict__ beta_ptr, const float* __restrict__ g_vd, float* __restrict__ gpart_ws,
     int ngroups, float* __restrict__ wl_ws, float* __restrict__ ds_ws, float* __restrict__ beta_partials) {
   __shared__ float s_red[8];
   const int b = blockIdx.y;
@@ -303,48 +306,40 @@ __global__ void __launch_bounds__(256) bev_bwd_composite_kernel(
   const bool live = col_raw < ncol;
   const int col = live ? col_raw : ncol - 1;
   const float beta = fabsf(__ldg(beta_ptr)) + g.beta_min;
-  float G[kMaxLevels], S[kMaxLevels];
-#pragma unroll
-  for (int l = 0; l < kMaxLevels; ++l) {
-    G[l] = 0.0f;
-    S[l] = 0.0f;
-    if (l < g.oZ) {
-      const size_t o = ((size_t)b * g.oZ + l) * ncol + col;
-      S[l] = ds_ws[o];                                   // sampled density feature parked by stage 1
-      for (int grp = 0; grp < ngroups; ++grp) G[l] += __ldg(gpart_ws + (size_t)grp * g.B * g.oZ * ncol + o);
-    }
-  }
-  // total = sum_l w_l G_l, then the front-to-back (top-down) recurrences
+  const size_t gstride = (size_t)g.B * g.oZ * ncol;
+  // total = sum_l w_l G_l, top-down
   float omega = 0.0f, tau = 0.0f;
-#pragma unroll
-  for (int l = 0; l < kMaxLevels; ++l) {
-    if (l < g.oZ) {
-      const float sigma = vb_density(g, S[l], beta);
-      const float sd = sigma * g.bev_delta;
-      const float w = (1.0f - expf(-sd)) * expf(-tau);
-      tau += sd;
-      omega = fmaf(w, G[l], omega);
-      if (live) wl_ws[((size_t)b * g.oZ + l) * ncol + col] = w;
+  for (int l = 0; l < g.oZ; ++l) {
+    const size_t o = ((size_t)b * g.oZ + l) * ncol + col;
+    float G = 0.0f;
+    for (int grp = 0; grp < ngroups; ++grp) G += gpart_ws[(size_t)grp * gstride + o];
+    const float sigma = vb_density(g, ds_ws[o], beta);                                   // S_l parked by stage 1
+    const float sd = sigma * g.bev_delta;
+    const float w = (1.0f - expf(-sd)) * expf(-tau);
+    tau += sd;
+    omega = fmaf(w, G, omega);
+    if (live) {
+      wl_ws[o] = w;
+      gpart_ws[o] = G;           // group 0's slot now holds the level's total (this thread is its only reader)
     }
   }
   float prefix = 0.0f, dbeta = 0.0f;
   tau = 0.0f;
-#pragma unroll
-  for (int l = 0; l < kMaxLevels; ++l) {
-    if (l < g.oZ) {
-      const DensityD dd = vb_density_with_grads(g, S[l], beta);
-      const float sd = dd.sigma * g.bev_delta;
-      const float trans = expf(-tau), e_sd = expf(-sd);
-      const float w = (1.0f - e_sd) * trans;
-      prefix = fmaf(w, G[l], prefix);
-      const float dsd = G[l] * (trans * e_sd) - (omega - prefix);
-      const float dsig = dsd * g.bev_delta + (g_vd ? __ldg(g_vd + ((size_t)b * g.oZ + l) * ncol + col) : 0.0f);
-      if (live) {
-        ds_ws[((size_t)b * g.oZ + l) * ncol + col] = dsig * dd.ds;
-        dbeta = fmaf(dsig, dd.dbeta, dbeta);
-      }
-      tau += sd;
+  for (int l = 0; l < g.oZ; ++l) {
+    const size_t o = ((size_t)b * g.oZ + l) * ncol + col;
+    const float G = gpart_ws[o];     // (a dead thread reads another column's slot: its result is discarded)
+    const DensityD dd = vb_density_with_grads(g, ds_ws[o], beta);
+    const float sd = dd.sigma * g.bev_delta;
+    const float trans = expf(-tau), e_sd = expf(-sd);
+    const float w = (1.0f - e_sd) * trans;
+    prefix = fmaf(w, G, prefix);
+    const float dsd = G * (trans * e_sd) - (omega - prefix);
+    const float dsig = dsd * g.bev_delta + (g_vd ? __ldg(g_vd + o) : 0.0f);
+    if (live) {
+      ds_ws[o] = dsig * dd.ds;
+      dbeta = fmaf(dsig, dd.dbeta, dbeta);
     }
+    tau += sd;
   }
   const float tot = block_sum(dbeta, s_red);
   if (threadIdx.x == 0) beta_partials[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;

@@ -97,7 +97,26 @@ bda = torch.eye(4, device="cuda")[None]
 t = timed(lambda: mod.occupancy(sem, den, bda, coords))
 P = coords.numel() // 3
 mb = (P * 3 * 4 + (cfg.K + 1) * P * 4 + (cfg.K + 1) * 16 * 200 * 200 * 4 * 0 + (cfg.K + 1) * cfg.vZ * cfg.vY * cfg.vX * 4 * (16.0 * 0.4 / 8.0) * (80.0 / 102.4) ** 2) / 1e6
-print(f"| occupancy queries (640k pts, 18 logits + sigma) fwd | {t:.3f} | {mb:.1f} | {mb / t:.0f} | {mb / t / 65.51:.1f} |")
+print(f"| occupancy queries (640k pts, 18 logits + sigma) fwd: the module call (2 ops + views + tanh) | {t:.3f} | {mb:.1f} | {mb / t:.0f} | {mb / t / 65.51:.1f} |")
+# the two query kernels alone (libvb200's per-launch CUDA events), with the grid queried x-fastest (what the module
+# does) and in the z-fastest order it arrives in
+for label, pts in (("x-fastest (module)", coords.permute(2, 1, 0, 3).reshape(-1, 3).contiguous()),
+                   ("z-fastest (as given)", coords.reshape(-1, 3).contiguous())):
+    rot = bda[:, :3, :3].contiguous()
+    def both():
+        ops.query_points_fwd(sem, pts, rot, None, mod.cfg_id, True, False, False)
+        ops.query_points_fwd(den, pts, rot, mod.density.beta, mod.cfg_id, False, True, False)
+    for _ in range(3):
+        both()
+    torch.cuda.synchronize()
+    cabi.trace_enable(True)
+    for _ in range(10):
+        both()
+    torch.cuda.synchronize()
+    tr = cabi.trace_collect()
+    cabi.trace_enable(False)
+    tk = sum(ms for ms, _ in tr.values()) / 10
+    print(f"| ... query kernels only, points {label} | {tk:.3f} | {mb:.1f} | {mb / tk:.0f} | {mb / tk / 65.51:.1f} |")
 
 print("\n## next row (SURVEY 8f 1): softmax over the 86 depth planes (BV2:551), R50 256x704\n")
 print("| case | ms | algorithmic MB | GB/s | % of 6551 GB/s |")

@@ -97,6 +97,7 @@ class LiftRenderB200(nn.Module):
         self.register_buffer("_unit_beta", torch.ones(()), persistent=False)
         self.channels_last_volume = channels_last_volume
         self._det_points = None       # cat_seg: det-grid voxel centres, built on first use
+        self._occ_pts = None          # occupancy(): the caller's Occ3D grid re-ordered x-fastest (identity + version keyed)
         st = ops.state(self.cfg_id)
         lat = st.lattice
         # the reference's buffers (BV2:146-160), rebuilt from the same 1-D axes
@@ -303,11 +304,17 @@ class LiftRenderB200(nn.Module):
         200x200x16 grid, rotated per sample by bda[:3,:3] (``bda_mat=None``: the unrotated grid of
         ``BaseLSSImpaintor``, base_lss_impaintor.py:611-616).  Returns (occ_logits (B,X,Y,Z,K),
         tanh(occ_density) (B,X,Y,Z,1)) like the reference's return tuple."""
-        shape = occ_coords.shape[:-1]
-        pts = occ_coords.reshape(-1, 3).to(semantic_logits.device)
+        # The grid arrives (X, Y, Z, 3) with z fastest; consecutive z are whole (y, x) planes apart in the volumes, so a
+        # warp of consecutive points would gather from 32 planes.  Query it x-fastest instead (neighbouring threads,
+        # neighbouring voxels) and hand the result back as the reference's (B, X, Y, Z, ch) view.
+        X, Y, Z = occ_coords.shape[:-1]
+        key = (occ_coords, occ_coords._version, semantic_logits.device)
+        if self._occ_pts is None or self._occ_pts[0][0] is not key[0] or self._occ_pts[0][1:] != key[1:]:
+            self._occ_pts = (key, occ_coords.to(semantic_logits.device).permute(2, 1, 0, 3).reshape(-1, 3).contiguous())
+        pts = self._occ_pts[1]
         rot = None if bda_mat is None else bda_mat[:, :3, :3].to(semantic_logits.device)
         logits, _ = ops.query_points_fwd(semantic_logits, pts, rot, None, self.cfg_id, True, False, False)
         dens, _ = ops.query_points_fwd(density_feature, pts, rot, self._beta(density_feature.device), self.cfg_id, False, True, False)
         B = semantic_logits.shape[0]
-        return (logits.reshape(B, -1, *shape).permute(0, 2, 3, 4, 1),
-                dens.reshape(B, 1, *shape).permute(0, 2, 3, 4, 1).tanh())
+        return (logits.reshape(B, -1, Z, Y, X).permute(0, 4, 3, 2, 1),
+                dens.reshape(B, 1, Z, Y, X).permute(0, 4, 3, 2, 1).tanh())

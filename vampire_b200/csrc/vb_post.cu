@@ -77,6 +77,35 @@ __global__ void __launch_bounds__(256) upsample_bwd_kernel(const float* __restri
   const int ox_lo = max(0, (int)floorf((float)(x - 1) / sx) - 1), ox_hi = min(OW - 1, (int)ceilf((float)(x + 1) / sx) + 1);
   const float* g = gout + (size_t)plane * OH * OW;
   float acc = 0.0f;
+  // the x weights do not depend on the output row: tabulate them once per thread (x4: the window is <= 12 columns)
+  constexpr int kWin = 14;
+  if (ox_hi - ox_lo < kWin) {
+    float wxv[kWin];
+#pragma unroll
+    for (int k = 0; k < kWin; ++k) {
+      const int ox = ox_lo + k;
+      wxv[k] = 0.0f;
+      if (ox <= ox_hi) {
+        int x0, x1;
+        float lx0, lx1;
+        up_axis(ox, sx, W, x0, x1, lx0, lx1);
+        wxv[k] = (x0 == x ? lx0 : 0.0f) + (x1 == x ? lx1 : 0.0f);
+      }
+    }
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      int y0, y1;
+      float ly0, ly1;
+      up_axis(oy, sy, H, y0, y1, ly0, ly1);
+      const float wy = (y0 == y ? ly0 : 0.0f) + (y1 == y ? ly1 : 0.0f);
+      if (wy == 0.0f) continue;
+      const float* row = g + (size_t)oy * OW + ox_lo;
+#pragma unroll
+      for (int k = 0; k < kWin; ++k)      // same order and the same products as the generic loop below
+        if (wxv[k] != 0.0f) acc = fmaf(wy * wxv[k], __ldg(row + k), acc);
+    }
+    gin[(size_t)plane * H * W + i] = acc;
+    return;
+  }
   for (int oy = oy_lo; oy <= oy_hi; ++oy) {
     int y0, y1;
     float ly0, ly1;

@@ -1,19 +1,20 @@
 """One pass over every libvb200 kernel family at the MINI geometry, for compute-sanitizer:
 
-    compute-sanitizer --tool memcheck python tools/memcheck_probe.py
+    compute-sanitizer --tool memcheck python tools/memcheck_probe.py [--full]
 """
 import dataclasses, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from vampire_b200 import cabi, ops, synth
-from vampire_b200.config import MINI
+from vampire_b200.config import MINI, R50_256x704
 from vampire_b200.matrices import prepare_matrices
 from vampire_b200.plan import PlanCache
 from vampire_b200.view_transform import LiftRenderB200
 
 torch.manual_seed(0)
-B = 2
-for cfg in (MINI, dataclasses.replace(MINI, density_mode="naive", cat_seg=True)):
+FULL = "--full" in sys.argv          # the R50 256x704 geometry, B = 1 (the fast paths the bench runs)
+BASE, B = (R50_256x704, 1) if FULL else (MINI, 2)
+for cfg in (BASE, dataclasses.replace(BASE, density_mode="naive", cat_seg=True)):
     mod = LiftRenderB200(plans="off", **cfg.backbone_kwargs()).cuda().train()
     mats = synth.make_mats(cfg, B, "stress")
     prep = prepare_matrices(mats["sensor2ego_mats"][:, 0], mats["intrin_mats"][:, 0], mats["ida_mats"][:, 0],

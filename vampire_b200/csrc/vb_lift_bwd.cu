@@ -188,7 +188,6 @@ __global__ void __launch_bounds__(kThreads, VB_LIFT_BWD_MINB) lift_bwd_kernel(Vb
   const int ya = max(y0, 0), yb = min(y0 + 1, g.fH - 1);
   const bool inx0 = x0 >= 0, inx1 = x0 + 1 < g.fW, iny0 = y0 >= 0, iny1 = y0 + 1 < g.fH;
   const int pxl[4] = {ya * g.fW + xa, ya * g.fW + xb, yb * g.fW + xa, yb * g.fW + xb};
-  const bool pin[4] = {iny0 && inx0, iny0 && inx1, iny1 && inx0, iny1 && inx1};
   const float* ccam = ctx_nhwc + (size_t)bn * HW * kC;
   for (int i = lane; i < 64; i += 32) cv[i] = __ldg(ccam + (size_t)pxl[i >> 4] * kC + (i & 15));
   for (int i = lane; i < 4 * D; i += 32) bins[i] = 0.0f;

@@ -1,7 +1,6 @@
 """GPU: SURVEY §8f row 4 -- the BaseBiLinear ablation's 2-D lift (base_bilinear.py:471-517) as the D = 1 case of
 the lift kernels: forward, backward and the bit-exact validity mask, against the torch oracle (which
 tests/test_oracle_vs_reference.py pins to the reference's own BaseBiLinear.get_voxel_feats)."""
-import numpy as np
 import pytest
 import torch
 

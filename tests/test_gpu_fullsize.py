@@ -1,7 +1,6 @@
 """GPU: BASELINE.json's full sizes.  Parity against the live torch oracle where it finishes in seconds,
 and size-independent properties (batch independence = the multi-GPU sharding invariant, linearity,
 determinism) at the bench workload's shape and dtype."""
-import numpy as np
 import pytest
 import torch
 

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import CASES, Case, assert_close_scaled
+from helpers import Case, assert_close_scaled
 from oracle import torch_path as tp
 
 pytestmark = pytest.mark.gpu

@@ -1,6 +1,5 @@
 """GPU: the callers right after the path: x4 bilinear upsample of the rendered maps
 and the point / occupancy queries, forward and backward, against the torch oracle."""
-import numpy as np
 import pytest
 import torch
 

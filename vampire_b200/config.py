@@ -7,7 +7,7 @@ dict straight through, exactly as it does to ``BaseVAMPIRE2.__init__``
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field, asdict
+from dataclasses import dataclass, asdict
 from typing import Sequence, Tuple
 
 

@@ -12,7 +12,7 @@ NCCL's own stream right after the render backward so it overlaps the lift backwa
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence
+from typing import List, Optional, Sequence
 
 import torch
 import torch.distributed as dist

@@ -12,7 +12,7 @@ the same bits are regenerated on every box.
 from __future__ import annotations
 
 import math
-from typing import Dict, Optional
+from typing import Dict
 
 import torch
 

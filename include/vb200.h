@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define VB200_VERSION 202 /* 0.2.0 */
+#define VB200_VERSION 203 /* 0.2.0 */
 
 enum vb200_status {
   VB200_OK = 0,
@@ -266,6 +266,10 @@ typedef struct VbRenderIn {
   const VbRenderPlan* plans; /* optional DEVICE array of B cached plans (forward only; ignored when geom is given):
                            the camera march reads its geometry from them instead of recomputing it */
   int32_t flags;        /* VB200_RENDER_* bits (forward only) */
+  const void* packed;   /* optional, BACKWARD only: the channels-last copy of density | sem | rgb that the forward built
+                           at the start of its workspace (B consecutive copies of vb200_render_packed_bytes() each,
+                           present when the forward's workspace held all B samples).  Given, vb200_render_bwd does
+                           not pack the volumes a second time; NULL = pack again */
 } VbRenderIn;
 
 /* voxel_output leaves vb200_render_fwd already multiplied by tanh(voxel_density) -- by voxel_density itself when

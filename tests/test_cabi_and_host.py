@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"libvb200.so does not export {name}"
     assert sorted(cabi.exported_symbols()) == declared
-    assert lib.vb200_version() == 202
+    assert lib.vb200_version() == 203
     assert b"sm_100" in lib.vb200_strerror(-3)
 
 

@@ -179,3 +179,24 @@ def test_negative_beta_parameter_sign():
         outs = ops.render_fwd(vols[0], vols[1], vols[2], vols[3], beta, prep, None, cid, True, 3)
         gs.append(torch.autograd.grad(outs[2].sum() + outs[5].sum(), beta)[0].item())
     assert gs[0] != 0 and abs(gs[0] + gs[1]) <= 1e-6 * abs(gs[0])
+
+
+def test_render_backward_reuses_the_forward_packed_volume():
+    """The forward op hands its workspace to autograd; the backward reads the channels-last copy in it instead of packing
+    density | sem | rgb again.  Same gradients as the backward that packs (vector atomics: last bits may differ)."""
+    case = Case("mini_stress")
+    ops, cid = _ops(case.cfg)
+    vols = [t.cuda() for t in (case.den, case.sem, case.rgb, case.feat)]
+    beta = torch.tensor(0.1, device="cuda")
+    prep = case.prep.cuda()
+    res = torch.ops.vampire_b200.render_fwd(*vols, beta, prep, None, cid, True, 3, None)
+    outs, ws = list(res[:8]), res[8]
+    cots = [c.cuda() for c in case.cotangents()[1:]]
+    cots[7] = cots[7].to(outs[7].dtype)
+    a = ops.render_bwd(cots, outs, *vols, beta, prep, None, cid, True, 3, ws)
+    b = ops.render_bwd(cots, outs, *vols, beta, prep, None, cid, True, 3, None)
+    for name, x, y in zip(("g_den", "g_sem", "g_rgb", "g_feat", "g_beta"), a, b):
+        assert torch.allclose(x, y, rtol=1e-4, atol=1e-5 * float(y.abs().max())), name
+    assert torch.equal(a[3], b[3])                      # the BEV feature gradient is a deterministic gather
+    with pytest.raises(ValueError):
+        ops.render_bwd(cots, outs, *vols, beta, prep, None, cid, True, 3, ws[:1024])

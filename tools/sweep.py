@@ -47,7 +47,7 @@ for name, cfg in (("256x704", R50_256x704), ("512x1408", R50_512x1408)):
     t_rf = timed(lambda: ops.render_fwd(den, sem, rgb, feat, beta, prep, None, cid, True, 3))
     outs = ops.render_fwd(den, sem, rgb, feat, beta, prep, None, cid, True, 3)
     gr = [torch.randn_like(o) for o in outs]
-    t_rb = timed(lambda: ops.render_bwd(gr, list(outs), den, sem, rgb, feat, beta, prep, None, cid, True, 3))
+    t_rb = timed(lambda: ops.render_bwd(gr, list(outs), den, sem, rgb, feat, beta, prep, None, cid, True, 3, None))
     pts = cfg.num_cams * cfg.D * cfg.fH * cfg.fW
     rays = cfg.num_cams * cfg.fH * cfg.fW
     print(f"| {name} | {t_lf:.3f} | {t_lb:.3f} | {t_rf:.3f} | {t_rb:.3f} | {pts} | {pts / t_lf / 1e6:.2f} | {rays / t_rf / 1e3:.1f} |")

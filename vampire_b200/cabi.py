@@ -58,7 +58,7 @@ class VbRenderPlan(C.Structure):
 
 class VbRenderIn(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("density", "sem", "rgb", "feat", "beta", "geom", "plans")] + \
-        [("flags", C.c_int32)]
+        [("flags", C.c_int32), ("packed", C.c_void_p)]
 
 
 RENDER_TANH_EPILOGUE = 1

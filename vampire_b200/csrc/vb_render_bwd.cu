@@ -551,7 +551,9 @@ int launch_render_bwd(const VbGrid* g, const VbTables* t, const float* d_mats, c
   const size_t gpacked_stride = vb_align256(nvox * cp * 4) / 4;
   if (cam) {
     if (cudaMemsetAsync(gpacked, 0, (size_t)g->B * gpacked_stride * 4, st) != cudaSuccess) return VB200_ERR_CUDA;
-    {
+    if (in->packed) {
+      packed = const_cast<T*>(reinterpret_cast<const T*>(in->packed));     // the forward's copy (read only here)
+    } else {
       VbTraceScope tr(VB_K_PACK, st);
       pack_cam_volume_kernel<T, K><<<dim3(vb_ceil_div(nvox, kPackThreads * PackVox<T>::n), g->B), kPackThreads, 0, st>>>(
           den, sem, rgb, packed, (int)nvox, packed_stride, nullptr);

@@ -409,9 +409,10 @@ def _render_out_shapes(cfg: PathConfig, B: int):
             (B, 1, cfg.oZ, cfg.oY, cfg.oX), (B, Cc, cfg.oZ, cfg.oY, cfg.oX)]
 
 
-def _render_in_struct(density, sem, rgb, feat, beta, geom, plan=None, flags=0):
+def _render_in_struct(density, sem, rgb, feat, beta, geom, plan=None, flags=0, packed=None):
     rin = cabi.VbRenderIn()
     rin.flags = flags
+    rin.packed = None if packed is None else packed.data_ptr()
     rin.density, rin.sem, rin.rgb, rin.feat = density.data_ptr(), sem.data_ptr(), rgb.data_ptr(), feat.data_ptr()
     rin.beta = beta.data_ptr()
     rin.geom = None if geom is None else geom.data_ptr()
@@ -452,8 +453,10 @@ def render_fwd(density: Tensor, sem: Tensor, rgb: Tensor, feat: Tensor, beta: Te
     if tanh_epilogue:
         if torch.is_grad_enabled() and any(t.requires_grad for t in (density, sem, rgb, feat, beta)):
             raise RuntimeError("render_fwd(tanh_epilogue=True) is forward-only; multiply outside when gradients are needed")
-        return _render_fwd(density, sem, rgb, feat, beta, mats, geom, cfg_id, has_bda, branches | _TANH_BIT, plan)
-    return _render_fwd(density, sem, rgb, feat, beta, mats, geom, cfg_id, has_bda, branches, plan)
+        return _render_fwd(density, sem, rgb, feat, beta, mats, geom, cfg_id, has_bda, branches | _TANH_BIT, plan)[:8]
+    # the op's ninth output is its workspace: autograd keeps it (the backward re-uses the packed volume in it), every
+    # other caller drops it here and the allocator gets it back at once
+    return _render_fwd(density, sem, rgb, feat, beta, mats, geom, cfg_id, has_bda, branches, plan)[:8]
 
 
 _TANH_BIT = 1 << 8     # rides in `branches` through the op schema (bit 0 / 1: camera / BEV branch)
@@ -481,8 +484,7 @@ def _render_fwd(density: Tensor, sem: Tensor, rgb: Tensor, feat: Tensor, beta: T
     outs.append(torch.empty(shapes[7], dtype=density.dtype, device=dev))
     g = st.grid(B, has_bda)
     lib = cabi.lib()
-    ws_bytes = lib.vb200_render_fwd_workspace(C.byref(g), dt) + \
-        lib.vb200_render_packed_bytes(C.byref(g), dt) * ((B if st.render_group <= 0 else min(B, st.render_group)) - 1)
+    ws_bytes = _render_ws_bytes(st, g, dt, B)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     flags = cabi.RENDER_TANH_EPILOGUE if branches & _TANH_BIT else 0
     branches &= 3
@@ -497,22 +499,33 @@ def _render_fwd(density: Tensor, sem: Tensor, rgb: Tensor, feat: Tensor, beta: T
     if not branches & cabi.BRANCH_BEV:
         for t in outs[3:]:
             t.zero_()
-    return outs
+    return outs + [ws]
+
+
+def _render_ws_bytes(st, g, dt, B):
+    lib = cabi.lib()
+    return lib.vb200_render_fwd_workspace(C.byref(g), dt) + \
+        lib.vb200_render_packed_bytes(C.byref(g), dt) * ((B if st.render_group <= 0 else min(B, st.render_group)) - 1)
 
 
 @_render_fwd.register_fake
 def _(density, sem, rgb, feat, beta, mats, geom, cfg_id, has_bda, branches, plan):
-    cfg = state(cfg_id).cfg
-    shapes = _render_out_shapes(cfg, density.shape[0])
+    st = state(cfg_id)
+    cfg = st.cfg
+    B = density.shape[0]
+    shapes = _render_out_shapes(cfg, B)
     outs = [density.new_empty(s, dtype=torch.float32) for s in shapes[:7]]
     outs.append(density.new_empty(shapes[7]))
-    return outs
+    ws_bytes = _render_ws_bytes(st, st.grid(B, has_bda), cabi.dtype_code(density.dtype), B)
+    return outs + [density.new_empty(ws_bytes, dtype=torch.uint8)]
 
 
 @torch.library.custom_op("vampire_b200::render_bwd", mutates_args=())
 def render_bwd(grads: List[Tensor], outs: List[Tensor], density: Tensor, sem: Tensor, rgb: Tensor, feat: Tensor,
                beta: Tensor, mats: Tensor, geom: Optional[Tensor], cfg_id: int, has_bda: bool,
-               branches: int) -> List[Tensor]:
+               branches: int, packed: Optional[Tensor]) -> List[Tensor]:
+    """``packed``: the forward's workspace when it holds the channels-last copy of all B samples (else None): the
+    backward then reads that copy instead of packing density | sem | rgb a second time."""
     st = state(cfg_id)
     cfg = st.cfg
     dev = _need_cuda(density, sem, rgb, feat, beta, mats, geom)
@@ -531,7 +544,11 @@ def render_bwd(grads: List[Tensor], outs: List[Tensor], density: Tensor, sem: Te
     lib = cabi.lib()
     ws_bytes = lib.vb200_render_bwd_workspace(C.byref(g), dt)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    rin = _render_in_struct(density, sem, rgb, feat, beta32, geom)
+    if packed is not None:
+        need = lib.vb200_render_packed_bytes(C.byref(g), dt) * B
+        if packed.dtype != torch.uint8 or packed.numel() < need or packed.device != dev:
+            raise ValueError("render_bwd: `packed` is not the forward's workspace of this batch")
+    rin = _render_in_struct(density, sem, rgb, feat, beta32, geom, packed=packed)
     ro = _render_out_struct(outs)
     rg = cabi.VbRenderGrad()
     for name, t in zip(("g_rgb", "g_seg", "g_depth", "g_bev_rgb", "g_bev_seg", "g_bev_height", "g_voxel_density",
@@ -547,7 +564,7 @@ def render_bwd(grads: List[Tensor], outs: List[Tensor], density: Tensor, sem: Te
 
 
 @render_bwd.register_fake
-def _(grads, outs, density, sem, rgb, feat, beta, mats, geom, cfg_id, has_bda, branches):
+def _(grads, outs, density, sem, rgb, feat, beta, mats, geom, cfg_id, has_bda, branches, packed):
     return [torch.empty_like(density), torch.empty_like(sem), torch.empty_like(rgb), torch.empty_like(feat),
             density.new_empty(1, dtype=torch.float32)]
 
@@ -556,15 +573,19 @@ def _render_setup(ctx, inputs, output):
     density, sem, rgb, feat, beta, mats, geom, cfg_id, has_bda, branches, _plan = inputs
     ctx.save_for_backward(density, sem, rgb, feat, beta, mats, geom, *output)
     ctx.cfg_id, ctx.has_bda, ctx.branches = cfg_id, has_bda, branches
+    # the workspace (last output) starts with the packed copies of ALL samples only when one pack round covered the batch
+    st = state(cfg_id)
+    ctx.packed_ok = bool(branches & cabi.BRANCH_CAM) and (st.render_group <= 0 or st.render_group >= density.shape[0])
 
 
 def _render_backward(ctx, grads):
     saved = ctx.saved_tensors
     density, sem, rgb, feat, beta, mats, geom = saved[:7]
-    outs = list(saved[7:])
-    grads = [gt if gt is not None else torch.zeros_like(o) for gt, o in zip(grads, outs)]
+    outs, ws = list(saved[7:15]), saved[15]
+    grads = [gt if gt is not None else torch.zeros_like(o) for gt, o in zip(grads[:8], outs)]
     g_den, g_sem, g_rgb, g_feat, g_beta = render_bwd(grads, outs, density, sem, rgb, feat, beta, mats, geom,
-                                                     ctx.cfg_id, ctx.has_bda, ctx.branches)
+                                                     ctx.cfg_id, ctx.has_bda, ctx.branches & 3,
+                                                     ws if ctx.packed_ok else None)
     return g_den, g_sem, g_rgb, g_feat, g_beta.reshape(beta.shape).to(beta.dtype), None, None, None, None, None, None
 
 

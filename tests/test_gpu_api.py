@@ -159,6 +159,7 @@ def test_module_api_with_host_matrices_vs_same_host_oracle(seed):
             assert_close_scaled(o.cpu().numpy(), r.numpy(), 1e-5, "module render " + n)
 
 
+@pytest.mark.filterwarnings("ignore:The AccumulateGrad node's stream does not match")
 def test_graphed_train_step_matches_the_eager_step():
     """dp.GraphedTrainStep (two CUDA graphs around the all-reduce call) replays exactly dp.train_step: same outputs,
     same gradients, also after the producer has written new inputs and new matrices into the captured tensors."""

@@ -60,3 +60,26 @@ def test_plan_cache_keys_by_content_and_evicts_lru(monkeypatch):
     assert len(built) == n + 1
     pc.clear()
     assert pc.nbytes() == 0
+
+
+def test_prepared_matrices_cache_follows_identity_and_version():
+    """LiftRenderB200 prepares the 4x4 matrices once per distinct mats_dict contents: same tensors at the same version hit,
+    an in-place write or a new tensor object misses, a dict without bda_mat is its own entry."""
+    from vampire_b200 import synth
+    from vampire_b200.config import MINI
+    from vampire_b200.view_transform import LiftRenderB200
+    mod = LiftRenderB200(**MINI.backbone_kwargs())
+    mats = synth.make_mats(MINI, 2, "stress")
+    a = mod._prep_dict_cached(mats, 0, "cpu")
+    assert mod._prep_dict_cached(mats, 0, "cpu") is a and a[1] is True and a[2] is not None
+    assert mod._prep_dict_cached(dict(mats), 0, "cpu") is a                 # another dict, the same tensor objects
+    mats["ida_mats"][0, 0, 0, 0, 3] += 1.0                                   # in-place write bumps the version counter
+    b = mod._prep_dict_cached(mats, 0, "cpu")
+    assert b is not a and not torch.equal(b[0], a[0])
+    clone = {k: v.clone() for k, v in mats.items()}                          # equal values, other objects: recomputed
+    c = mod._prep_dict_cached(clone, 0, "cpu")
+    assert c is not b and torch.equal(c[0], b[0])
+    nobda = {k: v for k, v in mats.items() if k != "bda_mat"}
+    d = mod._prep_dict_cached(nobda, 0, "cpu")
+    assert d[1] is False and d is not b
+    assert len(mod._prep_cache) <= 4
